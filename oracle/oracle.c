@@ -1,0 +1,329 @@
+/* TEST INFRASTRUCTURE — CPU restatement ("oracle") of the FinRL env step path.  See oracle.h.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC   (NO fused multiply-add, NO fast-math:
+ * the reference's arithmetic is plain IEEE double/float, one rounding per operation).
+ * Parity: pinned against the unmodified reference by tests/golden/*.npz.
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ======================================================================================= */
+/* building blocks                                                                         */
+/* ======================================================================================= */
+
+/* numpy/core/src/npymath/npy_math_internal.h.src: npy_divmod / npy_floor_divide (numpy 2.3).
+ * Reached from env_stocktrading.py:178-180 (`self.state[0] // (price * (1 + buy_cost_pct))`) and
+ * env_stocktrading_np.py:124 (`self.amount // price[index]`). */
+double ora_floor_divide_f64(double a, double b)
+{
+    if (b == 0.0) return a / b;
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0) {
+        if ((b < 0) != (mod < 0)) {
+            mod += b;
+            div -= 1.0;
+        }
+    }
+    double fl;
+    if (div != 0.0) {
+        fl = floor(div);
+        if (div - fl > 0.5) fl += 1.0;
+    } else {
+        fl = copysign(0.0, a / b);
+    }
+    return fl;
+}
+
+float ora_floor_divide_f32(float a, float b)
+{
+    if (b == 0.0f) return a / b;
+    float mod = fmodf(a, b);
+    float div = (a - mod) / b;
+    if (mod != 0.0f) {
+        if ((b < 0) != (mod < 0)) {
+            mod += b;
+            div -= 1.0f;
+        }
+    }
+    float fl;
+    if (div != 0.0f) {
+        fl = floorf(div);
+        if (div - fl > 0.5f) fl += 1.0f;
+    } else {
+        fl = copysignf(0.0f, a / b);
+    }
+    return fl;
+}
+
+/* np.argsort(int64) default kind on AVX2/AVX-512 hosts (x86-simd-sort) for n <= 256: an
+ * ascending bitonic network on next_pow2(max(n,8)) slots padded with INT64_MAX, whose
+ * compare-exchange swaps (key,index) only on strict `>` (so ties keep network order, which is
+ * NOT the stable order).  SURVEY.md H1; call site env_stocktrading.py:317. */
+void ora_argsort_i64(const int64_t *keys, int n, int32_t *order_out)
+{
+    int slots = 8;
+    while (slots < n) slots <<= 1;
+    int64_t *k = (int64_t *)malloc(sizeof(int64_t) * (size_t)slots);
+    int32_t *ix = (int32_t *)malloc(sizeof(int32_t) * (size_t)slots);
+    for (int j = 0; j < slots; ++j) {
+        k[j] = j < n ? keys[j] : INT64_MAX;
+        ix[j] = j;
+    }
+#define CEX(lo, hi)                                                                                \
+    do {                                                                                           \
+        if (k[lo] > k[hi]) {                                                                       \
+            int64_t tk = k[lo]; k[lo] = k[hi]; k[hi] = tk;                                         \
+            int32_t ti = ix[lo]; ix[lo] = ix[hi]; ix[hi] = ti;                                     \
+        }                                                                                          \
+    } while (0)
+    for (int blk = 2; blk <= slots; blk <<= 1) {
+        /* "flip" stage: mirror pairs inside each block */
+        for (int b = 0; b < slots; b += blk)
+            for (int i = 0; i < blk / 2; ++i) CEX(b + i, b + blk - 1 - i);
+        /* half-cleaners */
+        for (int d = blk / 4; d >= 1; d >>= 1)
+            for (int b = 0; b < slots; b += 2 * d)
+                for (int i = 0; i < d; ++i) CEX(b + i, b + i + d);
+    }
+#undef CEX
+    for (int j = 0; j < n; ++j) order_out[j] = ix[j];
+    free(k);
+    free(ix);
+}
+
+/* numpy/core/src/umath/loops_utils.h.src: pairwise_sum (ndarray.sum on a contiguous vector). */
+float ora_pairwise_sum_f32(const float *a, int n)
+{
+    if (n < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < n; ++i) res += a[i];
+        return res;
+    } else if (n <= 128) {
+        float r[8];
+        int i;
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return ora_pairwise_sum_f32(a, n2) + ora_pairwise_sum_f32(a + n2, n - n2);
+    }
+}
+
+double ora_pairwise_sum_f64(const double *a, int n)
+{
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res += a[i];
+        return res;
+    } else if (n <= 128) {
+        double r[8];
+        int i;
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return ora_pairwise_sum_f64(a, n2) + ora_pairwise_sum_f64(a + n2, n - n2);
+    }
+}
+
+/* ======================================================================================= */
+/* A1: StockTradingEnv — finrl/meta/env_stock_trading/env_stocktrading.py                  */
+/* ======================================================================================= */
+
+#define MAXD 256
+
+static inline int32_t trd_state_day(int32_t sday) { return sday < 0 ? -sday - 1 : sday; }
+
+/* _initiate_state / _update_state (env_stocktrading.py:398-478) followed by the float32 cast
+ * DummyVecEnv applies when it copies the list into its observation buffer. */
+static void trd_obs_one(const ora_trading_cfg *c, double cash, const int32_t *hold, int32_t sday,
+                        float *obs)
+{
+    const int D = c->stock_dim, K = c->n_tech, T = c->n_days;
+    const int sd = trd_state_day(sday);
+    obs[0] = (float)cash;
+    for (int i = 0; i < D; ++i) obs[1 + i] = (float)c->close[(size_t)sd * D + i];
+    for (int i = 0; i < D; ++i) obs[1 + D + i] = (float)(double)hold[i];
+    for (int k = 0; k < K; ++k)
+        for (int i = 0; i < D; ++i)
+            obs[1 + 2 * D + k * D + i] = (float)c->tech[((size_t)k * T + sd) * D + i];
+}
+
+void ora_trading_obs(const ora_trading_cfg *c, const ora_trading_state *s, float *obs)
+{
+    const int D = c->stock_dim, O = 1 + 2 * D + c->n_tech * D;
+    for (int n = 0; n < c->n_envs; ++n)
+        trd_obs_one(c, s->cash[n], s->hold + (size_t)n * D, s->sday[n], obs + (size_t)n * O);
+}
+
+/* __init__ (env_stocktrading.py:48-100) */
+void ora_trading_init(const ora_trading_cfg *c, ora_trading_state *s, int32_t day0)
+{
+    const int D = c->stock_dim;
+    for (int n = 0; n < c->n_envs; ++n) {
+        s->cash[n] = c->initial_amount;
+        for (int i = 0; i < D; ++i) s->hold[(size_t)n * D + i] = c->init_hold ? c->init_hold[i] : 0;
+        s->day[n] = day0;
+        s->sday[n] = -day0 - 1;
+        s->cost[n] = 0.0;
+        s->trades[n] = 0;
+        s->reward[n] = 0.0;
+        s->episode[n] = 0;
+    }
+}
+
+/* reset (env_stocktrading.py:359-393): the state list is rebuilt from whatever day's rows are
+ * still loaded (line 361) BEFORE day is set to 0 (line 380) — quirk Q1. */
+static void trd_reset_one(const ora_trading_cfg *c, ora_trading_state *s, int n)
+{
+    const int D = c->stock_dim;
+    s->cash[n] = c->initial_amount;
+    for (int i = 0; i < D; ++i) s->hold[(size_t)n * D + i] = c->init_hold ? c->init_hold[i] : 0;
+    s->sday[n] = -s->day[n] - 1;
+    s->day[n] = 0;
+    s->cost[n] = 0.0;
+    s->trades[n] = 0;
+    s->episode[n] += 1;
+}
+
+void ora_trading_reset(const ora_trading_cfg *c, ora_trading_state *s, const uint8_t *mask)
+{
+    for (int n = 0; n < c->n_envs; ++n)
+        if (!mask || mask[n]) trd_reset_one(c, s, n);
+}
+
+static void trd_step_one(const ora_trading_cfg *c, ora_trading_state *s, int n, const void *actions,
+                         int actions_f64, double *reward_out, uint8_t *flags_out, float *obs,
+                         int auto_reset)
+{
+    const int D = c->stock_dim, T = c->n_days, O = 1 + 2 * D + c->n_tech * D;
+    int32_t *hold = s->hold + (size_t)n * D;
+    uint8_t flags = 0;
+
+    /* step(): terminal branch (env_stocktrading.py:221-301): no state change, previous scaled
+     * reward is returned again (quirk Q3). */
+    if (s->day[n] >= T - 1) {
+        flags |= ORA_FLAG_DONE;
+        if (reward_out) reward_out[n] = s->reward[n];
+        if (auto_reset) trd_reset_one(c, s, n); /* DummyVecEnv.step_wait: obs = env.reset() */
+        if (obs) trd_obs_one(c, s->cash[n], hold, s->sday[n], obs + (size_t)n * O);
+        if (flags_out) flags_out[n] = flags;
+        return;
+    }
+
+    const int sd = trd_state_day(s->sday[n]);
+    const double turb = (s->sday[n] < 0) ? 0.0 : c->risk[sd];
+    const int liq = c->use_turbulence && (turb >= c->turbulence_threshold);
+    if (liq) flags |= ORA_FLAG_LIQUIDATE;
+    const double *price = c->close + (size_t)sd * D;
+    const double *tech0 = c->n_tech > 0 ? c->tech + (size_t)sd * D : NULL; /* first indicator */
+
+    /* actions = (actions * hmax).astype(int) in the INPUT dtype (lines 304-307) */
+    int64_t a[MAXD];
+    for (int i = 0; i < D; ++i) {
+        if (actions_f64) {
+            double v = ((const double *)actions)[(size_t)n * D + i] * c->hmax;
+            a[i] = (int64_t)v;
+        } else {
+            float v = ((const float *)actions)[(size_t)n * D + i] * (float)c->hmax;
+            a[i] = (int64_t)v;
+        }
+    }
+    if (liq)
+        for (int i = 0; i < D; ++i) a[i] = (int64_t)(-c->hmax); /* lines 308-310 */
+
+    /* begin_total_asset: Python sum(), sequential (lines 311-314) */
+    double acc = 0.0;
+    for (int i = 0; i < D; ++i) acc = acc + price[i] * (double)hold[i];
+    const double begin = s->cash[n] + acc;
+
+    int32_t order[MAXD];
+    ora_argsort_i64(a, D, order); /* line 317 */
+    int nsell = 0, nbuy = 0;
+    for (int i = 0; i < D; ++i) {
+        nsell += a[i] < 0;
+        nbuy += a[i] > 0;
+    }
+    double cash = s->cash[n], cost = s->cost[n];
+    int32_t trades = s->trades[n];
+    const double one_minus_sc = 1 - c->sell_cost_pct, one_plus_bc = 1 + c->buy_cost_pct;
+
+    /* _sell_stock (lines 102-169) */
+    for (int k = 0; k < nsell; ++k) {
+        const int i = order[k];
+        if (liq) {
+            if (price[i] > 0 && hold[i] > 0) {
+                const double nsh = (double)hold[i];
+                cash += price[i] * nsh * one_minus_sc;
+                hold[i] = 0;
+                cost += price[i] * nsh * c->sell_cost_pct;
+                trades += 1;
+            }
+        } else {
+            const int disabled = tech0 && (tech0[i] == 1.0); /* `state[...] != True` (Q2) */
+            if (!disabled && hold[i] > 0) {
+                int64_t m = a[i] < 0 ? -a[i] : a[i];
+                if ((int64_t)hold[i] < m) m = hold[i];
+                const double nsh = (double)m;
+                cash += price[i] * nsh * one_minus_sc;
+                hold[i] -= (int32_t)m;
+                cost += price[i] * nsh * c->sell_cost_pct;
+                trades += 1;
+            }
+        }
+    }
+    /* _buy_stock (lines 171-213); buy_index = argsort[::-1][:nbuy] (line 319) */
+    for (int k = 0; k < nbuy; ++k) {
+        const int i = order[D - 1 - k];
+        if (liq) continue; /* turbulence >= threshold: no buys (lines 204-211) */
+        const int disabled = tech0 && (tech0[i] == 1.0);
+        if (disabled) continue;
+        const double avail = ora_floor_divide_f64(cash, price[i] * one_plus_bc);
+        /* Python min(avail, action): returns action only if action < avail */
+        const double nsh = ((double)a[i] < avail) ? (double)a[i] : avail;
+        cash -= price[i] * nsh * one_plus_bc;
+        hold[i] += (int32_t)nsh;
+        cost += price[i] * nsh * c->buy_cost_pct;
+        trades += 1; /* even when nsh == 0 (Q5) */
+    }
+
+    /* state: s -> s+1 (lines 335-342) */
+    s->day[n] += 1;
+    s->sday[n] = s->day[n];
+    const double *pnew = c->close + (size_t)s->day[n] * D;
+    acc = 0.0;
+    for (int i = 0; i < D; ++i) acc = acc + pnew[i] * (double)hold[i];
+    const double end = cash + acc;
+    const double reward = (end - begin) * c->reward_scaling; /* lines 350-352 */
+
+    s->cash[n] = cash;
+    s->cost[n] = cost;
+    s->trades[n] = trades;
+    s->reward[n] = reward;
+    if (reward_out) reward_out[n] = reward;
+    if (flags_out) flags_out[n] = flags;
+    if (obs) trd_obs_one(c, cash, hold, s->sday[n], obs + (size_t)n * O);
+}
+
+void ora_trading_step(const ora_trading_cfg *c, ora_trading_state *s, const void *actions,
+                      int actions_f64, double *reward_out, uint8_t *flags_out, float *obs,
+                      int auto_reset)
+{
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < c->n_envs; ++n)
+        trd_step_one(c, s, n, actions, actions_f64, reward_out, flags_out, obs, auto_reset);
+}

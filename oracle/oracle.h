@@ -1,0 +1,85 @@
+/* TEST INFRASTRUCTURE — CPU restatement ("oracle") of the FinRL env step path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load this library.  The product (finrl_b200/) never links, imports or calls it.
+ *
+ * Every function restates an algorithm of the reference (superyuri/FinRL) and cites the
+ * file:line it follows (paths relative to /root/reference).  Parity is PINNED: the oracle is
+ * checked against golden vectors produced by executing the unmodified reference
+ * (tests/golden/make_golden.py, tests/test_oracle_golden.py).
+ *
+ * Layout is the natural row-major one ([env][stock]); it deliberately differs from the
+ * stock-major device layout of the CUDA engine so that a layout bug cannot cancel out.
+ */
+#ifndef FINRL_ORACLE_H
+#define FINRL_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORA_FLAG_DONE 1u
+#define ORA_FLAG_LIQUIDATE 2u
+#define ORA_FLAG_SHORTAGE 4u
+
+/* ---- building blocks ------------------------------------------------------------------ */
+
+/* numpy's float floor-division (npy_divmod), used by `cash // (price*(1+cost))`
+ * (finrl/meta/env_stock_trading/env_stocktrading.py:178-180). */
+double ora_floor_divide_f64(double a, double b);
+float ora_floor_divide_f32(float a, float b);
+
+/* numpy's default (unstable, SIMD bitonic-network) argsort tie order for n <= 256 int64 keys,
+ * as used by `np.argsort(actions)` (env_stocktrading.py:317).  SURVEY.md H1. */
+void ora_argsort_i64(const int64_t *keys, int n, int32_t *order_out);
+
+/* numpy pairwise float32 summation of x[0..n) (ndarray.sum on a contiguous f32 vector). */
+float ora_pairwise_sum_f32(const float *x, int n);
+double ora_pairwise_sum_f64(const double *x, int n);
+
+/* ---- A1: StockTradingEnv (env_stocktrading.py) ----------------------------------------- */
+
+typedef struct {
+    int32_t n_envs, stock_dim, n_tech, n_days;
+    double hmax;
+    double initial_amount;
+    double buy_cost_pct, sell_cost_pct;
+    double reward_scaling;
+    int32_t use_turbulence; /* turbulence_threshold is not None */
+    double turbulence_threshold;
+    const double *close;     /* [T][D] */
+    const double *tech;      /* [K][T][D] */
+    const double *risk;      /* [T] (risk_indicator_col) */
+    const int32_t *init_hold; /* [D] num_stock_shares (or previous_state holdings) */
+} ora_trading_cfg;
+
+typedef struct {
+    double *cash;     /* [N] */
+    int32_t *hold;    /* [N][D] */
+    int32_t *day;     /* [N] */
+    int32_t *sday;    /* [N] day whose prices/tech sit in the state list; < 0 means "fresh":
+                         prices of day (-sday-1), turbulence == 0 (after ctor / reset) */
+    double *cost;     /* [N] */
+    int32_t *trades;  /* [N] */
+    double *reward;   /* [N] last scaled reward (returned again by the terminal no-op step) */
+    int32_t *episode; /* [N] */
+} ora_trading_state;
+
+/* ctor semantics (env_stocktrading.py:48-100): day=day0, state from day0, fresh. */
+void ora_trading_init(const ora_trading_cfg *c, ora_trading_state *s, int32_t day0);
+/* reset semantics incl. the stale-day quirk (env_stocktrading.py:359-393). mask may be NULL. */
+void ora_trading_reset(const ora_trading_cfg *c, ora_trading_state *s, const uint8_t *mask);
+/* observation = float32 cast of the reference's state list (what DummyVecEnv hands an agent). */
+void ora_trading_obs(const ora_trading_cfg *c, const ora_trading_state *s, float *obs /*[N][O]*/);
+/* one step() for every env (env_stocktrading.py:220-357).  actions [N][D] f32 or f64.
+ * reward_out/flags_out/obs may be NULL.  auto_reset applies DummyVecEnv's reset-on-done. */
+void ora_trading_step(const ora_trading_cfg *c, ora_trading_state *s, const void *actions,
+                      int actions_f64, double *reward_out, uint8_t *flags_out, float *obs,
+                      int auto_reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,179 @@
+"""TEST INFRASTRUCTURE — ctypes front-end of the C oracle (oracle/oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module.  The product package ``finrl_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FLAG_DONE = 1
+FLAG_LIQUIDATE = 2
+FLAG_SHORTAGE = 4
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.ora_floor_divide_f64.restype = C.c_double
+        _LIB.ora_floor_divide_f64.argtypes = [C.c_double, C.c_double]
+        _LIB.ora_floor_divide_f32.restype = C.c_float
+        _LIB.ora_floor_divide_f32.argtypes = [C.c_float, C.c_float]
+        _LIB.ora_pairwise_sum_f32.restype = C.c_float
+        _LIB.ora_pairwise_sum_f64.restype = C.c_double
+    return _LIB
+
+
+def _p(a, ty=C.c_void_p):
+    return a.ctypes.data_as(ty) if a is not None else None
+
+
+def floor_divide_f64(a, b):
+    return lib().ora_floor_divide_f64(float(a), float(b))
+
+
+def floor_divide_f32(a, b):
+    return lib().ora_floor_divide_f32(float(a), float(b))
+
+
+def argsort_i64(keys):
+    keys = np.ascontiguousarray(keys, dtype=np.int64)
+    out = np.empty(keys.shape[0], dtype=np.int32)
+    lib().ora_argsort_i64(_p(keys), C.c_int(keys.shape[0]), _p(out))
+    return out
+
+
+def pairwise_sum_f32(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    return np.float32(lib().ora_pairwise_sum_f32(_p(x), C.c_int(x.shape[0])))
+
+
+def pairwise_sum_f64(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    return np.float64(lib().ora_pairwise_sum_f64(_p(x), C.c_int(x.shape[0])))
+
+
+# --------------------------------------------------------------------------------------------
+# A1
+# --------------------------------------------------------------------------------------------
+class _TradingCfg(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32),
+        ("stock_dim", C.c_int32),
+        ("n_tech", C.c_int32),
+        ("n_days", C.c_int32),
+        ("hmax", C.c_double),
+        ("initial_amount", C.c_double),
+        ("buy_cost_pct", C.c_double),
+        ("sell_cost_pct", C.c_double),
+        ("reward_scaling", C.c_double),
+        ("use_turbulence", C.c_int32),
+        ("turbulence_threshold", C.c_double),
+        ("close", C.c_void_p),
+        ("tech", C.c_void_p),
+        ("risk", C.c_void_p),
+        ("init_hold", C.c_void_p),
+    ]
+
+
+class _TradingState(C.Structure):
+    _fields_ = [
+        ("cash", C.c_void_p),
+        ("hold", C.c_void_p),
+        ("day", C.c_void_p),
+        ("sday", C.c_void_p),
+        ("cost", C.c_void_p),
+        ("trades", C.c_void_p),
+        ("reward", C.c_void_p),
+        ("episode", C.c_void_p),
+    ]
+
+
+class TradingOracle:
+    """N independent copies of the reference ``StockTradingEnv``
+    (finrl/meta/env_stock_trading/env_stocktrading.py), stepped on the CPU."""
+
+    def __init__(
+        self,
+        close,
+        tech,
+        risk,
+        n_envs,
+        hmax=100,
+        initial_amount=1_000_000,
+        buy_cost_pct=0.001,
+        sell_cost_pct=0.001,
+        reward_scaling=1e-4,
+        turbulence_threshold=None,
+        num_stock_shares=None,
+        day=0,
+    ):
+        self.close = np.ascontiguousarray(close, dtype=np.float64)
+        T, D = self.close.shape
+        self.tech = np.ascontiguousarray(tech, dtype=np.float64).reshape(-1, T, D)
+        K = self.tech.shape[0]
+        self.risk = np.ascontiguousarray(risk if risk is not None else np.zeros(T), dtype=np.float64)
+        self.N, self.D, self.K, self.T = int(n_envs), D, K, T
+        self.O = 1 + 2 * D + K * D
+        self.init_hold = np.ascontiguousarray(
+            num_stock_shares if num_stock_shares is not None else np.zeros(D), dtype=np.int32
+        )
+        N = self.N
+        self.cash = np.zeros(N)
+        self.hold = np.zeros((N, D), dtype=np.int32)
+        self.day = np.zeros(N, dtype=np.int32)
+        self.sday = np.zeros(N, dtype=np.int32)
+        self.cost = np.zeros(N)
+        self.trades = np.zeros(N, dtype=np.int32)
+        self.reward = np.zeros(N)
+        self.episode = np.zeros(N, dtype=np.int32)
+        self._cfg = _TradingCfg(
+            N, D, K, T, float(hmax), float(initial_amount), float(buy_cost_pct), float(sell_cost_pct),
+            float(reward_scaling), int(turbulence_threshold is not None),
+            float(turbulence_threshold if turbulence_threshold is not None else 0.0),
+            _p(self.close), _p(self.tech), _p(self.risk), _p(self.init_hold),
+        )
+        self._st = _TradingState(
+            _p(self.cash), _p(self.hold), _p(self.day), _p(self.sday), _p(self.cost), _p(self.trades),
+            _p(self.reward), _p(self.episode),
+        )
+        lib().ora_trading_init(C.byref(self._cfg), C.byref(self._st), C.c_int32(day))
+
+    def obs(self):
+        out = np.empty((self.N, self.O), dtype=np.float32)
+        lib().ora_trading_obs(C.byref(self._cfg), C.byref(self._st), _p(out))
+        return out
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        lib().ora_trading_reset(C.byref(self._cfg), C.byref(self._st), _p(m))
+        return self.obs()
+
+    def step(self, actions, auto_reset=False, want_obs=True):
+        a = np.ascontiguousarray(actions)
+        assert a.shape == (self.N, self.D) and a.dtype in (np.float32, np.float64)
+        reward = np.empty(self.N)
+        flags = np.empty(self.N, dtype=np.uint8)
+        obs = np.empty((self.N, self.O), dtype=np.float32) if want_obs else None
+        lib().ora_trading_step(
+            C.byref(self._cfg), C.byref(self._st), _p(a), C.c_int(a.dtype == np.float64), _p(reward), _p(flags),
+            _p(obs), C.c_int(int(auto_reset)),
+        )
+        return obs, reward, flags

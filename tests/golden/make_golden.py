@@ -1,0 +1,287 @@
+"""Generate golden vectors by EXECUTING THE UNMODIFIED REFERENCE (superyuri/FinRL).
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference env files are loaded as they lie (oracle/ref_loader.py installs inert stubs for
+gym / matplotlib / stable_baselines3, which are not installed and do not touch arithmetic), driven
+with seeded synthetic tables and actions, and every step's outputs are written to
+``tests/golden/*.npz``.  The fixtures travel to the GPU box; /root/reference does not.
+
+numpy {np} / pandas {pd} versions are recorded inside each fixture (argsort tie order and NEP-50
+promotion are numpy-version sensitive).
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from finrl_b200 import synthetic as syn  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+KIND = {float: 0, np.float32: 1, np.float64: 2, int: 0}
+
+
+def _meta():
+    return {"numpy_version": np.__version__, "pandas_version": pd.__version__}
+
+
+def _quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+# ------------------------------------------------------------------------------------------
+# A1  StockTradingEnv  (env_stocktrading.py)
+# ------------------------------------------------------------------------------------------
+def gen_trading(name, T, D, K, n_steps, seed, threshold, act_dtype, hmax=100, initial_amount=1_000_000,
+                num_stock_shares=None, plant_disable=(), cost=0.001, reward_scaling=1e-4, act_scale=1.0):
+    mod = ref_loader.load("env_stocktrading")
+    close, tech, turb = syn.make_tables(T, D, K, seed=seed)
+    for (t, i) in plant_disable:
+        tech[0, t, i] = 1.0
+    df = syn.make_frame(close, tech, turb)
+    shares = list(num_stock_shares) if num_stock_shares is not None else [0] * D
+    env = mod.StockTradingEnv(
+        df=df, stock_dim=D, hmax=hmax, initial_amount=initial_amount, num_stock_shares=list(shares),
+        buy_cost_pct=cost, sell_cost_pct=cost, reward_scaling=reward_scaling, state_space=1 + 2 * D + K * D,
+        action_space=D, tech_indicator_list=syn.INDICATORS[:K], turbulence_threshold=threshold,
+        print_verbosity=10**9,
+    )
+    actions = (syn.make_actions((n_steps, D), seed=seed + 1, dtype=np.float64) * act_scale).astype(act_dtype)
+    O = 1 + 2 * D + K * D
+    out = {
+        "obs0": np.asarray(env.state, dtype=np.float64),
+        "cash": np.zeros(n_steps), "hold": np.zeros((n_steps, D), dtype=np.int64), "reward": np.zeros(n_steps),
+        "done": np.zeros(n_steps, dtype=np.uint8), "liq": np.zeros(n_steps, dtype=np.uint8),
+        "trades": np.zeros(n_steps, dtype=np.int64), "cost": np.zeros(n_steps), "day": np.zeros(n_steps, dtype=np.int64),
+        "obs": np.zeros((n_steps, O), dtype=np.float32), "term_obs": np.zeros((n_steps, O), dtype=np.float32),
+        "begin_asset": np.zeros(n_steps),
+    }
+    with _quiet():
+        for s in range(n_steps):
+            liq = threshold is not None and env.turbulence >= threshold and env.day < T - 1
+            state, reward, done, _ = env.step(actions[s].copy())
+            out["liq"][s] = liq
+            out["reward"][s] = reward
+            out["done"][s] = done
+            # values BEFORE the auto-reset (the env's own post-step state)
+            out["trades"][s] = env.trades
+            out["cost"][s] = env.cost
+            out["term_obs"][s] = np.asarray(state, dtype=np.float64).astype(np.float32)
+            if done:  # what DummyVecEnv.step_wait does
+                state = env.reset()
+            out["cash"][s] = state[0]
+            out["hold"][s] = np.asarray(state[1 + D : 1 + 2 * D], dtype=np.float64).astype(np.int64)
+            out["day"][s] = env.day
+            out["obs"][s] = np.asarray(state, dtype=np.float64).astype(np.float32)
+            out["begin_asset"][s] = env.asset_memory[0]
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), close=close, tech=tech, risk=turb, actions=actions,
+        cfg=np.array([hmax, initial_amount, cost, cost, reward_scaling,
+                      -1.0 if threshold is None else 1.0, 0.0 if threshold is None else threshold]),
+        num_stock_shares=np.asarray(shares, dtype=np.int64), **out, **_meta(),
+    )
+    print(f"{name}: {n_steps} steps, dones={int(out['done'].sum())}, liq={int(out['liq'].sum())}, "
+          f"min cash={out['cash'].min():.3f}, trades[-1]={out['trades'][-1]}")
+
+
+# ------------------------------------------------------------------------------------------
+# A2  numpy / ElegantRL StockTradingEnv  (env_stocktrading_np.py)
+# ------------------------------------------------------------------------------------------
+def _kind(x):
+    return {float: 0, int: 0, np.float32: 1, np.float64: 2}[type(x)]
+
+
+def gen_np(name, T, D, K, n_steps, seed, if_train, thresh=99, **kw):
+    mod = ref_loader.load("env_stocktrading_np")
+    close, tech, turb = syn.make_tables(T, D, K, seed=seed)
+    price_array, tech_array, turb_array = syn.make_np_arrays(close, tech, turb)
+    cfg = {"price_array": price_array, "tech_array": tech_array, "turbulence_array": turb_array, "if_train": if_train}
+    env = mod.StockTradingEnv(cfg, turbulence_thresh=thresh, **kw)
+    np.random.seed(seed + 100)
+    obs0 = env.reset()
+    init = {"init_amount": np.float64(env.amount), "init_amount_kind": _kind(env.amount),
+            "init_stocks": env.stocks.copy(), "init_total": np.float64(env.total_asset),
+            "init_total_kind": _kind(env.total_asset)}
+    actions = syn.make_actions((n_steps, D), seed=seed + 1)
+    O = env.state_dim
+    out = {k: np.zeros(n_steps) for k in ("amount", "total", "gamma_reward", "reward", "episode_return")}
+    out.update({k: np.zeros(n_steps, dtype=np.uint8) for k in ("amount_kind", "total_kind", "gr_kind", "reward_kind", "done", "liq")})
+    out["stocks"] = np.zeros((n_steps, D), dtype=np.float32)
+    out["cool"] = np.zeros((n_steps, D), dtype=np.float32)
+    out["obs"] = np.zeros((n_steps, O), dtype=np.float32)
+    out["day"] = np.zeros(n_steps, dtype=np.int64)
+    resets = []
+    for s in range(n_steps):
+        state, reward, done, _ = env.step(actions[s])
+        out["liq"][s] = env.turbulence_bool[env.day] != 0
+        out["amount"][s] = env.amount
+        out["amount_kind"][s] = _kind(env.amount)
+        out["total"][s] = env.total_asset
+        out["total_kind"][s] = _kind(env.total_asset)
+        out["gamma_reward"][s] = env.gamma_reward
+        out["gr_kind"][s] = _kind(env.gamma_reward)
+        out["reward"][s] = reward
+        out["reward_kind"][s] = _kind(reward)
+        out["done"][s] = done
+        out["episode_return"][s] = env.episode_return
+        out["stocks"][s] = env.stocks
+        out["cool"][s] = env.stocks_cool_down
+        out["obs"][s] = state
+        out["day"][s] = env.day
+        assert state.dtype == np.float32
+        if done:
+            env.reset()
+            resets.append((np.float64(env.amount), _kind(env.amount), env.stocks.copy()))
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), price_array=price_array, tech_array=tech_array, turbulence_array=turb_array,
+        actions=actions, obs0=obs0, if_train=np.array(int(if_train)), thresh=np.array(float(thresh)),
+        reset_amount=np.array([r[0] for r in resets]), reset_amount_kind=np.array([r[1] for r in resets], dtype=np.uint8),
+        reset_stocks=np.array([r[2] for r in resets], dtype=np.float32).reshape(len(resets), D),
+        kw_keys=np.array(list(kw.keys()), dtype="U32"), kw_vals=np.array([float(v) for v in kw.values()]),
+        **init, **out, **_meta(),
+    )
+    print(f"{name}: {n_steps} steps, dones={int(out['done'].sum())}, liq={int(out['liq'].sum())}, "
+          f"min stocks={out['stocks'].min()}, kinds amount={sorted(set(out['amount_kind']))} reward={sorted(set(out['reward_kind']))}")
+
+
+# ------------------------------------------------------------------------------------------
+# A3  StockPortfolioEnv  (env_portfolio.py)
+# ------------------------------------------------------------------------------------------
+def gen_portfolio(name, T, D, K, n_steps, seed, act_dtype, lookback=252):
+    mod = ref_loader.load("env_portfolio")
+    close, tech, turb = syn.make_tables(T, D, K, seed=seed)
+    cov, first = syn.make_cov_table(close, lookback)
+    Te = T - first
+    close_e, tech_e, turb_e = close[first:], tech[:, first:], turb[first:]
+    df = syn.make_frame(close_e, tech_e, turb_e)
+    df["cov_list"] = [cov[t] for t in range(Te) for _ in range(D)]
+    env = mod.StockPortfolioEnv(
+        df=df, stock_dim=D, hmax=100, initial_amount=1_000_000, transaction_cost_pct=0.001, reward_scaling=1e-4,
+        state_space=D, action_space=D, tech_indicator_list=syn.INDICATORS[:K],
+    )
+    obs0 = np.asarray(env.reset(), dtype=np.float64)
+    actions = syn.make_actions((n_steps, D), seed=seed + 1, low=0.0, high=1.0, dtype=np.float64).astype(act_dtype)
+    out = {"pv": np.zeros(n_steps), "reward": np.zeros(n_steps), "done": np.zeros(n_steps, dtype=np.uint8),
+           "day": np.zeros(n_steps, dtype=np.int64), "weights": np.zeros((n_steps, D)),
+           "obs": np.zeros((n_steps, D + K, D)), "pret": np.zeros(n_steps)}
+    with _quiet():
+        for s in range(n_steps):
+            state, reward, done, _ = env.step(actions[s])
+            out["reward"][s] = reward
+            out["done"][s] = done
+            out["pret"][s] = env.portfolio_return_memory[-1]
+            out["weights"][s] = np.asarray(env.actions_memory[-1], dtype=np.float64)
+            if done:
+                state = env.reset()
+            out["pv"][s] = env.portfolio_value
+            out["day"][s] = env.day
+            out["obs"][s] = state
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), close=close_e, tech=tech_e, cov=cov, actions=actions,
+                        obs0=obs0, initial_amount=np.array(1_000_000.0), **out, **_meta())
+    print(f"{name}: {n_steps} steps, dones={int(out['done'].sum())}, pv[-1]={out['pv'][-1]:.6f}")
+
+
+# ------------------------------------------------------------------------------------------
+# A4  StockTradingEnvCashpenalty  (env_stocktrading_cashpenalty.py)
+# ------------------------------------------------------------------------------------------
+def gen_cashpenalty(name, T, D, n_steps, seed, act_dtype, threshold=None, patient=False, discrete=False, hmax=10,
+                    initial_amount=1e6, shares_increment=1, cols=("open", "close", "high", "low", "volume"),
+                    cost=3e-3, penalty=0.1):
+    mod = ref_loader.load("env_stocktrading_cashpenalty")
+    close, _tech, turb = syn.make_tables(T, D, 0, seed=seed)
+    o, h, l, v = syn.make_ohlv(close, seed)
+    df = syn.make_frame(close, np.zeros((0, T, D)), turb, tech_names=[], extra_cols={"open": o, "high": h, "low": l, "volume": v})
+    df = df.reset_index(drop=True)
+    with _quiet():
+        env = mod.StockTradingEnvCashpenalty(
+            df=df, buy_cost_pct=cost, sell_cost_pct=cost, hmax=hmax, discrete_actions=discrete,
+            shares_increment=shares_increment, turbulence_threshold=threshold, print_verbosity=10**9,
+            initial_amount=initial_amount, daily_information_cols=list(cols), cache_indicator_data=True,
+            cash_penalty_proportion=penalty, random_start=False, patient=patient,
+        )
+        obs0 = np.asarray(env.reset(), dtype=np.float64)
+    actions = syn.make_actions((n_steps, D), seed=seed + 1, dtype=np.float64).astype(act_dtype)
+    O = env.state_space
+    out = {"obs": np.zeros((n_steps, O)), "reward": np.zeros(n_steps), "done": np.zeros(n_steps, dtype=np.uint8),
+           "date_index": np.zeros(n_steps, dtype=np.int64), "liq": np.zeros(n_steps, dtype=np.uint8),
+           "term_obs": np.zeros((n_steps, O))}
+    with _quiet():
+        for s in range(n_steps):
+            liq = threshold is not None and env.turbulence >= threshold and env.date_index < T - 1
+            state, reward, done, _ = env.step(actions[s])
+            out["liq"][s] = liq
+            out["reward"][s] = reward
+            out["done"][s] = done
+            out["term_obs"][s] = np.asarray(state, dtype=np.float64)
+            if done:
+                state = env.reset()
+            out["obs"][s] = np.asarray(state, dtype=np.float64)
+            out["date_index"][s] = env.date_index
+    tables = {"close": close, "open": o, "high": h, "low": l, "volume": v, "turbulence": turb}
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), actions=actions, obs0=obs0, cols=np.array(list(cols), dtype="U16"),
+        cfg=np.array([cost, cost, hmax, float(discrete), shares_increment, -1.0 if threshold is None else 1.0,
+                      0.0 if threshold is None else threshold, initial_amount, penalty, float(patient)]),
+        **tables, **out, **_meta(),
+    )
+    print(f"{name}: {n_steps} steps, dones={int(out['done'].sum())}, liq={int(out['liq'].sum())}, "
+          f"min cash={out['obs'][:, 0].min():.3f}")
+
+
+def main():
+    assert ref_loader.available(), "needs /root/reference"
+    which = set(sys.argv[1:])
+
+    def want(k):
+        return not which or k in which
+
+    if want("trading"):
+        # DOW-30 shape, f32 actions, turbulence liquidation, planted disable flags, 3 episodes + stale resets
+        gen_trading("trading_d30_f32", T=40, D=30, K=8, n_steps=125, seed=0, threshold=70, act_dtype=np.float32,
+                    plant_disable=[(3, 4), (3, 17), (10, 0), (39, 2), (39, 29)])
+        # same shape but cash-starved (the sequential cash-constrained buys decide holdings)
+        gen_trading("trading_d30_starved", T=50, D=30, K=8, n_steps=110, seed=2, threshold=90, act_dtype=np.float32,
+                    initial_amount=150_000, plant_disable=[(5, 1), (20, 11)])
+        # D=5 (8 sort slots), f64 actions, no turbulence, non-zero initial holdings, tight cash
+        gen_trading("trading_d5_f64", T=25, D=5, K=2, n_steps=60, seed=3, threshold=None, act_dtype=np.float64,
+                    initial_amount=20_000, num_stock_shares=[5, 0, 7, 1, 0], hmax=50)
+        # D=13 (16 slots), f32, threshold 99, hmax 10 -> many tied actions
+        gen_trading("trading_d13_ties", T=30, D=13, K=3, n_steps=70, seed=5, threshold=99, act_dtype=np.float32, hmax=10,
+                    initial_amount=50_000)
+        # D=30, hmax=3: almost everything ties -> stresses the argsort tie rule; cash-starved
+        gen_trading("trading_d30_ties", T=60, D=30, K=1, n_steps=70, seed=7, threshold=None, act_dtype=np.float32, hmax=3,
+                    initial_amount=3_000)
+        # actions outside [-1,1] (the reference does not clip) and a high cost
+        gen_trading("trading_d8_wide", T=30, D=8, K=2, n_steps=40, seed=9, threshold=50, act_dtype=np.float64, hmax=100,
+                    initial_amount=100_000, cost=0.01, act_scale=3.0)
+    if want("np"):
+        gen_np("np_d30_eval", T=60, D=30, K=8, n_steps=130, seed=11, if_train=False)
+        gen_np("np_d30_train", T=40, D=30, K=8, n_steps=90, seed=12, if_train=True, thresh=60)
+        gen_np("np_d7_small", T=50, D=7, K=2, n_steps=110, seed=13, if_train=False, initial_capital=2e4, max_stock=50.0,
+               thresh=80)
+    if want("portfolio"):
+        gen_portfolio("portfolio_d30_f64", T=252 + 24, D=30, K=4, n_steps=50, seed=21, act_dtype=np.float64)
+        gen_portfolio("portfolio_d6_f32", T=40 + 12, D=6, K=2, n_steps=30, seed=22, act_dtype=np.float32, lookback=40)
+    if want("cashpenalty"):
+        gen_cashpenalty("cashpen_d10", T=30, D=10, n_steps=65, seed=31, act_dtype=np.float32, hmax=5000)
+        gen_cashpenalty("cashpen_d10_turb_patient", T=30, D=10, n_steps=65, seed=32, act_dtype=np.float64, threshold=70,
+                        patient=True, hmax=20000, initial_amount=1e5)
+        gen_cashpenalty("cashpen_d10_shortage", T=30, D=10, n_steps=40, seed=33, act_dtype=np.float32, hmax=20000,
+                        initial_amount=1e5)
+        gen_cashpenalty("cashpen_d6_discrete", T=24, D=6, n_steps=50, seed=34, act_dtype=np.float32, hmax=3000,
+                        discrete=True, shares_increment=3, threshold=90)
+
+
+if __name__ == "__main__":
+    main()

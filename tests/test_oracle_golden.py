@@ -1,0 +1,108 @@
+"""CPU: pin the oracle (oracle/oracle.c) against golden vectors made by the UNMODIFIED reference
+(tests/golden/make_golden.py) and against numpy itself for the numpy-defined building blocks."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as ora
+
+from conftest import GOLDEN
+
+
+# ---------------------------------------------------------------------------- building blocks
+def test_floor_divide_matches_numpy():
+    rng = np.random.default_rng(0)
+    a = np.concatenate([rng.uniform(-1e6, 1e6, 20000), rng.uniform(0, 50, 5000), [1.0, 0.0, -0.0, 5.0, -5.0, 1e-300]])
+    b = np.concatenate([rng.uniform(0.5, 500, 20000), rng.uniform(0.01, 3, 5000), [0.1, 3.0, 3.0, 5.0, 5.0, 7.0]])
+    # exact multiples (where floor(a/b) != numpy's divmod result most often)
+    k = rng.integers(-500, 500, 5000).astype(np.float64)
+    bb = rng.uniform(0.01, 300, 5000)
+    a = np.concatenate([a, k * bb, k * 0.1, k * 100.1])
+    b = np.concatenate([b, bb, np.full(5000, 0.1), np.full(5000, 100.1)])
+    want = np.floor_divide(a, b)
+    got = np.array([ora.floor_divide_f64(x, y) for x, y in zip(a, b)])
+    assert np.array_equal(want, got)
+    assert np.array_equal(np.signbit(want), np.signbit(got))
+    a32, b32 = a.astype(np.float32), b.astype(np.float32)
+    want32 = np.floor_divide(a32, b32)
+    got32 = np.array([ora.floor_divide_f32(x, y) for x, y in zip(a32, b32)], dtype=np.float32)
+    assert np.array_equal(want32, got32)
+    assert ora.floor_divide_f64(1.0, 0.1) == 9.0
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 8, 13, 16, 30, 32, 60, 64, 100, 128, 200, 256])
+def test_argsort_rule_matches_numpy(n):
+    """np.argsort's default tie order == the bitonic network rule.  Checked against the
+    numpy of THIS host; skipped (not failed) if the host's numpy dispatches another sort."""
+    rng = np.random.default_rng(n)
+    # self-check the host first: if numpy here disagrees on a canonical vector, the host lacks the
+    # AVX2/AVX-512 path the goldens were made with and the comparison is meaningless.
+    bad = 0
+    for trial in range(300):
+        hi = [2, 4, 11, 101][trial % 4]
+        keys = rng.integers(-hi, hi + 1, size=n).astype(np.int64)
+        if not np.array_equal(np.argsort(keys), ora.argsort_i64(keys)):
+            bad += 1
+    if bad and n <= 16:
+        pytest.skip(f"host numpy argsort does not use the SIMD network for n={n} ({bad}/300 differ)")
+    assert bad == 0
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 7, 8, 9, 30, 100, 127, 128, 129, 200, 1000])
+def test_pairwise_sum_matches_numpy(n):
+    rng = np.random.default_rng(n + 1)
+    for _ in range(50):
+        x = (rng.normal(0, 1000, n) * rng.uniform(0, 64, n)).astype(np.float32)
+        assert ora.pairwise_sum_f32(x) == x.sum()
+        y = x.astype(np.float64) * 1.000001
+        assert ora.pairwise_sum_f64(y) == y.sum()
+
+
+# ---------------------------------------------------------------------------- A1
+TRADING = sorted(glob.glob(os.path.join(GOLDEN, "trading_*.npz")))
+
+
+def trading_oracle_from_golden(g, n_envs=1):
+    hmax, init, bc, sc, rs, use_t, thr = g["cfg"]
+    return ora.TradingOracle(
+        g["close"], g["tech"], g["risk"], n_envs, hmax=hmax, initial_amount=init, buy_cost_pct=bc, sell_cost_pct=sc,
+        reward_scaling=rs, turbulence_threshold=(thr if use_t > 0 else None), num_stock_shares=g["num_stock_shares"],
+    )
+
+
+@pytest.mark.parametrize("path", TRADING, ids=[os.path.basename(p)[:-4] for p in TRADING])
+def test_trading_oracle_vs_reference(path):
+    g = np.load(path)
+    o = trading_oracle_from_golden(g)
+    assert np.array_equal(o.obs()[0], g["obs0"].astype(np.float32))
+    acts = g["actions"]
+    for s in range(acts.shape[0]):
+        obs, reward, flags = o.step(acts[s][None, :], auto_reset=True)
+        ctx = f"step {s}"
+        assert bool(flags[0] & ora.FLAG_DONE) == bool(g["done"][s]), ctx
+        assert bool(flags[0] & ora.FLAG_LIQUIDATE) == bool(g["liq"][s]), ctx
+        assert reward[0] == g["reward"][s], ctx  # bit-exact f64
+        assert o.cash[0] == g["cash"][s], ctx
+        assert np.array_equal(o.hold[0], g["hold"][s]), ctx
+        assert o.day[0] == g["day"][s], ctx
+        assert np.array_equal(obs[0], g["obs"][s]), ctx
+        if not g["done"][s]:
+            assert o.trades[0] == g["trades"][s], ctx
+            assert o.cost[0] == g["cost"][s], ctx
+
+
+def test_trading_oracle_no_auto_reset_terminal_is_noop():
+    g = np.load(os.path.join(GOLDEN, "trading_d5_f64.npz"))
+    o = trading_oracle_from_golden(g)
+    T = g["close"].shape[0]
+    acts = g["actions"]
+    for s in range(T - 1):
+        o.step(acts[s][None, :])
+    cash, hold, rew = o.cash.copy(), o.hold.copy(), o.reward.copy()
+    for s in range(3):  # terminal step: state unchanged, previous reward again (Q3)
+        obs, reward, flags = o.step(acts[T - 1 + s][None, :])
+        assert flags[0] & ora.FLAG_DONE
+        assert reward[0] == rew[0] and o.cash[0] == cash[0] and np.array_equal(o.hold, hold)
+        assert np.array_equal(obs[0], g["term_obs"][T - 1])
