@@ -1,0 +1,120 @@
+"""ctypes binding of include/finrl_b200.h — the only door between Python and the CUDA engine.
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, an exception
+is raised.  Nothing in this package computes an env step on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libfinrl_b200.so")
+
+FLAG_DONE = 1
+FLAG_LIQUIDATE = 2
+FLAG_SHORTAGE = 4
+
+OBS_NONE, OBS_LAST, OBS_ALL = 0, 1, 2
+N_STATS = 8
+STAT_NAMES = ("reward_sum", "reward_sqsum", "done_count", "episode_asset_sum", "asset_sum", "liq_count", "env_steps",
+              "trades_sum")
+
+ABI_VERSION = 1
+
+
+class EngineError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+
+class TradingParams(C.Structure):
+    """frl_trading_params (include/finrl_b200.h)."""
+
+    _fields_ = [
+        ("n_envs", C.c_int32),
+        ("stock_dim", C.c_int32),
+        ("n_tech", C.c_int32),
+        ("n_days", C.c_int32),
+        ("obs_dim", C.c_int32),
+        ("env_stride", C.c_int32),
+        ("hmax", C.c_double),
+        ("initial_amount", C.c_double),
+        ("buy_cost_pct", C.c_double),
+        ("sell_cost_pct", C.c_double),
+        ("reward_scaling", C.c_double),
+        ("use_turbulence", C.c_int32),
+        ("_pad0", C.c_int32),
+        ("turbulence_threshold", C.c_double),
+        ("close", C.c_void_p),
+        ("disable_mask", C.c_void_p),
+        ("risk", C.c_void_p),
+        ("obs_tmpl", C.c_void_p),
+        ("init_hold", C.c_void_p),
+        ("cash", C.c_void_p),
+        ("hold", C.c_void_p),
+        ("day", C.c_void_p),
+        ("sday", C.c_void_p),
+        ("cost", C.c_void_p),
+        ("trades", C.c_void_p),
+        ("reward", C.c_void_p),
+        ("episode", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/finrl_b200.h declares
+SIGNATURES = {
+    "frl_abi_version": (C.c_int32, []),
+    "frl_last_error": (C.c_char_p, []),
+    "frl_trading_init": (C.c_int32, [C.POINTER(TradingParams), C.c_int32, C.c_void_p]),
+    "frl_trading_reset": (C.c_int32, [C.POINTER(TradingParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "frl_trading_observe": (C.c_int32, [C.POINTER(TradingParams), C.c_void_p, C.c_void_p]),
+    "frl_trading_rollout": (
+        C.c_int32,
+        [C.POINTER(TradingParams), C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
+    ),
+    "frl_trading_step": (
+        C.c_int32,
+        [C.POINTER(TradingParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+         C.c_void_p],
+    ),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; fail loudly when it is missing (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                f"{LIB_PATH} not found: build it with `python -m finrl_b200.build` "
+                "(nvcc, sm_100a).  finrl_b200 has no CPU fallback."
+            )
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if l.frl_abi_version() != ABI_VERSION:
+            raise EngineError(f"ABI version mismatch: library {l.frl_abi_version()}, binding {ABI_VERSION}")
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().frl_last_error().decode("utf-8", "replace")
+        raise EngineError(f"{what} failed (status {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream(device):
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

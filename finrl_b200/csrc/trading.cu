@@ -1,0 +1,515 @@
+// A1 — StockTradingEnv (reference: finrl/meta/env_stock_trading/env_stocktrading.py).
+//
+// Mapping: ONE THREAD PER ENV for the arithmetic — the reference's sums are
+// sequential and the buys form a serial cash chain, so lanes of a warp run 32 independent envs in
+// lock-step instead of 32 lanes idling behind one chain — and ONE WARP PER 32-ENV TILE for the
+// memory traffic: actions are staged through shared memory with coalesced loads, the stock-major
+// state arrays are read/written coalesced straight from registers, and the observation rows (74 %
+// of the bytes of a step) are written by the whole warp, 128 B per store instruction.
+//
+// Bit-exactness: every product/sum on the cash path is an explicit __dmul_rn/__dadd_rn in the
+// reference's order; np.argsort's tie order is reproduced by running the same bitonic network
+//  on register-resident packed keys.
+#include "common.cuh"
+#include "sort_network.inc"
+
+namespace frl {
+namespace {
+
+constexpr int kMaxAbsAction = (1 << 26) - 1;  // |int(action*hmax)| is clamped to this (key packing)
+
+// keys are (a << 5) | index; swap only on STRICT a[lo] > a[hi] — ties keep network order.
+#define FRL_CEX(lo, hi)                                                                            \
+    {                                                                                              \
+        const bool sw_ = (lo) > ((hi) | 31);                                                       \
+        const int t_ = sw_ ? (hi) : (lo);                                                          \
+        (hi) = sw_ ? (lo) : (hi);                                                                  \
+        (lo) = t_;                                                                                 \
+    }
+
+// np.argsort(int64) tie order for n <= 32: ascending bitonic network (flip stage + half-cleaners),
+// emitted as straight-line code by gen_sort_network.py.
+template <int SLOTS>
+__device__ __forceinline__ void bitonic_network(int (&key)[SLOTS])
+{
+    static_assert(SLOTS == 8 || SLOTS == 16 || SLOTS == 32, "unsupported slot count");
+    if constexpr (SLOTS == 8) {
+        FRL_SORT_NETWORK_8(FRL_CEX, key)
+    } else if constexpr (SLOTS == 16) {
+        FRL_SORT_NETWORK_16(FRL_CEX, key)
+    } else {
+        FRL_SORT_NETWORK_32(FRL_CEX, key)
+    }
+}
+
+template <typename ActT>
+__device__ __forceinline__ int action_to_shares(ActT a, double hmax);
+template <>
+__device__ __forceinline__ int action_to_shares<float>(float a, double hmax)
+{
+    // float32 array * python int -> float32 product, then astype(int) truncates toward zero
+    const float v = fmul(a, (float)hmax);
+    long long t = __float2ll_rz(v);
+    t = t > kMaxAbsAction ? kMaxAbsAction : (t < -kMaxAbsAction ? -kMaxAbsAction : t);
+    return (int)t;
+}
+template <>
+__device__ __forceinline__ int action_to_shares<double>(double a, double hmax)
+{
+    const double v = dmul(a, hmax);
+    long long t = __double2ll_rz(v);
+    t = t > kMaxAbsAction ? kMaxAbsAction : (t < -kMaxAbsAction ? -kMaxAbsAction : t);
+    return (int)t;
+}
+
+constexpr int kHoldPitch = 33;  // hold_s[j][lane]: conflict-free both per-lane (compute) and per-row (obs)
+
+template <int SLOTS, typename ActT, int WARPS>
+struct alignas(16) WarpSmem {
+    // staged actions [32 envs][SLOTS+1].  Once a lane has turned ITS row into sort keys, the row is
+    // reused for that lane's sorted order (lane-private, so no cross-lane hazard and no barrier).
+    ActT act[32 * (SLOTS + 1)];
+    int hold[SLOTS * kHoldPitch];
+    float cashf[32];
+    int sd[32];
+};
+
+__device__ __forceinline__ int state_day(int sday) { return sday < 0 ? -sday - 1 : sday; }
+
+// sequential Python sum() of price*holding over the D stocks, then cash + that (:311-314, :344-347)
+template <int SLOTS>
+__device__ __forceinline__ double total_asset(double cash, const double *__restrict__ prow, const int *hold_s,
+                                              int lane, int D)
+{
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+        if (j < D) acc = dadd(acc, dmul(__ldg(prow + j), (double)hold_s[j * kHoldPitch + lane]));
+    }
+    return dadd(cash, acc);
+}
+
+// Warp-cooperative write of the 32 observation rows of a tile: row r = [cash, close[sd] x D,
+// holdings x D, tech[.][sd] x K*D] as float32.  Everything except the cash and holdings slots comes
+// from the per-day template row, which is identical for every env of the tile when they are in
+// lock-step (the common case): then it is loaded once into registers and only stored 32 times.
+template <int SLOTS, typename SM>
+__device__ __forceinline__ void write_obs_tile(const frl_trading_params &p, SM &sm, float *__restrict__ obs,
+                                               long long env0, int nvalid, int lane)
+{
+    const int O = p.obs_dim, D = p.stock_dim;
+    const int sd0 = sm.sd[0];
+    bool uniform = true;
+    if (lane < nvalid) uniform = (sm.sd[lane] == sd0);
+    uniform = __all_sync(0xffffffffu, uniform);
+    constexpr int kMaxChunks = 12;  // register-cached template covers O <= 384 (DOW-30: 301)
+    const int special_end = 2 * D + 1;  // positions [0, special_end) hold cash / close / holdings
+    if (uniform && O <= kMaxChunks * 32) {
+        float t[kMaxChunks];
+        const float *trow = p.obs_tmpl + (size_t)sd0 * O;
+#pragma unroll
+        for (int c = 0; c < kMaxChunks; ++c) {
+            const int pos = lane + 32 * c;
+            t[c] = pos < O ? __ldg(trow + pos) : 0.0f;
+        }
+        for (int r = 0; r < nvalid; ++r) {
+            float *orow = obs + (size_t)(env0 + r) * O;
+            const float cashf = sm.cashf[r];
+#pragma unroll
+            for (int c = 0; c < kMaxChunks; ++c) {
+                const int pos = lane + 32 * c;
+                if (pos < O) {
+                    float v = t[c];
+                    if (32 * c < special_end) {  // compile-time-ish per chunk, cheap otherwise
+                        if (pos == 0)
+                            v = cashf;
+                        else if (pos > D && pos < special_end)
+                            v = (float)sm.hold[(pos - 1 - D) * kHoldPitch + r];
+                    }
+                    orow[pos] = v;
+                }
+            }
+        }
+    } else {
+        for (int r = 0; r < nvalid; ++r) {
+            float *orow = obs + (size_t)(env0 + r) * O;
+            const float *trow = p.obs_tmpl + (size_t)sm.sd[r] * O;
+            const float cashf = sm.cashf[r];
+            for (int pos = lane; pos < O; pos += 32) {
+                float v = __ldg(trow + pos);
+                if (pos == 0)
+                    v = cashf;
+                else if (pos > D && pos < special_end)
+                    v = (float)sm.hold[(pos - 1 - D) * kHoldPitch + r];
+                orow[pos] = v;
+            }
+        }
+    }
+}
+
+template <int SLOTS, typename ActT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ actions, long long act_step_stride,
+                       long long act_env_stride, int n_steps, double *__restrict__ rewards,
+                       uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode, int auto_reset,
+                       double *__restrict__ stats)
+{
+    using SM = WarpSmem<SLOTS, ActT, WARPS>;
+    __shared__ SM smem[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SM &sm = smem[warp];
+    const int N = p.n_envs, D = p.stock_dim, T = p.n_days;
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;  // whole warp out of range (no block-level barriers are used)
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const bool valid = lane < nvalid;
+    const long long n = valid ? env0 + lane : (long long)N - 1;
+    constexpr int P = SLOTS + 1;
+
+    // ---- load state: one thread per env, stock-major holdings => coalesced ----
+    double cash = p.cash[n], cost = p.cost[n], last_reward = p.reward[n];
+    int day = p.day[n], sday = p.sday[n], trades = p.trades[n];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j)
+        sm.hold[j * kHoldPitch + lane] = (j < D) ? p.hold[(size_t)j * p.env_stride + n] : 0;
+
+    const double one_minus_sc = dsub(1.0, p.sell_cost_pct), one_plus_bc = dadd(1.0, p.buy_cost_pct);
+    const int hmax_i = (int)max(-(double)kMaxAbsAction, min((double)kMaxAbsAction, p.hmax));
+
+    double asset = 0.0;        // total asset of the current state when asset_ok
+    bool asset_ok = false;     // carried from the previous step of this launch (bitwise equal to a recompute)
+    double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_liq = 0.0;
+
+    for (int k = 0; k < n_steps; ++k) {
+        // ---- stage this step's actions for the tile (coalesced) ----
+        const ActT *abase = actions + (size_t)k * act_step_stride;
+        __syncwarp();
+        if (act_env_stride == D) {
+            const ActT *tile = abase + (size_t)env0 * D;
+            const int cnt = nvalid * D;
+            int row = 0, col = lane;
+            while (col >= D) { col -= D; ++row; }
+            for (int e = lane; e < cnt; e += 32) {
+                sm.act[row * P + col] = tile[e];
+                col += 32;
+                while (col >= D) { col -= D; ++row; }
+            }
+        } else {
+            for (int r = 0; r < nvalid; ++r)
+                if (lane < D) sm.act[r * P + lane] = abase[(size_t)(env0 + r) * act_env_stride + lane];
+        }
+        __syncwarp();
+
+        uint8_t flags = 0;
+        double reward;
+        if (day >= T - 1) {
+            // ---- terminal branch (:221-301): no state change, previous scaled reward again (Q3) ----
+            flags = FRL_FLAG_DONE;
+            reward = last_reward;
+            if (valid) {
+                const double *prow = p.close + (size_t)state_day(sday) * 32;
+                if (!asset_ok) asset = total_asset<SLOTS>(cash, prow, sm.hold, lane, D);
+                st_done += 1.0;
+                st_epi += asset;
+            }
+            if (auto_reset) {
+                // DummyVecEnv.step_wait -> env.reset() (:359-393): state list rebuilt from the rows
+                // of the day still loaded, THEN day = 0 (stale-day quirk Q1)
+                cash = p.initial_amount;
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j)
+                    if (j < D) sm.hold[j * kHoldPitch + lane] = p.init_hold ? __ldg(p.init_hold + j) : 0;
+                sday = -day - 1;
+                day = 0;
+                cost = 0.0;
+                trades = 0;
+                if (valid) p.episode[n] += 1;
+                asset_ok = false;
+            }
+        } else {
+            const int sd = state_day(sday);
+            const double turb = sday < 0 ? 0.0 : __ldg(p.risk + sd);
+            const bool liq = p.use_turbulence && (turb >= p.turbulence_threshold);
+            const double *prow = p.close + (size_t)sd * 32;
+            const double begin = asset_ok ? asset : total_asset<SLOTS>(cash, prow, sm.hold, lane, D);
+
+            if (liq) {
+                // actions = [-hmax]*D (:308-310): all keys tie, the network never swaps, so the sell
+                // order is the index order; liquidation checks price > 0, not the disable flag (:138-163)
+                flags = FRL_FLAG_LIQUIDATE;
+                if (hmax_i > 0) {
+#pragma unroll
+                    for (int j = 0; j < SLOTS; ++j) {
+                        if (j < D) {
+                            const double pj = __ldg(prow + j);
+                            const int h = sm.hold[j * kHoldPitch + lane];
+                            if (pj > 0.0 && h > 0) {
+                                const double pv = dmul(pj, (double)h);
+                                cash = dadd(cash, dmul(pv, one_minus_sc));
+                                sm.hold[j * kHoldPitch + lane] = 0;
+                                cost = dadd(cost, dmul(pv, p.sell_cost_pct));
+                                trades += 1;
+                            }
+                        }
+                    }
+                }
+            } else {
+                // ---- (actions * hmax).astype(int), packed sort keys, np.argsort order ----
+                int key[SLOTS];
+                int nsell = 0, nbuy = 0;
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    if (j < D) {
+                        const int a = valid ? action_to_shares<ActT>(sm.act[lane * P + j], p.hmax) : 0;
+                        nsell += a < 0;
+                        nbuy += a > 0;
+                        key[j] = a * 32 + j;
+                    } else {
+                        key[j] = 0x7fffffff;
+                    }
+                }
+                bitonic_network<SLOTS>(key);
+                int *ord = reinterpret_cast<int *>(sm.act) + lane * (P * (int)(sizeof(ActT) / sizeof(int)));
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) ord[s] = key[s];
+                const uint32_t dis = p.disable_mask ? __ldg(p.disable_mask + sd) : 0u;
+
+                // ---- sells, most negative first (:321-324, _sell_stock :102-135) ----
+                for (int s = 0; s < nsell; ++s) {
+                    const int kk = ord[s];
+                    const int a = kk >> 5, j = kk & 31;
+                    const int h = sm.hold[j * kHoldPitch + lane];
+                    if (!((dis >> j) & 1u) && h > 0) {
+                        const int m = min(-a, h);
+                        const double pv = dmul(__ldg(prow + j), (double)m);
+                        cash = dadd(cash, dmul(pv, one_minus_sc));
+                        sm.hold[j * kHoldPitch + lane] = h - m;
+                        cost = dadd(cost, dmul(pv, p.sell_cost_pct));
+                        trades += 1;
+                    }
+                }
+                // ---- buys, largest first, each limited by the cash left (:328-330, _buy_stock :171-201) ----
+                for (int s = 0; s < nbuy; ++s) {
+                    const int kk = ord[D - 1 - s];
+                    const int a = kk >> 5, j = kk & 31;
+                    if (!((dis >> j) & 1u)) {
+                        const double pj = __ldg(prow + j);
+                        const double unit = dmul(pj, one_plus_bc);
+                        double nsh = (double)a;
+                        // min(cash // unit, a): the quotient only matters when cash < (a+1)*unit
+                        if (!(cash >= dmul(nsh + 1.0, unit))) {
+                            const double avail = floor_div_f64(cash, unit);
+                            nsh = (nsh < avail) ? nsh : avail;
+                        }
+                        const double pv = dmul(pj, nsh);
+                        cash = dsub(cash, dmul(pv, one_plus_bc));
+                        sm.hold[j * kHoldPitch + lane] += (int)nsh;
+                        cost = dadd(cost, dmul(pv, p.buy_cost_pct));
+                        trades += 1;  // even when nsh == 0 (Q5)
+                    }
+                }
+            }
+            // ---- state: s -> s+1 (:335-352) ----
+            day += 1;
+            sday = day;
+            asset = total_asset<SLOTS>(cash, p.close + (size_t)day * 32, sm.hold, lane, D);
+            asset_ok = true;
+            reward = dmul(dsub(asset, begin), p.reward_scaling);
+            last_reward = reward;
+            if (liq && valid) st_liq += 1.0;
+        }
+
+        if (valid) {
+            if (rewards) rewards[(size_t)k * N + n] = reward;
+            if (flags_out) flags_out[(size_t)k * N + n] = flags;
+            st_r += reward;
+            st_r2 += reward * reward;
+        }
+        if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
+            sm.cashf[lane] = (float)cash;
+            sm.sd[lane] = state_day(sday);
+            __syncwarp();
+            float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
+            write_obs_tile<SLOTS>(p, sm, o, env0, nvalid, lane);
+        }
+    }
+
+    // ---- store state ----
+    if (valid) {
+        p.cash[n] = cash;
+        p.cost[n] = cost;
+        p.reward[n] = last_reward;
+        p.day[n] = day;
+        p.sday[n] = sday;
+        p.trades[n] = trades;
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j)
+            if (j < D) p.hold[(size_t)j * p.env_stride + n] = sm.hold[j * kHoldPitch + lane];
+    }
+    if (stats) {
+        double fin_asset = 0.0, fin_trades = 0.0, steps = 0.0;
+        if (valid) {
+            if (!asset_ok)
+                asset = total_asset<SLOTS>(cash, p.close + (size_t)state_day(sday) * 32, sm.hold, lane, D);
+            fin_asset = asset;
+            fin_trades = (double)trades;
+            steps = (double)n_steps;
+        }
+        double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, fin_asset, st_liq, steps, fin_trades};
+#pragma unroll
+        for (int i = 0; i < FRL_N_STATS; ++i) {
+            const double s = warp_sum(v[i]);
+            if (lane == 0 && s != 0.0) atomicAdd(stats + i, s);
+        }
+    }
+}
+
+// ---- init / reset / observe ------------------------------------------------------------------
+__global__ void trading_init_kernel(const frl_trading_params p, int day0)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.n_envs) return;
+    p.cash[n] = p.initial_amount;
+    for (int j = 0; j < p.stock_dim; ++j) p.hold[(size_t)j * p.env_stride + n] = p.init_hold ? p.init_hold[j] : 0;
+    p.day[n] = day0;
+    p.sday[n] = -day0 - 1;
+    p.cost[n] = 0.0;
+    p.trades[n] = 0;
+    p.reward[n] = 0.0;
+    p.episode[n] = 0;
+}
+
+__global__ void trading_reset_kernel(const frl_trading_params p, const uint8_t *__restrict__ mask)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.n_envs) return;
+    if (mask && !mask[n]) return;
+    p.cash[n] = p.initial_amount;
+    for (int j = 0; j < p.stock_dim; ++j) p.hold[(size_t)j * p.env_stride + n] = p.init_hold ? p.init_hold[j] : 0;
+    p.sday[n] = -p.day[n] - 1;  // state list built from the rows still loaded (Q1) ...
+    p.day[n] = 0;               // ... then day = 0
+    p.cost[n] = 0.0;
+    p.trades[n] = 0;
+    p.episode[n] += 1;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) trading_observe_kernel(const frl_trading_params p, float *__restrict__ obs)
+{
+    using SM = WarpSmem<32, float, WARPS>;
+    __shared__ SM smem[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SM &sm = smem[warp];
+    const int N = p.n_envs, D = p.stock_dim;
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const long long n = lane < nvalid ? env0 + lane : (long long)N - 1;
+    for (int j = 0; j < D; ++j) sm.hold[j * kHoldPitch + lane] = p.hold[(size_t)j * p.env_stride + n];
+    sm.cashf[lane] = (float)p.cash[n];
+    sm.sd[lane] = state_day(p.sday[n]);
+    __syncwarp();
+    write_obs_tile<32>(p, sm, obs, env0, nvalid, lane);
+}
+
+int32_t validate(const frl_trading_params *p)
+{
+    FRL_REQUIRE(p != nullptr, "trading: params is NULL");
+    FRL_REQUIRE(p->n_envs >= 1, "trading: n_envs must be >= 1 (got %d)", p->n_envs);
+    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 32, "trading: stock_dim must be in 1..32 (got %d)", p->stock_dim);
+    FRL_REQUIRE(p->n_tech >= 0 && p->n_days >= 1, "trading: bad n_tech/n_days (%d, %d)", p->n_tech, p->n_days);
+    FRL_REQUIRE(p->obs_dim == 1 + 2 * p->stock_dim + p->n_tech * p->stock_dim,
+                "trading: obs_dim %d != 1 + 2D + K*D = %d", p->obs_dim, 1 + 2 * p->stock_dim + p->n_tech * p->stock_dim);
+    FRL_REQUIRE(p->env_stride >= p->n_envs, "trading: env_stride %d < n_envs %d", p->env_stride, p->n_envs);
+    FRL_REQUIRE(p->close && p->risk && p->obs_tmpl, "trading: table pointer is NULL");
+    FRL_REQUIRE(p->cash && p->hold && p->day && p->sday && p->cost && p->trades && p->reward && p->episode,
+                "trading: state pointer is NULL");
+    return FRL_OK;
+}
+
+template <int SLOTS, typename ActT, int WARPS>
+void launch_rollout(const frl_trading_params &p, const void *actions, long long sstride, long long estride, int n_steps,
+                    double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats,
+                    cudaStream_t st)
+{
+    const long long tiles = ((long long)p.n_envs + 31) / 32;
+    const unsigned grid = (unsigned)((tiles + WARPS - 1) / WARPS);
+    trading_rollout_kernel<SLOTS, ActT, WARPS><<<grid, WARPS * 32, 0, st>>>(
+        p, (const ActT *)actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats);
+}
+
+}  // namespace
+}  // namespace frl
+
+using namespace frl;
+
+extern "C" int32_t frl_trading_init(const frl_trading_params *p, int32_t day0, void *stream)
+{
+    if (int32_t rc = validate(p)) return rc;
+    FRL_REQUIRE(day0 >= 0 && day0 < p->n_days, "trading_init: day0 %d outside [0, %d)", day0, p->n_days);
+    trading_init_kernel<<<(p->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p, day0);
+    return check_launch("trading_init");
+}
+
+extern "C" int32_t frl_trading_observe(const frl_trading_params *p, float *obs, void *stream)
+{
+    if (int32_t rc = validate(p)) return rc;
+    FRL_REQUIRE(obs != nullptr, "trading_observe: obs is NULL");
+    constexpr int W = 4;
+    const long long tiles = ((long long)p->n_envs + 31) / 32;
+    trading_observe_kernel<W><<<(unsigned)((tiles + W - 1) / W), W * 32, 0, (cudaStream_t)stream>>>(*p, obs);
+    return check_launch("trading_observe");
+}
+
+extern "C" int32_t frl_trading_reset(const frl_trading_params *p, const uint8_t *mask, float *obs, void *stream)
+{
+    if (int32_t rc = validate(p)) return rc;
+    trading_reset_kernel<<<(p->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p, mask);
+    if (int32_t rc = check_launch("trading_reset")) return rc;
+    if (obs) return frl_trading_observe(p, obs, stream);
+    return FRL_OK;
+}
+
+extern "C" int32_t frl_trading_rollout(const frl_trading_params *p, const void *actions, int32_t actions_f64,
+                                       int64_t act_step_stride, int64_t act_env_stride, int32_t n_steps,
+                                       double *rewards, uint8_t *flags, float *obs, int32_t obs_mode,
+                                       int32_t auto_reset, double *stats, void *stream)
+{
+    if (int32_t rc = validate(p)) return rc;
+    FRL_REQUIRE(actions != nullptr, "trading_rollout: actions is NULL");
+    FRL_REQUIRE(n_steps >= 1, "trading_rollout: n_steps must be >= 1 (got %d)", n_steps);
+    FRL_REQUIRE(act_env_stride >= p->stock_dim, "trading_rollout: act_env_stride %lld < stock_dim", (long long)act_env_stride);
+    FRL_REQUIRE(obs_mode >= FRL_OBS_NONE && obs_mode <= FRL_OBS_ALL, "trading_rollout: bad obs_mode %d", obs_mode);
+    FRL_REQUIRE(obs_mode == FRL_OBS_NONE || obs != nullptr, "trading_rollout: obs is NULL but obs_mode=%d", obs_mode);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = p->stock_dim;
+#define FRL_GO(SLOTS)                                                                                             \
+    do {                                                                                                          \
+        if (actions_f64)                                                                                          \
+            launch_rollout<SLOTS, double, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards,      \
+                                             flags, obs, obs_mode, auto_reset, stats, st);                        \
+        else                                                                                                      \
+            launch_rollout<SLOTS, float, 4>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards,       \
+                                            flags, obs, obs_mode, auto_reset, stats, st);                         \
+    } while (0)
+    if (D <= 8)
+        FRL_GO(8);
+    else if (D <= 16)
+        FRL_GO(16);
+    else
+        FRL_GO(32);
+#undef FRL_GO
+    return check_launch("trading_rollout");
+}
+
+extern "C" int32_t frl_trading_step(const frl_trading_params *p, const void *actions, int32_t actions_f64,
+                                    double *rewards, uint8_t *flags, float *obs, int32_t auto_reset, double *stats,
+                                    void *stream)
+{
+    if (p == nullptr) {
+        set_error("trading_step: params is NULL");
+        return FRL_E_INVALID;
+    }
+    return frl_trading_rollout(p, actions, actions_f64, (int64_t)p->n_envs * p->stock_dim, p->stock_dim, 1, rewards,
+                               flags, obs, obs ? FRL_OBS_LAST : FRL_OBS_NONE, auto_reset, stats, stream);
+}

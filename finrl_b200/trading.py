@@ -1,0 +1,282 @@
+"""Batched StockTradingEnv: N independent copies of the reference env stepped by one CUDA kernel.
+
+Reference: /root/reference/finrl/meta/env_stock_trading/env_stocktrading.py (``StockTradingEnv``).
+Same constructor keywords, same ``reset`` / ``step`` semantics (incl. quirks Q1-Q5 of SURVEY.md
+§8a), but every method acts on all N envs and returns device tensors.  The arithmetic happens in
+``finrl_b200/csrc/trading.cu`` behind the C-ABI of ``include/finrl_b200.h``; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from .tables import TradingTables
+
+
+def _scalar_cost(x, name):
+    """The reference only works with scalar costs (``1 + list`` raises, quirk Q7); its tutorials pass
+    ``[c] * D``.  Accept a scalar or a constant vector."""
+    if np.isscalar(x):
+        return float(x)
+    arr = np.asarray(x, dtype=np.float64).reshape(-1)
+    if arr.size == 0 or not np.all(arr == arr[0]):
+        raise NotImplementedError(f"{name}: per-stock costs that differ are not supported (the reference cannot consume them either)")
+    return float(arr[0])
+
+
+class BatchedStockTradingEnv:
+    """N lock-stepped (or not) ``StockTradingEnv`` instances on one GPU.
+
+    Parameters mirror ``StockTradingEnv.__init__`` (env_stocktrading.py:24-47); extra keywords:
+    ``n_envs``, ``device`` and ``tables`` (pre-built :class:`TradingTables`, instead of ``df``).
+    """
+
+    def __init__(
+        self,
+        df=None,
+        stock_dim: int = None,
+        hmax: float = 100,
+        initial_amount: float = 1_000_000,
+        num_stock_shares: Optional[Sequence[int]] = None,
+        buy_cost_pct=0.001,
+        sell_cost_pct=0.001,
+        reward_scaling: float = 1e-4,
+        state_space: Optional[int] = None,
+        action_space: Optional[int] = None,
+        tech_indicator_list: Sequence[str] = (),
+        turbulence_threshold=None,
+        risk_indicator_col="turbulence",
+        day: int = 0,
+        initial: bool = True,
+        previous_state: Sequence[float] = (),
+        *,
+        n_envs: int = 1,
+        device="cuda",
+        tables: Optional[TradingTables] = None,
+    ):
+        import torch
+
+        self._torch = torch
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _cabi.EngineError("finrl_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        _cabi.lib()  # fail loudly before any allocation if the extension is missing
+        if tables is None:
+            if df is None:
+                raise ValueError("either df or tables is required")
+            if turbulence_threshold is not None and risk_indicator_col not in df.columns:
+                raise KeyError(risk_indicator_col)
+            tables = TradingTables.from_frame(df, stock_dim, list(tech_indicator_list), risk_indicator_col, self.device)
+        self.tables = tables
+        self.df = df
+        D, K, T = tables.stock_dim, tables.n_tech, tables.n_days
+        if stock_dim is not None and int(stock_dim) != D:
+            raise ValueError(f"stock_dim={stock_dim} but the tables hold {D} stocks")
+        O = tables.obs_dim
+        if state_space is not None and int(state_space) != O:
+            raise ValueError(f"state_space={state_space} != 1 + 2*stock_dim + len(tech)*stock_dim = {O}")
+        if action_space is not None and int(action_space) != D:
+            raise ValueError(f"action_space={action_space} != stock_dim={D}")
+        self.n_envs, self.stock_dim, self.n_tech, self.n_days = int(n_envs), D, K, T
+        self.state_space = O
+        self.hmax = hmax
+        self.initial_amount = initial_amount
+        self.buy_cost_pct = _scalar_cost(buy_cost_pct, "buy_cost_pct")
+        self.sell_cost_pct = _scalar_cost(sell_cost_pct, "sell_cost_pct")
+        self.reward_scaling = reward_scaling
+        self.turbulence_threshold = turbulence_threshold
+        self.risk_indicator_col = risk_indicator_col
+        self.tech_indicator_list = list(tech_indicator_list)
+        self.initial = initial
+        self.previous_state = list(previous_state)
+        if int(hmax) * (T + 1) >= 2**31:
+            raise ValueError("hmax * n_days must stay below 2^31 (holdings are int32)")
+        if not 0 <= int(day) < T:
+            raise ValueError(f"day={day} outside [0, {T})")
+
+        if initial:
+            init_cash = float(initial_amount)
+            shares = [0] * D if num_stock_shares is None else list(num_stock_shares)
+        else:  # resume from a previous run's state list (env_stocktrading.py:423-450)
+            if len(self.previous_state) < 1 + 2 * D:
+                raise ValueError("previous_state must hold [cash, prices x D, holdings x D, ...]")
+            init_cash = float(self.previous_state[0])
+            shares = [int(round(float(v))) for v in self.previous_state[D + 1 : 2 * D + 1]]
+        if len(shares) != D:
+            raise ValueError(f"num_stock_shares must have {D} entries")
+        self.num_stock_shares = shares
+        self._init_cash = init_cash
+
+        N = self.n_envs
+        dev = self.device
+        self.init_hold = torch.tensor(shares, dtype=torch.int32, device=dev)
+        self.cash = torch.empty(N, dtype=torch.float64, device=dev)
+        self.hold = torch.empty((D, N), dtype=torch.int32, device=dev)  # stock-major
+        self.day = torch.empty(N, dtype=torch.int32, device=dev)
+        self.sday = torch.empty(N, dtype=torch.int32, device=dev)
+        self.cost = torch.empty(N, dtype=torch.float64, device=dev)
+        self.trades = torch.empty(N, dtype=torch.int32, device=dev)
+        self.reward = torch.empty(N, dtype=torch.float64, device=dev)
+        self.episode = torch.empty(N, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(_cabi.N_STATS, dtype=torch.float64, device=dev)
+        self._obs = torch.empty((N, O), dtype=torch.float32, device=dev)
+        self._flags = torch.empty(N, dtype=torch.uint8, device=dev)
+
+        p = _cabi.TradingParams()
+        p.n_envs, p.stock_dim, p.n_tech, p.n_days, p.obs_dim, p.env_stride = N, D, K, T, O, N
+        p.hmax = float(hmax)
+        p.initial_amount = init_cash
+        p.buy_cost_pct, p.sell_cost_pct = self.buy_cost_pct, self.sell_cost_pct
+        p.reward_scaling = float(reward_scaling)
+        p.use_turbulence = int(turbulence_threshold is not None)
+        p.turbulence_threshold = float(turbulence_threshold) if turbulence_threshold is not None else 0.0
+        p.close, p.disable_mask = tables.close.data_ptr(), tables.disable_mask.data_ptr()
+        p.risk, p.obs_tmpl = tables.risk.data_ptr(), tables.obs_tmpl.data_ptr()
+        p.init_hold = self.init_hold.data_ptr()
+        p.cash, p.hold, p.day, p.sday = self.cash.data_ptr(), self.hold.data_ptr(), self.day.data_ptr(), self.sday.data_ptr()
+        p.cost, p.trades = self.cost.data_ptr(), self.trades.data_ptr()
+        p.reward, p.episode = self.reward.data_ptr(), self.episode.data_ptr()
+        self._p = p
+        self.launches = 0  # kernels launched through the C-ABI (bench.py reports it)
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().frl_trading_init(C.byref(p), int(day), self._stream()), "frl_trading_init")
+        self.launches += 1
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return _cabi.current_stream(self.device)
+
+    def _as_actions(self, actions, ndim):
+        torch = self._torch
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions))
+        if actions.dtype not in (torch.float32, torch.float64):
+            actions = actions.to(torch.float32)
+        if actions.device != self.device:
+            actions = actions.to(self.device, non_blocking=True)
+        if actions.dim() != ndim or actions.shape[-1] != self.stock_dim:
+            raise ValueError(f"actions must have {ndim} dims ending in stock_dim={self.stock_dim}, got {tuple(actions.shape)}")
+        return actions
+
+    # ------------------------------------------------------------------------------------------
+    def observe(self, out=None):
+        """float32 image of every env's state list (``render()``), shape [N, O]."""
+        out = self._obs if out is None else out
+        with self._torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().frl_trading_observe(C.byref(self._p), _cabi.ptr(out), self._stream()), "frl_trading_observe")
+        self.launches += 1
+        return out
+
+    def reset(self, mask=None, out=None):
+        """``StockTradingEnv.reset`` for all envs (or those with ``mask[n] != 0``)."""
+        torch = self._torch
+        out = self._obs if out is None else out
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if mask.shape != (self.n_envs,):
+                raise ValueError("mask must have shape [n_envs]")
+        with torch.cuda.device(self.device):
+            _cabi.check(
+                _cabi.lib().frl_trading_reset(C.byref(self._p), _cabi.ptr(mask), _cabi.ptr(out), self._stream()),
+                "frl_trading_reset",
+            )
+        self.launches += 2
+        return out
+
+    def step(self, actions, auto_reset: bool = False, want_obs: bool = True, accumulate_stats: bool = False):
+        """One ``step`` of every env.  Returns (obs[N,O] f32, reward[N] f64, done[N] bool, flags[N] u8).
+        The returned tensors are engine-owned buffers that the next call overwrites."""
+        a = self._as_actions(actions, 2)
+        if a.shape[0] != self.n_envs:
+            raise ValueError(f"actions must have n_envs={self.n_envs} rows")
+        a = a.contiguous()
+        obs = self._obs if want_obs else None
+        with self._torch.cuda.device(self.device):
+            _cabi.check(
+                _cabi.lib().frl_trading_step(
+                    C.byref(self._p), _cabi.ptr(a), int(a.dtype == self._torch.float64), None, _cabi.ptr(self._flags),
+                    _cabi.ptr(obs), int(auto_reset), _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
+                ),
+                "frl_trading_step",
+            )
+        self.launches += 1
+        return obs, self.reward, (self._flags & _cabi.FLAG_DONE).bool(), self._flags
+
+    def rollout(self, actions, layout: str = "KND", obs_mode: str = "last", auto_reset: bool = True,
+                accumulate_stats: bool = True, rewards=None, flags=None, obs=None):
+        """Fused multi-step rollout: ``actions`` is [K, N, D] (layout "KND", time-major like SB3's
+        rollout buffer) or [N, K, D] ("NKD").  Returns (obs, rewards[K,N] f64, flags[K,N] u8) where
+        obs is None / [N,O] / [K,N,O] for obs_mode "none" / "last" / "all"."""
+        torch = self._torch
+        a = self._as_actions(actions, 3)
+        D, N = self.stock_dim, self.n_envs
+        if layout == "KND":
+            K = a.shape[0]
+            ok = a.shape[1] == N
+        elif layout == "NKD":
+            K = a.shape[1]
+            ok = a.shape[0] == N
+        else:
+            raise ValueError("layout must be 'KND' or 'NKD'")
+        if not ok:
+            raise ValueError(f"actions shape {tuple(a.shape)} does not match n_envs={N} for layout {layout}")
+        a = a.contiguous()
+        step_stride, env_stride = (N * D, D) if layout == "KND" else (D, K * D)
+        mode = {"none": _cabi.OBS_NONE, "last": _cabi.OBS_LAST, "all": _cabi.OBS_ALL}[obs_mode]
+        if rewards is None:
+            rewards = torch.empty((K, N), dtype=torch.float64, device=self.device)
+        if flags is None:
+            flags = torch.empty((K, N), dtype=torch.uint8, device=self.device)
+        if mode == _cabi.OBS_LAST and obs is None:
+            obs = self._obs
+        elif mode == _cabi.OBS_ALL and obs is None:
+            obs = torch.empty((K, N, self.state_space), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(
+                _cabi.lib().frl_trading_rollout(
+                    C.byref(self._p), _cabi.ptr(a), int(a.dtype == torch.float64), step_stride, env_stride, int(K),
+                    _cabi.ptr(rewards), _cabi.ptr(flags), _cabi.ptr(obs) if mode else None, mode, int(auto_reset),
+                    _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
+                ),
+                "frl_trading_rollout",
+            )
+        self.launches += 1
+        return (obs if mode else None), rewards, flags
+
+    # ------------------------------------------------------------------------------------------
+    def get_state(self):
+        """Per-env state in the natural [N, ...] layout (host-friendly; holdings transposed)."""
+        return {
+            "cash": self.cash.clone(), "hold": self.hold.t().contiguous(), "day": self.day.clone(),
+            "sday": self.sday.clone(), "cost": self.cost.clone(), "trades": self.trades.clone(),
+            "reward": self.reward.clone(), "episode": self.episode.clone(),
+        }
+
+    def set_state(self, **kw):
+        """Overwrite state arrays (``cash``, ``hold`` [N,D], ``day``, ``sday``, ``cost``, ``trades``,
+        ``reward``, ``episode``) — the batched form of the reference's ``previous_state`` resume."""
+        torch = self._torch
+        for k, v in kw.items():
+            dst = getattr(self, k)
+            v = torch.as_tensor(v, device=self.device)
+            if k == "hold":
+                v = v.to(torch.int32).reshape(self.n_envs, self.stock_dim).t()
+            dst.copy_(v.to(dst.dtype).reshape(dst.shape) if k != "hold" else v)
+
+    def total_asset(self):
+        """cash + sum(price * holdings) with the prices currently in the state list (fp64, torch)."""
+        torch = self._torch
+        sd = torch.where(self.sday < 0, -self.sday - 1, self.sday).long()
+        prices = self.tables.close[sd, : self.stock_dim]  # [N, D]
+        return self.cash + (prices * self.hold.t().double()).sum(dim=1)
+
+    def read_stats(self, reset: bool = False):
+        vals = self.stats.tolist()
+        if reset:
+            self.stats.zero_()
+        return dict(zip(_cabi.STAT_NAMES, vals))

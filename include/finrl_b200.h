@@ -1,0 +1,139 @@
+/* finrl_b200 — C-ABI of the B200-native batched trading-environment engine.
+ *
+ * Drop-in boundary for the env step path of superyuri/FinRL (reference paths below are relative
+ * to the reference checkout).  The reference has no FFI layer of its own — its boundary is the
+ * gym protocol of four Python classes — so every entry point here names the Python method whose
+ * body it replaces.  Host code (finrl_b200/*.py, or any other language with a C FFI) owns all
+ * memory; this library allocates nothing, keeps no global state except the last error string,
+ * and only enqueues kernels on the CUDA stream it is handed.
+ *
+ * Conventions
+ *   - every pointer inside a *_params struct is a DEVICE pointer (CUDA, sm_100a);
+ *     the struct itself is passed by pointer from HOST memory and copied at call time;
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; NULL = legacy default stream;
+ *   - return value: 0 = success, negative = FRL_E_* (see frl_last_error());
+ *   - N envs, D stocks, K technical indicators, T days, O observation length;
+ *   - "stock-major" arrays are laid out [D][env_stride] (env index fastest) so that one thread
+ *     per env reads and writes them coalesced.
+ */
+#ifndef FINRL_B200_H
+#define FINRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FRL_API __attribute__((visibility("default")))
+#else
+#define FRL_API
+#endif
+
+#define FRL_OK 0
+#define FRL_E_INVALID (-1) /* bad argument (shape, null pointer, unsupported size) */
+#define FRL_E_CUDA (-2)    /* CUDA runtime error at launch */
+
+/* per env-step flag byte written by every step/rollout entry point */
+#define FRL_FLAG_DONE 1u      /* the step returned done=True */
+#define FRL_FLAG_LIQUIDATE 2u /* turbulence liquidation branch taken in this step */
+#define FRL_FLAG_SHORTAGE 4u  /* cash-penalty env: CASH SHORTAGE branch taken */
+
+/* observation emission of a rollout */
+#define FRL_OBS_NONE 0
+#define FRL_OBS_LAST 1 /* obs[N][O] after the final step */
+#define FRL_OBS_ALL 2  /* obs[n_steps][N][O] after every step */
+
+/* slots of the f64 statistics vector a rollout accumulates into (atomicAdd; the multi-GPU
+ * layer all-reduces it with NCCL — there is no reference counterpart) */
+#define FRL_STAT_REWARD_SUM 0    /* sum of returned rewards over all env-steps */
+#define FRL_STAT_REWARD_SQSUM 1  /* sum of squares of the same */
+#define FRL_STAT_DONE_COUNT 2    /* number of done flags */
+#define FRL_STAT_EPISODE_ASSET 3 /* sum of end-of-episode total assets over those dones */
+#define FRL_STAT_ASSET_SUM 4     /* sum of total assets of all envs after the final step */
+#define FRL_STAT_LIQ_COUNT 5     /* number of liquidation env-steps */
+#define FRL_STAT_ENV_STEPS 6     /* env-steps processed */
+#define FRL_STAT_TRADES 7        /* sum of trade counters after the final step */
+#define FRL_N_STATS 8
+
+FRL_API int32_t frl_abi_version(void);
+/* thread-local, never NULL; valid until the next failing call on this thread */
+FRL_API const char *frl_last_error(void);
+
+/* =========================================================================================
+ * A1  StockTradingEnv — finrl/meta/env_stock_trading/env_stocktrading.py
+ * ========================================================================================= */
+typedef struct frl_trading_params {
+    int32_t n_envs;     /* N >= 1 */
+    int32_t stock_dim;  /* D, 1..32 (one sort slot per stock) */
+    int32_t n_tech;     /* K >= 0 */
+    int32_t n_days;     /* T >= 1 = len(df.index.unique()) */
+    int32_t obs_dim;    /* O = 1 + 2D + K*D (state_space) */
+    int32_t env_stride; /* leading dimension of `hold` (>= N) */
+    double hmax;
+    double initial_amount;
+    double buy_cost_pct, sell_cost_pct;
+    double reward_scaling;
+    int32_t use_turbulence; /* turbulence_threshold is not None */
+    int32_t _pad0;
+    double turbulence_threshold;
+    /* ---- tables (read-only, replicated per GPU) ---- */
+    const double *close;          /* [T][32]  close price, rows zero-padded to 32 */
+    const uint32_t *disable_mask; /* [T] bit i set <=> first tech indicator of stock i == 1.0
+                                     (the "disable" flag of env_stocktrading.py:105,174) */
+    const double *risk;           /* [T] risk_indicator_col (turbulence / vix) */
+    const float *obs_tmpl;        /* [T][O] float32 image of the state list of day t with the
+                                     cash and holdings slots zeroed */
+    const int32_t *init_hold;     /* [D] num_stock_shares (or previous_state holdings) */
+    /* ---- per-env state (read-write) ---- */
+    double *cash;     /* [N] state[0] */
+    int32_t *hold;    /* [D][env_stride] state[D+1 : 2D+1], integer-valued */
+    int32_t *day;     /* [N] self.day */
+    int32_t *sday;    /* [N] day whose prices/indicators sit in the state list.  >= 0: equals day,
+                         turbulence = risk[sday].  < 0: "fresh" (after __init__/reset): prices of
+                         day (-sday-1), turbulence = 0 (the stale-reset quirk, :359-393) */
+    double *cost;     /* [N] self.cost */
+    int32_t *trades;  /* [N] self.trades */
+    double *reward;   /* [N] self.reward (last scaled reward; returned again by the terminal step) */
+    int32_t *episode; /* [N] self.episode */
+} frl_trading_params;
+
+/* StockTradingEnv.__init__ (:24-100): day = day0, state built from day0, fresh. */
+FRL_API int32_t frl_trading_init(const frl_trading_params *p, int32_t day0, void *stream);
+
+/* StockTradingEnv.reset (:359-393) for envs with mask[n] != 0 (mask NULL = all).
+ * obs (nullable) receives the [N][O] float32 observation of ALL envs afterwards. */
+FRL_API int32_t frl_trading_reset(const frl_trading_params *p, const uint8_t *mask, float *obs, void *stream);
+
+/* StockTradingEnv.render / _update_state (:395-396, :453-478): obs[N][O] float32 of the
+ * current state list (the float32 cast SB3's DummyVecEnv applies). */
+FRL_API int32_t frl_trading_observe(const frl_trading_params *p, float *obs, void *stream);
+
+/* n_steps fused calls of StockTradingEnv.step (:220-357) for every env.
+ *   actions      element (k, n, j) at actions[k*act_step_stride + n*act_env_stride + j];
+ *                float32 (actions_f64 == 0) or float64; the `* hmax` product and the truncating
+ *                int cast are done in that dtype, as numpy does (:304-307)
+ *   rewards      [n_steps][N] f64, nullable (p->reward always receives the last one)
+ *   flags        [n_steps][N] u8 FRL_FLAG_*, nullable
+ *   obs          per obs_mode; float32
+ *   auto_reset   apply DummyVecEnv.step_wait's reset-on-done after a terminal step
+ *   stats        [FRL_N_STATS] f64 accumulators, nullable
+ */
+FRL_API int32_t frl_trading_rollout(const frl_trading_params *p, const void *actions, int32_t actions_f64,
+                            int64_t act_step_stride, int64_t act_env_stride, int32_t n_steps,
+                            double *rewards, uint8_t *flags, float *obs, int32_t obs_mode,
+                            int32_t auto_reset, double *stats, void *stream);
+
+/* One StockTradingEnv.step: frl_trading_rollout with n_steps = 1, contiguous [N][D] actions,
+ * FRL_OBS_LAST when obs != NULL. */
+FRL_API int32_t frl_trading_step(const frl_trading_params *p, const void *actions, int32_t actions_f64,
+                         double *rewards, uint8_t *flags, float *obs, int32_t auto_reset,
+                         double *stats, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FINRL_B200_H */
