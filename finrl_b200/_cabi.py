@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libfinrl_b200.so")
+# FINRL_B200_LIB overrides the library path (used for A/B builds of the same ABI while tuning)
+LIB_PATH = os.environ.get("FINRL_B200_LIB") or os.path.join(PKG, "libfinrl_b200.so")
 
 FLAG_DONE = 1
 FLAG_LIQUIDATE = 2

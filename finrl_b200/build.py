@@ -35,15 +35,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """Compile every .cu for sm_100a and link the shared library.  ``defines``/``out`` build a tuning
+    variant (e.g. defines=["FRL_ST_STREAM=1"], out="gpurun_out/libvariant.so") without touching LIB."""
+    lib_out = out or LIB
+    if not force and out is None and not needs_build():
         return LIB
     objs = []
     procs = []
+    tag = "" if out is None else "_" + os.path.basename(out).replace(".so", "")
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c",
+        obj = os.path.join(PKG, "build", src.replace(".cu", tag + ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c",
                os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -56,9 +60,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out:
             print(out, file=sys.stderr)
-    link = [_nvcc(), "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    link = [_nvcc(), "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_out, *objs]
     subprocess.check_call(link)
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":

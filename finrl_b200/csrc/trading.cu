@@ -13,8 +13,38 @@
 #include "common.cuh"
 #include "sort_network.inc"
 
+// tuning knobs (A/B-tested on B200, see profiles/)
+#ifndef FRL_LD_STREAM
+#define FRL_LD_STREAM 1  // ld.global.cs for the read-once state/action streams
+#endif
+#ifndef FRL_ST_STREAM
+#define FRL_ST_STREAM 0  // st.global.cs for the state write-back
+#endif
+#ifndef FRL_TRADING_MIN_BLOCKS
+#define FRL_TRADING_MIN_BLOCKS 4  // 128-thread blocks per SM the allocator must allow: 4 -> 128 regs, no remat (A/B: 6->0.43 ms, 5->0.39, 4->0.32, 3->0.37)
+#endif
+
 namespace frl {
 namespace {
+
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T *p)
+{
+#if FRL_LD_STREAM
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename T>
+__device__ __forceinline__ void st_stream(T *p, T v)
+{
+#if FRL_ST_STREAM
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 constexpr int kMaxAbsAction = (1 << 26) - 1;  // |int(action*hmax)| is clamped to this (key packing)
 
@@ -174,7 +204,7 @@ __device__ __forceinline__ void write_obs_tile(const frl_trading_params &p, SM &
 // DCT > 0 compiles the stock count in (DOW-30 fast path: every `j < D` guard and the sort-network
 // pads fold away); DCT == 0 reads it from the params.
 template <int SLOTS, int DCT, typename ActT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 768 / (WARPS * 32))
+__global__ void __launch_bounds__(WARPS * 32, FRL_TRADING_MIN_BLOCKS * 128 / (WARPS * 32))
 trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ actions, long long act_step_stride,
                        long long act_env_stride, int n_steps, double *__restrict__ rewards,
                        uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode, int auto_reset,
@@ -200,7 +230,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
         int hv[SLOTS];
         const int *hp = p.hold + n;
 #pragma unroll
-        for (int j = 0; j < SLOTS; ++j) hv[j] = (j < D) ? __ldcs(hp + j * ld) : 0;
+        for (int j = 0; j < SLOTS; ++j) hv[j] = (j < D) ? ld_stream(hp + j * ld) : 0;
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) sm.hold[j * kHoldPitch + lane] = hv[j];
     }
@@ -223,7 +253,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
             const int cnt = nvalid * D - lane;
             ActT av[SLOTS];
 #pragma unroll
-            for (int i = 0; i < SLOTS; ++i) av[i] = (i < D && 32 * i < cnt) ? __ldcs(tile + 32 * i) : ActT(0);
+            for (int i = 0; i < SLOTS; ++i) av[i] = (i < D && 32 * i < cnt) ? ld_stream(tile + 32 * i) : ActT(0);
 #pragma unroll
             for (int i = 0; i < SLOTS; ++i)
                 if (i < D) sm.act[lane + 32 * i] = av[i];
@@ -375,7 +405,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
         p.trades[n] = trades;
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j)
-            if (j < D) __stcs(p.hold + n + j * ld, sm.hold[j * kHoldPitch + lane]);
+            if (j < D) st_stream(p.hold + n + j * ld, sm.hold[j * kHoldPitch + lane]);
     }
     if (stats) {
         double fin_asset = 0.0, fin_trades = 0.0, steps = 0.0;
