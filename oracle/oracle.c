@@ -327,3 +327,190 @@ void ora_trading_step(const ora_trading_cfg *c, ora_trading_state *s, const void
     for (int n = 0; n < c->n_envs; ++n)
         trd_step_one(c, s, n, actions, actions_f64, reward_out, flags_out, obs, auto_reset);
 }
+
+/* ======================================================================================= */
+/* A2: numpy / ElegantRL StockTradingEnv — finrl/meta/env_stock_trading/env_stocktrading_np.py */
+/* ======================================================================================= */
+/* The reference mixes Python floats, np.float32 and np.float64 scalars; under NEP 50 the dtype of
+ * `amount`, `total_asset`, `gamma_reward` and `reward` is data dependent.  A value is
+ * carried as (double v, kind); kind PY behaves as f64 in Python-only arithmetic and is "weak"
+ * (adopts the other operand's dtype) when it meets a numpy scalar. */
+
+typedef struct { double v; int k; } nv; /* numpy/Python scalar */
+
+static inline nv nv_make(double v, int k) { nv r = {v, k}; return r; }
+
+/* x (kind kx) <op> y where y is a strong numpy scalar of kind ky (F32 or F64) */
+static inline nv nv_add(nv x, nv y)
+{
+    if (x.k == ORA_KIND_PY && y.k == ORA_KIND_PY) return nv_make(x.v + y.v, ORA_KIND_PY);
+    if (x.k == ORA_KIND_F64 || y.k == ORA_KIND_F64) return nv_make(x.v + y.v, ORA_KIND_F64);
+    return nv_make((double)((float)x.v + (float)y.v), ORA_KIND_F32); /* f32 (+ weak py) */
+}
+static inline nv nv_sub(nv x, nv y)
+{
+    if (x.k == ORA_KIND_PY && y.k == ORA_KIND_PY) return nv_make(x.v - y.v, ORA_KIND_PY);
+    if (x.k == ORA_KIND_F64 || y.k == ORA_KIND_F64) return nv_make(x.v - y.v, ORA_KIND_F64);
+    return nv_make((double)((float)x.v - (float)y.v), ORA_KIND_F32);
+}
+static inline nv nv_mul(nv x, nv y)
+{
+    if (x.k == ORA_KIND_PY && y.k == ORA_KIND_PY) return nv_make(x.v * y.v, ORA_KIND_PY);
+    if (x.k == ORA_KIND_F64 || y.k == ORA_KIND_F64) return nv_make(x.v * y.v, ORA_KIND_F64);
+    return nv_make((double)((float)x.v * (float)y.v), ORA_KIND_F32);
+}
+
+static float np_asset_f32(const ora_np_cfg *c, const float *stocks, const float *price)
+{
+    float prod[MAXD];
+    for (int i = 0; i < c->stock_dim; ++i) prod[i] = stocks[i] * price[i];
+    return ora_pairwise_sum_f32(prod, c->stock_dim); /* (self.stocks * price).sum() */
+}
+
+/* get_state (:149-162) */
+static void np_obs_one(const ora_np_cfg *c, const ora_np_state *s, int n, float *obs)
+{
+    const int D = c->stock_dim, day = s->day[n];
+    const float *price = c->price + (size_t)day * D;
+    const float scale = 0.015625f; /* 2**-6 */
+    /* np.array(self.amount * 2**-12, dtype=np.float32): a power-of-two scale commutes with the cast */
+    double a = s->amount[n];
+    obs[0] = (s->amount_kind[n] == ORA_KIND_F32) ? (float)a * 0.000244140625f : (float)(a * 0.000244140625);
+    obs[1] = c->turb_ary[day];
+    obs[2] = c->turb_bool[day];
+    for (int i = 0; i < D; ++i) obs[3 + i] = price[i] * scale;
+    for (int i = 0; i < D; ++i) obs[3 + D + i] = s->stocks[(size_t)n * D + i] * scale;
+    for (int i = 0; i < D; ++i) obs[3 + 2 * D + i] = s->cool[(size_t)n * D + i];
+    for (int i = 0; i < c->tech_dim; ++i) obs[3 + 3 * D + i] = c->tech[(size_t)day * c->tech_dim + i];
+}
+
+void ora_np_obs(const ora_np_cfg *c, const ora_np_state *s, float *obs)
+{
+    const int O = 3 + 3 * c->stock_dim + c->tech_dim;
+    for (int n = 0; n < c->n_envs; ++n) np_obs_one(c, s, n, obs + (size_t)n * O);
+}
+
+/* reset (:80-101) */
+void ora_np_reset(const ora_np_cfg *c, ora_np_state *s, const uint8_t *mask, const float *stocks0,
+                  const double *factor)
+{
+    const int D = c->stock_dim;
+    for (int n = 0; n < c->n_envs; ++n) {
+        if (mask && !mask[n]) continue;
+        float *st = s->stocks + (size_t)n * D;
+        s->day[n] = 0;
+        const float *price = c->price;
+        nv amount;
+        if (stocks0 && factor) { /* if_train: random initial position supplied by the caller */
+            for (int i = 0; i < D; ++i) st[i] = stocks0[(size_t)n * D + i];
+            /* initial_capital * rd.uniform(..)  [py*py]  -  (stocks*price).sum() [f32]  ->  f32 */
+            amount = nv_sub(nv_make(c->initial_capital * factor[n], ORA_KIND_PY),
+                            nv_make(np_asset_f32(c, st, price), ORA_KIND_F32));
+        } else {
+            for (int i = 0; i < D; ++i) st[i] = c->init_stocks ? c->init_stocks[i] : 0.0f;
+            amount = nv_make(c->initial_capital, ORA_KIND_PY);
+        }
+        for (int i = 0; i < D; ++i) s->cool[(size_t)n * D + i] = 0.0f;
+        nv total = nv_add(amount, nv_make(np_asset_f32(c, st, price), ORA_KIND_F32));
+        s->amount[n] = amount.v; s->amount_kind[n] = (uint8_t)amount.k;
+        s->total[n] = total.v;   s->total_kind[n] = (uint8_t)total.k;
+        s->init_total[n] = total.v;
+        s->gamma_reward[n] = 0.0; s->gr_kind[n] = ORA_KIND_PY;
+    }
+}
+
+static void np_step_one(const ora_np_cfg *c, ora_np_state *s, int n, const float *actions, double *reward_out,
+                        uint8_t *reward_kind_out, uint8_t *flags_out, float *obs)
+{
+    const int D = c->stock_dim, O = 3 + 3 * D + c->tech_dim;
+    float *stocks = s->stocks + (size_t)n * D, *cool = s->cool + (size_t)n * D;
+    const nv one_minus_sc = nv_make(1 - c->sell_cost_pct, ORA_KIND_PY);
+    const nv one_plus_bc = nv_make(1 + c->buy_cost_pct, ORA_KIND_PY);
+    uint8_t flags = 0;
+
+    /* actions = (actions * self.max_stock).astype(int)  — f32 array * Python float -> f32 (:104) */
+    int64_t a[MAXD];
+    for (int i = 0; i < D; ++i) a[i] = (int64_t)(actions[(size_t)n * D + i] * (float)c->max_stock);
+
+    s->day[n] += 1; /* trades happen at the NEW day's price (:106-107) */
+    const int day = s->day[n];
+    const float *price = c->price + (size_t)day * D;
+    for (int i = 0; i < D; ++i) cool[i] += 1.0f;
+    nv amount = nv_make(s->amount[n], s->amount_kind[n]);
+
+    if (c->turb_bool[day] == 0.0f) {
+        const int64_t min_action = (int64_t)(c->max_stock * c->min_stock_rate); /* int(...) (:111) */
+        for (int i = 0; i < D; ++i) { /* sells, ascending index (:112-119) */
+            if (a[i] < -min_action && price[i] > 0) {
+                /* min(self.stocks[index], -actions[index]) -> the int64 iff it is SMALLER */
+                nv x;
+                if ((double)(-a[i]) < (double)stocks[i]) {
+                    const double nsh = (double)(-a[i]); /* int64: f32 * int64 -> f64 */
+                    stocks[i] = (float)((double)stocks[i] - nsh);
+                    x = nv_mul(nv_make((double)price[i] * nsh, ORA_KIND_F64), one_minus_sc);
+                } else {
+                    const float nsh = stocks[i]; /* f32 */
+                    stocks[i] = stocks[i] - nsh;
+                    x = nv_mul(nv_make((double)(price[i] * nsh), ORA_KIND_F32), one_minus_sc);
+                }
+                amount = nv_add(amount, x);
+                cool[i] = 0.0f;
+            }
+        }
+        for (int i = 0; i < D; ++i) { /* buys, ascending index (:120-129) */
+            if (a[i] > min_action && price[i] > 0) {
+                /* self.amount // price[index]: f32 unless amount is already f64 */
+                nv avail;
+                if (amount.k == ORA_KIND_F64)
+                    avail = nv_make(ora_floor_divide_f64(amount.v, (double)price[i]), ORA_KIND_F64);
+                else
+                    avail = nv_make((double)ora_floor_divide_f32((float)amount.v, price[i]), ORA_KIND_F32);
+                nv x;
+                if ((double)a[i] < avail.v) { /* min(avail, action) -> the int64 */
+                    const double nsh = (double)a[i];
+                    stocks[i] = (float)((double)stocks[i] + nsh);
+                    x = nv_mul(nv_make((double)price[i] * nsh, ORA_KIND_F64), one_plus_bc);
+                } else if (avail.k == ORA_KIND_F64) {
+                    stocks[i] = (float)((double)stocks[i] + avail.v);
+                    x = nv_mul(nv_make((double)price[i] * avail.v, ORA_KIND_F64), one_plus_bc);
+                } else {
+                    const float nsh = (float)avail.v;
+                    stocks[i] = stocks[i] + nsh;
+                    x = nv_mul(nv_make((double)(price[i] * nsh), ORA_KIND_F32), one_plus_bc);
+                }
+                amount = nv_sub(amount, x);
+                cool[i] = 0.0f;
+            }
+        }
+    } else { /* sell everything when turbulence (:131-134) */
+        flags |= ORA_FLAG_LIQUIDATE;
+        nv x = nv_mul(nv_make((double)np_asset_f32(c, stocks, price), ORA_KIND_F32), one_minus_sc);
+        amount = nv_add(amount, x);
+        for (int i = 0; i < D; ++i) { stocks[i] = 0.0f; cool[i] = 0.0f; }
+    }
+    s->amount[n] = amount.v; s->amount_kind[n] = (uint8_t)amount.k;
+    if (obs) np_obs_one(c, s, n, obs + (size_t)n * O);
+
+    nv total = nv_add(amount, nv_make((double)np_asset_f32(c, stocks, price), ORA_KIND_F32));
+    nv reward = nv_mul(nv_sub(total, nv_make(s->total[n], s->total_kind[n])), nv_make(c->reward_scaling, ORA_KIND_PY));
+    s->total[n] = total.v; s->total_kind[n] = (uint8_t)total.k;
+    nv gr = nv_add(nv_mul(nv_make(s->gamma_reward[n], s->gr_kind[n]), nv_make(c->gamma, ORA_KIND_PY)), reward);
+    s->gamma_reward[n] = gr.v; s->gr_kind[n] = (uint8_t)gr.k;
+    if (day == c->n_days - 1) { /* done = self.day == self.max_step (:142-145) */
+        flags |= ORA_FLAG_DONE;
+        reward = gr;
+        /* total_asset / initial_total_asset: initial is np.float32 (reset), so f32 unless total is f64 */
+        s->episode_return[n] = (total.k == ORA_KIND_F64) ? total.v / s->init_total[n]
+                                                         : (double)((float)total.v / (float)s->init_total[n]);
+    }
+    if (reward_out) reward_out[n] = reward.v;
+    if (reward_kind_out) reward_kind_out[n] = (uint8_t)reward.k;
+    if (flags_out) flags_out[n] = flags;
+}
+
+void ora_np_step(const ora_np_cfg *c, ora_np_state *s, const float *actions, double *reward_out,
+                 uint8_t *reward_kind_out, uint8_t *flags_out, float *obs)
+{
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < c->n_envs; ++n) np_step_one(c, s, n, actions, reward_out, reward_kind_out, flags_out, obs);
+}

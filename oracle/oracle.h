@@ -79,6 +79,45 @@ void ora_trading_step(const ora_trading_cfg *c, ora_trading_state *s, const void
                       int actions_f64, double *reward_out, uint8_t *flags_out, float *obs,
                       int auto_reset);
 
+/* ---- A2: numpy / ElegantRL StockTradingEnv (env_stocktrading_np.py) ---------------------- */
+
+/* numpy scalar "kind" a Python-level variable carries under NEP 50 (numpy >= 2):
+ * 0 = Python float (weak), 1 = np.float32, 2 = np.float64.  Values are stored in doubles. */
+#define ORA_KIND_PY 0
+#define ORA_KIND_F32 1
+#define ORA_KIND_F64 2
+
+typedef struct {
+    int32_t n_envs, stock_dim, tech_dim /* columns of tech_ary = D*K */, n_days;
+    double gamma, max_stock, min_stock_rate, buy_cost_pct, sell_cost_pct, reward_scaling;
+    double initial_capital;
+    const float *price;      /* [T][D]  price_ary  (:27) */
+    const float *tech;       /* [T][tech_dim] tech_ary = f32(tech_array) * 2^-7 (:28,31) */
+    const float *turb_bool;  /* [T] (:32) */
+    const float *turb_ary;   /* [T] (:33-35) */
+    const float *init_stocks; /* [D] initial_stocks */
+} ora_np_cfg;
+
+typedef struct {
+    double *amount;      uint8_t *amount_kind;   /* [N] self.amount */
+    float *stocks;       /* [N][D] */
+    float *cool;         /* [N][D] stocks_cool_down */
+    int32_t *day;        /* [N] */
+    double *total;       uint8_t *total_kind;    /* [N] self.total_asset */
+    double *gamma_reward; uint8_t *gr_kind;      /* [N] */
+    double *init_total;  /* [N] initial_total_asset */
+    double *episode_return; /* [N] */
+} ora_np_state;
+
+/* reset() (:80-101).  stocks0 [N][D] / factor [N] non-NULL = the if_train branch with the random
+ * draws supplied by the caller (rd.randint(0,64,D) already added to initial_stocks; rd.uniform). */
+void ora_np_reset(const ora_np_cfg *c, ora_np_state *s, const uint8_t *mask, const float *stocks0,
+                  const double *factor);
+void ora_np_obs(const ora_np_cfg *c, const ora_np_state *s, float *obs /*[N][O]*/);
+/* step() (:103-147): reward_out f64 value + kind, flags ORA_FLAG_DONE|ORA_FLAG_LIQUIDATE. */
+void ora_np_step(const ora_np_cfg *c, ora_np_state *s, const float *actions, double *reward_out,
+                 uint8_t *reward_kind_out, uint8_t *flags_out, float *obs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,3 +177,90 @@ class TradingOracle:
             _p(obs), C.c_int(int(auto_reset)),
         )
         return obs, reward, flags
+
+
+# --------------------------------------------------------------------------------------------
+# A2
+# --------------------------------------------------------------------------------------------
+KIND_PY, KIND_F32, KIND_F64 = 0, 1, 2
+
+
+def np_tables(price_array, tech_array, turbulence_array, turbulence_thresh=99):
+    """The table transforms of the numpy env's constructor (env_stocktrading_np.py:27-35, 164-169)."""
+    price = np.ascontiguousarray(price_array.astype(np.float32))
+    tech = np.ascontiguousarray(tech_array.astype(np.float32) * 2**-7)
+    turb_bool = (turbulence_array > turbulence_thresh).astype(np.float32)
+
+    def sigmoid(x):
+        return 1 / (1 + np.exp(-x * np.e)) - 0.5
+
+    turb = (sigmoid(turbulence_array / turbulence_thresh) * turbulence_thresh * 2**-5).astype(np.float32)
+    return price, tech, turb_bool, turb
+
+
+class _NpCfg(C.Structure):
+    _fields_ = [
+        ("n_envs", C.c_int32), ("stock_dim", C.c_int32), ("tech_dim", C.c_int32), ("n_days", C.c_int32),
+        ("gamma", C.c_double), ("max_stock", C.c_double), ("min_stock_rate", C.c_double),
+        ("buy_cost_pct", C.c_double), ("sell_cost_pct", C.c_double), ("reward_scaling", C.c_double),
+        ("initial_capital", C.c_double),
+        ("price", C.c_void_p), ("tech", C.c_void_p), ("turb_bool", C.c_void_p), ("turb_ary", C.c_void_p),
+        ("init_stocks", C.c_void_p),
+    ]
+
+
+class _NpState(C.Structure):
+    _fields_ = [
+        ("amount", C.c_void_p), ("amount_kind", C.c_void_p), ("stocks", C.c_void_p), ("cool", C.c_void_p),
+        ("day", C.c_void_p), ("total", C.c_void_p), ("total_kind", C.c_void_p), ("gamma_reward", C.c_void_p),
+        ("gr_kind", C.c_void_p), ("init_total", C.c_void_p), ("episode_return", C.c_void_p),
+    ]
+
+
+class NpTradingOracle:
+    """N independent copies of the reference numpy ``StockTradingEnv``
+    (finrl/meta/env_stock_trading/env_stocktrading_np.py), stepped on the CPU."""
+
+    def __init__(self, price_array, tech_array, turbulence_array, n_envs, gamma=0.99, turbulence_thresh=99,
+                 min_stock_rate=0.1, max_stock=1e2, initial_capital=1e6, buy_cost_pct=1e-3, sell_cost_pct=1e-3,
+                 reward_scaling=2**-11, initial_stocks=None):
+        self.price, self.tech, self.turb_bool, self.turb_ary = np_tables(price_array, tech_array, turbulence_array, turbulence_thresh)
+        T, D = self.price.shape
+        N = int(n_envs)
+        self.N, self.D, self.T, self.TD = N, D, T, self.tech.shape[1]
+        self.O = 3 + 3 * D + self.TD
+        self.init_stocks = np.ascontiguousarray(initial_stocks if initial_stocks is not None else np.zeros(D), dtype=np.float32)
+        self.amount = np.zeros(N); self.amount_kind = np.zeros(N, dtype=np.uint8)
+        self.stocks = np.zeros((N, D), dtype=np.float32); self.cool = np.zeros((N, D), dtype=np.float32)
+        self.day = np.zeros(N, dtype=np.int32)
+        self.total = np.zeros(N); self.total_kind = np.zeros(N, dtype=np.uint8)
+        self.gamma_reward = np.zeros(N); self.gr_kind = np.zeros(N, dtype=np.uint8)
+        self.init_total = np.zeros(N); self.episode_return = np.zeros(N)
+        self._cfg = _NpCfg(N, D, self.TD, T, float(gamma), float(max_stock), float(min_stock_rate), float(buy_cost_pct),
+                           float(sell_cost_pct), float(reward_scaling), float(initial_capital), _p(self.price),
+                           _p(self.tech), _p(self.turb_bool), _p(self.turb_ary), _p(self.init_stocks))
+        self._st = _NpState(_p(self.amount), _p(self.amount_kind), _p(self.stocks), _p(self.cool), _p(self.day),
+                            _p(self.total), _p(self.total_kind), _p(self.gamma_reward), _p(self.gr_kind),
+                            _p(self.init_total), _p(self.episode_return))
+        self.reset()
+
+    def obs(self):
+        out = np.empty((self.N, self.O), dtype=np.float32)
+        lib().ora_np_obs(C.byref(self._cfg), C.byref(self._st), _p(out))
+        return out
+
+    def reset(self, mask=None, stocks0=None, factor=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        s0 = None if stocks0 is None else np.ascontiguousarray(stocks0, dtype=np.float32).reshape(self.N, self.D)
+        f = None if factor is None else np.ascontiguousarray(factor, dtype=np.float64).reshape(self.N)
+        lib().ora_np_reset(C.byref(self._cfg), C.byref(self._st), _p(m), _p(s0), _p(f))
+        return self.obs()
+
+    def step(self, actions, want_obs=True):
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        assert a.shape == (self.N, self.D)
+        reward = np.empty(self.N); rk = np.empty(self.N, dtype=np.uint8)
+        flags = np.empty(self.N, dtype=np.uint8)
+        obs = np.empty((self.N, self.O), dtype=np.float32) if want_obs else None
+        lib().ora_np_step(C.byref(self._cfg), C.byref(self._st), _p(a), _p(reward), _p(rk), _p(flags), _p(obs))
+        return obs, reward, rk, flags

@@ -102,7 +102,7 @@ def _kind(x):
     return {float: 0, int: 0, np.float32: 1, np.float64: 2}[type(x)]
 
 
-def gen_np(name, T, D, K, n_steps, seed, if_train, thresh=99, **kw):
+def gen_np(name, T, D, K, n_steps, seed, if_train, thresh=99, quiet_steps=0, **kw):
     mod = ref_loader.load("env_stocktrading_np")
     close, tech, turb = syn.make_tables(T, D, K, seed=seed)
     price_array, tech_array, turb_array = syn.make_np_arrays(close, tech, turb)
@@ -114,6 +114,9 @@ def gen_np(name, T, D, K, n_steps, seed, if_train, thresh=99, **kw):
             "init_stocks": env.stocks.copy(), "init_total": np.float64(env.total_asset),
             "init_total_kind": _kind(env.total_asset)}
     actions = syn.make_actions((n_steps, D), seed=seed + 1)
+    if quiet_steps:  # dead-band / capped-only prefix: amount stays a Python float or np.float32 for a while
+        actions[:quiet_steps] *= 0.09
+        actions[quiet_steps : 2 * quiet_steps] = -np.abs(actions[quiet_steps : 2 * quiet_steps])
     O = env.state_dim
     out = {k: np.zeros(n_steps) for k in ("amount", "total", "gamma_reward", "reward", "episode_return")}
     out.update({k: np.zeros(n_steps, dtype=np.uint8) for k in ("amount_kind", "total_kind", "gr_kind", "reward_kind", "done", "liq")})
@@ -146,9 +149,12 @@ def gen_np(name, T, D, K, n_steps, seed, if_train, thresh=99, **kw):
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"), price_array=price_array, tech_array=tech_array, turbulence_array=turb_array,
         actions=actions, obs0=obs0, if_train=np.array(int(if_train)), thresh=np.array(float(thresh)),
+        rng_seed=np.array(seed + 100),
         reset_amount=np.array([r[0] for r in resets]), reset_amount_kind=np.array([r[1] for r in resets], dtype=np.uint8),
         reset_stocks=np.array([r[2] for r in resets], dtype=np.float32).reshape(len(resets), D),
-        kw_keys=np.array(list(kw.keys()), dtype="U32"), kw_vals=np.array([float(v) for v in kw.values()]),
+        kw_keys=np.array([k for k in kw if k != "initial_stocks"], dtype="U32"),
+        kw_vals=np.array([float(v) for k, v in kw.items() if k != "initial_stocks"]),
+        initial_stocks=np.asarray(kw.get("initial_stocks", np.zeros(D)), dtype=np.float32),
         **init, **out, **_meta(),
     )
     print(f"{name}: {n_steps} steps, dones={int(out['done'].sum())}, liq={int(out['liq'].sum())}, "
@@ -270,6 +276,9 @@ def main():
         gen_np("np_d30_train", T=40, D=30, K=8, n_steps=90, seed=12, if_train=True, thresh=60)
         gen_np("np_d7_small", T=50, D=7, K=2, n_steps=110, seed=13, if_train=False, initial_capital=2e4, max_stock=50.0,
                thresh=80)
+        gen_np("np_d30_kinds", T=40, D=30, K=8, n_steps=90, seed=14, if_train=True, thresh=99, quiet_steps=6)
+        gen_np("np_d12_kinds_eval", T=40, D=12, K=3, n_steps=90, seed=15, if_train=False, thresh=70, quiet_steps=5,
+               initial_stocks=np.arange(12, dtype=np.float32))
     if want("portfolio"):
         gen_portfolio("portfolio_d30_f64", T=252 + 24, D=30, K=4, n_steps=50, seed=21, act_dtype=np.float64)
         gen_portfolio("portfolio_d6_f32", T=40 + 12, D=6, K=2, n_steps=30, seed=22, act_dtype=np.float32, lookback=40)

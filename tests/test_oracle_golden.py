@@ -106,3 +106,64 @@ def test_trading_oracle_no_auto_reset_terminal_is_noop():
         assert flags[0] & ora.FLAG_DONE
         assert reward[0] == rew[0] and o.cash[0] == cash[0] and np.array_equal(o.hold, hold)
         assert np.array_equal(obs[0], g["term_obs"][T - 1])
+
+
+# ---------------------------------------------------------------------------- A2
+NP = sorted(glob.glob(os.path.join(GOLDEN, "np_*.npz")))
+
+
+def np_kwargs_from_golden(g):
+    kw = {str(k): float(v) for k, v in zip(g["kw_keys"], g["kw_vals"])}
+    kw["turbulence_thresh"] = float(g["thresh"])
+    kw["initial_stocks"] = g["initial_stocks"]
+    return kw
+
+
+class NpResetDraws:
+    """Replays the reference's global-RNG draws of reset() (env_stocktrading_np.py:85-92): per reset
+    rd.randint(0, 64, D) then rd.uniform(0.95, 1.05)."""
+
+    def __init__(self, g):
+        self.rs = np.random.RandomState(int(g["rng_seed"]))
+        self.init = g["initial_stocks"]
+        self.train = bool(g["if_train"])
+
+    def draw(self):
+        if not self.train:
+            return None, None
+        stocks0 = (self.init + self.rs.randint(0, 64, size=self.init.shape)).astype(np.float32)
+        return stocks0[None, :], np.array([self.rs.uniform(0.95, 1.05)])
+
+
+@pytest.mark.parametrize("path", NP, ids=[os.path.basename(p)[:-4] for p in NP])
+def test_np_oracle_vs_reference(path):
+    g = np.load(path)
+    o = ora.NpTradingOracle(g["price_array"], g["tech_array"], g["turbulence_array"], 1, **np_kwargs_from_golden(g))
+    draws = NpResetDraws(g)
+    s0, f = draws.draw()
+    obs = o.reset(stocks0=s0, factor=f)
+    assert np.array_equal(obs[0], g["obs0"])
+    assert o.amount[0] == g["init_amount"] and o.amount_kind[0] == g["init_amount_kind"]
+    assert o.total[0] == g["init_total"] and o.total_kind[0] == g["init_total_kind"]
+    acts = g["actions"]
+    nreset = 0
+    for s in range(acts.shape[0]):
+        obs, reward, rk, flags = o.step(acts[s][None, :])
+        ctx = f"step {s}"
+        assert bool(flags[0] & ora.FLAG_DONE) == bool(g["done"][s]), ctx
+        assert bool(flags[0] & ora.FLAG_LIQUIDATE) == bool(g["liq"][s]), ctx
+        assert np.array_equal(o.stocks[0], g["stocks"][s]), ctx
+        assert np.array_equal(o.cool[0], g["cool"][s]), ctx
+        assert (o.amount[0], o.amount_kind[0]) == (g["amount"][s], g["amount_kind"][s]), ctx
+        assert (o.total[0], o.total_kind[0]) == (g["total"][s], g["total_kind"][s]), ctx
+        assert (o.gamma_reward[0], o.gr_kind[0]) == (g["gamma_reward"][s], g["gr_kind"][s]), ctx
+        assert (reward[0], rk[0]) == (g["reward"][s], g["reward_kind"][s]), ctx
+        assert o.day[0] == g["day"][s], ctx
+        assert np.array_equal(obs[0], g["obs"][s]), ctx
+        if g["done"][s]:
+            assert o.episode_return[0] == g["episode_return"][s], ctx
+            s0, f = draws.draw()
+            o.reset(stocks0=s0, factor=f)
+            assert o.amount[0] == g["reset_amount"][nreset] and o.amount_kind[0] == g["reset_amount_kind"][nreset]
+            assert np.array_equal(o.stocks[0], g["reset_stocks"][nreset])
+            nreset += 1
