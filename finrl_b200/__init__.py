@@ -8,5 +8,6 @@ anywhere, constructing one without the built library or a CUDA device raises.
 from ._cabi import EngineError, FLAG_DONE, FLAG_LIQUIDATE, FLAG_SHORTAGE  # noqa: F401
 from .tables import TradingTables, frame_to_arrays  # noqa: F401
 from .trading import BatchedStockTradingEnv  # noqa: F401
+from .nptrading import BatchedNpStockTradingEnv, NpTables  # noqa: F401
 
 __version__ = "0.1.0"

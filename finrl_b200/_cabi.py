@@ -62,6 +62,42 @@ class TradingParams(C.Structure):
     ]
 
 
+class NpParams(C.Structure):
+    """frl_np_params (include/finrl_b200.h)."""
+
+    _fields_ = [
+        ("n_envs", C.c_int32),
+        ("stock_dim", C.c_int32),
+        ("tech_dim", C.c_int32),
+        ("n_days", C.c_int32),
+        ("obs_dim", C.c_int32),
+        ("env_stride", C.c_int32),
+        ("gamma", C.c_double),
+        ("max_stock", C.c_double),
+        ("min_stock_rate", C.c_double),
+        ("buy_cost_pct", C.c_double),
+        ("sell_cost_pct", C.c_double),
+        ("reward_scaling", C.c_double),
+        ("initial_capital", C.c_double),
+        ("price", C.c_void_p),
+        ("turb_bool", C.c_void_p),
+        ("obs_tmpl", C.c_void_p),
+        ("init_stocks", C.c_void_p),
+        ("amount", C.c_void_p),
+        ("kinds", C.c_void_p),
+        ("stocks", C.c_void_p),
+        ("cool", C.c_void_p),
+        ("day", C.c_void_p),
+        ("total", C.c_void_p),
+        ("gamma_reward", C.c_void_p),
+        ("init_total", C.c_void_p),
+        ("episode_return", C.c_void_p),
+    ]
+
+
+KIND_PY, KIND_F32, KIND_F64 = 0, 1, 2
+NP_REWARD_KIND_SHIFT = 4
+
 # name -> (restype, argtypes); every symbol include/finrl_b200.h declares
 SIGNATURES = {
     "frl_abi_version": (C.c_int32, []),
@@ -77,6 +113,18 @@ SIGNATURES = {
     "frl_trading_step": (
         C.c_int32,
         [C.POINTER(TradingParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+         C.c_void_p],
+    ),
+    "frl_np_reset": (C.c_int32, [C.POINTER(NpParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "frl_np_observe": (C.c_int32, [C.POINTER(NpParams), C.c_void_p, C.c_void_p]),
+    "frl_np_rollout": (
+        C.c_int32,
+        [C.POINTER(NpParams), C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
+    ),
+    "frl_np_step": (
+        C.c_int32,
+        [C.POINTER(NpParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
          C.c_void_p],
     ),
 }

@@ -1,0 +1,592 @@
+// A2 — numpy / ElegantRL StockTradingEnv (reference: finrl/meta/env_stock_trading/env_stocktrading_np.py).
+//
+// Same mapping as trading.cu: one thread per env for the arithmetic, one warp per 32-env tile for
+// coalesced I/O.  There is no sort here (sells then buys run in ascending stock index, :112,:120), so
+// stocks / cool-down counters live in shared memory with static indices and registers stay light.
+//
+// Bit-exactness: the reference silently mixes Python floats, np.float32 and np.float64 (NEP 50); the
+// dtype of `amount`, `total_asset`, `gamma_reward` and `reward` depends on which `min()` branch ran
+// (SURVEY.md H3).  Each of those is carried as (double value, 2-bit kind) and every operation is done
+// in the precision numpy would pick, with explicit round-to-nearest intrinsics (no FMA contraction).
+// (stocks*price).sum() is numpy's pairwise float32 summation.
+#include "common.cuh"
+
+#ifndef FRL_NP_MIN_BLOCKS
+#define FRL_NP_MIN_BLOCKS 8  // 64-thread blocks per SM the register allocator must allow
+#endif
+
+namespace frl {
+namespace {
+
+struct NV {  // a numpy / Python scalar: value + NEP-50 kind
+    double v;
+    int k;
+};
+__device__ __forceinline__ NV nv(double v, int k) { return NV{v, k}; }
+__device__ __forceinline__ NV nv_add(NV x, NV y)
+{
+    if (x.k == FRL_KIND_PY && y.k == FRL_KIND_PY) return nv(dadd(x.v, y.v), FRL_KIND_PY);
+    if (x.k == FRL_KIND_F64 || y.k == FRL_KIND_F64) return nv(dadd(x.v, y.v), FRL_KIND_F64);
+    return nv((double)fadd((float)x.v, (float)y.v), FRL_KIND_F32);  // f32 (a weak Python float adopts it)
+}
+__device__ __forceinline__ NV nv_sub(NV x, NV y)
+{
+    if (x.k == FRL_KIND_PY && y.k == FRL_KIND_PY) return nv(dsub(x.v, y.v), FRL_KIND_PY);
+    if (x.k == FRL_KIND_F64 || y.k == FRL_KIND_F64) return nv(dsub(x.v, y.v), FRL_KIND_F64);
+    return nv((double)fsub((float)x.v, (float)y.v), FRL_KIND_F32);
+}
+__device__ __forceinline__ NV nv_mul(NV x, NV y)
+{
+    if (x.k == FRL_KIND_PY && y.k == FRL_KIND_PY) return nv(dmul(x.v, y.v), FRL_KIND_PY);
+    if (x.k == FRL_KIND_F64 || y.k == FRL_KIND_F64) return nv(dmul(x.v, y.v), FRL_KIND_F64);
+    return nv((double)fmul((float)x.v, (float)y.v), FRL_KIND_F32);
+}
+
+constexpr int kPitch = 33;
+
+template <int SLOTS, typename ActT>
+struct alignas(16) NpWarpSmem {
+    ActT act[32 * SLOTS];            // staged actions, flat [32 envs][D]
+    float sc[2 * SLOTS * kPitch];    // rows 0..D-1: stocks[j][lane]; rows D..2D-1: cool-down[j][lane]
+    float amountf[32];
+    int day[32];
+};
+
+template <typename ActT>
+__device__ __forceinline__ int np_action_to_shares(ActT a, double max_stock);
+template <>
+__device__ __forceinline__ int np_action_to_shares<float>(float a, double max_stock)
+{
+    return __float2int_rz(fmul(a, (float)max_stock));  // f32 array * Python float -> f32; astype(int)
+}
+template <>
+__device__ __forceinline__ int np_action_to_shares<double>(double a, double max_stock)
+{
+    return __double2int_rz(dmul(a, max_stock));
+}
+
+// (self.stocks * price).sum(): float32 products, numpy pairwise summation (n < 8 sequential; else 8
+// accumulators over the full blocks of 8, tree-combined, then the tail sequentially).
+template <int SLOTS>
+__device__ __forceinline__ float np_asset_f32(const float *sc, const float *__restrict__ prow, int lane, int D)
+{
+    float x[SLOTS];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) x[j] = (j < D) ? fmul(sc[j * kPitch + lane], __ldg(prow + j)) : 0.0f;
+    if (D < 8) {
+        float res = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8 && j < SLOTS; ++j)
+            if (j < D) res = fadd(res, x[j]);
+        return res;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = x[j];
+    const int nb = D >> 3;
+#pragma unroll
+    for (int b = 1; b < SLOTS / 8; ++b) {
+        if (b < nb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = fadd(r[j], x[8 * b + j]);
+        }
+    }
+    float res = fadd(fadd(fadd(r[0], r[1]), fadd(r[2], r[3])), fadd(fadd(r[4], r[5]), fadd(r[6], r[7])));
+#pragma unroll
+    for (int j = 8; j < SLOTS; ++j)
+        if (j >= 8 * nb && j < D) res = fadd(res, x[j]);
+    return res;
+}
+
+// np.array(self.amount * 2**-12, dtype=np.float32): the power-of-two scale commutes with the cast
+__device__ __forceinline__ float np_amount_obs(NV amount) { return fmul((float)amount.v, 0.000244140625f); }
+
+// ---- observation rows: [amount, turb, turb_bool, price*2^-6 x D, stocks*2^-6 x D, cool x D, tech] ----
+template <int NCH, typename SM>
+__device__ __forceinline__ void np_write_obs_rows_uniform(const frl_np_params &p, SM &sm, float *__restrict__ obs,
+                                                          long long env0, int nvalid, int lane, int day0)
+{
+    const int O = p.obs_dim, D = p.stock_dim;
+    const int s_beg = 3 + D, c_beg = 3 + 2 * D, sp_end = 3 + 3 * D;
+    float t[NCH];
+    const float *trow = p.obs_tmpl + (size_t)day0 * O + lane;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) t[c] = (c < NCH - 1 || lane + 32 * c < O) ? __ldg(trow + 32 * c) : 0.0f;
+    constexpr int NSP = NCH < 4 ? NCH : 4;  // 3 + 3D <= 99 -> at most 4 chunks touch per-env slots
+    int soff[NSP];
+    float mul[NSP];
+#pragma unroll
+    for (int c = 0; c < NSP; ++c) {
+        const int pos = lane + 32 * c;
+        soff[c] = -1;
+        mul[c] = 1.0f;
+        if (pos >= s_beg && pos < c_beg) {
+            soff[c] = (pos - s_beg) * kPitch;
+            mul[c] = 0.015625f;  // 2**-6
+        } else if (pos >= c_beg && pos < sp_end) {
+            soff[c] = (D + pos - c_beg) * kPitch;
+        }
+    }
+    const bool tail_ok = lane + 32 * (NCH - 1) < O;
+    float *orow = obs + (size_t)env0 * O + lane;
+#pragma unroll 2
+    for (int r = 0; r < nvalid; ++r) {
+        float v[NSP];
+#pragma unroll
+        for (int c = 0; c < NSP; ++c) v[c] = (soff[c] >= 0) ? fmul(sm.sc[soff[c] + r], mul[c]) : t[c];
+        const float am = sm.amountf[r];
+        if (lane == 0) v[0] = am;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const float x = c < NSP ? v[c] : t[c];
+            if (c < NCH - 1 || tail_ok) orow[32 * c] = x;
+        }
+        orow += O;
+    }
+}
+
+template <typename SM>
+__device__ __forceinline__ void np_write_obs_tile(const frl_np_params &p, SM &sm, float *__restrict__ obs,
+                                                  long long env0, int nvalid, int lane)
+{
+    const int O = p.obs_dim, D = p.stock_dim;
+    const int day0 = sm.day[0];
+    bool uniform = true;
+    if (lane < nvalid) uniform = (sm.day[lane] == day0);
+    uniform = __all_sync(0xffffffffu, uniform);
+    const int nch = (O + 31) >> 5;
+    if (uniform && nch <= 12) {
+        switch (nch) {
+#define FRL_CASE(N)                                                                                \
+    case N:                                                                                        \
+        np_write_obs_rows_uniform<N>(p, sm, obs, env0, nvalid, lane, day0);                        \
+        break;
+            FRL_CASE(1) FRL_CASE(2) FRL_CASE(3) FRL_CASE(4) FRL_CASE(5) FRL_CASE(6)
+            FRL_CASE(7) FRL_CASE(8) FRL_CASE(9) FRL_CASE(10) FRL_CASE(11) FRL_CASE(12)
+#undef FRL_CASE
+        }
+    } else {
+        const int s_beg = 3 + D, c_beg = 3 + 2 * D, sp_end = 3 + 3 * D;
+        for (int r = 0; r < nvalid; ++r) {
+            float *orow = obs + (size_t)(env0 + r) * O;
+            const float *trow = p.obs_tmpl + (size_t)sm.day[r] * O;
+            for (int pos = lane; pos < O; pos += 32) {
+                float v = __ldg(trow + pos);
+                if (pos == 0)
+                    v = sm.amountf[r];
+                else if (pos >= s_beg && pos < c_beg)
+                    v = fmul(sm.sc[(pos - s_beg) * kPitch + r], 0.015625f);
+                else if (pos >= c_beg && pos < sp_end)
+                    v = sm.sc[(D + pos - c_beg) * kPitch + r];
+                orow[pos] = v;
+            }
+        }
+    }
+}
+
+// reset (:80-101), deterministic branch, for the calling thread's env (state in registers / smem)
+template <int SLOTS>
+__device__ __forceinline__ void np_reset_regs(const frl_np_params &p, float *sc, int lane, int D, NV &amount,
+                                              NV &total, NV &gr, double &init_total, int &day)
+{
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+        if (j < D) {
+            sc[j * kPitch + lane] = p.init_stocks ? __ldg(p.init_stocks + j) : 0.0f;
+            sc[(D + j) * kPitch + lane] = 0.0f;
+        }
+    }
+    day = 0;
+    amount = nv(p.initial_capital, FRL_KIND_PY);
+    total = nv_add(amount, nv((double)np_asset_f32<SLOTS>(sc, p.price, lane, D), FRL_KIND_F32));
+    init_total = total.v;
+    gr = nv(0.0, FRL_KIND_PY);
+}
+
+template <int SLOTS, typename ActT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, FRL_NP_MIN_BLOCKS * 64 / (WARPS * 32))
+np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long long act_step_stride,
+                  long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
+                  float *__restrict__ obs, int obs_mode, int auto_reset, double *__restrict__ stats)
+{
+    using SM = NpWarpSmem<SLOTS, ActT>;
+    __shared__ SM smem[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SM &sm = smem[warp];
+    const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const bool valid = lane < nvalid;
+    const long long n = valid ? env0 + lane : (long long)N - 1;
+
+    // ---- load state ----
+    const int kinds = p.kinds[n];
+    NV amount = nv(p.amount[n], kinds & 3);
+    NV total = nv(p.total[n], (kinds >> 2) & 3);
+    NV gr = nv(p.gamma_reward[n], (kinds >> 4) & 3);
+    int day = p.day[n];
+    double init_total = 0.0;
+    bool init_total_loaded = false;
+    {
+        float sv[SLOTS], cv[SLOTS];
+        const float *sp = p.stocks + n, *cp = p.cool + n;
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {
+            sv[j] = (j < D) ? __ldcs(sp + j * ld) : 0.0f;
+            cv[j] = (j < D) ? __ldcs(cp + j * ld) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {
+            if (j < D) {
+                sm.sc[j * kPitch + lane] = sv[j];
+                sm.sc[(D + j) * kPitch + lane] = cv[j];
+            }
+        }
+    }
+    const NV one_minus_sc = nv(dsub(1.0, p.sell_cost_pct), FRL_KIND_PY);
+    const NV one_plus_bc = nv(dadd(1.0, p.buy_cost_pct), FRL_KIND_PY);
+    const int min_action = (int)dmul(p.max_stock, p.min_stock_rate);  // int(max_stock * min_stock_rate) (:111)
+    double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_liq = 0.0;
+
+    for (int k = 0; k < n_steps; ++k) {
+        // ---- stage this step's actions (coalesced, flat) ----
+        const ActT *abase = actions + (size_t)k * act_step_stride;
+        __syncwarp();
+        if (act_env_stride == D) {
+            const ActT *tile = abase + (size_t)env0 * D + lane;
+            const int cnt = nvalid * D - lane;
+            ActT av[SLOTS];
+#pragma unroll
+            for (int i = 0; i < SLOTS; ++i) av[i] = (i < D && 32 * i < cnt) ? __ldcs(tile + 32 * i) : ActT(0);
+#pragma unroll
+            for (int i = 0; i < SLOTS; ++i)
+                if (i < D) sm.act[lane + 32 * i] = av[i];
+        } else {
+            for (int r = 0; r < 32; ++r)
+                if (lane < D)
+                    sm.act[r * D + lane] = r < nvalid ? abase[(size_t)(env0 + r) * act_env_stride + lane] : ActT(0);
+        }
+        __syncwarp();
+
+        int flags = 0;
+        NV reward = nv(0.0, FRL_KIND_PY);
+        if (day >= T - 1) {
+            // already past the last day (the reference would raise IndexError): inert, done again
+            flags = FRL_FLAG_DONE;
+        } else {
+            int a[SLOTS];
+            const ActT *arow = sm.act + lane * D;
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j) a[j] = (j < D) ? np_action_to_shares<ActT>(arow[j], p.max_stock) : 0;
+
+            day += 1;  // trades happen at the NEW day's prices (:106-107)
+            const float *prow = p.price + (size_t)day * 32;
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j)
+                if (j < D) sm.sc[(D + j) * kPitch + lane] = fadd(sm.sc[(D + j) * kPitch + lane], 1.0f);  // cool_down += 1
+
+            if (__ldg(p.turb_bool + day) == 0.0f) {
+                // ---- sells in ascending index (:112-119) ----
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    if (j < D && a[j] < -min_action) {
+                        const float pj = __ldg(prow + j);
+                        if (pj > 0.0f) {
+                            float st = sm.sc[j * kPitch + lane];
+                            NV x;
+                            if ((double)(-a[j]) < (double)st) {  // min(stocks, -action) -> the int64
+                                const double nsh = (double)(-a[j]);
+                                st = (float)dsub((double)st, nsh);
+                                x = nv_mul(nv(dmul((double)pj, nsh), FRL_KIND_F64), one_minus_sc);
+                            } else {  // -> the float32 holding
+                                x = nv_mul(nv((double)fmul(pj, st), FRL_KIND_F32), one_minus_sc);
+                                st = fsub(st, st);
+                            }
+                            sm.sc[j * kPitch + lane] = st;
+                            amount = nv_add(amount, x);
+                            sm.sc[(D + j) * kPitch + lane] = 0.0f;
+                        }
+                    }
+                }
+                // ---- buys in ascending index; the divisor has NO cost term (:120-129, quirk Q6) ----
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    if (j < D && a[j] > min_action) {
+                        const float pj = __ldg(prow + j);
+                        if (pj > 0.0f) {
+                            float st = sm.sc[j * kPitch + lane];
+                            NV x;
+                            double avail;
+                            if (amount.k == FRL_KIND_F64)
+                                avail = floor_div_f64(amount.v, (double)pj);
+                            else
+                                avail = (double)floor_div_f32((float)amount.v, pj);
+                            if ((double)a[j] < avail) {  // min(avail, action) -> the int64
+                                const double nsh = (double)a[j];
+                                st = (float)dadd((double)st, nsh);
+                                x = nv_mul(nv(dmul((double)pj, nsh), FRL_KIND_F64), one_plus_bc);
+                            } else if (amount.k == FRL_KIND_F64) {
+                                st = (float)dadd((double)st, avail);
+                                x = nv_mul(nv(dmul((double)pj, avail), FRL_KIND_F64), one_plus_bc);
+                            } else {
+                                const float nsh = (float)avail;
+                                st = fadd(st, nsh);
+                                x = nv_mul(nv((double)fmul(pj, nsh), FRL_KIND_F32), one_plus_bc);
+                            }
+                            sm.sc[j * kPitch + lane] = st;
+                            amount = nv_sub(amount, x);
+                            sm.sc[(D + j) * kPitch + lane] = 0.0f;
+                        }
+                    }
+                }
+            } else {
+                // ---- sell everything when turbulence (:131-134) ----
+                flags |= FRL_FLAG_LIQUIDATE;
+                const NV x = nv_mul(nv((double)np_asset_f32<SLOTS>(sm.sc, prow, lane, D), FRL_KIND_F32), one_minus_sc);
+                amount = nv_add(amount, x);
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    if (j < D) {
+                        sm.sc[j * kPitch + lane] = 0.0f;
+                        sm.sc[(D + j) * kPitch + lane] = 0.0f;
+                    }
+                }
+                if (valid) st_liq += 1.0;
+            }
+            // ---- reward bookkeeping (:136-145) ----
+            const NV tot = nv_add(amount, nv((double)np_asset_f32<SLOTS>(sm.sc, prow, lane, D), FRL_KIND_F32));
+            reward = nv_mul(nv_sub(tot, total), nv(p.reward_scaling, FRL_KIND_PY));
+            total = tot;
+            gr = nv_add(nv_mul(gr, nv(p.gamma, FRL_KIND_PY)), reward);
+            if (day == T - 1) {
+                flags |= FRL_FLAG_DONE;
+                reward = gr;
+                if (!init_total_loaded) {
+                    init_total = p.init_total[n];
+                    init_total_loaded = true;
+                }
+                const double er = (total.k == FRL_KIND_F64) ? __ddiv_rn(total.v, init_total)
+                                                             : (double)__fdiv_rn((float)total.v, (float)init_total);
+                if (valid) {
+                    p.episode_return[n] = er;
+                    st_done += 1.0;
+                    st_epi += total.v;
+                }
+            }
+        }
+        if (valid) {
+            if (rewards) rewards[(size_t)k * N + n] = reward.v;
+            if (flags_out) flags_out[(size_t)k * N + n] = (uint8_t)(flags | (reward.k << FRL_NP_REWARD_KIND_SHIFT));
+            st_r += reward.v;
+            st_r2 += reward.v * reward.v;
+        }
+        if ((flags & FRL_FLAG_DONE) && auto_reset) {
+            np_reset_regs<SLOTS>(p, sm.sc, lane, D, amount, total, gr, init_total, day);
+            init_total_loaded = true;
+            if (valid) p.init_total[n] = init_total;
+        }
+        if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
+            sm.amountf[lane] = np_amount_obs(amount);
+            sm.day[lane] = day;
+            __syncwarp();
+            float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
+            np_write_obs_tile(p, sm, o, env0, nvalid, lane);
+        }
+    }
+
+    // ---- store state ----
+    if (valid) {
+        p.amount[n] = amount.v;
+        p.total[n] = total.v;
+        p.gamma_reward[n] = gr.v;
+        p.kinds[n] = (uint8_t)(amount.k | (total.k << 2) | (gr.k << 4));
+        p.day[n] = day;
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {
+            if (j < D) {
+                p.stocks[n + j * ld] = sm.sc[j * kPitch + lane];
+                p.cool[n + j * ld] = sm.sc[(D + j) * kPitch + lane];
+            }
+        }
+    }
+    if (stats) {
+        double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, valid ? total.v : 0.0, st_liq,
+                                 valid ? (double)n_steps : 0.0, 0.0};
+#pragma unroll
+        for (int w = 4; w >= 1; w >>= 1) {
+            const bool up = (lane & w) != 0;
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+                const double keep = up ? v[i + w] : v[i];
+                const double send = up ? v[i] : v[i + w];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+            }
+        }
+        double s = v[0];
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if (lane < 8 && s != 0.0) atomicAdd(stats + lane, s);
+    }
+}
+
+// ---- reset / observe ---------------------------------------------------------------------------
+__global__ void np_reset_kernel(const frl_np_params p, const uint8_t *__restrict__ mask,
+                                const float *__restrict__ stocks0, const double *__restrict__ factor)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.n_envs) return;
+    if (mask && !mask[n]) return;
+    const int D = p.stock_dim, ld = p.env_stride;
+    // (stocks * price[0]).sum() with numpy's pairwise order, from a thread-private copy
+    float x[32];
+    for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+    for (int j = 0; j < D; ++j) {
+        const float st = (stocks0 && factor) ? stocks0[n + (size_t)j * ld] : (p.init_stocks ? p.init_stocks[j] : 0.0f);
+        p.stocks[n + (size_t)j * ld] = st;
+        p.cool[n + (size_t)j * ld] = 0.0f;
+        x[j] = fmul(st, p.price[j]);
+    }
+    float asset;
+    if (D < 8) {
+        asset = 0.0f;
+        for (int j = 0; j < D; ++j) asset = fadd(asset, x[j]);
+    } else {
+        float r[8];
+        for (int j = 0; j < 8; ++j) r[j] = x[j];
+        const int nb = D >> 3;
+        for (int b = 1; b < nb; ++b)
+            for (int j = 0; j < 8; ++j) r[j] = fadd(r[j], x[8 * b + j]);
+        asset = fadd(fadd(fadd(r[0], r[1]), fadd(r[2], r[3])), fadd(fadd(r[4], r[5]), fadd(r[6], r[7])));
+        for (int j = 8 * nb; j < D; ++j) asset = fadd(asset, x[j]);
+    }
+    NV amount;
+    if (stocks0 && factor)  // initial_capital * rd.uniform() [py] - (stocks*price).sum() [f32] -> f32
+        amount = nv_sub(nv(dmul(p.initial_capital, factor[n]), FRL_KIND_PY), nv((double)asset, FRL_KIND_F32));
+    else
+        amount = nv(p.initial_capital, FRL_KIND_PY);
+    const NV total = nv_add(amount, nv((double)asset, FRL_KIND_F32));
+    p.day[n] = 0;
+    p.amount[n] = amount.v;
+    p.total[n] = total.v;
+    p.init_total[n] = total.v;
+    p.gamma_reward[n] = 0.0;
+    p.kinds[n] = (uint8_t)(amount.k | (total.k << 2) | (FRL_KIND_PY << 4));
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) np_observe_kernel(const frl_np_params p, float *__restrict__ obs)
+{
+    using SM = NpWarpSmem<32, float>;
+    __shared__ SM smem[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SM &sm = smem[warp];
+    const int N = p.n_envs, D = p.stock_dim;
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const long long n = lane < nvalid ? env0 + lane : (long long)N - 1;
+    for (int j = 0; j < D; ++j) {
+        sm.sc[j * kPitch + lane] = p.stocks[n + (size_t)j * p.env_stride];
+        sm.sc[(D + j) * kPitch + lane] = p.cool[n + (size_t)j * p.env_stride];
+    }
+    sm.amountf[lane] = np_amount_obs(nv(p.amount[n], p.kinds[n] & 3));
+    sm.day[lane] = p.day[n];
+    __syncwarp();
+    np_write_obs_tile(p, sm, obs, env0, nvalid, lane);
+}
+
+int32_t np_validate(const frl_np_params *p)
+{
+    FRL_REQUIRE(p != nullptr, "np: params is NULL");
+    FRL_REQUIRE(p->n_envs >= 1, "np: n_envs must be >= 1 (got %d)", p->n_envs);
+    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 32, "np: stock_dim must be in 1..32 (got %d)", p->stock_dim);
+    FRL_REQUIRE(p->tech_dim >= 0 && p->n_days >= 2, "np: bad tech_dim/n_days (%d, %d)", p->tech_dim, p->n_days);
+    FRL_REQUIRE(p->obs_dim == 3 + 3 * p->stock_dim + p->tech_dim, "np: obs_dim %d != 1 + 2 + 3D + tech_dim = %d",
+                p->obs_dim, 3 + 3 * p->stock_dim + p->tech_dim);
+    FRL_REQUIRE(p->env_stride >= p->n_envs, "np: env_stride %d < n_envs %d", p->env_stride, p->n_envs);
+    FRL_REQUIRE((long long)p->env_stride * 32 < (1LL << 31), "np: env_stride %d too large", p->env_stride);
+    FRL_REQUIRE(p->price && p->turb_bool && p->obs_tmpl, "np: table pointer is NULL");
+    FRL_REQUIRE(p->amount && p->kinds && p->stocks && p->cool && p->day && p->total && p->gamma_reward &&
+                    p->init_total && p->episode_return,
+                "np: state pointer is NULL");
+    return FRL_OK;
+}
+
+template <int SLOTS, typename ActT, int WARPS>
+void np_launch(const frl_np_params &p, const void *actions, long long sstride, long long estride, int n_steps,
+               double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
+{
+    const long long tiles = ((long long)p.n_envs + 31) / 32;
+    const unsigned grid = (unsigned)((tiles + WARPS - 1) / WARPS);
+    np_rollout_kernel<SLOTS, ActT, WARPS><<<grid, WARPS * 32, 0, st>>>(p, (const ActT *)actions, sstride, estride, n_steps,
+                                                                       rewards, flags, obs, obs_mode, auto_reset, stats);
+}
+
+}  // namespace
+}  // namespace frl
+
+using namespace frl;
+
+extern "C" int32_t frl_np_observe(const frl_np_params *p, float *obs, void *stream)
+{
+    if (int32_t rc = np_validate(p)) return rc;
+    FRL_REQUIRE(obs != nullptr, "np_observe: obs is NULL");
+    constexpr int W = 2;
+    const long long tiles = ((long long)p->n_envs + 31) / 32;
+    np_observe_kernel<W><<<(unsigned)((tiles + W - 1) / W), W * 32, 0, (cudaStream_t)stream>>>(*p, obs);
+    return check_launch("np_observe");
+}
+
+extern "C" int32_t frl_np_reset(const frl_np_params *p, const uint8_t *mask, const float *stocks0, const double *factor,
+                                float *obs, void *stream)
+{
+    if (int32_t rc = np_validate(p)) return rc;
+    FRL_REQUIRE((stocks0 == nullptr) == (factor == nullptr), "np_reset: stocks0 and factor must be given together");
+    np_reset_kernel<<<(p->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p, mask, stocks0, factor);
+    if (int32_t rc = check_launch("np_reset")) return rc;
+    if (obs) return frl_np_observe(p, obs, stream);
+    return FRL_OK;
+}
+
+extern "C" int32_t frl_np_rollout(const frl_np_params *p, const void *actions, int32_t actions_f64, int64_t act_step_stride,
+                                  int64_t act_env_stride, int32_t n_steps, double *rewards, uint8_t *flags, float *obs,
+                                  int32_t obs_mode, int32_t auto_reset, double *stats, void *stream)
+{
+    if (int32_t rc = np_validate(p)) return rc;
+    FRL_REQUIRE(actions != nullptr, "np_rollout: actions is NULL");
+    FRL_REQUIRE(n_steps >= 1, "np_rollout: n_steps must be >= 1 (got %d)", n_steps);
+    FRL_REQUIRE(act_env_stride >= p->stock_dim, "np_rollout: act_env_stride %lld < stock_dim", (long long)act_env_stride);
+    FRL_REQUIRE(obs_mode >= FRL_OBS_NONE && obs_mode <= FRL_OBS_ALL, "np_rollout: bad obs_mode %d", obs_mode);
+    FRL_REQUIRE(obs_mode == FRL_OBS_NONE || obs != nullptr, "np_rollout: obs is NULL but obs_mode=%d", obs_mode);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = p->stock_dim;
+#define FRL_GO(SLOTS)                                                                                             \
+    do {                                                                                                          \
+        if (actions_f64)                                                                                          \
+            np_launch<SLOTS, double, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags,    \
+                                        obs, obs_mode, auto_reset, stats, st);                                    \
+        else                                                                                                      \
+            np_launch<SLOTS, float, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags,     \
+                                       obs, obs_mode, auto_reset, stats, st);                                     \
+    } while (0)
+    if (D <= 8)
+        FRL_GO(8);
+    else if (D <= 16)
+        FRL_GO(16);
+    else
+        FRL_GO(32);
+#undef FRL_GO
+    return check_launch("np_rollout");
+}
+
+extern "C" int32_t frl_np_step(const frl_np_params *p, const void *actions, int32_t actions_f64, double *rewards,
+                               uint8_t *flags, float *obs, int32_t auto_reset, double *stats, void *stream)
+{
+    if (p == nullptr) {
+        set_error("np_step: params is NULL");
+        return FRL_E_INVALID;
+    }
+    return frl_np_rollout(p, actions, actions_f64, (int64_t)p->n_envs * p->stock_dim, p->stock_dim, 1, rewards, flags, obs,
+                          obs ? FRL_OBS_LAST : FRL_OBS_NONE, auto_reset, stats, stream);
+}

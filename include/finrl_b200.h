@@ -133,6 +133,62 @@ FRL_API int32_t frl_trading_step(const frl_trading_params *p, const void *action
                          double *rewards, uint8_t *flags, float *obs, int32_t auto_reset,
                          double *stats, void *stream);
 
+/* =========================================================================================
+ * A2  numpy / ElegantRL StockTradingEnv — finrl/meta/env_stock_trading/env_stocktrading_np.py
+ * ========================================================================================= */
+/* numpy scalar kinds the reference's Python-level variables carry under NEP 50 */
+#define FRL_KIND_PY 0  /* Python float (weak) */
+#define FRL_KIND_F32 1 /* np.float32 */
+#define FRL_KIND_F64 2 /* np.float64 */
+/* flag byte of this env: bits 0-1 FRL_FLAG_DONE / FRL_FLAG_LIQUIDATE, bits 4-5 kind of the reward */
+#define FRL_NP_REWARD_KIND_SHIFT 4
+
+typedef struct frl_np_params {
+    int32_t n_envs;     /* N */
+    int32_t stock_dim;  /* D, 1..32 */
+    int32_t tech_dim;   /* columns of tech_array (= D*K, stock-major) */
+    int32_t n_days;     /* T; max_step = T-1 */
+    int32_t obs_dim;    /* O = state_dim = 1 + 2 + 3D + tech_dim (:63) */
+    int32_t env_stride; /* leading dimension of stocks / cool (>= N) */
+    double gamma, max_stock, min_stock_rate;
+    double buy_cost_pct, sell_cost_pct, reward_scaling;
+    double initial_capital;
+    /* ---- tables ---- */
+    const float *price;       /* [T][32] price_ary = f32(price_array), rows zero-padded (:27) */
+    const float *turb_bool;   /* [T] f32(turbulence_array > thresh) (:32) */
+    const float *obs_tmpl;    /* [T][O] get_state() row of day t with amount/stocks/cool-down zeroed:
+                                 [0, turbulence_ary[t], turbulence_bool[t], price*2^-6, 0.., 0.., tech_ary[t]] */
+    const float *init_stocks; /* [D] initial_stocks */
+    /* ---- per-env state ---- */
+    double *amount;         /* [N] self.amount (value) */
+    uint8_t *kinds;         /* [N] bits 0-1 kind of amount, 2-3 of total_asset, 4-5 of gamma_reward */
+    float *stocks;          /* [D][env_stride] self.stocks */
+    float *cool;            /* [D][env_stride] self.stocks_cool_down */
+    int32_t *day;           /* [N] */
+    double *total;          /* [N] self.total_asset */
+    double *gamma_reward;   /* [N] */
+    double *init_total;     /* [N] self.initial_total_asset */
+    double *episode_return; /* [N] self.episode_return (written when done) */
+} frl_np_params;
+
+/* StockTradingEnv.reset (:80-101) for envs with mask[n] != 0 (NULL = all).  stocks0 ([D][env_stride]
+ * f32) and factor ([N] f64), both non-NULL, select the if_train branch with the caller's random
+ * draws (initial_stocks + randint(0,64) and uniform(0.95,1.05)); otherwise the deterministic branch.
+ * obs (nullable) receives [N][O]. */
+FRL_API int32_t frl_np_reset(const frl_np_params *p, const uint8_t *mask, const float *stocks0,
+                             const double *factor, float *obs, void *stream);
+/* get_state (:149-162) of every env. */
+FRL_API int32_t frl_np_observe(const frl_np_params *p, float *obs, void *stream);
+/* n_steps fused StockTradingEnv.step (:103-147).  Same conventions as frl_trading_rollout; rewards
+ * are the f64 values (their numpy kind is in the flag byte).  auto_reset applies the deterministic
+ * reset right after a done step (the returned obs is then the reset obs). */
+FRL_API int32_t frl_np_rollout(const frl_np_params *p, const void *actions, int32_t actions_f64,
+                               int64_t act_step_stride, int64_t act_env_stride, int32_t n_steps,
+                               double *rewards, uint8_t *flags, float *obs, int32_t obs_mode,
+                               int32_t auto_reset, double *stats, void *stream);
+FRL_API int32_t frl_np_step(const frl_np_params *p, const void *actions, int32_t actions_f64, double *rewards,
+                            uint8_t *flags, float *obs, int32_t auto_reset, double *stats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,170 @@
+"""GPU parity: the CUDA numpy/ElegantRL StockTradingEnv path (through the C-ABI) vs golden vectors
+made by the unmodified reference and vs the CPU oracle.  Bit-exact, including the data-dependent
+numpy kinds (Python float / np.float32 / np.float64) of amount, total_asset, gamma_reward, reward."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from test_oracle_golden import NpResetDraws, np_kwargs_from_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+NP = sorted(glob.glob(os.path.join(GOLDEN, "np_*.npz")))
+
+
+@pytest.mark.parametrize("path", NP, ids=[os.path.basename(p)[:-4] for p in NP])
+def test_golden_single_env(path):
+    from finrl_b200 import BatchedNpStockTradingEnv
+
+    g = np.load(path)
+    cfg = {"price_array": g["price_array"], "tech_array": g["tech_array"], "turbulence_array": g["turbulence_array"],
+           "if_train": False}
+    env = BatchedNpStockTradingEnv(cfg, n_envs=1, **np_kwargs_from_golden(g))
+    draws = NpResetDraws(g)
+    s0, f = draws.draw()
+    obs = env.reset(stocks0=s0, factor=f)
+    assert np.array_equal(obs.cpu().numpy()[0], g["obs0"])
+    st = env.get_state()
+    assert st["amount"][0].item() == g["init_amount"] and st["amount_kind"][0].item() == g["init_amount_kind"]
+    assert st["total"][0].item() == g["init_total"] and st["total_kind"][0].item() == g["init_total_kind"]
+    acts = g["actions"]
+    nreset = 0
+    for s in range(acts.shape[0]):
+        obs, reward, done, flags = env.step(torch.from_numpy(acts[s][None, :]).cuda())
+        st = env.get_state()
+        ctx = f"step {s}"
+        fl = int(flags[0])
+        assert bool(fl & 1) == bool(g["done"][s]), ctx
+        assert bool(fl & 2) == bool(g["liq"][s]), ctx
+        assert np.array_equal(st["stocks"][0].cpu().numpy(), g["stocks"][s]), ctx
+        assert np.array_equal(st["cool"][0].cpu().numpy(), g["cool"][s]), ctx
+        assert (st["amount"][0].item(), st["amount_kind"][0].item()) == (g["amount"][s], g["amount_kind"][s]), ctx
+        assert (st["total"][0].item(), st["total_kind"][0].item()) == (g["total"][s], g["total_kind"][s]), ctx
+        assert (st["gamma_reward"][0].item(), st["gr_kind"][0].item()) == (g["gamma_reward"][s], g["gr_kind"][s]), ctx
+        assert (reward[0].item(), fl >> 4) == (g["reward"][s], g["reward_kind"][s]), ctx
+        assert st["day"][0].item() == g["day"][s], ctx
+        assert np.array_equal(obs[0].cpu().numpy(), g["obs"][s]), ctx
+        if g["done"][s]:
+            assert st["episode_return"][0].item() == g["episode_return"][s], ctx
+            s0, f = draws.draw()
+            env.reset(stocks0=s0, factor=f)
+            st = env.get_state()
+            assert st["amount"][0].item() == g["reset_amount"][nreset]
+            assert st["amount_kind"][0].item() == g["reset_amount_kind"][nreset]
+            assert np.array_equal(st["stocks"][0].cpu().numpy(), g["reset_stocks"][nreset])
+            nreset += 1
+
+
+def _make(N, T=50, D=30, K=8, seed=0, thresh=80, **kw):
+    from finrl_b200 import BatchedNpStockTradingEnv, synthetic as syn
+    from oracle import oracle as ora
+
+    close, tech, turb = syn.make_tables(T, D, K, seed=seed)
+    pa, ta, tu = syn.make_np_arrays(close, tech, turb)
+    args = dict(turbulence_thresh=thresh, initial_capital=3e5)
+    args.update(kw)
+    env = BatchedNpStockTradingEnv({"price_array": pa, "tech_array": ta, "turbulence_array": tu, "if_train": False},
+                                   n_envs=N, **args)
+    o = ora.NpTradingOracle(pa, ta, tu, N, **args)
+    return env, o
+
+
+def _compare(env, o, ctx=""):
+    st = env.get_state()
+    assert np.array_equal(st["amount"].cpu().numpy(), o.amount), ctx
+    assert np.array_equal(st["amount_kind"].cpu().numpy(), o.amount_kind), ctx
+    assert np.array_equal(st["stocks"].cpu().numpy(), o.stocks), ctx
+    assert np.array_equal(st["cool"].cpu().numpy(), o.cool), ctx
+    assert np.array_equal(st["day"].cpu().numpy(), o.day), ctx
+    assert np.array_equal(st["total"].cpu().numpy(), o.total), ctx
+    assert np.array_equal(st["total_kind"].cpu().numpy(), o.total_kind), ctx
+    assert np.array_equal(st["gamma_reward"].cpu().numpy(), o.gamma_reward), ctx
+    assert np.array_equal(st["gr_kind"].cpu().numpy(), o.gr_kind), ctx
+
+
+@pytest.mark.parametrize("N,D", [(1, 30), (77, 30), (2048 + 5, 30), (300, 7), (300, 16)])
+def test_step_vs_oracle(N, D):
+    """Random train-style initial positions, distinct actions, several episodes (manual resets)."""
+    from finrl_b200 import synthetic as syn
+
+    T = 50
+    env, o = _make(N, T=T, D=D, K=3)
+    rng = np.random.RandomState(3)
+    acts = syn.make_actions((2 * T + 7, N, D), seed=6)
+    acts[:4] *= 0.08  # dead band: amount keeps its Python-float / f32 kind for a while
+
+    def reset_both():
+        s0 = rng.randint(0, 64, size=(N, D)).astype(np.float32)
+        f = rng.uniform(0.95, 1.05, size=N)
+        obs = env.reset(stocks0=s0, factor=f)
+        assert np.array_equal(obs.cpu().numpy(), o.reset(stocks0=s0, factor=f))
+
+    reset_both()
+    for s in range(acts.shape[0]):
+        obs, reward, done, flags = env.step(torch.from_numpy(acts[s]).cuda())
+        oobs, orew, ork, ofl = o.step(acts[s])
+        ctx = f"step {s}"
+        assert np.array_equal(flags.cpu().numpy(), ofl | (ork << 4)), ctx
+        assert np.array_equal(reward.cpu().numpy(), orew), ctx
+        assert np.array_equal(obs.cpu().numpy(), oobs), ctx
+        _compare(env, o, ctx)
+        if done.all():
+            assert np.array_equal(env.episode_return.cpu().numpy(), o.episode_return)
+            reset_both()
+
+
+@pytest.mark.parametrize("layout", ["KND", "NKD"])
+def test_rollout_auto_reset_vs_oracle(layout):
+    """Fused K-step rollouts with the deterministic auto-reset after each done step."""
+    from finrl_b200 import synthetic as syn
+
+    N, K, T, D = 1024, 40, 60, 30
+    env, o = _make(N, T=T, D=D)
+    for r in range(4):
+        acts = syn.make_actions((K, N, D), seed=30 + r)
+        a_dev = torch.from_numpy(acts).cuda()
+        if layout == "NKD":
+            a_dev = a_dev.permute(1, 0, 2).contiguous()
+        obs, rewards, flags = env.rollout(a_dev, layout=layout, obs_mode="last", auto_reset=True)
+        orew = np.empty((K, N))
+        ofl = np.empty((K, N), dtype=np.uint8)
+        for k in range(K):
+            oobs, orew[k], ork, f = o.step(acts[k])
+            ofl[k] = f | (ork << 4)
+            if f[0] & 1:
+                oobs = o.reset()
+        assert np.array_equal(flags.cpu().numpy(), ofl)
+        assert np.array_equal(rewards.cpu().numpy(), orew)
+        assert np.array_equal(obs.cpu().numpy(), oobs)
+        _compare(env, o, f"rollout {r}")
+    st = env.read_stats()
+    assert st["env_steps"] == 4 * K * N and st["done_count"] == N * (4 * K // (T - 1))
+
+
+def test_full_size_properties():
+    """1M envs (config 3): identical actions -> every env equals the 1-env oracle; obs consistent."""
+    from finrl_b200 import synthetic as syn
+
+    N, T, K = 1 << 20, 40, 16
+    env, _ = _make(N, T=T, seed=4)
+    o1 = _make(1, T=T, seed=4)[1]
+    acts = syn.make_actions((K, 1, 30), seed=8)
+    obs, rewards, flags = env.rollout(torch.from_numpy(acts).cuda().expand(K, N, 30).contiguous(), obs_mode="last",
+                                      auto_reset=False)
+    for k in range(K):
+        oobs, orew, ork, ofl = o1.step(acts[k])
+        assert bool((rewards[k] == float(orew[0])).all())
+        assert bool((flags[k] == int(ofl[0] | (ork[0] << 4))).all())
+    assert bool((env.amount == float(o1.amount[0])).all())
+    assert bool((env.stocks == torch.from_numpy(o1.stocks[0]).cuda()[:, None]).all())
+    assert bool((obs == torch.from_numpy(oobs[0]).cuda()[None, :]).all())
+    acts2 = torch.from_numpy(syn.make_actions((N, 30), seed=9)).cuda()
+    obs, reward, done, fl = env.step(acts2)
+    assert bool((obs[:, 0] == (env.amount.float() * 2.0**-12)).all())
+    assert bool((obs[:, 33:63] == env.stocks.t() * 2.0**-6).all())
+    assert bool((obs[:, 63:93] == env.cool.t()).all())
