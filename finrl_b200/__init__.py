@@ -9,5 +9,6 @@ from ._cabi import EngineError, FLAG_DONE, FLAG_LIQUIDATE, FLAG_SHORTAGE  # noqa
 from .tables import TradingTables, frame_to_arrays  # noqa: F401
 from .trading import BatchedStockTradingEnv  # noqa: F401
 from .nptrading import BatchedNpStockTradingEnv, NpTables  # noqa: F401
+from .portfolio import BatchedStockPortfolioEnv, PortfolioTables  # noqa: F401
 
 __version__ = "0.1.0"

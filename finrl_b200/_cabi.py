@@ -95,6 +95,25 @@ class NpParams(C.Structure):
     ]
 
 
+class PortfolioParams(C.Structure):
+    """frl_portfolio_params (include/finrl_b200.h)."""
+
+    _fields_ = [
+        ("n_envs", C.c_int32),
+        ("stock_dim", C.c_int32),
+        ("n_tech", C.c_int32),
+        ("n_days", C.c_int32),
+        ("obs_dim", C.c_int32),
+        ("_pad0", C.c_int32),
+        ("initial_amount", C.c_double),
+        ("ret", C.c_void_p),
+        ("obs_table", C.c_void_p),
+        ("pv", C.c_void_p),
+        ("day", C.c_void_p),
+        ("reward", C.c_void_p),
+    ]
+
+
 KIND_PY, KIND_F32, KIND_F64 = 0, 1, 2
 NP_REWARD_KIND_SHIFT = 4
 
@@ -125,6 +144,18 @@ SIGNATURES = {
     "frl_np_step": (
         C.c_int32,
         [C.POINTER(NpParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+         C.c_void_p],
+    ),
+    "frl_portfolio_reset": (C.c_int32, [C.POINTER(PortfolioParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "frl_portfolio_observe": (C.c_int32, [C.POINTER(PortfolioParams), C.c_void_p, C.c_void_p]),
+    "frl_portfolio_rollout": (
+        C.c_int32,
+        [C.POINTER(PortfolioParams), C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
+    ),
+    "frl_portfolio_step": (
+        C.c_int32,
+        [C.POINTER(PortfolioParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
          C.c_void_p],
     ),
 }

@@ -1,0 +1,325 @@
+// A3 — StockPortfolioEnv (reference: finrl/meta/env_portfolio_allocation/env_portfolio.py).
+//
+// One thread per env: softmax weights exp(a)/sum(exp(a)) in the action dtype with numpy's pairwise
+// sum and NO max-subtraction (quirk Q8), the sequential weighted return over the D stocks, and
+// portfolio_value *= 1 + return.  The (D+K) x D observation depends only on the day, so it is either
+// not written at all (callers index obs_table with the day vector) or broadcast from a register-
+// cached table row by the whole warp.  The env-independent ratio close[t]/close[t-1]-1 is a per-day
+// table row built on the host with the reference's own numpy expression.
+#include "common.cuh"
+
+namespace frl {
+namespace {
+
+template <int SLOTS, typename ActT>
+struct alignas(16) PfWarpSmem {
+    ActT act[32 * SLOTS];
+    int day[32];
+};
+
+template <typename T>
+__device__ __forceinline__ T pf_exp(T x);
+template <>
+__device__ __forceinline__ float pf_exp<float>(float x) { return expf(x); }
+template <>
+__device__ __forceinline__ double pf_exp<double>(double x) { return exp(x); }
+template <typename T>
+__device__ __forceinline__ T pf_add(T a, T b);
+template <>
+__device__ __forceinline__ float pf_add<float>(float a, float b) { return fadd(a, b); }
+template <>
+__device__ __forceinline__ double pf_add<double>(double a, double b) { return dadd(a, b); }
+template <typename T>
+__device__ __forceinline__ T pf_div(T a, T b);
+template <>
+__device__ __forceinline__ float pf_div<float>(float a, float b) { return __fdiv_rn(a, b); }
+template <>
+__device__ __forceinline__ double pf_div<double>(double a, double b) { return __ddiv_rn(a, b); }
+
+// np.sum over a contiguous vector: numpy's pairwise summation (n < 8 sequential, else 8 accumulators)
+template <int SLOTS, typename T>
+__device__ __forceinline__ T pf_pairwise_sum(const T (&x)[SLOTS], int D)
+{
+    if (D < 8) {
+        T res = T(0);
+#pragma unroll
+        for (int j = 0; j < 8 && j < SLOTS; ++j)
+            if (j < D) res = pf_add(res, x[j]);
+        return res;
+    }
+    T r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = x[j];
+    const int nb = D >> 3;
+#pragma unroll
+    for (int b = 1; b < SLOTS / 8; ++b) {
+        if (b < nb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = pf_add(r[j], x[8 * b + j]);
+        }
+    }
+    T res = pf_add(pf_add(pf_add(r[0], r[1]), pf_add(r[2], r[3])), pf_add(pf_add(r[4], r[5]), pf_add(r[6], r[7])));
+#pragma unroll
+    for (int j = 8; j < SLOTS; ++j)
+        if (j >= 8 * nb && j < D) res = pf_add(res, x[j]);
+    return res;
+}
+
+// broadcast the day's observation row to the tile's envs (obs[N][O] float32)
+__device__ __forceinline__ void pf_write_obs_tile(const frl_portfolio_params &p, const int *day_s,
+                                                  float *__restrict__ obs, long long env0, int nvalid, int lane)
+{
+    const int O = p.obs_dim;
+    const int d0 = day_s[0];
+    bool uniform = true;
+    if (lane < nvalid) uniform = (day_s[lane] == d0);
+    uniform = __all_sync(0xffffffffu, uniform);
+    if (uniform) {
+        const float *trow = p.obs_table + (size_t)d0 * O;
+        for (int base = 0; base < O; base += 256) {  // 8 x 128 B of the row per pass, cached in registers
+            float t[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int pos = base + 32 * c + lane;
+                t[c] = pos < O ? __ldg(trow + pos) : 0.0f;
+            }
+            float *orow = obs + (size_t)env0 * O + base + lane;
+            for (int r = 0; r < nvalid; ++r) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (base + 32 * c + lane < O) orow[32 * c] = t[c];
+                orow += O;
+            }
+        }
+    } else {
+        for (int r = 0; r < nvalid; ++r) {
+            const float *trow = p.obs_table + (size_t)day_s[r] * O;
+            float *orow = obs + (size_t)(env0 + r) * O;
+            for (int pos = lane; pos < O; pos += 32) orow[pos] = __ldg(trow + pos);
+        }
+    }
+}
+
+template <int SLOTS, typename ActT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+portfolio_rollout_kernel(const frl_portfolio_params p, const ActT *__restrict__ actions, long long act_step_stride,
+                         long long act_env_stride, int n_steps, double *__restrict__ rewards,
+                         uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode, int auto_reset,
+                         double *__restrict__ stats)
+{
+    using SM = PfWarpSmem<SLOTS, ActT>;
+    __shared__ SM smem[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SM &sm = smem[warp];
+    const int N = p.n_envs, D = p.stock_dim, T = p.n_days;
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const bool valid = lane < nvalid;
+    const long long n = valid ? env0 + lane : (long long)N - 1;
+
+    double pv = p.pv[n], last_reward = p.reward[n];
+    int day = p.day[n];
+    double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0;
+
+    for (int k = 0; k < n_steps; ++k) {
+        const ActT *abase = actions + (size_t)k * act_step_stride;
+        __syncwarp();
+        if (act_env_stride == D) {
+            const ActT *tile = abase + (size_t)env0 * D + lane;
+            const int cnt = nvalid * D - lane;
+            ActT av[SLOTS];
+#pragma unroll
+            for (int i = 0; i < SLOTS; ++i) av[i] = (i < D && 32 * i < cnt) ? __ldcs(tile + 32 * i) : ActT(0);
+#pragma unroll
+            for (int i = 0; i < SLOTS; ++i)
+                if (i < D) sm.act[lane + 32 * i] = av[i];
+        } else {
+            for (int r = 0; r < 32; ++r)
+                if (lane < D)
+                    sm.act[r * D + lane] = r < nvalid ? abase[(size_t)(env0 + r) * act_env_stride + lane] : ActT(0);
+        }
+        __syncwarp();
+
+        uint8_t flags = 0;
+        double reward;
+        if (day >= T - 1) {
+            // terminal branch (:127-156): no state change, the previous reward again
+            flags = FRL_FLAG_DONE;
+            reward = last_reward;
+            if (valid) {
+                st_done += 1.0;
+                st_epi += pv;
+            }
+            if (auto_reset) {  // DummyVecEnv.step_wait -> reset (:202-220)
+                pv = p.initial_amount;
+                day = 0;
+            }
+        } else {
+            // softmax_normalization (:225-229)
+            ActT e[SLOTS];
+            const ActT *arow = sm.act + lane * D;
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j) e[j] = (j < D) ? pf_exp<ActT>(arow[j]) : ActT(0);
+            const ActT den = pf_pairwise_sum<SLOTS, ActT>(e, D);
+            day += 1;
+            const double *rrow = p.ret + (size_t)day * 32;
+            // sum(((close_new / close_old) - 1) * weights): Python sum, sequential (:183-185)
+            double pr = 0.0;
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j)
+                if (j < D) pr = dadd(pr, dmul(__ldg(rrow + j), (double)pf_div<ActT>(e[j], den)));
+            pv = dmul(pv, dadd(1.0, pr));
+            reward = pv;  // reward = new portfolio value, unscaled (:196)
+            last_reward = reward;
+        }
+        if (valid) {
+            if (rewards) rewards[(size_t)k * N + n] = reward;
+            if (flags_out) flags_out[(size_t)k * N + n] = flags;
+            st_r += reward;
+            st_r2 += reward * reward;
+        }
+        if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
+            sm.day[lane] = day;
+            __syncwarp();
+            float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
+            pf_write_obs_tile(p, sm.day, o, env0, nvalid, lane);
+        }
+    }
+    if (valid) {
+        p.pv[n] = pv;
+        p.day[n] = day;
+        p.reward[n] = last_reward;
+    }
+    if (stats) {
+        double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, valid ? pv : 0.0, 0.0, valid ? (double)n_steps : 0.0, 0.0};
+#pragma unroll
+        for (int w = 4; w >= 1; w >>= 1) {
+            const bool up = (lane & w) != 0;
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+                const double keep = up ? v[i + w] : v[i];
+                const double send = up ? v[i] : v[i + w];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+            }
+        }
+        double s = v[0];
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if (lane < 8 && s != 0.0) atomicAdd(stats + lane, s);
+    }
+}
+
+__global__ void portfolio_reset_kernel(const frl_portfolio_params p, const uint8_t *__restrict__ mask)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.n_envs) return;
+    if (mask && !mask[n]) return;
+    p.pv[n] = p.initial_amount;
+    p.day[n] = 0;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) portfolio_observe_kernel(const frl_portfolio_params p, float *__restrict__ obs)
+{
+    __shared__ int day_s[WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = p.n_envs;
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    day_s[warp][lane] = p.day[lane < nvalid ? env0 + lane : (long long)N - 1];
+    __syncwarp();
+    pf_write_obs_tile(p, day_s[warp], obs, env0, nvalid, lane);
+}
+
+int32_t pf_validate(const frl_portfolio_params *p)
+{
+    FRL_REQUIRE(p != nullptr, "portfolio: params is NULL");
+    FRL_REQUIRE(p->n_envs >= 1, "portfolio: n_envs must be >= 1 (got %d)", p->n_envs);
+    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 32, "portfolio: stock_dim must be in 1..32 (got %d)", p->stock_dim);
+    FRL_REQUIRE(p->n_tech >= 0 && p->n_days >= 1, "portfolio: bad n_tech/n_days (%d, %d)", p->n_tech, p->n_days);
+    FRL_REQUIRE(p->obs_dim == (p->stock_dim + p->n_tech) * p->stock_dim, "portfolio: obs_dim %d != (D+K)*D = %d",
+                p->obs_dim, (p->stock_dim + p->n_tech) * p->stock_dim);
+    FRL_REQUIRE(p->ret && p->obs_table, "portfolio: table pointer is NULL");
+    FRL_REQUIRE(p->pv && p->day && p->reward, "portfolio: state pointer is NULL");
+    return FRL_OK;
+}
+
+template <int SLOTS, typename ActT, int WARPS>
+void pf_launch(const frl_portfolio_params &p, const void *actions, long long sstride, long long estride, int n_steps,
+               double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
+{
+    const long long tiles = ((long long)p.n_envs + 31) / 32;
+    const unsigned grid = (unsigned)((tiles + WARPS - 1) / WARPS);
+    portfolio_rollout_kernel<SLOTS, ActT, WARPS><<<grid, WARPS * 32, 0, st>>>(
+        p, (const ActT *)actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats);
+}
+
+}  // namespace
+}  // namespace frl
+
+using namespace frl;
+
+extern "C" int32_t frl_portfolio_observe(const frl_portfolio_params *p, float *obs, void *stream)
+{
+    if (int32_t rc = pf_validate(p)) return rc;
+    FRL_REQUIRE(obs != nullptr, "portfolio_observe: obs is NULL");
+    constexpr int W = 4;
+    const long long tiles = ((long long)p->n_envs + 31) / 32;
+    portfolio_observe_kernel<W><<<(unsigned)((tiles + W - 1) / W), W * 32, 0, (cudaStream_t)stream>>>(*p, obs);
+    return check_launch("portfolio_observe");
+}
+
+extern "C" int32_t frl_portfolio_reset(const frl_portfolio_params *p, const uint8_t *mask, float *obs, void *stream)
+{
+    if (int32_t rc = pf_validate(p)) return rc;
+    portfolio_reset_kernel<<<(p->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*p, mask);
+    if (int32_t rc = check_launch("portfolio_reset")) return rc;
+    if (obs) return frl_portfolio_observe(p, obs, stream);
+    return FRL_OK;
+}
+
+extern "C" int32_t frl_portfolio_rollout(const frl_portfolio_params *p, const void *actions, int32_t actions_f64,
+                                         int64_t act_step_stride, int64_t act_env_stride, int32_t n_steps,
+                                         double *rewards, uint8_t *flags, float *obs, int32_t obs_mode,
+                                         int32_t auto_reset, double *stats, void *stream)
+{
+    if (int32_t rc = pf_validate(p)) return rc;
+    FRL_REQUIRE(actions != nullptr, "portfolio_rollout: actions is NULL");
+    FRL_REQUIRE(n_steps >= 1, "portfolio_rollout: n_steps must be >= 1 (got %d)", n_steps);
+    FRL_REQUIRE(act_env_stride >= p->stock_dim, "portfolio_rollout: act_env_stride %lld < stock_dim", (long long)act_env_stride);
+    FRL_REQUIRE(obs_mode >= FRL_OBS_NONE && obs_mode <= FRL_OBS_ALL, "portfolio_rollout: bad obs_mode %d", obs_mode);
+    FRL_REQUIRE(obs_mode == FRL_OBS_NONE || obs != nullptr, "portfolio_rollout: obs is NULL but obs_mode=%d", obs_mode);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = p->stock_dim;
+#define FRL_GO(SLOTS)                                                                                             \
+    do {                                                                                                          \
+        if (actions_f64)                                                                                          \
+            pf_launch<SLOTS, double, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags,    \
+                                        obs, obs_mode, auto_reset, stats, st);                                    \
+        else                                                                                                      \
+            pf_launch<SLOTS, float, 4>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags,     \
+                                       obs, obs_mode, auto_reset, stats, st);                                     \
+    } while (0)
+    if (D <= 8)
+        FRL_GO(8);
+    else if (D <= 16)
+        FRL_GO(16);
+    else
+        FRL_GO(32);
+#undef FRL_GO
+    return check_launch("portfolio_rollout");
+}
+
+extern "C" int32_t frl_portfolio_step(const frl_portfolio_params *p, const void *actions, int32_t actions_f64,
+                                      double *rewards, uint8_t *flags, float *obs, int32_t auto_reset, double *stats,
+                                      void *stream)
+{
+    if (p == nullptr) {
+        set_error("portfolio_step: params is NULL");
+        return FRL_E_INVALID;
+    }
+    return frl_portfolio_rollout(p, actions, actions_f64, (int64_t)p->n_envs * p->stock_dim, p->stock_dim, 1, rewards,
+                                 flags, obs, obs ? FRL_OBS_LAST : FRL_OBS_NONE, auto_reset, stats, stream);
+}

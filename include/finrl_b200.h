@@ -189,6 +189,43 @@ FRL_API int32_t frl_np_rollout(const frl_np_params *p, const void *actions, int3
 FRL_API int32_t frl_np_step(const frl_np_params *p, const void *actions, int32_t actions_f64, double *rewards,
                             uint8_t *flags, float *obs, int32_t auto_reset, double *stats, void *stream);
 
+/* =========================================================================================
+ * A3  StockPortfolioEnv — finrl/meta/env_portfolio_allocation/env_portfolio.py
+ * ========================================================================================= */
+typedef struct frl_portfolio_params {
+    int32_t n_envs;    /* N */
+    int32_t stock_dim; /* D, 1..32 */
+    int32_t n_tech;    /* K */
+    int32_t n_days;    /* T */
+    int32_t obs_dim;   /* (D + K) * D : np.append(cov (D x D), tech rows (K x D), axis=0) flattened */
+    int32_t _pad0;
+    double initial_amount;
+    /* ---- tables ---- */
+    const double *ret;      /* [T][32] ret[t][j] = close[t][j] / close[t-1][j] - 1 (row 0 unused), the
+                               env-independent factor of the weighted return (:183-185) */
+    const float *obs_table; /* [T][obs_dim] float32 image of the day's state matrix */
+    /* ---- per-env state ---- */
+    double *pv;     /* [N] self.portfolio_value */
+    int32_t *day;   /* [N] self.day */
+    double *reward; /* [N] self.reward (returned again by the terminal step) */
+} frl_portfolio_params;
+
+/* StockPortfolioEnv.reset (:202-220) for envs with mask[n] != 0 (NULL = all). obs nullable [N][obs_dim]. */
+FRL_API int32_t frl_portfolio_reset(const frl_portfolio_params *p, const uint8_t *mask, float *obs, void *stream);
+/* materialise the state matrix of every env: obs[N][obs_dim] float32 (it depends on the day only, so
+ * callers may instead index obs_table with p->day and skip this traffic entirely). */
+FRL_API int32_t frl_portfolio_observe(const frl_portfolio_params *p, float *obs, void *stream);
+/* n_steps fused StockPortfolioEnv.step (:125-200): softmax weights (no max-subtraction), weighted
+ * one-day return, portfolio value update; reward = new portfolio value.  Conventions as
+ * frl_trading_rollout.  Floating point: np.exp is reproduced to 1 ulp, not bit for bit. */
+FRL_API int32_t frl_portfolio_rollout(const frl_portfolio_params *p, const void *actions, int32_t actions_f64,
+                                      int64_t act_step_stride, int64_t act_env_stride, int32_t n_steps,
+                                      double *rewards, uint8_t *flags, float *obs, int32_t obs_mode,
+                                      int32_t auto_reset, double *stats, void *stream);
+FRL_API int32_t frl_portfolio_step(const frl_portfolio_params *p, const void *actions, int32_t actions_f64,
+                                   double *rewards, uint8_t *flags, float *obs, int32_t auto_reset, double *stats,
+                                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -514,3 +514,83 @@ void ora_np_step(const ora_np_cfg *c, ora_np_state *s, const float *actions, dou
 #pragma omp parallel for schedule(static)
     for (int n = 0; n < c->n_envs; ++n) np_step_one(c, s, n, actions, reward_out, reward_kind_out, flags_out, obs);
 }
+
+/* ======================================================================================= */
+/* A3: StockPortfolioEnv — finrl/meta/env_portfolio_allocation/env_portfolio.py              */
+/* ======================================================================================= */
+
+void ora_portfolio_reset(const ora_portfolio_cfg *c, ora_portfolio_state *s, const uint8_t *mask)
+{
+    for (int n = 0; n < c->n_envs; ++n) { /* reset (:202-220): no stale-day quirk here */
+        if (mask && !mask[n]) continue;
+        s->pv[n] = c->initial_amount;
+        s->day[n] = 0;
+    }
+}
+
+void ora_portfolio_obs(const ora_portfolio_cfg *c, const ora_portfolio_state *s, double *obs)
+{
+    const int D = c->stock_dim, K = c->n_tech, T = c->n_days;
+    const size_t O = (size_t)(D + K) * D;
+    for (int n = 0; n < c->n_envs; ++n) {
+        const int day = s->day[n];
+        double *o = obs + (size_t)n * O;
+        memcpy(o, c->cov + (size_t)day * D * D, sizeof(double) * (size_t)D * D);
+        for (int k = 0; k < K; ++k)
+            memcpy(o + (size_t)(D + k) * D, c->tech + ((size_t)k * T + day) * D, sizeof(double) * (size_t)D);
+    }
+}
+
+static void pf_step_one(const ora_portfolio_cfg *c, ora_portfolio_state *s, int n, const void *actions,
+                        int actions_f64, double *reward_out, uint8_t *flags_out, double *weights_out,
+                        double *pret_out, int auto_reset)
+{
+    const int D = c->stock_dim, T = c->n_days;
+    if (s->day[n] >= T - 1) { /* terminal branch (:127-156): previous reward again */
+        if (reward_out) reward_out[n] = s->reward[n];
+        if (flags_out) flags_out[n] = ORA_FLAG_DONE;
+        if (pret_out) pret_out[n] = 0.0;
+        if (auto_reset) {
+            s->pv[n] = c->initial_amount;
+            s->day[n] = 0;
+        }
+        return;
+    }
+    /* softmax_normalization (:225-229): exp in the input dtype, np.sum pairwise, no max-subtraction (Q8) */
+    double w[MAXD];
+    if (actions_f64) {
+        const double *a = (const double *)actions + (size_t)n * D;
+        double e[MAXD];
+        for (int i = 0; i < D; ++i) e[i] = exp(a[i]);
+        const double den = ora_pairwise_sum_f64(e, D);
+        for (int i = 0; i < D; ++i) w[i] = e[i] / den;
+    } else {
+        const float *a = (const float *)actions + (size_t)n * D;
+        float e[MAXD];
+        for (int i = 0; i < D; ++i) e[i] = expf(a[i]);
+        const float den = ora_pairwise_sum_f32(e, D);
+        for (int i = 0; i < D; ++i) w[i] = (double)(e[i] / den);
+    }
+    const double *c0 = c->close + (size_t)s->day[n] * D;
+    s->day[n] += 1;
+    const double *c1 = c->close + (size_t)s->day[n] * D;
+    /* portfolio_return = sum(((close_new / close_old) - 1) * weights): Python sum, sequential (:183-185) */
+    double pr = 0.0;
+    for (int i = 0; i < D; ++i) pr = pr + ((c1[i] / c0[i]) - 1.0) * w[i];
+    const double pv = s->pv[n] * (1.0 + pr);
+    s->pv[n] = pv;
+    s->reward[n] = pv; /* reward = new portfolio value, unscaled (:196) */
+    if (reward_out) reward_out[n] = pv;
+    if (flags_out) flags_out[n] = 0;
+    if (pret_out) pret_out[n] = pr;
+    if (weights_out)
+        for (int i = 0; i < D; ++i) weights_out[(size_t)n * D + i] = w[i];
+}
+
+void ora_portfolio_step(const ora_portfolio_cfg *c, ora_portfolio_state *s, const void *actions, int actions_f64,
+                        double *reward_out, uint8_t *flags_out, double *weights_out, double *pret_out, int auto_reset)
+{
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < c->n_envs; ++n)
+        pf_step_one(c, s, n, actions, actions_f64, reward_out, flags_out, weights_out, pret_out, auto_reset);
+}

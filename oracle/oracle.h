@@ -118,6 +118,29 @@ void ora_np_obs(const ora_np_cfg *c, const ora_np_state *s, float *obs /*[N][O]*
 void ora_np_step(const ora_np_cfg *c, ora_np_state *s, const float *actions, double *reward_out,
                  uint8_t *reward_kind_out, uint8_t *flags_out, float *obs);
 
+/* ---- A3: StockPortfolioEnv (env_portfolio_allocation/env_portfolio.py) --------------------- */
+typedef struct {
+    int32_t n_envs, stock_dim, n_tech, n_days;
+    double initial_amount;
+    const double *close; /* [T][D] */
+    const double *cov;   /* [T][D][D] cov_list of each day */
+    const double *tech;  /* [K][T][D] */
+} ora_portfolio_cfg;
+
+typedef struct {
+    double *pv;     /* [N] portfolio_value */
+    int32_t *day;   /* [N] */
+    double *reward; /* [N] self.reward (returned again by the terminal step) */
+} ora_portfolio_state;
+
+void ora_portfolio_reset(const ora_portfolio_cfg *c, ora_portfolio_state *s, const uint8_t *mask);
+/* state = np.append(cov, tech rows, axis=0): obs[N][(D+K)*D] f64 */
+void ora_portfolio_obs(const ora_portfolio_cfg *c, const ora_portfolio_state *s, double *obs);
+/* step (:125-200). actions [N][D] f32 or f64 (np.exp runs in that dtype).  weights_out [N][D] f64
+ * (nullable) receives the softmax weights, pret_out [N] the portfolio return. */
+void ora_portfolio_step(const ora_portfolio_cfg *c, ora_portfolio_state *s, const void *actions, int actions_f64,
+                        double *reward_out, uint8_t *flags_out, double *weights_out, double *pret_out, int auto_reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -264,3 +264,52 @@ class NpTradingOracle:
         obs = np.empty((self.N, self.O), dtype=np.float32) if want_obs else None
         lib().ora_np_step(C.byref(self._cfg), C.byref(self._st), _p(a), _p(reward), _p(rk), _p(flags), _p(obs))
         return obs, reward, rk, flags
+
+
+# --------------------------------------------------------------------------------------------
+# A3
+# --------------------------------------------------------------------------------------------
+class _PfCfg(C.Structure):
+    _fields_ = [("n_envs", C.c_int32), ("stock_dim", C.c_int32), ("n_tech", C.c_int32), ("n_days", C.c_int32),
+                ("initial_amount", C.c_double), ("close", C.c_void_p), ("cov", C.c_void_p), ("tech", C.c_void_p)]
+
+
+class _PfState(C.Structure):
+    _fields_ = [("pv", C.c_void_p), ("day", C.c_void_p), ("reward", C.c_void_p)]
+
+
+class PortfolioOracle:
+    """N independent copies of the reference ``StockPortfolioEnv``
+    (finrl/meta/env_portfolio_allocation/env_portfolio.py), stepped on the CPU."""
+
+    def __init__(self, close, cov, tech, n_envs, initial_amount=1_000_000):
+        self.close = np.ascontiguousarray(close, dtype=np.float64)
+        T, D = self.close.shape
+        self.cov = np.ascontiguousarray(cov, dtype=np.float64).reshape(T, D, D)
+        self.tech = np.ascontiguousarray(tech, dtype=np.float64).reshape(-1, T, D)
+        K = self.tech.shape[0]
+        N = int(n_envs)
+        self.N, self.D, self.K, self.T = N, D, K, T
+        self.pv = np.zeros(N); self.day = np.zeros(N, dtype=np.int32); self.reward = np.zeros(N)
+        self._cfg = _PfCfg(N, D, K, T, float(initial_amount), _p(self.close), _p(self.cov), _p(self.tech))
+        self._st = _PfState(_p(self.pv), _p(self.day), _p(self.reward))
+        self.reset()
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        lib().ora_portfolio_reset(C.byref(self._cfg), C.byref(self._st), _p(m))
+        return self.obs()
+
+    def obs(self):
+        out = np.empty((self.N, self.D + self.K, self.D))
+        lib().ora_portfolio_obs(C.byref(self._cfg), C.byref(self._st), _p(out))
+        return out
+
+    def step(self, actions, auto_reset=False):
+        a = np.ascontiguousarray(actions)
+        assert a.shape == (self.N, self.D) and a.dtype in (np.float32, np.float64)
+        reward = np.empty(self.N); flags = np.empty(self.N, dtype=np.uint8)
+        w = np.empty((self.N, self.D)); pr = np.empty(self.N)
+        lib().ora_portfolio_step(C.byref(self._cfg), C.byref(self._st), _p(a), C.c_int(a.dtype == np.float64),
+                                 _p(reward), _p(flags), _p(w), _p(pr), C.c_int(int(auto_reset)))
+        return reward, flags, w, pr
