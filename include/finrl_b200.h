@@ -226,6 +226,56 @@ FRL_API int32_t frl_portfolio_step(const frl_portfolio_params *p, const void *ac
                                    double *rewards, uint8_t *flags, float *obs, int32_t auto_reset, double *stats,
                                    void *stream);
 
+/* =========================================================================================
+ * A4  StockTradingEnvCashpenalty — finrl/meta/env_stock_trading/env_stocktrading_cashpenalty.py
+ * ========================================================================================= */
+typedef struct frl_cashpenalty_params {
+    int32_t n_envs;    /* N */
+    int32_t stock_dim; /* D = len(assets), 1..128 */
+    int32_t n_cols;    /* C = len(daily_information_cols) */
+    int32_t n_days;    /* T = len(dates) */
+    int32_t obs_dim;   /* O = state_space = 1 + D + D*C (:88-90) */
+    int32_t discrete_actions;
+    int32_t shares_increment;
+    int32_t use_turbulence; /* turbulence_threshold is not None */
+    int32_t patient;
+    int32_t _pad0;
+    double buy_cost_pct, sell_cost_pct;
+    double hmax; /* currency per trade (scalar) */
+    double turbulence_threshold;
+    double initial_amount;
+    double cash_penalty_proportion;
+    /* ---- tables ---- */
+    const double *close;   /* [T][D] closings per date */
+    const double *turb;    /* [T] "turbulence" column (read only when use_turbulence) */
+    const float *obs_tmpl; /* [T][O] float32: [0, 0 x D, get_date_vector(t) asset-major (:160-173)] */
+    /* ---- per-env state (env-major: one warp per env reads its rows coalesced) ---- */
+    double *cash;        /* [N] cash_on_hand */
+    double *hold;        /* [N][D] holdings (fractional unless discrete_actions) */
+    int32_t *date_index; /* [N] */
+    int32_t *start;      /* [N] starting_point */
+    uint8_t *fresh;      /* [N] 1 while self.turbulence is still the 0 set by reset */
+    double *last_cash;   /* [N] account_information["cash"][-1] */
+    double *last_total;  /* [N] account_information["total_assets"][-1] */
+    double *sum_trades;  /* [N] */
+} frl_cashpenalty_params;
+
+/* reset (:132-158) for envs with mask[n] != 0 (NULL = all); start_points [N] (NULL = 0, i.e.
+ * random_start=False). obs nullable [N][O]. */
+FRL_API int32_t frl_cashpenalty_reset(const frl_cashpenalty_params *p, const uint8_t *mask, const int32_t *start_points,
+                                      float *obs, void *stream);
+FRL_API int32_t frl_cashpenalty_observe(const frl_cashpenalty_params *p, float *obs, void *stream);
+/* n_steps fused step (:300-372) incl. get_transactions (:258-298) and get_reward (:246-256).
+ * Conventions as frl_trading_rollout; flags add FRL_FLAG_SHORTAGE.  np.dot's summation order is
+ * BLAS-specific, so fp64 results agree with the reference to 1e-9 relative, not bit for bit. */
+FRL_API int32_t frl_cashpenalty_rollout(const frl_cashpenalty_params *p, const void *actions, int32_t actions_f64,
+                                        int64_t act_step_stride, int64_t act_env_stride, int32_t n_steps,
+                                        double *rewards, uint8_t *flags, float *obs, int32_t obs_mode,
+                                        int32_t auto_reset, double *stats, void *stream);
+FRL_API int32_t frl_cashpenalty_step(const frl_cashpenalty_params *p, const void *actions, int32_t actions_f64,
+                                     double *rewards, uint8_t *flags, float *obs, int32_t auto_reset, double *stats,
+                                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

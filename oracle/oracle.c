@@ -594,3 +594,162 @@ void ora_portfolio_step(const ora_portfolio_cfg *c, ora_portfolio_state *s, cons
     for (int n = 0; n < c->n_envs; ++n)
         pf_step_one(c, s, n, actions, actions_f64, reward_out, flags_out, weights_out, pret_out, auto_reset);
 }
+
+/* ======================================================================================= */
+/* A4: StockTradingEnvCashpenalty — finrl/meta/env_stock_trading/env_stocktrading_cashpenalty.py */
+/* ======================================================================================= */
+
+static void cp_reset_one(const ora_cp_cfg *c, ora_cp_state *s, int n, int32_t start)
+{
+    /* reset (:132-158) with random_start=False or a caller-supplied starting point */
+    s->cash[n] = c->initial_amount;
+    for (int i = 0; i < c->stock_dim; ++i) s->hold[(size_t)n * c->stock_dim + i] = 0.0;
+    s->date_index[n] = start;
+    s->start[n] = start;
+    s->fresh[n] = 1;
+    s->sum_trades[n] = 0.0;
+    /* account_information is emptied; last_* are only read after a step has logged them */
+    s->last_cash[n] = 0.0;
+    s->last_total[n] = 0.0;
+}
+
+void ora_cp_reset(const ora_cp_cfg *c, ora_cp_state *s, const uint8_t *mask, const int32_t *start_points)
+{
+    for (int n = 0; n < c->n_envs; ++n)
+        if (!mask || mask[n]) cp_reset_one(c, s, n, start_points ? start_points[n] : 0);
+}
+
+void ora_cp_obs(const ora_cp_cfg *c, const ora_cp_state *s, double *obs)
+{
+    const int D = c->stock_dim, DC = D * c->n_cols, O = 1 + D + DC;
+    for (int n = 0; n < c->n_envs; ++n) {
+        double *o = obs + (size_t)n * O;
+        o[0] = s->cash[n];
+        for (int i = 0; i < D; ++i) o[1 + i] = s->hold[(size_t)n * D + i];
+        memcpy(o + 1 + D, c->info + (size_t)s->date_index[n] * DC, sizeof(double) * (size_t)DC);
+    }
+}
+
+/* get_reward (:246-256) from the last logged (total_assets, cash) pair */
+static double cp_reward(const ora_cp_cfg *c, double assets, double cash, int current_step)
+{
+    if (current_step == 0) return 0.0;
+    double pen = assets * c->cash_penalty_proportion - cash;
+    if (!(pen > 0.0)) pen = 0.0; /* max(0, x) */
+    assets -= pen;
+    double r = (assets / c->initial_amount) - 1;
+    r /= current_step;
+    return r;
+}
+
+static int64_t cp_floordiv_i64(int64_t a, int64_t b)
+{
+    int64_t q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) q -= 1;
+    return q;
+}
+
+static void cp_step_one(const ora_cp_cfg *c, ora_cp_state *s, int n, const void *actions, int actions_f64,
+                        double *reward_out, uint8_t *flags_out, int auto_reset)
+{
+    const int D = c->stock_dim, T = c->n_days;
+    double *hold = s->hold + (size_t)n * D;
+    uint8_t flags = 0;
+    /* self.sum_trades += np.sum(np.abs(actions)) (:302): summed in the action dtype (pairwise), then added */
+    {
+        if (actions_f64) {
+            double tmp[MAXD];
+            for (int i = 0; i < D; ++i) tmp[i] = fabs(((const double *)actions)[(size_t)n * D + i]);
+            s->sum_trades[n] += ora_pairwise_sum_f64(tmp, D);
+        } else {
+            float tmp[MAXD];
+            for (int i = 0; i < D; ++i) tmp[i] = fabsf(((const float *)actions)[(size_t)n * D + i]);
+            s->sum_trades[n] += (double)ora_pairwise_sum_f32(tmp, D);
+        }
+    }
+    const int di = s->date_index[n];
+    const int current_step = di - s->start[n];
+    if (di == T - 1) { /* last date (:308-310): reward from the previously logged pair, state unchanged */
+        flags = ORA_FLAG_DONE;
+        if (reward_out) reward_out[n] = cp_reward(c, s->last_total[n], s->last_cash[n], current_step);
+        if (flags_out) flags_out[n] = flags;
+        if (auto_reset) cp_reset_one(c, s, n, 0);
+        return;
+    }
+    const double *close = c->close + (size_t)di * D;
+    const double begin_cash = s->cash[n];
+    double asset_value = 0.0; /* np.dot(holdings, closings) (:319) */
+    for (int i = 0; i < D; ++i) asset_value += hold[i] * close[i];
+    s->last_cash[n] = begin_cash;
+    s->last_total[n] = begin_cash + asset_value;
+    const double reward = cp_reward(c, s->last_total[n], s->last_cash[n], current_step); /* before trading (:326) */
+
+    /* get_transactions (:258-298) */
+    double tx[MAXD];
+    const double turbulence = s->fresh[n] ? 0.0 : c->turb[di];
+    const int liq = c->use_turbulence && turbulence >= c->turbulence_threshold;
+    for (int i = 0; i < D; ++i) {
+        double a; /* actions * hmax in the input dtype */
+        if (actions_f64)
+            a = ((const double *)actions)[(size_t)n * D + i] * c->hmax;
+        else
+            a = (double)(((const float *)actions)[(size_t)n * D + i] * (float)c->hmax);
+        if (!(close[i] > 0)) a = 0.0; /* np.where(closings > 0, actions, 0) */
+        if (c->discrete_actions) {
+            /* actions // closings (float floor-div), astype(int), then toward-zero multiples of the increment */
+            int64_t q = (int64_t)ora_floor_divide_f64(a, close[i]);
+            const int64_t inc = c->shares_increment;
+            q = (q >= 0) ? cp_floordiv_i64(q, inc) * inc : cp_floordiv_i64(q + inc, inc) * inc;
+            a = (double)q;
+        } else {
+            a = a / close[i];
+        }
+        tx[i] = (a > -hold[i]) ? a : -hold[i]; /* np.maximum(actions, -holdings) */
+    }
+    if (liq) {
+        flags |= ORA_FLAG_LIQUIDATE;
+        for (int i = 0; i < D; ++i) tx[i] = -hold[i];
+    }
+    /* proceeds / spend (:333-340) */
+    double proceeds = 0.0, spend = 0.0;
+    for (int i = 0; i < D; ++i) {
+        const double sell = -(tx[i] < 0 ? tx[i] : 0.0);
+        proceeds += sell * close[i];
+    }
+    double costs = proceeds * c->sell_cost_pct;
+    double coh = begin_cash + proceeds;
+    for (int i = 0; i < D; ++i) {
+        const double buy = tx[i] > 0 ? tx[i] : 0.0;
+        spend += buy * close[i];
+    }
+    costs += spend * c->buy_cost_pct;
+    if ((spend + costs) > coh) {
+        flags |= ORA_FLAG_SHORTAGE;
+        if (c->patient) { /* don't buy; NOTE the sell costs are dropped too (quirk Q9) */
+            for (int i = 0; i < D; ++i)
+                if (tx[i] > 0) tx[i] = 0.0;
+            spend = 0.0;
+            costs = 0.0;
+        } else { /* CASH SHORTAGE termination (:349-353): unchanged state, current reward */
+            flags |= ORA_FLAG_DONE;
+            if (reward_out) reward_out[n] = reward;
+            if (flags_out) flags_out[n] = flags;
+            if (auto_reset) cp_reset_one(c, s, n, 0);
+            return;
+        }
+    }
+    coh = coh - spend - costs;
+    for (int i = 0; i < D; ++i) hold[i] = hold[i] + tx[i];
+    s->cash[n] = coh;
+    s->date_index[n] = di + 1;
+    s->fresh[n] = c->use_turbulence ? 0 : 1; /* self.turbulence is only refreshed when a threshold is set */
+    if (reward_out) reward_out[n] = reward;
+    if (flags_out) flags_out[n] = flags;
+}
+
+void ora_cp_step(const ora_cp_cfg *c, ora_cp_state *s, const void *actions, int actions_f64, double *reward_out,
+                 uint8_t *flags_out, int auto_reset)
+{
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < c->n_envs; ++n) cp_step_one(c, s, n, actions, actions_f64, reward_out, flags_out, auto_reset);
+}

@@ -141,6 +141,36 @@ void ora_portfolio_obs(const ora_portfolio_cfg *c, const ora_portfolio_state *s,
 void ora_portfolio_step(const ora_portfolio_cfg *c, ora_portfolio_state *s, const void *actions, int actions_f64,
                         double *reward_out, uint8_t *flags_out, double *weights_out, double *pret_out, int auto_reset);
 
+/* ---- A4: StockTradingEnvCashpenalty (env_stocktrading_cashpenalty.py) --------------------- */
+typedef struct {
+    int32_t n_envs, stock_dim, n_cols /* len(daily_information_cols) */, n_days;
+    double buy_cost_pct, sell_cost_pct, hmax;
+    int32_t discrete_actions, shares_increment;
+    int32_t use_turbulence;
+    double turbulence_threshold;
+    double initial_amount, cash_penalty_proportion;
+    int32_t patient;
+    const double *close; /* [T][D] */
+    const double *turb;  /* [T] "turbulence" column (only read when use_turbulence) */
+    const double *info;  /* [T][D*C] get_date_vector(date): asset-major daily information */
+} ora_cp_cfg;
+
+typedef struct {
+    double *cash;        /* [N] state_memory[-1][0] */
+    double *hold;        /* [N][D] */
+    int32_t *date_index; /* [N] */
+    int32_t *start;      /* [N] starting_point */
+    uint8_t *fresh;      /* [N] 1 after reset: self.turbulence == 0 until the first completed step */
+    double *last_cash;   /* [N] account_information["cash"][-1] */
+    double *last_total;  /* [N] account_information["total_assets"][-1] */
+    double *sum_trades;  /* [N] */
+} ora_cp_state;
+
+void ora_cp_reset(const ora_cp_cfg *c, ora_cp_state *s, const uint8_t *mask, const int32_t *start_points);
+void ora_cp_obs(const ora_cp_cfg *c, const ora_cp_state *s, double *obs /*[N][1+D+D*C]*/);
+void ora_cp_step(const ora_cp_cfg *c, ora_cp_state *s, const void *actions, int actions_f64, double *reward_out,
+                 uint8_t *flags_out, int auto_reset);
+
 #ifdef __cplusplus
 }
 #endif

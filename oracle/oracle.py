@@ -313,3 +313,66 @@ class PortfolioOracle:
         lib().ora_portfolio_step(C.byref(self._cfg), C.byref(self._st), _p(a), C.c_int(a.dtype == np.float64),
                                  _p(reward), _p(flags), _p(w), _p(pr), C.c_int(int(auto_reset)))
         return reward, flags, w, pr
+
+
+# --------------------------------------------------------------------------------------------
+# A4
+# --------------------------------------------------------------------------------------------
+class _CpCfg(C.Structure):
+    _fields_ = [("n_envs", C.c_int32), ("stock_dim", C.c_int32), ("n_cols", C.c_int32), ("n_days", C.c_int32),
+                ("buy_cost_pct", C.c_double), ("sell_cost_pct", C.c_double), ("hmax", C.c_double),
+                ("discrete_actions", C.c_int32), ("shares_increment", C.c_int32), ("use_turbulence", C.c_int32),
+                ("turbulence_threshold", C.c_double), ("initial_amount", C.c_double),
+                ("cash_penalty_proportion", C.c_double), ("patient", C.c_int32),
+                ("close", C.c_void_p), ("turb", C.c_void_p), ("info", C.c_void_p)]
+
+
+class _CpState(C.Structure):
+    _fields_ = [("cash", C.c_void_p), ("hold", C.c_void_p), ("date_index", C.c_void_p), ("start", C.c_void_p),
+                ("fresh", C.c_void_p), ("last_cash", C.c_void_p), ("last_total", C.c_void_p), ("sum_trades", C.c_void_p)]
+
+
+class CashPenaltyOracle:
+    """N independent copies of the reference ``StockTradingEnvCashpenalty``
+    (finrl/meta/env_stock_trading/env_stocktrading_cashpenalty.py), stepped on the CPU.
+    ``info`` is [T, D, C]: the daily_information_cols of every asset (asset-major like get_date_vector)."""
+
+    def __init__(self, close, info, turb, n_envs, buy_cost_pct=3e-3, sell_cost_pct=3e-3, hmax=10, discrete_actions=False,
+                 shares_increment=1, turbulence_threshold=None, initial_amount=1e6, cash_penalty_proportion=0.1,
+                 patient=False):
+        self.close = np.ascontiguousarray(close, dtype=np.float64)
+        T, D = self.close.shape
+        self.info = np.ascontiguousarray(info, dtype=np.float64).reshape(T, -1)
+        Cc = self.info.shape[1] // D
+        self.turb = np.ascontiguousarray(turb if turb is not None else np.zeros(T), dtype=np.float64)
+        N = int(n_envs)
+        self.N, self.D, self.C, self.T, self.O = N, D, Cc, T, 1 + D + D * Cc
+        self.cash = np.zeros(N); self.hold = np.zeros((N, D)); self.date_index = np.zeros(N, dtype=np.int32)
+        self.start = np.zeros(N, dtype=np.int32); self.fresh = np.zeros(N, dtype=np.uint8)
+        self.last_cash = np.zeros(N); self.last_total = np.zeros(N); self.sum_trades = np.zeros(N)
+        self._cfg = _CpCfg(N, D, Cc, T, float(buy_cost_pct), float(sell_cost_pct), float(hmax), int(discrete_actions),
+                           int(shares_increment), int(turbulence_threshold is not None),
+                           float(turbulence_threshold if turbulence_threshold is not None else 0.0), float(initial_amount),
+                           float(cash_penalty_proportion), int(patient), _p(self.close), _p(self.turb), _p(self.info))
+        self._st = _CpState(_p(self.cash), _p(self.hold), _p(self.date_index), _p(self.start), _p(self.fresh),
+                            _p(self.last_cash), _p(self.last_total), _p(self.sum_trades))
+        self.reset()
+
+    def reset(self, mask=None, start_points=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        sp = None if start_points is None else np.ascontiguousarray(start_points, dtype=np.int32)
+        lib().ora_cp_reset(C.byref(self._cfg), C.byref(self._st), _p(m), _p(sp))
+        return self.obs()
+
+    def obs(self):
+        out = np.empty((self.N, self.O))
+        lib().ora_cp_obs(C.byref(self._cfg), C.byref(self._st), _p(out))
+        return out
+
+    def step(self, actions, auto_reset=False):
+        a = np.ascontiguousarray(actions)
+        assert a.shape == (self.N, self.D) and a.dtype in (np.float32, np.float64)
+        reward = np.empty(self.N); flags = np.empty(self.N, dtype=np.uint8)
+        lib().ora_cp_step(C.byref(self._cfg), C.byref(self._st), _p(a), C.c_int(a.dtype == np.float64), _p(reward),
+                          _p(flags), C.c_int(int(auto_reset)))
+        return reward, flags

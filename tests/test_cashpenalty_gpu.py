@@ -1,0 +1,143 @@
+"""GPU parity: the CUDA StockTradingEnvCashpenalty path vs reference goldens and the CPU oracle.
+np.dot's summation order is BLAS-specific, so fp64 values are compared at 1e-9 relative
+(north_star); done / liquidation / shortage flags and the date index are exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from test_oracle_golden import cashpen_args_from_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+CP = sorted(glob.glob(os.path.join(GOLDEN, "cashpen_*.npz")))
+RT = 1e-9
+
+
+def _close(a, b, ctx="", atol=1e-7):
+    np.testing.assert_allclose(a, b, rtol=RT, atol=atol, err_msg=ctx)
+
+
+@pytest.mark.parametrize("path", CP, ids=[os.path.basename(p)[:-4] for p in CP])
+def test_golden_single_env(path):
+    from finrl_b200 import BatchedStockTradingEnvCashpenalty, CashPenaltyTables
+
+    g = np.load(path)
+    close, info, turb, kw = cashpen_args_from_golden(g)
+    env = BatchedStockTradingEnvCashpenalty(tables=CashPenaltyTables.from_arrays(close, info, turb, "cuda"), n_envs=1,
+                                            random_start=False, **kw)
+    D = close.shape[1]
+    assert np.array_equal(env.reset().cpu().numpy()[0], g["obs0"].astype(np.float32))
+    acts = g["actions"]
+    for s in range(acts.shape[0]):
+        obs, reward, done, flags = env.step(torch.from_numpy(acts[s][None, :]).cuda(), auto_reset=True)
+        ctx = f"step {s}"
+        assert bool(done[0]) == bool(g["done"][s]), ctx
+        assert bool(int(flags[0]) & 2) == bool(g["liq"][s]), ctx
+        assert env.date_index[0].item() == g["date_index"][s], ctx
+        _close(reward[0].item(), g["reward"][s], ctx, atol=1e-15)
+        _close(env.cash[0].item(), g["obs"][s][0], ctx)
+        _close(env.holdings[0].cpu().numpy(), g["obs"][s][1 : 1 + D], ctx)
+        np.testing.assert_allclose(obs[0].cpu().numpy(), g["obs"][s].astype(np.float32), rtol=2e-7, atol=1e-6, err_msg=ctx)
+
+
+def _make(N, T=40, D=100, seed=0, **kw):
+    from finrl_b200 import BatchedStockTradingEnvCashpenalty, CashPenaltyTables, synthetic as syn
+    from oracle import oracle as ora
+
+    close, _, turb = syn.make_tables(T, D, 0, seed=seed)
+    o_, h_, l_, v_ = syn.make_ohlv(close, seed)
+    info = np.stack([o_, close, h_, l_, v_], axis=2)
+    args = dict(hmax=5000, initial_amount=1e6)
+    args.update(kw)
+    env = BatchedStockTradingEnvCashpenalty(tables=CashPenaltyTables.from_arrays(close, info, turb, "cuda"), n_envs=N,
+                                            random_start=False, **args)
+    return env, ora.CashPenaltyOracle(close, info, turb, N, **args)
+
+
+@pytest.mark.parametrize("N,D,dtype,kw", [
+    (1, 100, np.float32, {}),
+    (777, 100, np.float32, dict(turbulence_threshold=70)),
+    (512, 100, np.float64, dict(patient=True, hmax=60000, initial_amount=2e5, turbulence_threshold=90)),
+    (512, 30, np.float32, dict(hmax=40000, initial_amount=1e5)),            # CASH SHORTAGE terminations
+    (300, 128, np.float32, dict(discrete_actions=True, shares_increment=2)),
+    (300, 7, np.float32, dict(discrete_actions=True, shares_increment=1, turbulence_threshold=80)),
+])
+def test_step_vs_oracle(N, D, dtype, kw):
+    from finrl_b200 import synthetic as syn
+
+    T = 40
+    env, o = _make(N, T=T, D=D, **kw)
+    acts = syn.make_actions((T + 25, N, D), seed=7, dtype=dtype)
+    seen = 0
+    for s in range(acts.shape[0]):
+        obs, reward, done, flags = env.step(torch.from_numpy(acts[s]).cuda(), auto_reset=True)
+        orew, ofl = o.step(acts[s], auto_reset=True)
+        ctx = f"step {s}"
+        assert np.array_equal(flags.cpu().numpy(), ofl), ctx
+        assert np.array_equal(env.date_index.cpu().numpy(), o.date_index), ctx
+        _close(reward.cpu().numpy(), orew, ctx, atol=1e-15)
+        _close(env.cash.cpu().numpy(), o.cash, ctx)
+        _close(env.holdings.cpu().numpy(), o.hold, ctx)
+        np.testing.assert_allclose(obs.cpu().numpy(), o.obs().astype(np.float32), rtol=2e-7, atol=1e-6, err_msg=ctx)
+        seen |= int(np.bitwise_or.reduce(ofl))
+    assert seen & 1
+    if kw.get("turbulence_threshold") is not None:
+        assert seen & 2
+    if kw.get("hmax", 0) >= 40000:
+        assert seen & 4
+
+
+def test_rollout_config5_shape():
+    """Config 5 shape: D=100 assets, 5 info columns (O=601), fused rollouts vs the oracle."""
+    from finrl_b200 import synthetic as syn
+
+    N, K, T, D = 2048, 24, 60, 100
+    env, o = _make(N, T=T, D=D, turbulence_threshold=85)
+    for r in range(3):
+        acts = syn.make_actions((K, N, D), seed=40 + r)
+        obs, rewards, flags = env.rollout(torch.from_numpy(acts).cuda(), obs_mode="last", auto_reset=True)
+        orew = np.empty((K, N))
+        ofl = np.empty((K, N), dtype=np.uint8)
+        for k in range(K):
+            orew[k], ofl[k] = o.step(acts[k], auto_reset=True)
+        assert np.array_equal(flags.cpu().numpy(), ofl)
+        _close(rewards.cpu().numpy(), orew, atol=1e-15)
+        _close(env.cash.cpu().numpy(), o.cash)
+        _close(env.holdings.cpu().numpy(), o.hold)
+        np.testing.assert_allclose(obs.cpu().numpy(), o.obs().astype(np.float32), rtol=2e-7, atol=1e-6)
+    st = env.read_stats()
+    assert st["env_steps"] == 3 * K * N and st["done_count"] == float(N * (3 * K // T))
+
+
+def test_reference_invariants_zero_step_and_patient():
+    """The two data-independent invariants of the reference's own tests, on synthetic frames
+    (/root/reference/tests/environments/test_cash_penalty.py:29-52 and :55-75)."""
+    from finrl_b200 import BatchedStockTradingEnvCashpenalty, CashPenaltyTables, synthetic as syn
+
+    T, D = 20, 2
+    close, _, turb = syn.make_tables(T, D, 0, seed=1)
+    o_, h_, l_, v_ = syn.make_ohlv(close, 1)
+    info = np.stack([o_, close, h_, l_, v_], axis=2)
+    tables = CashPenaltyTables.from_arrays(close, info, turb, "cuda")
+    # test_zero_step: zero actions -> cash stays initial, holdings 0, asset value 0, step counter advances
+    init = 1e6
+    env = BatchedStockTradingEnvCashpenalty(tables=tables, n_envs=4, initial_amount=init, random_start=False)
+    for i in range(T - 1):
+        obs, reward, done, flags = env.step(torch.zeros((4, D), device="cuda"))
+        assert bool((env.cash == init).all()) and bool((env.holdings == 0).all())
+        assert bool((env.last_total - env.last_cash == 0).all())
+        assert bool((env.date_index - env.starting_point == i + 1).all())
+    # test_patient: cash == one close of asset 0, hmax = 100 x that close, buy everything, patient -> no done, no holdings
+    aapl_first_close = float(close[0, 0])
+    env = BatchedStockTradingEnvCashpenalty(tables=tables, n_envs=3, initial_amount=aapl_first_close,
+                                            hmax=aapl_first_close * 100, cash_penalty_proportion=0, patient=True,
+                                            random_start=False)
+    for _ in range(T - 2):
+        obs, reward, done, flags = env.step(torch.ones((3, D), device="cuda"))
+        assert not bool(done.any())
+        assert bool((env.holdings == 0).all())

@@ -194,3 +194,35 @@ def test_portfolio_oracle_vs_reference(path):
             assert np.allclose(w[0], g["weights"][s], rtol=tol, atol=0), ctx
             assert abs(pr[0] - g["pret"][s]) <= tol * max(abs(g["pret"][s]), 1e-3), ctx
         assert np.array_equal(o.obs()[0], g["obs"][s]), ctx
+
+
+# ---------------------------------------------------------------------------- A4
+CP = sorted(glob.glob(os.path.join(GOLDEN, "cashpen_*.npz")))
+
+
+def cashpen_args_from_golden(g):
+    bc, sc, hmax, disc, inc, use_t, thr, init, pen, patient = g["cfg"]
+    cols = [str(c) for c in g["cols"]]
+    info = np.stack([g[c] for c in cols], axis=2)  # [T, D, C] asset-major like get_date_vector
+    kw = dict(buy_cost_pct=bc, sell_cost_pct=sc, hmax=hmax, discrete_actions=bool(disc), shares_increment=int(inc),
+              turbulence_threshold=(thr if use_t > 0 else None), initial_amount=init, cash_penalty_proportion=pen,
+              patient=bool(patient))
+    return g["close"], info, g["turbulence"], kw
+
+
+@pytest.mark.parametrize("path", CP, ids=[os.path.basename(p)[:-4] for p in CP])
+def test_cashpenalty_oracle_vs_reference(path):
+    """np.dot is BLAS ddot (order unspecified) -> 1e-12 relative on values; flags/date exact."""
+    g = np.load(path)
+    close, info, turb, kw = cashpen_args_from_golden(g)
+    o = ora.CashPenaltyOracle(close, info, turb, 1, **kw)
+    np.testing.assert_allclose(o.obs()[0], g["obs0"], rtol=0, atol=0)
+    acts = g["actions"]
+    for s in range(acts.shape[0]):
+        reward, flags = o.step(acts[s][None, :], auto_reset=True)
+        ctx = f"step {s}"
+        assert bool(flags[0] & ora.FLAG_DONE) == bool(g["done"][s]), ctx
+        assert bool(flags[0] & ora.FLAG_LIQUIDATE) == bool(g["liq"][s]), ctx
+        assert o.date_index[0] == g["date_index"][s], ctx
+        np.testing.assert_allclose(reward[0], g["reward"][s], rtol=1e-12, atol=1e-18, err_msg=ctx)
+        np.testing.assert_allclose(o.obs()[0], g["obs"][s], rtol=1e-12, atol=1e-9, err_msg=ctx)
