@@ -59,6 +59,7 @@ class TradingParams(C.Structure):
         ("trades", C.c_void_p),
         ("reward", C.c_void_p),
         ("episode", C.c_void_p),
+        ("asset_out", C.c_void_p),
     ]
 
 

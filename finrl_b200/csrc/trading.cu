@@ -407,6 +407,13 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
         for (int j = 0; j < SLOTS; ++j)
             if (j < D) st_stream(p.hold + n + j * ld, sm.hold[j * kHoldPitch + lane]);
     }
+    if (p.asset_out) {
+        if (!asset_ok) {
+            asset = total_asset<SLOTS>(cash, p.close + (size_t)state_day(sday) * 32, sm.hold, lane, D);
+            asset_ok = true;
+        }
+        if (valid) p.asset_out[n] = asset;
+    }
     if (stats) {
         double fin_asset = 0.0, fin_trades = 0.0, steps = 0.0;
         if (valid) {

@@ -56,6 +56,7 @@ class BatchedStockTradingEnv:
         n_envs: int = 1,
         device="cuda",
         tables: Optional[TradingTables] = None,
+        track_asset: bool = False,
     ):
         import torch
 
@@ -141,6 +142,9 @@ class BatchedStockTradingEnv:
         p.cash, p.hold, p.day, p.sday = self.cash.data_ptr(), self.hold.data_ptr(), self.day.data_ptr(), self.sday.data_ptr()
         p.cost, p.trades = self.cost.data_ptr(), self.trades.data_ptr()
         p.reward, p.episode = self.reward.data_ptr(), self.episode.data_ptr()
+        # optional: the reference's end_total_asset of every env after each launch (asset_memory)
+        self.asset = torch.zeros(N, dtype=torch.float64, device=dev) if track_asset else None
+        p.asset_out = self.asset.data_ptr() if track_asset else None
         self._p = p
         self.launches = 0  # kernels launched through the C-ABI (bench.py reports it)
         self.kernel_events = None  # set to a list to collect (start, end) CUDA events around each step launch

@@ -99,6 +99,9 @@ typedef struct frl_trading_params {
     int32_t *trades;  /* [N] self.trades */
     double *reward;   /* [N] self.reward (last scaled reward; returned again by the terminal step) */
     int32_t *episode; /* [N] self.episode */
+    /* ---- optional per-env output ---- */
+    double *asset_out; /* [N] or NULL: total asset (cash + sum price*holding, the reference's
+                          end_total_asset / asset_memory entry) of the state after the last step */
 } frl_trading_params;
 
 /* StockTradingEnv.__init__ (:24-100): day = day0, state built from day0, fresh. */

@@ -1,0 +1,205 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol (no compute calls),
+the host-side table builders, the optional-dependency shims, and the 2-rank sharding layer on gloo."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from finrl_b200 import _cabi, build
+
+    build.build()
+    lib = _cabi.lib()  # resolves every name in SIGNATURES or raises
+    header = open(os.path.join(ROOT, "include", "finrl_b200.h")).read()
+    declared = set(re.findall(r"FRL_API\s+[\w\s\*]+?\b(frl_\w+)\s*\(", header))
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.frl_abi_version() == _cabi.ABI_VERSION
+    assert lib.frl_last_error() is not None
+
+
+def test_abi_rejects_bad_arguments_without_a_gpu():
+    """Argument validation happens on the host before any CUDA call: status + message, no crash."""
+    import ctypes as C
+
+    from finrl_b200 import _cabi
+
+    lib = _cabi.lib()
+    p = _cabi.TradingParams()
+    p.n_envs, p.stock_dim, p.n_tech, p.n_days, p.obs_dim, p.env_stride = 4, 40, 1, 10, 121, 4
+    rc = lib.frl_trading_step(C.byref(p), None, 0, None, None, None, 0, None, None)
+    assert rc == -1 and b"stock_dim" in lib.frl_last_error()
+    q = _cabi.CashPenaltyParams()
+    q.n_envs, q.stock_dim, q.n_cols, q.n_days, q.obs_dim = 1, 500, 5, 10, 3001
+    assert lib.frl_cashpenalty_observe(C.byref(q), None, None) == -1
+    assert lib.frl_trading_step(None, None, 0, None, None, None, 0, None, None) == -1
+
+
+def test_struct_layouts_match_the_header():
+    """ctypes mirrors vs the C structs: compile a tiny C program printing sizeof/offsetof."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+
+    from finrl_b200 import _cabi
+
+    checks = {
+        "frl_trading_params": (_cabi.TradingParams, ["n_envs", "hmax", "turbulence_threshold", "close", "cash", "episode", "asset_out"]),
+        "frl_np_params": (_cabi.NpParams, ["gamma", "initial_capital", "price", "amount", "episode_return"]),
+        "frl_portfolio_params": (_cabi.PortfolioParams, ["initial_amount", "ret", "reward"]),
+        "frl_cashpenalty_params": (_cabi.CashPenaltyParams, ["patient", "buy_cost_pct", "cash_penalty_proportion", "close", "sum_trades"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "finrl_b200.h"', "int main(){"]
+    for st, (_, fields) in checks.items():
+        lines.append(f'printf("%zu\\n", sizeof({st}));')
+        for f in fields:
+            lines.append(f'printf("%zu\\n", offsetof({st}, {f}));')
+    lines.append("return 0;}")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        open(src, "w").write("\n".join(lines))
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", os.path.join(d, "t")])
+        vals = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    it = iter(vals)
+    for st, (cls, fields) in checks.items():
+        assert next(it) == C.sizeof(cls), st
+        for f in fields:
+            assert next(it) == getattr(cls, f).offset, (st, f)
+
+
+def test_frame_to_arrays_and_templates():
+    from finrl_b200 import synthetic as syn
+    from finrl_b200.tables import frame_to_arrays
+
+    T, D, K = 12, 5, 3
+    close, tech, turb = syn.make_tables(T, D, K, seed=2)
+    df = syn.make_frame(close, tech, turb)
+    c2, t2, r2 = frame_to_arrays(df, D, syn.INDICATORS[:K], "turbulence")
+    assert np.array_equal(c2, close) and np.array_equal(t2, tech) and np.array_equal(r2, turb)
+    with pytest.raises(ValueError):
+        frame_to_arrays(df.iloc[:-1], D, syn.INDICATORS[:K], "turbulence")
+    df_bad = df.copy()
+    df_bad.index = np.arange(len(df_bad))
+    with pytest.raises(ValueError):
+        frame_to_arrays(df_bad, D, syn.INDICATORS[:K], "turbulence")
+
+
+def test_cashpenalty_frame_ingest_matches_reference_order():
+    from finrl_b200 import synthetic as syn
+    from finrl_b200.cashpenalty import frame_to_cashpenalty_arrays
+
+    T, D = 6, 4
+    close, _, turb = syn.make_tables(T, D, 0, seed=3)
+    o, h, l, v = syn.make_ohlv(close, 3)
+    df = syn.make_frame(close, np.zeros((0, T, D)), turb, tech_names=[], extra_cols={"open": o, "high": h, "low": l, "volume": v})
+    df = df.reset_index(drop=True).sample(frac=1.0, random_state=0)  # row order must not matter beyond asset order
+    c2, info, t2, dates, assets = frame_to_cashpenalty_arrays(df, ["open", "close", "high", "low", "volume"])
+    order = [syn.tickers(D).index(a) for a in assets]
+    assert np.array_equal(c2, close[:, order]) and np.array_equal(t2, turb)
+    assert np.array_equal(info[:, :, 0], o[:, order]) and np.array_equal(info[:, :, 4], v[:, order])
+
+
+def test_no_cpu_fallback_without_cuda():
+    """Constructing an env on a box without CUDA must fail loudly, not fall back."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from finrl_b200 import BatchedStockTradingEnv, EngineError, synthetic as syn
+
+    close, tech, turb = syn.make_tables(8, 3, 1, seed=0)
+    with pytest.raises((EngineError, RuntimeError, AssertionError)):
+        BatchedStockTradingEnv(df=syn.make_frame(close, tech, turb), stock_dim=3, tech_indicator_list=syn.INDICATORS[:1], n_envs=2)
+    with pytest.raises(EngineError):
+        BatchedStockTradingEnv(df=syn.make_frame(close, tech, turb), stock_dim=3, tech_indicator_list=syn.INDICATORS[:1], device="cpu")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "finrl_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+            assert "liboracle" not in src, fn
+
+
+def test_spaces_and_lazy_infos():
+    from finrl_b200.spaces import Box
+    from finrl_b200.vec_env import _LazyInfos
+
+    b = Box(low=-1, high=1, shape=(7,))
+    assert tuple(b.shape) == (7,) and b.sample().shape == (7,)
+    infos = _LazyInfos(5, {3: np.ones(2)})
+    assert len(infos) == 5 and infos[0] == {} and np.array_equal(infos[3]["terminal_observation"], np.ones(2))
+    assert [bool(i) for i in infos] == [False, False, False, True, False]
+
+
+def test_shard_range_partitions_exactly():
+    from finrl_b200.dist import shard_range
+
+    for n in (1, 7, 8, 1 << 20, (1 << 20) + 5):
+        for w in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+            for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+                assert s0 + c0 == s1
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, N, K, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from finrl_b200 import synthetic as syn
+    from finrl_b200.dist import allreduce_stats, init_from_env, shard_range, summarize
+    from oracle import oracle as ora
+
+    r, w, _ = init_from_env(backend="gloo")
+    start, count = shard_range(N, r, w)
+    close, tech, turb = syn.make_tables(30, 30, 2, seed=0)  # tables replicated on every rank
+    o = ora.TradingOracle(close, tech, turb, count, hmax=100, initial_amount=2e5, turbulence_threshold=90)
+    acts = syn.make_actions((K, N, 30), seed=1)[:, start : start + count]  # this rank's env-index slice
+    stats = torch.zeros(8, dtype=torch.float64)
+    for k in range(K):
+        _, rew, fl = o.step(acts[k], auto_reset=True, want_obs=False)
+        stats[0] += rew.sum(); stats[1] += (rew ** 2).sum(); stats[2] += float((fl & 1).sum()); stats[6] += count
+    allreduce_stats(stats)  # the only collective on the path
+    np.savez(os.path.join(out_dir, f"rank{r}.npz"), cash=o.cash, hold=o.hold, stats=stats.numpy(), start=start)
+    s = summarize(stats)
+    assert s["env_steps"] == N * K
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_equals_single_process(tmp_path):
+    """world_size 2 on gloo: env-index sharding with replicated tables reproduces the unsharded run
+    env for env, and the all-reduced statistics equal the global sums."""
+    import torch.multiprocessing as mp
+
+    from finrl_b200 import synthetic as syn
+    from oracle import oracle as ora
+
+    N, K, world = 101, 35, 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(world, port, N, K, str(tmp_path)), nprocs=world, join=True)
+    close, tech, turb = syn.make_tables(30, 30, 2, seed=0)
+    o = ora.TradingOracle(close, tech, turb, N, hmax=100, initial_amount=2e5, turbulence_threshold=90)
+    acts = syn.make_actions((K, N, 30), seed=1)
+    tot = np.zeros(8)
+    for k in range(K):
+        _, rew, fl = o.step(acts[k], auto_reset=True, want_obs=False)
+        tot[0] += rew.sum(); tot[1] += (rew ** 2).sum(); tot[2] += (fl & 1).sum(); tot[6] += N
+    parts = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+    assert np.array_equal(np.concatenate([p["cash"] for p in parts]), o.cash)
+    assert np.array_equal(np.concatenate([p["hold"] for p in parts]), o.hold)
+    for p in parts:
+        np.testing.assert_allclose(p["stats"], tot, rtol=1e-12)
+        assert p["stats"][2] == tot[2] and p["stats"][6] == tot[6]
