@@ -1,17 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — env-steps/s of the StockTradingEnv step path on B200 (BASELINE.json's metric).
+"""bench.py — env-steps/s of the FinRL env step path on B200 (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs E]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload W] [--envs E]
 
-Workload (config.workload): StockTradingEnv, DOW-30 shape (D=30 stocks, K=8 indicators, T=2500 days,
-O=301), E = 1,048,576 envs PER GPU, one ``step()`` of every env per bench step, float32 actions
-U(-1,1) distinct per env and step, turbulence threshold 99, auto-reset at episode ends.  A "step" is
-one pass of the hot path over the whole batch.
+Default workload (the one BASELINE.json's metric is quoted on): StockTradingEnv, DOW-30 shape (D=30
+stocks, K=8 indicators, T=2500 days, O=301), E = 1,048,576 envs PER GPU, one ``step()`` of every env per
+bench step, float32 actions U(-1,1) distinct per env and step, turbulence threshold 99, auto-reset at
+episode ends.  A "step" is one pass of the hot path over the whole batch.  Other workloads (the other
+BASELINE configs) are selected with --workload; they are not the driver's bench line.
 
 * value        env-steps/s with inputs resident in HBM (CUDA events, max over ranks, whole job)
 * e2e          same metric through the numpy-in / numpy-out VecEnv-style call: pinned HOST actions
-               -> H2D -> step -> D2H of obs + reward + done, every step inside the timed region
-* roofline     algorithmic bytes per launch (1621 B/env-step) / measured kernel time
+               -> H2D -> step -> D2H of obs + reward + flags, every step inside the timed region
+* roofline     algorithmic bytes per launch (SURVEY.md §8d figure x envs) / measured kernel time
 * cpu_baseline the CPU oracle port (oracle/oracle.c, OpenMP over all host threads) on a bounded sample
 
 --impl reference times that CPU port as the reference arm (the reference itself is pure Python and
@@ -34,15 +35,181 @@ if ROOT not in sys.path:
 
 METRIC = "env-steps/sec"
 UNIT = "env-steps/s"
-D, K_TECH, T_DAYS = 30, 8, 2500
-OBS = 1 + 2 * D + K_TECH * D
-BYTES_PER_ENV_STEP = 1621  # SURVEY.md §8(d) "Config 2' single step (DOW-30)"
-ENV_KW = dict(hmax=100, initial_amount=1_000_000, buy_cost_pct=0.001, sell_cost_pct=0.001, reward_scaling=1e-4,
+T_DAYS = 2500
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads: how to build the engine, its CPU port, and the algorithmic bytes per env-step
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    name = ""
+    D = 30
+    act_low, act_high = -1.0, 1.0
+    act_dtype = "float32"
+    bytes_per_env_step = 0
+    kernel = ""
+    default_envs = 1 << 20
+    rollout_k = 1            # env steps fused per launch
+
+    def describe(self, envs):
+        raise NotImplementedError
+
+    def make_env(self, dev, envs):
+        raise NotImplementedError
+
+    def make_cpu(self, envs):
+        raise NotImplementedError
+
+    def obs_numel(self, env):
+        return int(env._obs.shape[1]) if getattr(env, "_obs", None) is not None else 0
+
+
+class TradingStep(Workload):
+    name = "trading_step"
+    K_TECH = 8
+    bytes_per_env_step = 1621  # "Config 2' single step (DOW-30)"
+    kernel = "trading_rollout_kernel<32,30,float,4>"
+    KW = dict(hmax=100, initial_amount=1_000_000, buy_cost_pct=0.001, sell_cost_pct=0.001, reward_scaling=1e-4,
               turbulence_threshold=99)
 
+    def describe(self, envs):
+        return f"StockTradingEnv DOW-30 single step, {envs} envs/GPU, D=30 K=8 T=2500 O=301, f32 actions, f32 obs"
 
-def workload_name(envs):
-    return f"StockTradingEnv DOW-30 single step, {envs} envs/GPU, D=30 K=8 T=2500 O=301, f32 actions, f32 obs"
+    def tables(self):
+        from finrl_b200 import synthetic as syn
+
+        return syn.make_tables(T_DAYS, self.D, self.K_TECH, seed=0)
+
+    def make_env(self, dev, envs):
+        from finrl_b200 import BatchedStockTradingEnv, TradingTables
+
+        return BatchedStockTradingEnv(tables=TradingTables.from_arrays(*self.tables(), dev), n_envs=envs, device=dev, **self.KW)
+
+    def make_cpu(self, envs):
+        from oracle import oracle as ora
+
+        o = ora.TradingOracle(*self.tables(), envs, **self.KW)
+        return lambda a: o.step(a, auto_reset=True)
+
+
+class TradingRollout(TradingStep):
+    name = "trading_rollout"
+    default_envs = 4096
+    rollout_k = 64
+    bytes_per_env_step = 152.3  # config 2: K=64 fused, obs_mode=last
+
+    def describe(self, envs):
+        return f"StockTradingEnv DOW-30 fused K=64 rollout (obs after the last step), {envs} envs/GPU, D=30 K=8 T=2500"
+
+
+class NpStep(Workload):
+    name = "np_step"
+    bytes_per_env_step = 2015  # config 3
+    kernel = "np_rollout_kernel<32,float,2>"
+
+    def describe(self, envs):
+        return f"env_stocktrading_np (ElegantRL) single step, {envs} envs/GPU, D=30 K=8 T=2500 O=333, turbulence_thresh 99"
+
+    def arrays(self):
+        from finrl_b200 import synthetic as syn
+
+        return syn.make_np_arrays(*syn.make_tables(T_DAYS, self.D, 8, seed=0))
+
+    def make_env(self, dev, envs):
+        from finrl_b200 import BatchedNpStockTradingEnv
+
+        pa, ta, tu = self.arrays()
+        return BatchedNpStockTradingEnv({"price_array": pa, "tech_array": ta, "turbulence_array": tu, "if_train": False},
+                                        n_envs=envs, device=dev)
+
+    def make_cpu(self, envs):
+        from oracle import oracle as ora
+
+        o = ora.NpTradingOracle(*self.arrays(), envs)
+
+        def step(a):
+            _, _, _, fl = o.step(a)
+            if fl[0] & 1:
+                o.reset()
+
+        return step
+
+
+class PortfolioStep(Workload):
+    name = "portfolio_step"
+    act_low, act_high = 0.0, 1.0
+    act_dtype = "float64"
+    default_envs = 262144
+    bytes_per_env_step = 4353  # config 4 with the (34,30) f32 observation materialised per env
+    kernel = "portfolio_rollout_kernel<32,double,2>"
+
+    def describe(self, envs):
+        return (f"StockPortfolioEnv softmax allocation, {envs} envs/GPU, D=30 K=4, 252-day covariance state "
+                "materialised per env (f32), f64 actions")
+
+    def arrays(self):
+        from finrl_b200 import synthetic as syn
+
+        close, tech, _ = syn.make_tables(252 + 600, self.D, 4, seed=0)
+        cov, first = syn.make_cov_table(close, 252)
+        return close[first:], cov, tech[:, first:]
+
+    def make_env(self, dev, envs):
+        from finrl_b200 import BatchedStockPortfolioEnv, PortfolioTables
+
+        env = BatchedStockPortfolioEnv(tables=PortfolioTables.from_arrays(*self.arrays(), dev), n_envs=envs, device=dev)
+        env._obs_buf()
+        return env
+
+    def make_cpu(self, envs):
+        from oracle import oracle as ora
+
+        o = ora.PortfolioOracle(*self.arrays(), envs)
+
+        def step(a):
+            o.step(a, auto_reset=True)
+            o.obs()
+
+        return step
+
+
+class CashPenaltyStep(Workload):
+    name = "cashpenalty_step"
+    D = 100
+    default_envs = 1 << 18
+    bytes_per_env_step = 4485  # config 5
+    kernel = "cashpenalty_rollout_kernel<float,8>"
+
+    def describe(self, envs):
+        return f"StockTradingEnvCashpenalty NASDAQ-100 shape, {envs} envs/GPU, D=100 C=5 T=5000 O=601, random_start=False"
+
+    def arrays(self):
+        from finrl_b200 import synthetic as syn
+
+        close, _, turb = syn.make_tables(5000, self.D, 0, seed=0)
+        o, h, l, v = syn.make_ohlv(close, 0)
+        return close, np.stack([o, close, h, l, v], axis=2), turb
+
+    def make_env(self, dev, envs):
+        from finrl_b200 import BatchedStockTradingEnvCashpenalty, CashPenaltyTables
+
+        return BatchedStockTradingEnvCashpenalty(tables=CashPenaltyTables.from_arrays(*self.arrays(), dev), n_envs=envs,
+                                                 device=dev, random_start=False, turbulence_threshold=99)
+
+    def make_cpu(self, envs):
+        from oracle import oracle as ora
+
+        close, info, turb = self.arrays()
+        o = ora.CashPenaltyOracle(close, info, turb, envs, turbulence_threshold=99)
+
+        def step(a):
+            o.step(a, auto_reset=True)
+            o.obs()
+
+        return step
+
+
+WORKLOADS = {w.name: w for w in (TradingStep, TradingRollout, NpStep, PortfolioStep, CashPenaltyStep)}
 
 
 def measured_peak():
@@ -93,7 +260,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def start(self):
         if self.nv is not None:
@@ -108,22 +275,25 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_port_rate(budget_s=12.0, envs=65536, threads=None):
+def _cpu_actions(wl, envs, n=4):
+    from finrl_b200 import synthetic as syn
+
+    return [syn.make_actions((envs, wl.D), seed=100 + i, low=wl.act_low, high=wl.act_high, dtype=np.dtype(wl.act_dtype))
+            for i in range(n)]
+
+
+def cpu_port_rate(wl, budget_s=12.0, envs=65536):
     """Time the CPU oracle port on a bounded sample of the same workload.  Returns (env-steps/s,
     threads, description).  This is the one place bench.py executes oracle/."""
-    from finrl_b200 import synthetic as syn
-    from oracle import oracle as ora
-
-    threads = threads or os.cpu_count() or 1
+    threads = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    close, tech, turb = syn.make_tables(T_DAYS, D, K_TECH, seed=0)
-    o = ora.TradingOracle(close, tech, turb, envs, **ENV_KW)
-    pool = [syn.make_actions((envs, D), seed=100 + i) for i in range(4)]
+    step = wl.make_cpu(envs)
+    pool = _cpu_actions(wl, envs)
     for i in range(3):
-        o.step(pool[i % 4], auto_reset=True)
+        step(pool[i % 4])
     steps, t0 = 0, time.perf_counter()
     while True:
-        o.step(pool[steps % 4], auto_reset=True)
+        step(pool[steps % 4])
         steps += 1
         el = time.perf_counter() - t0
         if el >= budget_s:
@@ -131,25 +301,21 @@ def cpu_port_rate(budget_s=12.0, envs=65536, threads=None):
     return envs * steps / el, threads, f"{envs} envs x {steps} steps ({el:.1f} s), obs written, OpenMP static over envs"
 
 
-def run_reference(args):
+def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each "step" is one pass of the CPU port over a bounded sample of the workload
-    from finrl_b200 import synthetic as syn
-    from oracle import oracle as ora
-
     threads = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
     envs = args.ref_envs
-    close, tech, turb = syn.make_tables(T_DAYS, D, K_TECH, seed=0)
-    o = ora.TradingOracle(close, tech, turb, envs, **ENV_KW)
-    pool = [syn.make_actions((envs, D), seed=100 + i) for i in range(4)]
+    step = wl.make_cpu(envs)
+    pool = _cpu_actions(wl, envs)
+    # each "step" is one pass of the CPU port over a bounded sample of the workload
     for i in range(args.warmup):
-        o.step(pool[i % 4], auto_reset=True)
+        step(pool[i % 4])
     t0 = time.perf_counter()
     for i in range(args.steps):
-        o.step(pool[i % 4], auto_reset=True)
+        step(pool[i % 4])
     el = time.perf_counter() - t0
     v = envs * args.steps / el
     sample = f"{envs} envs per step (bounded sample of the {args.envs} envs/GPU workload), obs written"
@@ -157,19 +323,18 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.envs), "cpu_sample_envs": envs},
+        "config": {"workload": wl.describe(args.envs), "cpu_sample_envs": envs},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is pure Python (pandas/numpy) and cannot travel; this arm is its C restatement "
-                "(oracle/oracle.c) on all host threads. Survey-time reference itself: ~159 env-steps/s on 1 core.",
+        "note": "the reference is pure Python (pandas/numpy) and cannot travel to the GPU box; this arm is its C "
+                "restatement (oracle/oracle.c) on all host threads. Survey-time numbers of the reference itself "
+                "(1 core): StockTradingEnv ~159, numpy env ~5.4k, portfolio ~930, cash-penalty ~4 env-steps/s.",
     }))
 
 
-def run_ours(args):
+def run_ours(args, wl):
     import torch
     import torch.distributed as dist
-
-    from finrl_b200 import BatchedStockTradingEnv, TradingTables, synthetic as syn
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,26 +343,36 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N = args.envs
-    close, tech, turb = syn.make_tables(T_DAYS, D, K_TECH, seed=0)
-    tables = TradingTables.from_arrays(close, tech, turb, dev)  # replicated per GPU
-    env = BatchedStockTradingEnv(tables=tables, n_envs=N, device=dev, **ENV_KW)
+    N, D, KR = args.envs, wl.D, wl.rollout_k
+    env = wl.make_env(dev, N)  # tables replicated per GPU, envs sharded by index
+    tdt = torch.float32 if wl.act_dtype == "float32" else torch.float64
     g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)  # envs are sharded by index: every rank owns different envs/actions
+    g.manual_seed(1234 + rank)  # every rank owns different envs, hence different actions
     POOL = 3
-    pool = [(torch.rand((N, D), generator=g, device=dev, dtype=torch.float32) * 2.0 - 1.0) for _ in range(POOL)]
+    shape = (N, D) if KR == 1 else (KR, N, D)
+    span = wl.act_high - wl.act_low
+    pool = [(torch.rand(shape, generator=g, device=dev, dtype=tdt) * span + wl.act_low) for _ in range(POOL)]
     stats_global = torch.zeros_like(env.stats)
+    ev_list = []
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(i):
-        env.step(pool[i % POOL], auto_reset=True, want_obs=True, accumulate_stats=True, want_done=False)
+    if KR == 1:
+        def one_step(i):
+            env.step(pool[i % POOL], auto_reset=True, want_obs=True, accumulate_stats=True, want_done=False)
+    else:
+        def one_step(i):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            env.rollout(pool[i % POOL], obs_mode="last", auto_reset=True, accumulate_stats=True)
+            e1.record()
+            ev_list.append((e0, e1))
 
     def reduce_stats():
-        # the only collective on the path: <=64 B episode-return / asset statistics over NVLink
+        # the only collective on the path: 64 B of episode-return / asset statistics over NVLink
         stats_global.copy_(env.stats)
         if world > 1:
             dist.all_reduce(stats_global)
@@ -211,7 +386,9 @@ def run_ours(args):
     sampler.start()
     launches0 = env.launches
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    env.kernel_events = []  # CUDA events right around every kernel launch, on the launching stream
+    if KR == 1:
+        env.kernel_events = []  # CUDA events right around every kernel launch, on the launching stream
+    ev_list.clear()
     barrier()
     t_start.record()
     for i in range(args.steps):
@@ -222,28 +399,34 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in env.kernel_events]))
+    events = env.kernel_events if KR == 1 else ev_list
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in events]))
     env.kernel_events = None
     launches = env.launches - launches0
     el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     elapsed_ms = float(el.item())
-    value = N * world * args.steps / (elapsed_ms * 1e-3)
+    value = N * world * args.steps * KR / (elapsed_ms * 1e-3)
 
-    # ---- end to end through the numpy-facing call: host actions in, host obs/reward/done out ----
-    h_act = [torch.empty((N, D), dtype=torch.float32).pin_memory() for _ in range(POOL)]
+    # ---- end to end through the numpy-facing call: host actions in, host obs/reward/flags out ----
+    OBS = wl.obs_numel(env)
+    h_act = [torch.empty(shape, dtype=tdt).pin_memory() for _ in range(POOL)]
     for h, d in zip(h_act, pool):
         h.copy_(d)
     h_obs = torch.empty((N, OBS), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty(N, dtype=torch.float64).pin_memory()
-    h_flag = torch.empty(N, dtype=torch.uint8).pin_memory()
-    d_act = torch.empty((N, D), dtype=torch.float32, device=dev)
+    rshape = (N,) if KR == 1 else (KR, N)
+    h_rew = torch.empty(rshape, dtype=torch.float64).pin_memory()
+    h_flag = torch.empty(rshape, dtype=torch.uint8).pin_memory()
+    d_act = torch.empty(shape, dtype=tdt, device=dev)
 
     def e2e_step(i):
         d_act.copy_(h_act[i % POOL], non_blocking=True)
-        obs, rew, done, fl = env.step(d_act, auto_reset=True, want_obs=True)
-        h_obs.copy_(obs, non_blocking=True)
+        if KR == 1:
+            obs, rew, _, fl = env.step(d_act, auto_reset=True, want_obs=True, want_done=False)
+        else:
+            obs, rew, fl = env.rollout(d_act, obs_mode="last", auto_reset=True, accumulate_stats=False)
+        h_obs.copy_(obs.reshape(N, OBS), non_blocking=True)
         h_rew.copy_(rew, non_blocking=True)
         h_flag.copy_(fl, non_blocking=True)
         torch.cuda.synchronize()  # the caller reads numpy arrays after every step
@@ -259,44 +442,47 @@ def run_ours(args):
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = N * world * e2e_steps / float(e2e_t.item())
-    h2d = N * D * 4
-    d2h = N * OBS * 4 + N * 8 + N
+    e2e_value = N * world * e2e_steps * KR / float(e2e_t.item())
+    h2d = d_act.numel() * d_act.element_size()
+    d2h = h_obs.numel() * 4 + h_rew.numel() * 8 + h_flag.numel()
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = BYTES_PER_ENV_STEP * N / (kernel_ms * 1e-3) / 1e9
+        achieved = wl.bytes_per_env_step * N * KR / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("trading_step_dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get(wl.name + "_dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        big = wl.bytes_per_env_step * N * KR > 2.5e8
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": workload_name(N), "envs_per_gpu": N, "total_envs": N * world,
-                "l2": "per-step traffic (~1.7 GB) exceeds the 126 MB L2; no explicit flush",
+                "workload": wl.describe(N), "envs_per_gpu": N, "total_envs": N * world, "env_steps_per_launch": N * KR,
+                "l2": ("per-step traffic exceeds the 126 MB L2 and consecutive steps use different action buffers; "
+                       "no explicit flush") if big else
+                      "working set fits in L2 (latency-bound configuration); the roofline is quoted on the 1M-env workload",
                 "parallelism": f"env-index sharding x{world}, tables replicated, NCCL all-reduce of 64 B stats every 16 steps",
                 "auto_reset": True,
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "trading_rollout_kernel<32,float,4>",
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
+                "traffic": traffic, "peak_source": peak_src, "kernel": wl.kernel, "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_env_step": wl.bytes_per_env_step,
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "BatchedStockTradingEnv.step with pinned host actions in, obs+reward+done copied to host"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "Batched*Env.step/rollout with pinned host actions in; obs + reward + flags copied back to host"},
             "gpu_launches": launches,
             "clocks": clocks,
             "stats": dict(zip(("reward_sum", "reward_sqsum", "done_count", "episode_asset_sum", "asset_sum", "liq_count",
-                               "env_steps", "trades_sum"), stats_global.tolist())),
+                               "env_steps", "slot7"), stats_global.tolist())),
         }
         if world == 1 and not args.no_cpu:
-            v, cores, sample = cpu_port_rate(args.cpu_seconds)
+            v, cores, sample = cpu_port_rate(wl, args.cpu_seconds)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(out))
     if world > 1:
@@ -306,20 +492,25 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--workload", default="trading_step", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU")
     ap.add_argument("--ref-envs", type=int, default=65536, help="envs per step of the CPU reference arm")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]()
+    args.envs = args.envs or wl.default_envs
     args.warmup = max(args.warmup, 3)
+    if args.steps is None:
+        args.steps = 200 if args.impl == "reference" else 2000
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, wl)
     else:
-        run_ours(args)
+        run_ours(args, wl)
 
 
 if __name__ == "__main__":
