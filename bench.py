@@ -285,8 +285,9 @@ def _cpu_actions(wl, envs, n=4):
 def cpu_port_rate(wl, budget_s=12.0, envs=65536):
     """Time the CPU oracle port on a bounded sample of the same workload.  Returns (env-steps/s,
     threads, description).  This is the one place bench.py executes oracle/."""
-    threads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    from oracle import oracle as ora
+
+    threads = ora.set_threads(os.cpu_count() or 1)  # all host threads, even under torchrun's OMP_NUM_THREADS=1
     step = wl.make_cpu(envs)
     pool = _cpu_actions(wl, envs)
     for i in range(3):
@@ -305,8 +306,9 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    from oracle import oracle as ora
+
+    threads = ora.set_threads(os.cpu_count() or 1)  # all host threads, even under torchrun's OMP_NUM_THREADS=1
     envs = args.ref_envs
     step = wl.make_cpu(envs)
     pool = _cpu_actions(wl, envs)

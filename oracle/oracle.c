@@ -9,6 +9,22 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* thread count of the env-parallel loops (bench.py's CPU baseline uses every host thread; torchrun
+ * exports OMP_NUM_THREADS=1, so the environment variable alone is not enough) */
+int ora_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 /* ======================================================================================= */
 /* building blocks                                                                         */

@@ -24,6 +24,9 @@ extern "C" {
 #define ORA_FLAG_LIQUIDATE 2u
 #define ORA_FLAG_SHORTAGE 4u
 
+/* OpenMP threads used by the *_step loops over envs; returns the count in effect. */
+int ora_set_threads(int n);
+
 /* ---- building blocks ------------------------------------------------------------------ */
 
 /* numpy's float floor-division (npy_divmod), used by `cash // (price*(1+cost))`

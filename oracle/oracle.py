@@ -41,6 +41,11 @@ def lib():
     return _LIB
 
 
+def set_threads(n: int) -> int:
+    """Force the OpenMP thread count of the env-parallel loops (torchrun exports OMP_NUM_THREADS=1)."""
+    return int(lib().ora_set_threads(C.c_int(int(n))))
+
+
 def _p(a, ty=C.c_void_p):
     return a.ctypes.data_as(ty) if a is not None else None
 
