@@ -12,7 +12,10 @@
 #include "common.cuh"
 
 #ifndef FRL_NP_MIN_BLOCKS
-#define FRL_NP_MIN_BLOCKS 8  // 64-thread blocks per SM the register allocator must allow
+#define FRL_NP_MIN_BLOCKS 8  // 64-thread units per SM the register allocator must allow (8 -> 128 regs)
+#endif
+#ifndef FRL_NP_WARPS
+#define FRL_NP_WARPS 4
 #endif
 
 namespace frl {
@@ -46,8 +49,12 @@ constexpr int kPitch = 33;
 
 template <int SLOTS, typename ActT>
 struct alignas(16) NpWarpSmem {
-    ActT act[32 * SLOTS];            // staged actions, flat [32 envs][D]
-    float sc[2 * SLOTS * kPitch];    // rows 0..D-1: stocks[j][lane]; rows D..2D-1: cool-down[j][lane]
+    // the two big buffers are never live together: `act` holds the step's staged actions until the trade
+    // loops have consumed them, `sc` is the transposition buffer of the observation writer afterwards
+    union {
+        ActT act[32 * SLOTS];          // staged actions, flat [32 envs][D]
+        float sc[2 * SLOTS * kPitch];  // rows 0..D-1: stocks[j][lane]; rows D..2D-1: cool-down[j][lane]
+    };
     float amountf[32];
     int day[32];
 };
@@ -68,11 +75,11 @@ __device__ __forceinline__ int np_action_to_shares<double>(double a, double max_
 // (self.stocks * price).sum(): float32 products, numpy pairwise summation (n < 8 sequential; else 8
 // accumulators over the full blocks of 8, tree-combined, then the tail sequentially).
 template <int SLOTS>
-__device__ __forceinline__ float np_asset_f32(const float *sc, const float *__restrict__ prow, int lane, int D)
+__device__ __forceinline__ float np_asset_f32(const float (&stv)[SLOTS], const float *__restrict__ prow, int D)
 {
     float x[SLOTS];
 #pragma unroll
-    for (int j = 0; j < SLOTS; ++j) x[j] = (j < D) ? fmul(sc[j * kPitch + lane], __ldg(prow + j)) : 0.0f;
+    for (int j = 0; j < SLOTS; ++j) x[j] = (j < D) ? fmul(stv[j], __ldg(prow + j)) : 0.0f;
     if (D < 8) {
         float res = 0.0f;
 #pragma unroll
@@ -102,11 +109,11 @@ __device__ __forceinline__ float np_asset_f32(const float *sc, const float *__re
 __device__ __forceinline__ float np_amount_obs(NV amount) { return fmul((float)amount.v, 0.000244140625f); }
 
 // ---- observation rows: [amount, turb, turb_bool, price*2^-6 x D, stocks*2^-6 x D, cool x D, tech] ----
-template <int NCH, typename SM>
+template <int NCH, int DCT, typename SM>
 __device__ __forceinline__ void np_write_obs_rows_uniform(const frl_np_params &p, SM &sm, float *__restrict__ obs,
                                                           long long env0, int nvalid, int lane, int day0)
 {
-    const int O = p.obs_dim, D = p.stock_dim;
+    const int O = p.obs_dim, D = DCT > 0 ? DCT : p.stock_dim;
     const int s_beg = 3 + D, c_beg = 3 + 2 * D, sp_end = 3 + 3 * D;
     float t[NCH];
     const float *trow = p.obs_tmpl + (size_t)day0 * O + lane;
@@ -145,11 +152,11 @@ __device__ __forceinline__ void np_write_obs_rows_uniform(const frl_np_params &p
     }
 }
 
-template <typename SM>
+template <int DCT, typename SM>
 __device__ __forceinline__ void np_write_obs_tile(const frl_np_params &p, SM &sm, float *__restrict__ obs,
                                                   long long env0, int nvalid, int lane)
 {
-    const int O = p.obs_dim, D = p.stock_dim;
+    const int O = p.obs_dim, D = DCT > 0 ? DCT : p.stock_dim;
     const int day0 = sm.day[0];
     bool uniform = true;
     if (lane < nvalid) uniform = (sm.day[lane] == day0);
@@ -159,7 +166,7 @@ __device__ __forceinline__ void np_write_obs_tile(const frl_np_params &p, SM &sm
         switch (nch) {
 #define FRL_CASE(N)                                                                                \
     case N:                                                                                        \
-        np_write_obs_rows_uniform<N>(p, sm, obs, env0, nvalid, lane, day0);                        \
+        np_write_obs_rows_uniform<N, DCT>(p, sm, obs, env0, nvalid, lane, day0);                        \
         break;
             FRL_CASE(1) FRL_CASE(2) FRL_CASE(3) FRL_CASE(4) FRL_CASE(5) FRL_CASE(6)
             FRL_CASE(7) FRL_CASE(8) FRL_CASE(9) FRL_CASE(10) FRL_CASE(11) FRL_CASE(12)
@@ -184,26 +191,24 @@ __device__ __forceinline__ void np_write_obs_tile(const frl_np_params &p, SM &sm
     }
 }
 
-// reset (:80-101), deterministic branch, for the calling thread's env (state in registers / smem)
+// reset (:80-101), deterministic branch, for the calling thread's env (state in registers)
 template <int SLOTS>
-__device__ __forceinline__ void np_reset_regs(const frl_np_params &p, float *sc, int lane, int D, NV &amount,
-                                              NV &total, NV &gr, double &init_total, int &day)
+__device__ __forceinline__ void np_reset_regs(const frl_np_params &p, float (&stv)[SLOTS], float (&clv)[SLOTS], int D,
+                                              NV &amount, NV &total, NV &gr, double &init_total, int &day)
 {
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
-        if (j < D) {
-            sc[j * kPitch + lane] = p.init_stocks ? __ldg(p.init_stocks + j) : 0.0f;
-            sc[(D + j) * kPitch + lane] = 0.0f;
-        }
+        stv[j] = (j < D && p.init_stocks) ? __ldg(p.init_stocks + j) : 0.0f;
+        clv[j] = 0.0f;
     }
     day = 0;
     amount = nv(p.initial_capital, FRL_KIND_PY);
-    total = nv_add(amount, nv((double)np_asset_f32<SLOTS>(sc, p.price, lane, D), FRL_KIND_F32));
+    total = nv_add(amount, nv((double)np_asset_f32<SLOTS>(stv, p.price, D), FRL_KIND_F32));
     init_total = total.v;
     gr = nv(0.0, FRL_KIND_PY);
 }
 
-template <int SLOTS, typename ActT, int WARPS>
+template <int SLOTS, int DCT, typename ActT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, FRL_NP_MIN_BLOCKS * 64 / (WARPS * 32))
 np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long long act_step_stride,
                   long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
@@ -213,7 +218,7 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
     __shared__ SM smem[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SM &sm = smem[warp];
-    const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;
+    const int N = p.n_envs, D = DCT > 0 ? DCT : p.stock_dim, T = p.n_days, ld = p.env_stride;
     const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
     if (env0 >= N) return;
     const int nvalid = (int)min((long long)32, (long long)N - env0);
@@ -228,20 +233,15 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
     int day = p.day[n];
     double init_total = 0.0;
     bool init_total_loaded = false;
+    // stocks / cool-down stay in REGISTERS for the arithmetic (all indices are static here); shared
+    // memory is only the transposition buffer of the observation writer
+    float stv[SLOTS], clv[SLOTS];
     {
-        float sv[SLOTS], cv[SLOTS];
         const float *sp = p.stocks + n, *cp = p.cool + n;
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) {
-            sv[j] = (j < D) ? __ldcs(sp + j * ld) : 0.0f;
-            cv[j] = (j < D) ? __ldcs(cp + j * ld) : 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < SLOTS; ++j) {
-            if (j < D) {
-                sm.sc[j * kPitch + lane] = sv[j];
-                sm.sc[(D + j) * kPitch + lane] = cv[j];
-            }
+            stv[j] = (j < D) ? __ldcs(sp + j * ld) : 0.0f;
+            clv[j] = (j < D) ? __ldcs(cp + j * ld) : 0.0f;
         }
     }
     const NV one_minus_sc = nv(dsub(1.0, p.sell_cost_pct), FRL_KIND_PY);
@@ -275,55 +275,60 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
             // already past the last day (the reference would raise IndexError): inert, done again
             flags = FRL_FLAG_DONE;
         } else {
-            int a[SLOTS];
+            // (actions * max_stock).astype(int) is recomputed from the staged row where needed (two uses per
+            // stock) instead of holding D more registers
             const ActT *arow = sm.act + lane * D;
-#pragma unroll
-            for (int j = 0; j < SLOTS; ++j) a[j] = (j < D) ? np_action_to_shares<ActT>(arow[j], p.max_stock) : 0;
+#define FRL_A(j) np_action_to_shares<ActT>(arow[j], p.max_stock)
 
             day += 1;  // trades happen at the NEW day's prices (:106-107)
             const float *prow = p.price + (size_t)day * 32;
 #pragma unroll
-            for (int j = 0; j < SLOTS; ++j)
-                if (j < D) sm.sc[(D + j) * kPitch + lane] = fadd(sm.sc[(D + j) * kPitch + lane], 1.0f);  // cool_down += 1
+            for (int j = 0; j < SLOTS; ++j) clv[j] = fadd(clv[j], 1.0f);  // cool_down += 1
 
             if (__ldg(p.turb_bool + day) == 0.0f) {
                 // ---- sells in ascending index (:112-119) ----
 #pragma unroll
                 for (int j = 0; j < SLOTS; ++j) {
-                    if (j < D && a[j] < -min_action) {
+                    const int aj = (j < D) ? FRL_A(j) : 0;
+                    if (j < D && aj < -min_action) {
                         const float pj = __ldg(prow + j);
                         if (pj > 0.0f) {
-                            float st = sm.sc[j * kPitch + lane];
+                            float st = stv[j];
                             NV x;
-                            if ((double)(-a[j]) < (double)st) {  // min(stocks, -action) -> the int64
-                                const double nsh = (double)(-a[j]);
+                            if ((double)(-aj) < (double)st) {  // min(stocks, -action) -> the int64
+                                const double nsh = (double)(-aj);
                                 st = (float)dsub((double)st, nsh);
                                 x = nv_mul(nv(dmul((double)pj, nsh), FRL_KIND_F64), one_minus_sc);
                             } else {  // -> the float32 holding
                                 x = nv_mul(nv((double)fmul(pj, st), FRL_KIND_F32), one_minus_sc);
                                 st = fsub(st, st);
                             }
-                            sm.sc[j * kPitch + lane] = st;
+                            stv[j] = st;
                             amount = nv_add(amount, x);
-                            sm.sc[(D + j) * kPitch + lane] = 0.0f;
+                            clv[j] = 0.0f;
                         }
                     }
                 }
                 // ---- buys in ascending index; the divisor has NO cost term (:120-129, quirk Q6) ----
 #pragma unroll
                 for (int j = 0; j < SLOTS; ++j) {
-                    if (j < D && a[j] > min_action) {
+                    const int aj = (j < D) ? FRL_A(j) : 0;
+                    if (j < D && aj > min_action) {
                         const float pj = __ldg(prow + j);
                         if (pj > 0.0f) {
-                            float st = sm.sc[j * kPitch + lane];
+                            float st = stv[j];
                             NV x;
-                            double avail;
-                            if (amount.k == FRL_KIND_F64)
-                                avail = floor_div_f64(amount.v, (double)pj);
-                            else
-                                avail = (double)floor_div_f32((float)amount.v, pj);
-                            if ((double)a[j] < avail) {  // min(avail, action) -> the int64
-                                const double nsh = (double)a[j];
+                            // avail = amount // price is an exact floor, so `action < avail` <=> amount >=
+                            // (action+1)*price, which is exact in fp64 (24-bit price x small int): the
+                            // division only runs for the cash-limited buys
+                            const double am = amount.k == FRL_KIND_F64 ? amount.v : (double)(float)amount.v;
+                            const bool plenty = am >= dmul((double)(aj + 1), (double)pj);
+                            double avail = 0.0;
+                            if (!plenty)
+                                avail = amount.k == FRL_KIND_F64 ? floor_div_f64(am, (double)pj)
+                                                                  : (double)floor_div_f32((float)am, pj);
+                            if (plenty) {  // min(avail, action) -> the int64
+                                const double nsh = (double)aj;
                                 st = (float)dadd((double)st, nsh);
                                 x = nv_mul(nv(dmul((double)pj, nsh), FRL_KIND_F64), one_plus_bc);
                             } else if (amount.k == FRL_KIND_F64) {
@@ -334,28 +339,27 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
                                 st = fadd(st, nsh);
                                 x = nv_mul(nv((double)fmul(pj, nsh), FRL_KIND_F32), one_plus_bc);
                             }
-                            sm.sc[j * kPitch + lane] = st;
+                            stv[j] = st;
                             amount = nv_sub(amount, x);
-                            sm.sc[(D + j) * kPitch + lane] = 0.0f;
+                            clv[j] = 0.0f;
                         }
                     }
                 }
             } else {
                 // ---- sell everything when turbulence (:131-134) ----
                 flags |= FRL_FLAG_LIQUIDATE;
-                const NV x = nv_mul(nv((double)np_asset_f32<SLOTS>(sm.sc, prow, lane, D), FRL_KIND_F32), one_minus_sc);
+                const NV x = nv_mul(nv((double)np_asset_f32<SLOTS>(stv, prow, D), FRL_KIND_F32), one_minus_sc);
                 amount = nv_add(amount, x);
 #pragma unroll
                 for (int j = 0; j < SLOTS; ++j) {
-                    if (j < D) {
-                        sm.sc[j * kPitch + lane] = 0.0f;
-                        sm.sc[(D + j) * kPitch + lane] = 0.0f;
-                    }
+                    stv[j] = 0.0f;
+                    clv[j] = 0.0f;
                 }
                 if (valid) st_liq += 1.0;
             }
+#undef FRL_A
             // ---- reward bookkeeping (:136-145) ----
-            const NV tot = nv_add(amount, nv((double)np_asset_f32<SLOTS>(sm.sc, prow, lane, D), FRL_KIND_F32));
+            const NV tot = nv_add(amount, nv((double)np_asset_f32<SLOTS>(stv, prow, D), FRL_KIND_F32));
             reward = nv_mul(nv_sub(tot, total), nv(p.reward_scaling, FRL_KIND_PY));
             total = tot;
             gr = nv_add(nv_mul(gr, nv(p.gamma, FRL_KIND_PY)), reward);
@@ -382,16 +386,24 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
             st_r2 += reward.v * reward.v;
         }
         if ((flags & FRL_FLAG_DONE) && auto_reset) {
-            np_reset_regs<SLOTS>(p, sm.sc, lane, D, amount, total, gr, init_total, day);
+            np_reset_regs<SLOTS>(p, stv, clv, D, amount, total, gr, init_total, day);
             init_total_loaded = true;
             if (valid) p.init_total[n] = init_total;
         }
         if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
+            __syncwarp();  // the previous step's rows have been consumed
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j) {
+                if (j < D) {
+                    sm.sc[j * kPitch + lane] = stv[j];
+                    sm.sc[(D + j) * kPitch + lane] = clv[j];
+                }
+            }
             sm.amountf[lane] = np_amount_obs(amount);
             sm.day[lane] = day;
             __syncwarp();
             float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
-            np_write_obs_tile(p, sm, o, env0, nvalid, lane);
+            np_write_obs_tile<DCT>(p, sm, o, env0, nvalid, lane);
         }
     }
 
@@ -405,8 +417,8 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) {
             if (j < D) {
-                p.stocks[n + j * ld] = sm.sc[j * kPitch + lane];
-                p.cool[n + j * ld] = sm.sc[(D + j) * kPitch + lane];
+                p.stocks[n + j * ld] = stv[j];
+                p.cool[n + j * ld] = clv[j];
             }
         }
     }
@@ -493,7 +505,7 @@ __global__ void __launch_bounds__(WARPS * 32) np_observe_kernel(const frl_np_par
     sm.amountf[lane] = np_amount_obs(nv(p.amount[n], p.kinds[n] & 3));
     sm.day[lane] = p.day[n];
     __syncwarp();
-    np_write_obs_tile(p, sm, obs, env0, nvalid, lane);
+    np_write_obs_tile<0>(p, sm, obs, env0, nvalid, lane);
 }
 
 int32_t np_validate(const frl_np_params *p)
@@ -513,13 +525,13 @@ int32_t np_validate(const frl_np_params *p)
     return FRL_OK;
 }
 
-template <int SLOTS, typename ActT, int WARPS>
+template <int SLOTS, int DCT, typename ActT, int WARPS>
 void np_launch(const frl_np_params &p, const void *actions, long long sstride, long long estride, int n_steps,
                double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
 {
     const long long tiles = ((long long)p.n_envs + 31) / 32;
     const unsigned grid = (unsigned)((tiles + WARPS - 1) / WARPS);
-    np_rollout_kernel<SLOTS, ActT, WARPS><<<grid, WARPS * 32, 0, st>>>(p, (const ActT *)actions, sstride, estride, n_steps,
+    np_rollout_kernel<SLOTS, DCT, ActT, WARPS><<<grid, WARPS * 32, 0, st>>>(p, (const ActT *)actions, sstride, estride, n_steps,
                                                                        rewards, flags, obs, obs_mode, auto_reset, stats);
 }
 
@@ -561,21 +573,23 @@ extern "C" int32_t frl_np_rollout(const frl_np_params *p, const void *actions, i
     FRL_REQUIRE(obs_mode == FRL_OBS_NONE || obs != nullptr, "np_rollout: obs is NULL but obs_mode=%d", obs_mode);
     cudaStream_t st = (cudaStream_t)stream;
     const int D = p->stock_dim;
-#define FRL_GO(SLOTS)                                                                                             \
+#define FRL_GO(SLOTS, DCT)                                                                                        \
     do {                                                                                                          \
         if (actions_f64)                                                                                          \
-            np_launch<SLOTS, double, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags,    \
-                                        obs, obs_mode, auto_reset, stats, st);                                    \
+            np_launch<SLOTS, DCT, double, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards,      \
+                                             flags, obs, obs_mode, auto_reset, stats, st);                        \
         else                                                                                                      \
-            np_launch<SLOTS, float, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags,     \
-                                       obs, obs_mode, auto_reset, stats, st);                                     \
+            np_launch<SLOTS, DCT, float, FRL_NP_WARPS>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards,       \
+                                            flags, obs, obs_mode, auto_reset, stats, st);                         \
     } while (0)
     if (D <= 8)
-        FRL_GO(8);
+        FRL_GO(8, 0);
     else if (D <= 16)
-        FRL_GO(16);
+        FRL_GO(16, 0);
+    else if (D == 30)
+        FRL_GO(32, 30);  // DOW-30: stock count compiled in
     else
-        FRL_GO(32);
+        FRL_GO(32, 0);
 #undef FRL_GO
     return check_launch("np_rollout");
 }
