@@ -31,12 +31,38 @@ __device__ __forceinline__ long long floordiv_ll(long long a, long long b)
     return q;
 }
 
+// four independent butterflies interleaved (ILP): every lane ends with the same bits for each sum
+__device__ __forceinline__ void warp_sum4(double &a, double &b, double &c, double &d)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+        const double tc = __shfl_xor_sync(0xffffffffu, c, o), td = __shfl_xor_sync(0xffffffffu, d, o);
+        a += ta;
+        b += tb;
+        c += tc;
+        d += td;
+    }
+}
+
+constexpr int kTmplChunks = 20;  // register-cached template covers O <= 640 (NASDAQ-100 x 5 columns: 601)
+
 // one observation row: [coh, holdings x D, daily information of date di] as float32
 __device__ __forceinline__ void cp_write_obs_row(const frl_cashpenalty_params &p, float *__restrict__ orow, double cash,
-                                                 const double (&h)[kPerLane], int di, int lane)
+                                                 const double (&h)[kPerLane], int di, int lane, float (&t)[kTmplChunks],
+                                                 int &cached_di)
 {
     const int O = p.obs_dim, D = p.stock_dim;
     const float *trow = p.obs_tmpl + (size_t)di * O;
+    const bool use_cache = O <= kTmplChunks * 32;
+    if (use_cache && di != cached_di) {  // warp-uniform: consecutive envs of a warp usually share the date
+#pragma unroll
+        for (int c = 0; c < kTmplChunks; ++c) {
+            const int pos = lane + 32 * c;
+            t[c] = pos < O ? __ldg(trow + pos) : 0.0f;
+        }
+        cached_di = di;
+    }
     const int src = (lane - 1) & 31;
     float hf[kPerLane];
 #pragma unroll
@@ -46,8 +72,8 @@ __device__ __forceinline__ void cp_write_obs_row(const frl_cashpenalty_params &p
     for (int c = 0; c <= kPerLane; ++c) {
         const int pos = lane + 32 * c;
         if (32 * c > D) break;  // warp-uniform
-        const float same = __shfl_sync(0xffffffffu, c < kPerLane ? hf[c] : 0.0f, src);        // lanes >= 1: slot c
-        const float prev = __shfl_sync(0xffffffffu, c > 0 ? hf[c - 1] : 0.0f, src);           // lane 0: slot c-1
+        const float same = __shfl_sync(0xffffffffu, c < kPerLane ? hf[c] : 0.0f, src);  // lanes >= 1: slot c
+        const float prev = __shfl_sync(0xffffffffu, c > 0 ? hf[c - 1] : 0.0f, src);     // lane 0: slot c-1
         if (pos < O) {
             float v;
             if (pos == 0)
@@ -55,12 +81,18 @@ __device__ __forceinline__ void cp_write_obs_row(const frl_cashpenalty_params &p
             else if (pos <= D)
                 v = lane == 0 ? prev : same;
             else
-                v = __ldg(trow + pos);
+                v = use_cache ? t[c] : __ldg(trow + pos);
             orow[pos] = v;
         }
     }
-    const int first = ((D >> 5) + 1) << 5;  // first chunk entirely past the holdings
-    for (int pos = first + lane; pos < O; pos += 32) orow[pos] = __ldg(trow + pos);
+    const int first_c = (D >> 5) + 1;  // first chunk entirely past the holdings
+    if (use_cache) {
+#pragma unroll
+        for (int c = 1; c < kTmplChunks; ++c)
+            if (c >= first_c && lane + 32 * c < O) orow[lane + 32 * c] = t[c];
+    } else {
+        for (int pos = (first_c << 5) + lane; pos < O; pos += 32) orow[pos] = __ldg(trow + pos);
+    }
 }
 
 template <typename ActT, int WARPS>
@@ -75,6 +107,8 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
     const long long nwarps = (long long)gridDim.x * WARPS;
     const int N = p.n_envs, D = p.stock_dim, T = p.n_days, O = p.obs_dim;
     double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_asset = 0.0, st_liq = 0.0, st_steps = 0.0, st_short = 0.0;
+    float tmpl[kTmplChunks];
+    int tmpl_di = -1;
 
     for (long long n = warp0; n < N; n += nwarps) {
         // ---- load state (scalars replicated in every lane; holdings: 4 assets per lane) ----
@@ -97,13 +131,13 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
                 a[i] = j < D ? arow[j] : ActT(0);
                 asum += fabs((double)a[i]);
             }
-            sum_trades += warp_sum(asum);  // self.sum_trades += np.sum(np.abs(actions)) (:302), logging only
             int flags = 0;
             double reward;
             const int current_step = di - start;
             bool reset_now = false;
             if (di == T - 1) {
                 // last date (:308-310): reward from the previously logged (assets, cash); state unchanged
+                sum_trades += warp_sum(asum);  // self.sum_trades += np.sum(np.abs(actions)) (:302), logging only
                 flags = FRL_FLAG_DONE;
                 reward = cp_reward(p, last_total, last_cash, current_step);
                 reset_now = auto_reset != 0;
@@ -116,11 +150,7 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
                     c[i] = j < D ? __ldg(crow + j) : 0.0;
                     part += h[i] * c[i];
                 }
-                const double asset_value = warp_sum(part);  // np.dot(holdings, closings) (:319)
                 const double begin_cash = cash;
-                last_cash = begin_cash;
-                last_total = dadd(begin_cash, asset_value);
-                reward = cp_reward(p, last_total, last_cash, current_step);  // BEFORE trading (:326)
 
                 // ---- get_transactions (:258-298) ----
                 const double turbulence = fresh ? 0.0 : __ldg(p.turb + di);
@@ -154,8 +184,16 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
                     pbuy += (v > 0.0 ? v : 0.0) * c[i];
                 }
                 if (liq) flags |= FRL_FLAG_LIQUIDATE;
-                const double proceeds = warp_sum(psell);  // np.dot(sells, closings)
-                double spend = warp_sum(pbuy);            // np.dot(buys, closings)
+                // np.sum(|actions|), np.dot(holdings, closings) (:319), np.dot(sells, closings), np.dot(buys,
+                // closings) (:334,:339): one fused reduction
+                warp_sum4(asum, part, psell, pbuy);
+                sum_trades += asum;
+                const double asset_value = part;
+                last_cash = begin_cash;
+                last_total = dadd(begin_cash, asset_value);
+                reward = cp_reward(p, last_total, last_cash, current_step);  // computed BEFORE trading (:326)
+                const double proceeds = psell;
+                double spend = pbuy;
                 double costs = dmul(proceeds, p.sell_cost_pct);
                 double coh = dadd(begin_cash, proceeds);
                 costs = dadd(costs, dmul(spend, p.buy_cost_pct));
@@ -209,7 +247,7 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
             }
             if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
                 float *orow = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * O : (size_t)0) + (size_t)n * O;
-                cp_write_obs_row(p, orow, cash, h, di, lane);
+                cp_write_obs_row(p, orow, cash, h, di, lane, tmpl, tmpl_di);
             }
         }
         // ---- store state ----
@@ -268,7 +306,9 @@ __global__ void cashpenalty_observe_kernel(const frl_cashpenalty_params p, float
         const int j = lane + 32 * i;
         h[i] = j < p.stock_dim ? p.hold[(size_t)w * p.stock_dim + j] : 0.0;
     }
-    cp_write_obs_row(p, obs + (size_t)w * p.obs_dim, p.cash[w], h, p.date_index[w], lane);
+    float tmpl[kTmplChunks];
+    int tmpl_di = -1;
+    cp_write_obs_row(p, obs + (size_t)w * p.obs_dim, p.cash[w], h, p.date_index[w], lane, tmpl, tmpl_di);
 }
 
 int32_t cp_validate(const frl_cashpenalty_params *p)

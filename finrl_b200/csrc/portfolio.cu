@@ -74,7 +74,32 @@ __device__ __forceinline__ void pf_write_obs_tile(const frl_portfolio_params &p,
     bool uniform = true;
     if (lane < nvalid) uniform = (day_s[lane] == d0);
     uniform = __all_sync(0xffffffffu, uniform);
-    if (uniform) {
+    if (uniform && (O & 3) == 0 && ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(p.obs_table)) & 15) == 0) {
+        // rows are 16-B aligned: 128-bit stores, 8 x 512 B of the row per pass cached in registers
+        const int O4 = O >> 2;
+        const float4 *trow = reinterpret_cast<const float4 *>(p.obs_table + (size_t)d0 * O);
+        for (int base = 0; base < O4; base += 256) {
+            float4 t[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int pos = base + 32 * c + lane;
+                t[c] = pos < O4 ? __ldg(trow + pos) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float4 *orow = reinterpret_cast<float4 *>(obs + (size_t)env0 * O) + base + lane;
+            const int full = min(8, (O4 - base) >> 5);           // chunks entirely inside the row
+            const bool tail = (base + 32 * full + lane) < O4;     // the partial chunk after them
+            for (int r = 0; r < nvalid; ++r) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < full)
+                        __stcs(orow + 32 * c, t[c]);
+                    else if (c == full && tail)
+                        __stcs(orow + 32 * c, t[c]);
+                }
+                orow += O4;
+            }
+        }
+    } else if (uniform) {
         const float *trow = p.obs_table + (size_t)d0 * O;
         for (int base = 0; base < O; base += 256) {  // 8 x 128 B of the row per pass, cached in registers
             float t[8];
