@@ -221,3 +221,24 @@ def test_full_size_properties():
     assert bool((obs[:, 31:61] == env.hold.t().float()).all())
     assert bool((obs[:, 61:] == env.tables.obs_tmpl[env.day.long()][:, 61:]).all())
     assert abs(env.read_stats()["env_steps"] - K * N) < 0.5
+
+
+def test_output_buffers_have_no_out_of_bounds_writes():
+    """compute-sanitizer is closed on this GPU pool, so guard the outputs ourselves: ragged tile
+    (N % 32 != 0), buffers embedded in sentinel-filled allocations, every obs mode."""
+    from finrl_b200 import synthetic as syn
+
+    N, K, T, D = 4096 + 13, 5, 30, 30
+    env, o = _make(N, T=T)
+    O = env.state_space
+    acts = torch.from_numpy(syn.make_actions((K, N, D), seed=3)).cuda()
+    pad = 64
+    for mode, oshape in (("all", (K, N, O)), ("last", (N, O))):
+        big_obs = torch.full((int(np.prod(oshape)) + 2 * pad,), -7.25, dtype=torch.float32, device="cuda")
+        big_rew = torch.full((K * N + 2 * pad,), -7.25, dtype=torch.float64, device="cuda")
+        big_fl = torch.full((K * N + 2 * pad,), 99, dtype=torch.uint8, device="cuda")
+        obs = big_obs[pad:-pad].view(*oshape)
+        env.rollout(acts, obs_mode=mode, rewards=big_rew[pad:-pad].view(K, N), flags=big_fl[pad:-pad].view(K, N), obs=obs)
+        for big, val in ((big_obs, -7.25), (big_rew, -7.25), (big_fl, 99)):
+            assert bool((big[:pad] == val).all()) and bool((big[-pad:] == val).all())
+        assert not bool((obs == -7.25).any()) and not bool((big_fl[pad:-pad] == 99).any())
