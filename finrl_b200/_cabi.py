@@ -80,6 +80,7 @@ class NpParams(C.Structure):
         ("sell_cost_pct", C.c_double),
         ("reward_scaling", C.c_double),
         ("initial_capital", C.c_double),
+        ("obs_amount_floor", C.c_double),
         ("price", C.c_void_p),
         ("turb_bool", C.c_void_p),
         ("obs_tmpl", C.c_void_p),

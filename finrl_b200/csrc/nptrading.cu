@@ -106,7 +106,12 @@ __device__ __forceinline__ float np_asset_f32(const float (&stv)[SLOTS], const f
 }
 
 // np.array(self.amount * 2**-12, dtype=np.float32): the power-of-two scale commutes with the cast
-__device__ __forceinline__ float np_amount_obs(NV amount) { return fmul((float)amount.v, 0.000244140625f); }
+// (StockEnvNAS100 shows max(amount, 1e4): Python's max returns the float floor only when it is larger)
+__device__ __forceinline__ float np_amount_obs(NV amount, double floor_)
+{
+    const double a = floor_ > amount.v ? floor_ : amount.v;
+    return fmul((float)a, 0.000244140625f);
+}
 
 // ---- observation rows: [amount, turb, turb_bool, price*2^-6 x D, stocks*2^-6 x D, cool x D, tech] ----
 template <int NCH, int DCT, typename SM>
@@ -399,7 +404,7 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
                     sm.sc[(D + j) * kPitch + lane] = clv[j];
                 }
             }
-            sm.amountf[lane] = np_amount_obs(amount);
+            sm.amountf[lane] = np_amount_obs(amount, p.obs_amount_floor);
             sm.day[lane] = day;
             __syncwarp();
             float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
@@ -502,7 +507,7 @@ __global__ void __launch_bounds__(WARPS * 32) np_observe_kernel(const frl_np_par
         sm.sc[j * kPitch + lane] = p.stocks[n + (size_t)j * p.env_stride];
         sm.sc[(D + j) * kPitch + lane] = p.cool[n + (size_t)j * p.env_stride];
     }
-    sm.amountf[lane] = np_amount_obs(nv(p.amount[n], p.kinds[n] & 3));
+    sm.amountf[lane] = np_amount_obs(nv(p.amount[n], p.kinds[n] & 3), p.obs_amount_floor);
     sm.day[lane] = p.day[n];
     __syncwarp();
     np_write_obs_tile<0>(p, sm, obs, env0, nvalid, lane);

@@ -22,11 +22,11 @@ _KINDS = {0: float, 1: np.float32, 2: np.float64}
 class StockTradingEnv:
     def __init__(self, config, initial_account=1e6, gamma=0.99, turbulence_thresh=99, min_stock_rate=0.1,
                  max_stock=1e2, initial_capital=1e6, buy_cost_pct=1e-3, sell_cost_pct=1e-3, reward_scaling=2**-11,
-                 initial_stocks=None, device="cuda"):
+                 initial_stocks=None, device="cuda", obs_amount_floor=None):
         self._kw = dict(initial_account=initial_account, gamma=gamma, turbulence_thresh=turbulence_thresh,
                         min_stock_rate=min_stock_rate, max_stock=max_stock, initial_capital=initial_capital,
                         buy_cost_pct=buy_cost_pct, sell_cost_pct=sell_cost_pct, reward_scaling=reward_scaling,
-                        initial_stocks=initial_stocks)
+                        initial_stocks=initial_stocks, obs_amount_floor=obs_amount_floor)
         self._config, self._device = config, device
         self.engine = e = BatchedNpStockTradingEnv(config, n_envs=1, device=device, **self._kw)
         t = e.tables

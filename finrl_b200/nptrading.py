@@ -74,7 +74,7 @@ class BatchedNpStockTradingEnv:
 
     def __init__(self, config=None, initial_account=1e6, gamma=0.99, turbulence_thresh=99, min_stock_rate=0.1,
                  max_stock=1e2, initial_capital=1e6, buy_cost_pct=1e-3, sell_cost_pct=1e-3, reward_scaling=2**-11,
-                 initial_stocks=None, *, n_envs=1, device="cuda", tables=None, if_train=None):
+                 initial_stocks=None, *, n_envs=1, device="cuda", tables=None, if_train=None, obs_amount_floor=None):
         import torch
 
         self._torch = torch
@@ -129,6 +129,8 @@ class BatchedNpStockTradingEnv:
         p.gamma, p.max_stock, p.min_stock_rate = float(gamma), float(max_stock), float(min_stock_rate)
         p.buy_cost_pct, p.sell_cost_pct, p.reward_scaling = float(buy_cost_pct), float(sell_cost_pct), float(reward_scaling)
         p.initial_capital = float(initial_capital)
+        # StockEnvNAS100's get_state shows max(amount, 1e4) (env_nas100_wrds.py:157)
+        p.obs_amount_floor = float("-inf") if obs_amount_floor is None else float(obs_amount_floor)
         p.price, p.turb_bool, p.obs_tmpl = tables.price.data_ptr(), tables.turb_bool.data_ptr(), tables.obs_tmpl.data_ptr()
         p.init_stocks = self._init_stocks.data_ptr()
         p.amount, p.kinds, p.stocks, p.cool = self.amount.data_ptr(), self.kinds.data_ptr(), self.stocks.data_ptr(), self.cool.data_ptr()

@@ -156,6 +156,8 @@ typedef struct frl_np_params {
     double gamma, max_stock, min_stock_rate;
     double buy_cost_pct, sell_cost_pct, reward_scaling;
     double initial_capital;
+    double obs_amount_floor; /* get_state shows max(amount, floor): 1e4 for the sibling StockEnvNAS100
+                                (env_nas100_wrds.py:157), -inf for env_stocktrading_np */
     /* ---- tables ---- */
     const float *price;       /* [T][32] price_ary = f32(price_array), rows zero-padded (:27) */
     const float *turb_bool;   /* [T] f32(turbulence_array > thresh) (:32) */

@@ -391,7 +391,12 @@ static void np_obs_one(const ora_np_cfg *c, const ora_np_state *s, int n, float 
     const float scale = 0.015625f; /* 2**-6 */
     /* np.array(self.amount * 2**-12, dtype=np.float32): a power-of-two scale commutes with the cast */
     double a = s->amount[n];
-    obs[0] = (s->amount_kind[n] == ORA_KIND_F32) ? (float)a * 0.000244140625f : (float)(a * 0.000244140625);
+    int ak = s->amount_kind[n];
+    if (c->obs_amount_floor > a) { /* Python max(self.amount, 1e4) returns the float 1e4 only if it is larger */
+        a = c->obs_amount_floor;
+        ak = ORA_KIND_PY;
+    }
+    obs[0] = (ak == ORA_KIND_F32) ? (float)a * 0.000244140625f : (float)(a * 0.000244140625);
     obs[1] = c->turb_ary[day];
     obs[2] = c->turb_bool[day];
     for (int i = 0; i < D; ++i) obs[3 + i] = price[i] * scale;

@@ -94,6 +94,8 @@ typedef struct {
     int32_t n_envs, stock_dim, tech_dim /* columns of tech_ary = D*K */, n_days;
     double gamma, max_stock, min_stock_rate, buy_cost_pct, sell_cost_pct, reward_scaling;
     double initial_capital;
+    double obs_amount_floor; /* get_state shows max(amount, floor): 1e4 in StockEnvNAS100
+                                (env_nas100_wrds.py:157); -inf for env_stocktrading_np */
     const float *price;      /* [T][D]  price_ary  (:27) */
     const float *tech;       /* [T][tech_dim] tech_ary = f32(tech_array) * 2^-7 (:28,31) */
     const float *turb_bool;  /* [T] (:32) */

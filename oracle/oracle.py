@@ -208,7 +208,7 @@ class _NpCfg(C.Structure):
         ("n_envs", C.c_int32), ("stock_dim", C.c_int32), ("tech_dim", C.c_int32), ("n_days", C.c_int32),
         ("gamma", C.c_double), ("max_stock", C.c_double), ("min_stock_rate", C.c_double),
         ("buy_cost_pct", C.c_double), ("sell_cost_pct", C.c_double), ("reward_scaling", C.c_double),
-        ("initial_capital", C.c_double),
+        ("initial_capital", C.c_double), ("obs_amount_floor", C.c_double),
         ("price", C.c_void_p), ("tech", C.c_void_p), ("turb_bool", C.c_void_p), ("turb_ary", C.c_void_p),
         ("init_stocks", C.c_void_p),
     ]
@@ -228,7 +228,7 @@ class NpTradingOracle:
 
     def __init__(self, price_array, tech_array, turbulence_array, n_envs, gamma=0.99, turbulence_thresh=99,
                  min_stock_rate=0.1, max_stock=1e2, initial_capital=1e6, buy_cost_pct=1e-3, sell_cost_pct=1e-3,
-                 reward_scaling=2**-11, initial_stocks=None):
+                 reward_scaling=2**-11, initial_stocks=None, obs_amount_floor=None):
         self.price, self.tech, self.turb_bool, self.turb_ary = np_tables(price_array, tech_array, turbulence_array, turbulence_thresh)
         T, D = self.price.shape
         N = int(n_envs)
@@ -242,7 +242,8 @@ class NpTradingOracle:
         self.gamma_reward = np.zeros(N); self.gr_kind = np.zeros(N, dtype=np.uint8)
         self.init_total = np.zeros(N); self.episode_return = np.zeros(N)
         self._cfg = _NpCfg(N, D, self.TD, T, float(gamma), float(max_stock), float(min_stock_rate), float(buy_cost_pct),
-                           float(sell_cost_pct), float(reward_scaling), float(initial_capital), _p(self.price),
+                           float(sell_cost_pct), float(reward_scaling), float(initial_capital),
+                           float("-inf") if obs_amount_floor is None else float(obs_amount_floor), _p(self.price),
                            _p(self.tech), _p(self.turb_bool), _p(self.turb_ary), _p(self.init_stocks))
         self._st = _NpState(_p(self.amount), _p(self.amount_kind), _p(self.stocks), _p(self.cool), _p(self.day),
                             _p(self.total), _p(self.total_kind), _p(self.gamma_reward), _p(self.gr_kind),

@@ -22,6 +22,7 @@ ENV_FILES = {
     "env_stocktrading_np": "finrl/meta/env_stock_trading/env_stocktrading_np.py",
     "env_stocktrading_cashpenalty": "finrl/meta/env_stock_trading/env_stocktrading_cashpenalty.py",
     "env_portfolio": "finrl/meta/env_portfolio_allocation/env_portfolio.py",
+    "env_nas100_wrds": "finrl/meta/env_stock_trading/env_nas100_wrds.py",
 }
 
 

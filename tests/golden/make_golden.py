@@ -102,12 +102,21 @@ def _kind(x):
     return {float: 0, int: 0, np.float32: 1, np.float64: 2}[type(x)]
 
 
-def gen_np(name, T, D, K, n_steps, seed, if_train, thresh=99, quiet_steps=0, **kw):
-    mod = ref_loader.load("env_stocktrading_np")
+def gen_np(name, T, D, K, n_steps, seed, if_train, thresh=99, quiet_steps=0, nas100=False, **kw):
     close, tech, turb = syn.make_tables(T, D, K, seed=seed)
     price_array, tech_array, turb_array = syn.make_np_arrays(close, tech, turb)
-    cfg = {"price_array": price_array, "tech_array": tech_array, "turbulence_array": turb_array, "if_train": if_train}
-    env = mod.StockTradingEnv(cfg, turbulence_thresh=thresh, **kw)
+    if nas100:
+        # StockEnvNAS100 (env_nas100_wrds.py): the same step, get_state shows max(amount, 1e4); its arrays come
+        # from load_data() as float32 and the ctor slices [0:211210:data_gap] in eval mode
+        mod = ref_loader.load("env_nas100_wrds")
+        price_array, tech_array = price_array.astype(np.float32), tech_array.astype(np.float32)
+        env = mod.StockEnvNAS100(cwd=None, price_ary=price_array, tech_ary=tech_array, turbulence_ary=turb_array,
+                                 turbulence_thresh=thresh, data_gap=1, if_eval=True, **kw)
+        env.stocks_cool_down = None
+    else:
+        mod = ref_loader.load("env_stocktrading_np")
+        cfg = {"price_array": price_array, "tech_array": tech_array, "turbulence_array": turb_array, "if_train": if_train}
+        env = mod.StockTradingEnv(cfg, turbulence_thresh=thresh, **kw)
     np.random.seed(seed + 100)
     obs0 = env.reset()
     init = {"init_amount": np.float64(env.amount), "init_amount_kind": _kind(env.amount),
@@ -139,7 +148,7 @@ def gen_np(name, T, D, K, n_steps, seed, if_train, thresh=99, quiet_steps=0, **k
         out["done"][s] = done
         out["episode_return"][s] = env.episode_return
         out["stocks"][s] = env.stocks
-        out["cool"][s] = env.stocks_cool_down
+        out["cool"][s] = env.stocks_cd if nas100 else env.stocks_cool_down
         out["obs"][s] = state
         out["day"][s] = env.day
         assert state.dtype == np.float32
@@ -149,7 +158,7 @@ def gen_np(name, T, D, K, n_steps, seed, if_train, thresh=99, quiet_steps=0, **k
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"), price_array=price_array, tech_array=tech_array, turbulence_array=turb_array,
         actions=actions, obs0=obs0, if_train=np.array(int(if_train)), thresh=np.array(float(thresh)),
-        rng_seed=np.array(seed + 100),
+        rng_seed=np.array(seed + 100), nas100=np.array(int(nas100)),
         reset_amount=np.array([r[0] for r in resets]), reset_amount_kind=np.array([r[1] for r in resets], dtype=np.uint8),
         reset_stocks=np.array([r[2] for r in resets], dtype=np.float32).reshape(len(resets), D),
         kw_keys=np.array([k for k in kw if k != "initial_stocks"], dtype="U32"),
@@ -277,6 +286,8 @@ def main():
         gen_np("np_d7_small", T=50, D=7, K=2, n_steps=110, seed=13, if_train=False, initial_capital=2e4, max_stock=50.0,
                thresh=80)
         gen_np("np_d30_kinds", T=40, D=30, K=8, n_steps=90, seed=14, if_train=True, thresh=99, quiet_steps=6)
+        gen_np("np_nas100_d20", T=45, D=20, K=4, n_steps=100, seed=16, if_train=True, thresh=60, nas100=True,
+               initial_capital=6e4, gamma=0.999)
         gen_np("np_d12_kinds_eval", T=40, D=12, K=3, n_steps=90, seed=15, if_train=False, thresh=70, quiet_steps=5,
                initial_stocks=np.arange(12, dtype=np.float32))
     if want("portfolio"):

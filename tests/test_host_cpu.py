@@ -51,7 +51,7 @@ def test_struct_layouts_match_the_header():
 
     checks = {
         "frl_trading_params": (_cabi.TradingParams, ["n_envs", "hmax", "turbulence_threshold", "close", "cash", "episode", "asset_out"]),
-        "frl_np_params": (_cabi.NpParams, ["gamma", "initial_capital", "price", "amount", "episode_return"]),
+        "frl_np_params": (_cabi.NpParams, ["gamma", "initial_capital", "obs_amount_floor", "price", "amount", "episode_return"]),
         "frl_portfolio_params": (_cabi.PortfolioParams, ["initial_amount", "ret", "reward"]),
         "frl_cashpenalty_params": (_cabi.CashPenaltyParams, ["patient", "buy_cost_pct", "cash_penalty_proportion", "close", "sum_trades"]),
     }

@@ -116,6 +116,8 @@ def np_kwargs_from_golden(g):
     kw = {str(k): float(v) for k, v in zip(g["kw_keys"], g["kw_vals"])}
     kw["turbulence_thresh"] = float(g["thresh"])
     kw["initial_stocks"] = g["initial_stocks"]
+    if "nas100" in g.files and int(g["nas100"]):
+        kw["obs_amount_floor"] = 1e4  # StockEnvNAS100.get_state (env_nas100_wrds.py:157)
     return kw
 
 

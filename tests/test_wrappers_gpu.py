@@ -185,3 +185,28 @@ def test_np_vectorized_elegantrl_convention():
     for _ in range(31):
         s, r, d, _ = vec.step(torch.rand((64, 30), device="cuda") * 2 - 1)
     assert tuple(s.shape) == (64, 333) and tuple(r.shape) == (64,) and d.dtype == torch.bool
+
+
+def test_nas100_sibling_class_matches_reference():
+    from finrl_b200.env_nas100_wrds import StockEnvNAS100
+
+    g = np.load(os.path.join(GOLDEN, "np_nas100_d20.npz"))
+    kw = np_kwargs_from_golden(g)
+    kw.pop("obs_amount_floor")
+    np.random.seed(int(g["rng_seed"]))
+    env = StockEnvNAS100(cwd=None, price_ary=g["price_array"], tech_ary=g["tech_array"], turbulence_ary=g["turbulence_array"],
+                         data_gap=1, if_eval=True, **kw)
+    np.random.seed(int(g["rng_seed"]))
+    assert np.array_equal(env.reset(), g["obs0"]) and env.env_name == "StockEnvNAS"
+    floor_seen = 0
+    for s in range(g["actions"].shape[0]):
+        state, reward, done, _ = env.step(g["actions"][s])
+        assert done == bool(g["done"][s]) and reward == g["reward"][s], f"step {s}"
+        assert np.array_equal(state, g["obs"][s]) and np.array_equal(env.stocks_cd, g["cool"][s]), f"step {s}"
+        floor_seen += int(state[0] == np.float32(1e4 * 2**-12) and env.amount < 1e4)
+        if done:
+            env.reset()
+    assert floor_seen > 0  # the max(amount, 1e4) branch was exercised
+    with pytest.raises(TypeError):
+        StockEnvNAS100(cwd=None, price_ary=g["price_array"].astype(np.float64), tech_ary=g["tech_array"],
+                       turbulence_ary=g["turbulence_array"])
