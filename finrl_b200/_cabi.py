@@ -129,7 +129,7 @@ class CashPenaltyParams(C.Structure):
         ("shares_increment", C.c_int32),
         ("use_turbulence", C.c_int32),
         ("patient", C.c_int32),
-        ("_pad0", C.c_int32),
+        ("env_stride", C.c_int32),
         ("buy_cost_pct", C.c_double),
         ("sell_cost_pct", C.c_double),
         ("hmax", C.c_double),

@@ -3,7 +3,7 @@
 Reference: /root/reference/finrl/meta/env_stock_trading/env_stocktrading_cashpenalty.py.  Fractional
 (or discretised) share trading with ``hmax`` in currency, reward = cash-penalised gain per elapsed
 step computed BEFORE trading, CASH SHORTAGE termination or ``patient`` mode (incl. quirk Q9), and
-turbulence liquidation.  One warp per env (finrl_b200/csrc/cashpenalty.cu).
+turbulence liquidation.  One thread per env, two streaming passes over the assets (finrl_b200/csrc/cashpenalty.cu).
 """
 from __future__ import annotations
 
@@ -110,7 +110,7 @@ class BatchedStockTradingEnvCashpenalty:
         self.daily_information_cols = list(daily_information_cols)
         dev = self.device
         self.cash = torch.empty(N, dtype=torch.float64, device=dev)
-        self.holdings = torch.empty((N, D), dtype=torch.float64, device=dev)
+        self.hold = torch.empty((D, N), dtype=torch.float64, device=dev)  # stock-major
         self.date_index = torch.empty(N, dtype=torch.int32, device=dev)
         self.starting_point = torch.empty(N, dtype=torch.int32, device=dev)
         self.fresh = torch.empty(N, dtype=torch.uint8, device=dev)
@@ -122,14 +122,14 @@ class BatchedStockTradingEnvCashpenalty:
         self._rew = torch.empty(N, dtype=torch.float64, device=dev)
         self._flags = torch.empty(N, dtype=torch.uint8, device=dev)
         p = _cabi.CashPenaltyParams()
-        p.n_envs, p.stock_dim, p.n_cols, p.n_days, p.obs_dim = N, D, tables.n_cols, T, O
+        p.n_envs, p.stock_dim, p.n_cols, p.n_days, p.obs_dim, p.env_stride = N, D, tables.n_cols, T, O, N
         p.discrete_actions, p.shares_increment = int(bool(discrete_actions)), int(shares_increment)
         p.use_turbulence, p.patient = int(turbulence_threshold is not None), int(bool(patient))
         p.buy_cost_pct, p.sell_cost_pct, p.hmax = float(buy_cost_pct), float(sell_cost_pct), float(hmax)
         p.turbulence_threshold = float(turbulence_threshold) if turbulence_threshold is not None else 0.0
         p.initial_amount, p.cash_penalty_proportion = float(initial_amount), float(cash_penalty_proportion)
         p.close, p.turb, p.obs_tmpl = tables.close.data_ptr(), tables.turb.data_ptr(), tables.obs_tmpl.data_ptr()
-        p.cash, p.hold, p.date_index, p.start = self.cash.data_ptr(), self.holdings.data_ptr(), self.date_index.data_ptr(), self.starting_point.data_ptr()
+        p.cash, p.hold, p.date_index, p.start = self.cash.data_ptr(), self.hold.data_ptr(), self.date_index.data_ptr(), self.starting_point.data_ptr()
         p.fresh, p.last_cash, p.last_total, p.sum_trades = self.fresh.data_ptr(), self.last_cash.data_ptr(), self.last_total.data_ptr(), self.sum_trades.data_ptr()
         self._p = p
         self.launches = 0
@@ -138,6 +138,11 @@ class BatchedStockTradingEnvCashpenalty:
 
     def _stream(self):
         return _cabi.current_stream(self.device)
+
+    @property
+    def holdings(self):
+        """Holdings in the natural [N, D] layout (a transposed view of the stock-major device array)."""
+        return self.hold.t()
 
     def _as_actions(self, actions, ndim):
         torch = self._torch

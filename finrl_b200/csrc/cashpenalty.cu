@@ -1,17 +1,25 @@
 // A4 — StockTradingEnvCashpenalty (reference: finrl/meta/env_stock_trading/env_stocktrading_cashpenalty.py).
 //
-// This env is vector arithmetic over D (up to NASDAQ-100) assets with three dot products and NO
-// sequential per-stock dependency, and its state is dominated by D fractional fp64 holdings — so the
-// mapping is ONE WARP PER ENV: lane l owns assets l, l+32, l+64, l+96 in registers, the three np.dot
-// reductions are xor-shuffle butterflies (every lane ends with the same bits), and every global
-// access (action row, holdings row, 601-float observation row) is a coalesced row access with no
-// shared-memory staging.  Warps walk the env range with a grid stride.
+// Mapping: ONE THREAD PER ENV, one warp per 32-env tile (the layout of trading.cu).  A first version ran
+// one warp per env (lanes = assets, shuffle-reduced dot products): every scalar decision was replicated
+// in 32 lanes and it issued ~650-800 warp-instructions per env-step (43-47 % of the HBM roofline).  Per
+// thread the same work is two streaming passes over the D assets:
+//   pass 1  read holding (stock-major, coalesced), closing price (warp-uniform, L1), staged action;
+//           form the transaction and accumulate np.dot(holdings, closings), proceeds, spend, sum|a|
+//   decide  cash shortage -> terminate / patient (scalar, per lane)
+//   pass 2  re-form the transaction (same ops => same bits), update the holding, store it, and drop its
+//           float32 image into the lane's own staging row, which the observation writer then reads
+//           row-wise — the action staging buffer doubles as the transposition buffer.
+// np.dot's order is BLAS-specific (tolerance 1e-9 in the tests); the sums here are sequential in asset
+// order, which happens to be the CPU oracle's order as well.
 #include "common.cuh"
+
+#ifndef FRL_CP_MIN_BLOCKS
+#define FRL_CP_MIN_BLOCKS 4  // 128-thread blocks per SM the register allocator must allow
+#endif
 
 namespace frl {
 namespace {
-
-constexpr int kPerLane = 4;  // D <= 128
 
 __device__ __forceinline__ double cp_reward(const frl_cashpenalty_params &p, double assets, double cash, int current_step)
 {
@@ -31,300 +39,421 @@ __device__ __forceinline__ long long floordiv_ll(long long a, long long b)
     return q;
 }
 
-// four independent butterflies interleaved (ILP): every lane ends with the same bits for each sum
-__device__ __forceinline__ void warp_sum4(double &a, double &b, double &c, double &d)
+// get_transactions (:258-298) for one asset: actions*hmax in the input dtype, zero where the price is
+// not positive, shares = currency / price (or the discretised floor), never sell more than held,
+// turbulence clears the position.
+template <typename ActT>
+__device__ __forceinline__ double cp_transaction(const frl_cashpenalty_params &p, ActT a, double c, double h, bool liq)
 {
+    double v;
+    if (sizeof(ActT) == 4)
+        v = (double)fmul((float)a, (float)p.hmax);
+    else
+        v = dmul((double)a, p.hmax);
+    if (!(c > 0.0)) v = 0.0;  // np.where(closings > 0, actions, 0)
+    if (p.discrete_actions) {
+        long long q = (long long)floor_div_f64(v, c);  // actions // closings, astype(int)
+        const long long inc = p.shares_increment;
+        q = (q >= 0) ? floordiv_ll(q, inc) * inc : floordiv_ll(q + inc, inc) * inc;
+        v = (double)q;
+    } else {
+        v = __ddiv_rn(v, c);
+    }
+    v = (v > -h) ? v : -h;  // np.maximum(actions, -holdings)
+    if (liq) v = -h;        // turbulence: clear out all positions
+    return v;
+}
+
+// Warp-cooperative write of the tile's observation rows: [coh, holdings x D, daily information].
+// Env r's staging row holds its float32 holdings after pass 2.  NCH = ceil(O/32) is compiled in so the
+// row loop is NCH plain stores; only the first (D/32)+1 chunks need the cash / holdings patch-up.
+template <int NCH, typename ActT>
+__device__ __forceinline__ void cp_write_obs_rows_uniform(const frl_cashpenalty_params &p, const ActT *stage, int P,
+                                                          const float *cashf, float *__restrict__ obs, long long env0,
+                                                          int nvalid, int lane, int d0)
+{
+    const int O = p.obs_dim, D = p.stock_dim;
+    constexpr int step = sizeof(ActT) / sizeof(float);  // the float image sits in the low word of each slot
+    constexpr int NSP = NCH < 5 ? NCH : 5;              // D <= 128: holdings end inside chunk 4
+    float t[NCH];
+    const float *trow = p.obs_tmpl + (size_t)d0 * O + lane;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
-        const double tc = __shfl_xor_sync(0xffffffffu, c, o), td = __shfl_xor_sync(0xffffffffu, d, o);
-        a += ta;
-        b += tb;
-        c += tc;
-        d += td;
+    for (int c = 0; c < NCH; ++c) t[c] = (c < NCH - 1 || lane + 32 * c < O) ? __ldg(trow + 32 * c) : 0.0f;
+    int hoff[NSP];
+#pragma unroll
+    for (int c = 0; c < NSP; ++c) {
+        const int pos = lane + 32 * c;
+        hoff[c] = (pos >= 1 && pos <= D) ? (pos - 1) * step : -1;
+    }
+    const bool tail_ok = lane + 32 * (NCH - 1) < O;
+    const float *hrow = reinterpret_cast<const float *>(stage);
+    float *orow = obs + (size_t)env0 * O + lane;
+    const int pitch = P * step;
+#pragma unroll 2
+    for (int r = 0; r < nvalid; ++r) {
+        float v[NSP];
+#pragma unroll
+        for (int c = 0; c < NSP; ++c) v[c] = hoff[c] >= 0 ? hrow[hoff[c]] : t[c];
+        const float cf = cashf[r];
+        if (lane == 0) v[0] = cf;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const float x = c < NSP ? v[c] : t[c];
+            if (c < NCH - 1 || tail_ok) orow[32 * c] = x;
+        }
+        orow += O;
+        hrow += pitch;
     }
 }
 
-constexpr int kTmplChunks = 20;  // register-cached template covers O <= 640 (NASDAQ-100 x 5 columns: 601)
-
-// one observation row: [coh, holdings x D, daily information of date di] as float32
-__device__ __forceinline__ void cp_write_obs_row(const frl_cashpenalty_params &p, float *__restrict__ orow, double cash,
-                                                 const double (&h)[kPerLane], int di, int lane, float (&t)[kTmplChunks],
-                                                 int &cached_di)
+template <typename ActT>
+__device__ __forceinline__ void cp_write_obs_tile(const frl_cashpenalty_params &p, const ActT *stage, int P,
+                                                  const float *cashf, const int *di_s, float *__restrict__ obs,
+                                                  long long env0, int nvalid, int lane)
 {
     const int O = p.obs_dim, D = p.stock_dim;
-    const float *trow = p.obs_tmpl + (size_t)di * O;
-    const bool use_cache = O <= kTmplChunks * 32;
-    if (use_cache && di != cached_di) {  // warp-uniform: consecutive envs of a warp usually share the date
-#pragma unroll
-        for (int c = 0; c < kTmplChunks; ++c) {
-            const int pos = lane + 32 * c;
-            t[c] = pos < O ? __ldg(trow + pos) : 0.0f;
+    const int d0 = di_s[0];
+    bool uniform = true;
+    if (lane < nvalid) uniform = (di_s[lane] == d0);
+    uniform = __all_sync(0xffffffffu, uniform);
+    const int nch = (O + 31) >> 5;
+    if (uniform && nch <= 24) {
+        switch (nch) {
+#define FRL_CASE(N)                                                                                \
+    case N:                                                                                        \
+        cp_write_obs_rows_uniform<N, ActT>(p, stage, P, cashf, obs, env0, nvalid, lane, d0);       \
+        break;
+            FRL_CASE(1) FRL_CASE(2) FRL_CASE(3) FRL_CASE(4) FRL_CASE(5) FRL_CASE(6) FRL_CASE(7) FRL_CASE(8)
+            FRL_CASE(9) FRL_CASE(10) FRL_CASE(11) FRL_CASE(12) FRL_CASE(13) FRL_CASE(14) FRL_CASE(15) FRL_CASE(16)
+            FRL_CASE(17) FRL_CASE(18) FRL_CASE(19) FRL_CASE(20) FRL_CASE(21) FRL_CASE(22) FRL_CASE(23) FRL_CASE(24)
+#undef FRL_CASE
         }
-        cached_di = di;
-    }
-    const int src = (lane - 1) & 31;
-    float hf[kPerLane];
-#pragma unroll
-    for (int i = 0; i < kPerLane; ++i) hf[i] = (float)h[i];
-    // positions 1..D hold holdings[pos-1]; asset j lives in lane j%32, slot j/32
-#pragma unroll
-    for (int c = 0; c <= kPerLane; ++c) {
-        const int pos = lane + 32 * c;
-        if (32 * c > D) break;  // warp-uniform
-        const float same = __shfl_sync(0xffffffffu, c < kPerLane ? hf[c] : 0.0f, src);  // lanes >= 1: slot c
-        const float prev = __shfl_sync(0xffffffffu, c > 0 ? hf[c - 1] : 0.0f, src);     // lane 0: slot c-1
-        if (pos < O) {
-            float v;
-            if (pos == 0)
-                v = (float)cash;
-            else if (pos <= D)
-                v = lane == 0 ? prev : same;
-            else
-                v = use_cache ? t[c] : __ldg(trow + pos);
-            orow[pos] = v;
-        }
-    }
-    const int first_c = (D >> 5) + 1;  // first chunk entirely past the holdings
-    if (use_cache) {
-#pragma unroll
-        for (int c = 1; c < kTmplChunks; ++c)
-            if (c >= first_c && lane + 32 * c < O) orow[lane + 32 * c] = t[c];
     } else {
-        for (int pos = (first_c << 5) + lane; pos < O; pos += 32) orow[pos] = __ldg(trow + pos);
+        for (int r = 0; r < nvalid; ++r) {
+            const float *hrow = reinterpret_cast<const float *>(stage + (size_t)r * P);
+            constexpr int step = sizeof(ActT) / sizeof(float);
+            const float *trow = p.obs_tmpl + (size_t)di_s[r] * O;
+            float *orow = obs + (size_t)(env0 + r) * O;
+            for (int pos = lane; pos < O; pos += 32) {
+                float v;
+                if (pos == 0)
+                    v = cashf[r];
+                else if (pos <= D)
+                    v = hrow[(pos - 1) * step];
+                else
+                    v = __ldg(trow + pos);
+                orow[pos] = v;
+            }
+        }
     }
 }
 
 template <typename ActT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, FRL_CP_MIN_BLOCKS * 128 / (WARPS * 32))
 cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restrict__ actions, long long act_step_stride,
                            long long act_env_stride, int n_steps, double *__restrict__ rewards,
                            uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode, int auto_reset,
                            double *__restrict__ stats)
 {
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * WARPS;
-    const int N = p.n_envs, D = p.stock_dim, T = p.n_days, O = p.obs_dim;
-    double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_asset = 0.0, st_liq = 0.0, st_steps = 0.0, st_short = 0.0;
-    float tmpl[kTmplChunks];
-    int tmpl_di = -1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;
+    const int P = D | 1;  // odd row pitch: conflict-free per-lane row walks
+    const size_t warp_bytes = (size_t)32 * P * sizeof(ActT) + 32 * sizeof(float) + 32 * sizeof(int);
+    unsigned char *base = smem_raw + warp * ((warp_bytes + 15) & ~(size_t)15);
+    ActT *stage = reinterpret_cast<ActT *>(base);                       // [32 envs][P]
+    float *cashf = reinterpret_cast<float *>(base + (size_t)32 * P * sizeof(ActT));
+    int *di_s = reinterpret_cast<int *>(cashf + 32);
 
-    for (long long n = warp0; n < N; n += nwarps) {
-        // ---- load state (scalars replicated in every lane; holdings: 4 assets per lane) ----
-        double cash = p.cash[n], last_cash = p.last_cash[n], last_total = p.last_total[n], sum_trades = p.sum_trades[n];
-        int di = p.date_index[n], start = p.start[n];
-        bool fresh = p.fresh[n] != 0;
-        double h[kPerLane];
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const bool valid = lane < nvalid;
+    const long long n = valid ? env0 + lane : (long long)N - 1;
+
+    double cash = p.cash[n], last_cash = p.last_cash[n], last_total = p.last_total[n], sum_trades = p.sum_trades[n];
+    int di = p.date_index[n], start = p.start[n];
+    bool fresh = p.fresh[n] != 0;
+    double *hp = p.hold + n;  // hold[j][n] at hp[j * ld]
+    ActT *myrow = stage + (size_t)lane * P;
+    double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_liq = 0.0, st_short = 0.0;
+
+    for (int k = 0; k < n_steps; ++k) {
+        // ---- stage this step's actions (coalesced) into [env][P] rows ----
+        const ActT *abase = actions + (size_t)k * act_step_stride;
+        __syncwarp();
+        if (act_env_stride == D) {
+            const ActT *tile = abase + (size_t)env0 * D;
+            const int cnt = nvalid * D;
+            int row = 0, col = lane;
+            while (col >= D) { col -= D; ++row; }
+            // batches of 8 independent coalesced loads in flight per lane, then parked row-wise
+            for (int e0 = lane; e0 < 32 * D; e0 += 32 * 8) {
+                ActT v[8];
 #pragma unroll
-        for (int i = 0; i < kPerLane; ++i) {
-            const int j = lane + 32 * i;
-            h[i] = j < D ? p.hold[(size_t)n * D + j] : 0.0;
-        }
-        for (int k = 0; k < n_steps; ++k) {
-            const ActT *arow = actions + (size_t)k * act_step_stride + (size_t)n * act_env_stride;
-            ActT a[kPerLane];
-            double asum = 0.0;
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + 32 * u;
+                    v[u] = e < cnt ? __ldcs(tile + e) : ActT(0);
+                }
 #pragma unroll
-            for (int i = 0; i < kPerLane; ++i) {
-                const int j = lane + 32 * i;
-                a[i] = j < D ? arow[j] : ActT(0);
-                asum += fabs((double)a[i]);
+                for (int u = 0; u < 8; ++u) {
+                    if (e0 + 32 * u < 32 * D) stage[row * P + col] = v[u];
+                    col += 32;
+                    while (col >= D) { col -= D; ++row; }
+                }
             }
-            int flags = 0;
-            double reward;
-            const int current_step = di - start;
-            bool reset_now = false;
-            if (di == T - 1) {
-                // last date (:308-310): reward from the previously logged (assets, cash); state unchanged
-                sum_trades += warp_sum(asum);  // self.sum_trades += np.sum(np.abs(actions)) (:302), logging only
-                flags = FRL_FLAG_DONE;
-                reward = cp_reward(p, last_total, last_cash, current_step);
+        } else {
+            for (int r = 0; r < 32; ++r)
+                for (int j = lane; j < D; j += 32)
+                    stage[r * P + j] = r < nvalid ? abase[(size_t)(env0 + r) * act_env_stride + j] : ActT(0);
+        }
+        __syncwarp();
+
+        int flags = 0;
+        double reward;
+        const int current_step = di - start;
+        bool reset_now = false, moved = false;
+        if (di == T - 1) {
+            // last date (:308-310): reward from the previously logged (assets, cash); state unchanged
+            double asum = 0.0;
+            for (int j = 0; j < D; ++j) asum += fabs((double)myrow[j]);
+            sum_trades += asum;
+            flags = FRL_FLAG_DONE;
+            reward = cp_reward(p, last_total, last_cash, current_step);
+            reset_now = auto_reset != 0;
+        } else {
+            const double *crow = p.close + (size_t)di * D;
+            const double turbulence = fresh ? 0.0 : __ldg(p.turb + di);
+            const bool liq = p.use_turbulence && turbulence >= p.turbulence_threshold;
+            if (liq) flags |= FRL_FLAG_LIQUIDATE;
+            // ---- pass 1: np.sum(|actions|), np.dot(holdings, closings), proceeds, spend ----
+            double asum = 0.0, asset_value = 0.0, proceeds = 0.0, spend = 0.0;
+            const double *hq = hp;
+            for (int j0 = 0; j0 < D; j0 += 8) {
+                // 8 independent holding loads in flight per thread (the holdings stream is the DRAM-latency
+                // critical path of this pass)
+                double hb[8], cb[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = j0 + u;
+                    hb[u] = j < D ? __ldcg(hq) : 0.0;
+                    cb[u] = j < D ? __ldg(crow + j) : 1.0;
+                    hq += ld;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = j0 + u;
+                    if (j < D) {
+                        const ActT a = myrow[j];
+                        const double v = cp_transaction<ActT>(p, a, cb[u], hb[u], liq);
+                        asum += fabs((double)a);
+                        asset_value = dadd(asset_value, dmul(hb[u], cb[u]));
+                        proceeds = dadd(proceeds, dmul(v < 0.0 ? -v : 0.0, cb[u]));
+                        spend = dadd(spend, dmul(v > 0.0 ? v : 0.0, cb[u]));
+                    }
+                }
+            }
+            sum_trades += asum;  // (:302), logging only
+            const double begin_cash = cash;
+            last_cash = begin_cash;
+            last_total = dadd(begin_cash, asset_value);
+            reward = cp_reward(p, last_total, last_cash, current_step);  // computed BEFORE trading (:326)
+            double costs = dmul(proceeds, p.sell_cost_pct);
+            double coh = dadd(begin_cash, proceeds);
+            costs = dadd(costs, dmul(spend, p.buy_cost_pct));
+            bool terminate = false, no_buys = false;
+            if (dadd(spend, costs) > coh) {
+                flags |= FRL_FLAG_SHORTAGE;
+                if (p.patient) {  // no buys until there is cash again; the sell costs are dropped too (Q9)
+                    no_buys = true;
+                    spend = 0.0;
+                    costs = 0.0;
+                } else {
+                    terminate = true;  // CASH SHORTAGE (:349-353): state unchanged, current reward, done
+                }
+            }
+            if (terminate) {
+                flags |= FRL_FLAG_DONE;
                 reset_now = auto_reset != 0;
             } else {
-                const double *crow = p.close + (size_t)di * D;
-                double c[kPerLane], part = 0.0;
+                // ---- pass 2: apply the transactions (holdings_updated = holdings + transactions) ----
+                cash = dsub(dsub(coh, spend), costs);
+                double *hw = hp;
+                const double *hq2 = hp;
+                for (int j0 = 0; j0 < D; j0 += 8) {
+                    double hb[8], cb[8];
 #pragma unroll
-                for (int i = 0; i < kPerLane; ++i) {
-                    const int j = lane + 32 * i;
-                    c[i] = j < D ? __ldg(crow + j) : 0.0;
-                    part += h[i] * c[i];
-                }
-                const double begin_cash = cash;
-
-                // ---- get_transactions (:258-298) ----
-                const double turbulence = fresh ? 0.0 : __ldg(p.turb + di);
-                const bool liq = p.use_turbulence && turbulence >= p.turbulence_threshold;
-                double tx[kPerLane], psell = 0.0, pbuy = 0.0;
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = j0 + u;
+                        hb[u] = j < D ? __ldcg(hq2) : 0.0;  // L2 hit: pass 1 just streamed it
+                        cb[u] = j < D ? __ldg(crow + j) : 1.0;
+                        hq2 += ld;
+                    }
 #pragma unroll
-                for (int i = 0; i < kPerLane; ++i) {
-                    const int j = lane + 32 * i;
-                    double v;  // actions * hmax in the input dtype
-                    if (sizeof(ActT) == 4)
-                        v = (double)fmul((float)a[i], (float)p.hmax);
-                    else
-                        v = dmul((double)a[i], p.hmax);
-                    if (!(c[i] > 0.0)) v = 0.0;  // np.where(closings > 0, actions, 0)
-                    if (j < D) {
-                        if (p.discrete_actions) {
-                            long long q = (long long)floor_div_f64(v, c[i]);  // actions // closings, astype(int)
-                            const long long inc = p.shares_increment;
-                            q = (q >= 0) ? floordiv_ll(q, inc) * inc : floordiv_ll(q + inc, inc) * inc;
-                            v = (double)q;
-                        } else {
-                            v = __ddiv_rn(v, c[i]);
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = j0 + u;
+                        if (j < D) {
+                            double v = cp_transaction<ActT>(p, myrow[j], cb[u], hb[u], liq);
+                            if (no_buys && v > 0.0) v = 0.0;
+                            const double hn = dadd(hb[u], v);
+                            if (valid) *hw = hn;
+                            *reinterpret_cast<float *>(myrow + j) = (float)hn;  // observation image, lane-private slot
                         }
-                        v = (v > -h[i]) ? v : -h[i];  // np.maximum(actions, -holdings)
-                        if (liq) v = -h[i];           // turbulence: clear out all positions
-                    } else {
-                        v = 0.0;
-                    }
-                    tx[i] = v;
-                    psell += (v < 0.0 ? -v : 0.0) * c[i];
-                    pbuy += (v > 0.0 ? v : 0.0) * c[i];
-                }
-                if (liq) flags |= FRL_FLAG_LIQUIDATE;
-                // np.sum(|actions|), np.dot(holdings, closings) (:319), np.dot(sells, closings), np.dot(buys,
-                // closings) (:334,:339): one fused reduction
-                warp_sum4(asum, part, psell, pbuy);
-                sum_trades += asum;
-                const double asset_value = part;
-                last_cash = begin_cash;
-                last_total = dadd(begin_cash, asset_value);
-                reward = cp_reward(p, last_total, last_cash, current_step);  // computed BEFORE trading (:326)
-                const double proceeds = psell;
-                double spend = pbuy;
-                double costs = dmul(proceeds, p.sell_cost_pct);
-                double coh = dadd(begin_cash, proceeds);
-                costs = dadd(costs, dmul(spend, p.buy_cost_pct));
-                bool terminate = false;
-                if (dadd(spend, costs) > coh) {
-                    flags |= FRL_FLAG_SHORTAGE;
-                    if (p.patient) {  // no buys until there is cash again; sell costs are dropped too (Q9)
-#pragma unroll
-                        for (int i = 0; i < kPerLane; ++i)
-                            if (tx[i] > 0.0) tx[i] = 0.0;
-                        spend = 0.0;
-                        costs = 0.0;
-                    } else {
-                        terminate = true;  // CASH SHORTAGE (:349-353): state unchanged, current reward, done
+                        hw += ld;
                     }
                 }
-                if (terminate) {
-                    flags |= FRL_FLAG_DONE;
-                    reset_now = auto_reset != 0;
-                } else {
-                    cash = dsub(dsub(coh, spend), costs);
-#pragma unroll
-                    for (int i = 0; i < kPerLane; ++i) h[i] = dadd(h[i], tx[i]);
-                    di += 1;
-                    if (p.use_turbulence) fresh = false;  // self.turbulence is refreshed only with a threshold
-                }
-            }
-            if (lane == 0) {
-                if (rewards) rewards[(size_t)k * N + n] = reward;
-                if (flags_out) flags_out[(size_t)k * N + n] = (uint8_t)flags;
-                st_r += reward;
-                st_r2 += reward * reward;
-                st_steps += 1.0;
-                if (flags & FRL_FLAG_DONE) {
-                    st_done += 1.0;
-                    st_epi += last_total;
-                }
-                if (flags & FRL_FLAG_LIQUIDATE) st_liq += 1.0;
-                if (flags & FRL_FLAG_SHORTAGE) st_short += 1.0;
-            }
-            if (reset_now) {  // DummyVecEnv.step_wait -> reset (:132-158), random_start=False
-                cash = p.initial_amount;
-#pragma unroll
-                for (int i = 0; i < kPerLane; ++i) h[i] = 0.0;
-                di = 0;
-                start = 0;
-                fresh = true;
-                sum_trades = 0.0;
-                last_cash = 0.0;
-                last_total = 0.0;
-            }
-            if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
-                float *orow = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * O : (size_t)0) + (size_t)n * O;
-                cp_write_obs_row(p, orow, cash, h, di, lane, tmpl, tmpl_di);
+                moved = true;
+                di += 1;
+                if (p.use_turbulence) fresh = false;  // self.turbulence is refreshed only with a threshold
             }
         }
-        // ---- store state ----
-#pragma unroll
-        for (int i = 0; i < kPerLane; ++i) {
-            const int j = lane + 32 * i;
-            if (j < D) p.hold[(size_t)n * D + j] = h[i];
+        if (valid) {
+            if (rewards) rewards[(size_t)k * N + n] = reward;
+            if (flags_out) flags_out[(size_t)k * N + n] = (uint8_t)flags;
+            st_r += reward;
+            st_r2 += reward * reward;
+            if (flags & FRL_FLAG_DONE) {
+                st_done += 1.0;
+                st_epi += last_total;
+            }
+            if (flags & FRL_FLAG_LIQUIDATE) st_liq += 1.0;
+            if (flags & FRL_FLAG_SHORTAGE) st_short += 1.0;
         }
-        if (lane == 0) {
-            p.cash[n] = cash;
-            p.date_index[n] = di;
-            p.start[n] = start;
-            p.fresh[n] = fresh ? 1 : 0;
-            p.last_cash[n] = last_cash;
-            p.last_total[n] = last_total;
-            p.sum_trades[n] = sum_trades;
-            st_asset += last_total;
+        if (reset_now) {  // DummyVecEnv.step_wait -> reset (:132-158), random_start=False
+            cash = p.initial_amount;
+            for (int j = 0; j < D; ++j) {
+                if (valid) hp[(size_t)j * ld] = 0.0;
+                *reinterpret_cast<float *>(myrow + j) = 0.0f;
+            }
+            moved = true;
+            di = 0;
+            start = 0;
+            fresh = true;
+            sum_trades = 0.0;
+            last_cash = 0.0;
+            last_total = 0.0;
+        }
+        if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
+            if (!moved) {  // terminal / terminated without reset: image of the unchanged holdings
+                for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = (float)hp[(size_t)j * ld];
+            }
+            cashf[lane] = (float)cash;
+            di_s[lane] = di;
+            __syncwarp();
+            float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
+            cp_write_obs_tile<ActT>(p, stage, P, cashf, di_s, o, env0, nvalid, lane);
         }
     }
-    if (stats && lane == 0) {
-        const double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, st_asset, st_liq, st_steps, st_short};
+    if (valid) {
+        p.cash[n] = cash;
+        p.date_index[n] = di;
+        p.start[n] = start;
+        p.fresh[n] = fresh ? 1 : 0;
+        p.last_cash[n] = last_cash;
+        p.last_total[n] = last_total;
+        p.sum_trades[n] = sum_trades;
+    }
+    if (stats) {
+        double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, valid ? last_total : 0.0, st_liq,
+                                 valid ? (double)n_steps : 0.0, st_short};
 #pragma unroll
-        for (int i = 0; i < FRL_N_STATS; ++i)
-            if (v[i] != 0.0) atomicAdd(stats + i, v[i]);
+        for (int w = 4; w >= 1; w >>= 1) {
+            const bool up = (lane & w) != 0;
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+                const double keep = up ? v[i + w] : v[i];
+                const double send = up ? v[i] : v[i + w];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+            }
+        }
+        double s = v[0];
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if (lane < 8 && s != 0.0) atomicAdd(stats + lane, s);
     }
 }
 
 __global__ void cashpenalty_reset_kernel(const frl_cashpenalty_params p, const uint8_t *__restrict__ mask,
                                          const int32_t *__restrict__ start_points)
 {
-    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= p.n_envs) return;
-    if (mask && !mask[w]) return;
-    for (int j = lane; j < p.stock_dim; j += 32) p.hold[(size_t)w * p.stock_dim + j] = 0.0;
-    if (lane == 0) {
-        const int sp = start_points ? start_points[w] : 0;
-        p.cash[w] = p.initial_amount;
-        p.date_index[w] = sp;
-        p.start[w] = sp;
-        p.fresh[w] = 1;
-        p.last_cash[w] = 0.0;
-        p.last_total[w] = 0.0;
-        p.sum_trades[w] = 0.0;
-    }
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.n_envs) return;
+    if (mask && !mask[n]) return;
+    for (int j = 0; j < p.stock_dim; ++j) p.hold[(size_t)j * p.env_stride + n] = 0.0;
+    const int sp = start_points ? start_points[n] : 0;
+    p.cash[n] = p.initial_amount;
+    p.date_index[n] = sp;
+    p.start[n] = sp;
+    p.fresh[n] = 1;
+    p.last_cash[n] = 0.0;
+    p.last_total[n] = 0.0;
+    p.sum_trades[n] = 0.0;
 }
 
-__global__ void cashpenalty_observe_kernel(const frl_cashpenalty_params p, float *__restrict__ obs)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) cashpenalty_observe_kernel(const frl_cashpenalty_params p, float *__restrict__ obs)
 {
-    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= p.n_envs) return;
-    double h[kPerLane];
-#pragma unroll
-    for (int i = 0; i < kPerLane; ++i) {
-        const int j = lane + 32 * i;
-        h[i] = j < p.stock_dim ? p.hold[(size_t)w * p.stock_dim + j] : 0.0;
-    }
-    float tmpl[kTmplChunks];
-    int tmpl_di = -1;
-    cp_write_obs_row(p, obs + (size_t)w * p.obs_dim, p.cash[w], h, p.date_index[w], lane, tmpl, tmpl_di);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = p.n_envs, D = p.stock_dim;
+    const int P = D | 1;
+    const size_t warp_bytes = (size_t)32 * P * sizeof(float) + 32 * sizeof(float) + 32 * sizeof(int);
+    unsigned char *base = smem_raw + warp * ((warp_bytes + 15) & ~(size_t)15);
+    float *stage = reinterpret_cast<float *>(base);
+    float *cashf = stage + (size_t)32 * P;
+    int *di_s = reinterpret_cast<int *>(cashf + 32);
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const long long n = lane < nvalid ? env0 + lane : (long long)N - 1;
+    for (int j = 0; j < D; ++j) stage[(size_t)lane * P + j] = (float)p.hold[(size_t)j * p.env_stride + n];
+    cashf[lane] = (float)p.cash[n];
+    di_s[lane] = p.date_index[n];
+    __syncwarp();
+    cp_write_obs_tile<float>(p, stage, P, cashf, di_s, obs, env0, nvalid, lane);
 }
 
 int32_t cp_validate(const frl_cashpenalty_params *p)
 {
     FRL_REQUIRE(p != nullptr, "cashpenalty: params is NULL");
     FRL_REQUIRE(p->n_envs >= 1, "cashpenalty: n_envs must be >= 1 (got %d)", p->n_envs);
-    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 32 * kPerLane, "cashpenalty: stock_dim must be in 1..128 (got %d)",
-                p->stock_dim);
+    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 128, "cashpenalty: stock_dim must be in 1..128 (got %d)", p->stock_dim);
     FRL_REQUIRE(p->n_cols >= 0 && p->n_days >= 1, "cashpenalty: bad n_cols/n_days (%d, %d)", p->n_cols, p->n_days);
     FRL_REQUIRE(p->obs_dim == 1 + p->stock_dim + p->stock_dim * p->n_cols, "cashpenalty: obs_dim %d != 1 + D + D*C = %d",
                 p->obs_dim, 1 + p->stock_dim + p->stock_dim * p->n_cols);
+    FRL_REQUIRE(p->env_stride >= p->n_envs, "cashpenalty: env_stride %d < n_envs %d", p->env_stride, p->n_envs);
     FRL_REQUIRE(!p->discrete_actions || p->shares_increment >= 1, "cashpenalty: shares_increment must be >= 1");
     FRL_REQUIRE(p->close && p->obs_tmpl && (!p->use_turbulence || p->turb), "cashpenalty: table pointer is NULL");
     FRL_REQUIRE(p->cash && p->hold && p->date_index && p->start && p->fresh && p->last_cash && p->last_total && p->sum_trades,
                 "cashpenalty: state pointer is NULL");
     return FRL_OK;
+}
+
+size_t cp_smem_bytes(int D, size_t elem, int warps)
+{
+    const int P = D | 1;
+    const size_t warp_bytes = (size_t)32 * P * elem + 32 * sizeof(float) + 32 * sizeof(int);
+    return warps * ((warp_bytes + 15) & ~(size_t)15);
+}
+
+template <typename ActT, int WARPS>
+int32_t cp_launch(const frl_cashpenalty_params &p, const void *actions, long long sstride, long long estride, int n_steps,
+                  double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
+{
+    const size_t smem = cp_smem_bytes(p.stock_dim, sizeof(ActT), WARPS);
+    auto kern = cashpenalty_rollout_kernel<ActT, WARPS>;
+    if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cashpenalty_rollout: cannot reserve %zu B of shared memory (%s)", smem, cudaGetErrorString(e));
+            return FRL_E_CUDA;
+        }
+    }
+    const long long tiles = ((long long)p.n_envs + 31) / 32;
+    const unsigned grid = (unsigned)((tiles + WARPS - 1) / WARPS);
+    kern<<<grid, WARPS * 32, smem, st>>>(p, (const ActT *)actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode,
+                                         auto_reset, stats);
+    return check_launch("cashpenalty_rollout");
 }
 
 }  // namespace
@@ -336,8 +465,10 @@ extern "C" int32_t frl_cashpenalty_observe(const frl_cashpenalty_params *p, floa
 {
     if (int32_t rc = cp_validate(p)) return rc;
     FRL_REQUIRE(obs != nullptr, "cashpenalty_observe: obs is NULL");
-    const long long threads = (long long)p->n_envs * 32;
-    cashpenalty_observe_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*p, obs);
+    constexpr int W = 2;
+    const long long tiles = ((long long)p->n_envs + 31) / 32;
+    const size_t smem = cp_smem_bytes(p->stock_dim, sizeof(float), W);
+    cashpenalty_observe_kernel<W><<<(unsigned)((tiles + W - 1) / W), W * 32, smem, (cudaStream_t)stream>>>(*p, obs);
     return check_launch("cashpenalty_observe");
 }
 
@@ -345,8 +476,7 @@ extern "C" int32_t frl_cashpenalty_reset(const frl_cashpenalty_params *p, const 
                                          float *obs, void *stream)
 {
     if (int32_t rc = cp_validate(p)) return rc;
-    const long long threads = (long long)p->n_envs * 32;
-    cashpenalty_reset_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*p, mask, start_points);
+    cashpenalty_reset_kernel<<<(p->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p, mask, start_points);
     if (int32_t rc = check_launch("cashpenalty_reset")) return rc;
     if (obs) return frl_cashpenalty_observe(p, obs, stream);
     return FRL_OK;
@@ -363,23 +493,12 @@ extern "C" int32_t frl_cashpenalty_rollout(const frl_cashpenalty_params *p, cons
     FRL_REQUIRE(act_env_stride >= p->stock_dim, "cashpenalty_rollout: act_env_stride %lld < stock_dim", (long long)act_env_stride);
     FRL_REQUIRE(obs_mode >= FRL_OBS_NONE && obs_mode <= FRL_OBS_ALL, "cashpenalty_rollout: bad obs_mode %d", obs_mode);
     FRL_REQUIRE(obs_mode == FRL_OBS_NONE || obs != nullptr, "cashpenalty_rollout: obs is NULL but obs_mode=%d", obs_mode);
-    constexpr int W = 8;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // persistent-style grid: a multiple of the SM count, warps stride over the env range
-    const long long need = ((long long)p->n_envs + W - 1) / W;
-    const unsigned grid = (unsigned)(need < (long long)sms * 8 ? need : (long long)sms * 8);
     cudaStream_t st = (cudaStream_t)stream;
     if (actions_f64)
-        cashpenalty_rollout_kernel<double, W><<<grid, W * 32, 0, st>>>(*p, (const double *)actions, act_step_stride,
-                                                                       act_env_stride, n_steps, rewards, flags, obs,
-                                                                       obs_mode, auto_reset, stats);
-    else
-        cashpenalty_rollout_kernel<float, W><<<grid, W * 32, 0, st>>>(*p, (const float *)actions, act_step_stride,
-                                                                      act_env_stride, n_steps, rewards, flags, obs,
-                                                                      obs_mode, auto_reset, stats);
-    return check_launch("cashpenalty_rollout");
+        return cp_launch<double, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags, obs, obs_mode,
+                                    auto_reset, stats, st);
+    return cp_launch<float, 4>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags, obs, obs_mode,
+                               auto_reset, stats, st);
 }
 
 extern "C" int32_t frl_cashpenalty_step(const frl_cashpenalty_params *p, const void *actions, int32_t actions_f64,

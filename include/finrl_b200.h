@@ -244,7 +244,7 @@ typedef struct frl_cashpenalty_params {
     int32_t shares_increment;
     int32_t use_turbulence; /* turbulence_threshold is not None */
     int32_t patient;
-    int32_t _pad0;
+    int32_t env_stride; /* leading dimension of `hold` (>= N) */
     double buy_cost_pct, sell_cost_pct;
     double hmax; /* currency per trade (scalar) */
     double turbulence_threshold;
@@ -254,9 +254,9 @@ typedef struct frl_cashpenalty_params {
     const double *close;   /* [T][D] closings per date */
     const double *turb;    /* [T] "turbulence" column (read only when use_turbulence) */
     const float *obs_tmpl; /* [T][O] float32: [0, 0 x D, get_date_vector(t) asset-major (:160-173)] */
-    /* ---- per-env state (env-major: one warp per env reads its rows coalesced) ---- */
+    /* ---- per-env state ---- */
     double *cash;        /* [N] cash_on_hand */
-    double *hold;        /* [N][D] holdings (fractional unless discrete_actions) */
+    double *hold;        /* [D][env_stride] holdings, stock-major (fractional unless discrete_actions) */
     int32_t *date_index; /* [N] */
     int32_t *start;      /* [N] starting_point */
     uint8_t *fresh;      /* [N] 1 while self.turbulence is still the 0 set by reset */

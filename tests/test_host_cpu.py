@@ -36,7 +36,7 @@ def test_abi_rejects_bad_arguments_without_a_gpu():
     rc = lib.frl_trading_step(C.byref(p), None, 0, None, None, None, 0, None, None)
     assert rc == -1 and b"stock_dim" in lib.frl_last_error()
     q = _cabi.CashPenaltyParams()
-    q.n_envs, q.stock_dim, q.n_cols, q.n_days, q.obs_dim = 1, 500, 5, 10, 3001
+    q.n_envs, q.stock_dim, q.n_cols, q.n_days, q.obs_dim, q.env_stride = 1, 500, 5, 10, 3001, 1
     assert lib.frl_cashpenalty_observe(C.byref(q), None, None) == -1
     assert lib.frl_trading_step(None, None, 0, None, None, None, 0, None, None) == -1
 
@@ -53,7 +53,7 @@ def test_struct_layouts_match_the_header():
         "frl_trading_params": (_cabi.TradingParams, ["n_envs", "hmax", "turbulence_threshold", "close", "cash", "episode", "asset_out"]),
         "frl_np_params": (_cabi.NpParams, ["gamma", "initial_capital", "obs_amount_floor", "price", "amount", "episode_return"]),
         "frl_portfolio_params": (_cabi.PortfolioParams, ["initial_amount", "ret", "reward"]),
-        "frl_cashpenalty_params": (_cabi.CashPenaltyParams, ["patient", "buy_cost_pct", "cash_penalty_proportion", "close", "sum_trades"]),
+        "frl_cashpenalty_params": (_cabi.CashPenaltyParams, ["patient", "env_stride", "buy_cost_pct", "cash_penalty_proportion", "close", "sum_trades"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "finrl_b200.h"', "int main(){"]
     for st, (_, fields) in checks.items():
