@@ -422,7 +422,12 @@ def run_ours(args, wl):
     h_flag = torch.empty(rshape, dtype=torch.uint8).pin_memory()
     d_act = torch.empty(shape, dtype=tdt, device=dev)
 
+    use_pipelined = hasattr(env, "step_host") and KR == 1 and not args.no_pipeline
+
     def e2e_step(i):
+        if use_pipelined:  # chunked H2D / kernel / D2H over three streams (BatchedStockTradingEnv.step_host)
+            env.step_host(h_act[i % POOL], h_obs, h_rew, h_flag, auto_reset=True, n_chunks=args.e2e_chunks)
+            return
         d_act.copy_(h_act[i % POOL], non_blocking=True)
         if KR == 1:
             obs, rew, _, fl = env.step(d_act, auto_reset=True, want_obs=True, want_done=False)
@@ -477,7 +482,9 @@ def run_ours(args, wl):
                 "algorithmic_bytes_per_env_step": wl.bytes_per_env_step,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "Batched*Env.step/rollout with pinned host actions in; obs + reward + flags copied back to host"},
+                    "api": ("BatchedStockTradingEnv.step_host: pinned host actions in, obs + reward + flags back to pinned host "
+                            f"memory, pipelined in {args.e2e_chunks} env slices over 3 streams") if use_pipelined else
+                           "Batched*Env.step/rollout with pinned host actions in; obs + reward + flags copied back to host"},
             "gpu_launches": launches,
             "clocks": clocks,
             "stats": dict(zip(("reward_sum", "reward_sqsum", "done_count", "episode_asset_sum", "asset_sum", "liq_count",
@@ -503,6 +510,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="e2e through plain step() + copies instead of step_host()")
+    ap.add_argument("--e2e-chunks", type=int, default=4)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]()
     args.envs = args.envs or wl.default_envs

@@ -262,6 +262,68 @@ class BatchedStockTradingEnv:
         return (obs if mode else None), rewards, flags
 
     # ------------------------------------------------------------------------------------------
+    def _chunk_params(self, start: int, count: int):
+        """A params struct addressing envs [start, start+count): same tables, state pointers offset,
+        stock-major arrays keep the full leading dimension (that is what env_stride is for)."""
+        q = _cabi.TradingParams()
+        C.memmove(C.byref(q), C.byref(self._p), C.sizeof(q))
+        q.n_envs = count
+        q.cash = self.cash.data_ptr() + 8 * start
+        q.hold = self.hold.data_ptr() + 4 * start
+        q.day = self.day.data_ptr() + 4 * start
+        q.sday = self.sday.data_ptr() + 4 * start
+        q.cost = self.cost.data_ptr() + 8 * start
+        q.trades = self.trades.data_ptr() + 4 * start
+        q.reward = self.reward.data_ptr() + 8 * start
+        q.episode = self.episode.data_ptr() + 4 * start
+        q.asset_out = (self.asset.data_ptr() + 8 * start) if self.asset is not None else None
+        return q
+
+    def step_host(self, actions_host, obs_host, reward_host, flags_host, auto_reset: bool = True, n_chunks: int = 8):
+        """Host-resident agents: one ``step`` with pinned HOST buffers in and out, software-pipelined.
+
+        The env range is cut into ``n_chunks`` slices; slice c's action upload (H2D), its kernel and its
+        observation / reward / flag download (D2H) run on one of three streams, so the PCIe link stays busy
+        in both directions while kernels run.  Returns after everything has landed in the host buffers."""
+        torch = self._torch
+        N, D, O = self.n_envs, self.stock_dim, self.state_space
+        if not (actions_host.is_pinned() and obs_host.is_pinned() and reward_host.is_pinned() and flags_host.is_pinned()):
+            raise ValueError("step_host needs pinned host tensors")
+        if actions_host.shape != (N, D) or obs_host.shape != (N, O) or actions_host.dtype not in (torch.float32, torch.float64):
+            raise ValueError("step_host: bad buffer shapes")
+        if getattr(self, "_host_streams", None) is None:
+            self._host_streams = [torch.cuda.Stream(self.device) for _ in range(3)]
+            self._host_act = torch.empty((N, D), dtype=actions_host.dtype, device=self.device)
+        if self._host_act.dtype != actions_host.dtype:
+            self._host_act = torch.empty((N, D), dtype=actions_host.dtype, device=self.device)
+        per = -(-N // n_chunks)
+        per = -(-per // 32) * 32  # keep slices warp-tile aligned
+        lib = _cabi.lib()
+        f64 = int(actions_host.dtype == torch.float64)
+        cur = torch.cuda.current_stream(self.device)
+        for st in self._host_streams:
+            st.wait_stream(cur)
+        rc = 0
+        with torch.cuda.device(self.device):
+            for c, start in enumerate(range(0, N, per)):
+                cnt = min(per, N - start)
+                st = self._host_streams[c % len(self._host_streams)]
+                with torch.cuda.stream(st):
+                    d_act = self._host_act[start : start + cnt]
+                    d_act.copy_(actions_host[start : start + cnt], non_blocking=True)
+                    q = self._chunk_params(start, cnt)
+                    rc |= lib.frl_trading_step(C.byref(q), _cabi.ptr(d_act), f64, None, C.c_void_p(self._flags.data_ptr() + start),
+                                               C.c_void_p(self._obs.data_ptr() + 4 * O * start), int(auto_reset), None,
+                                               C.c_void_p(st.cuda_stream))
+                    obs_host[start : start + cnt].copy_(self._obs[start : start + cnt], non_blocking=True)
+                    reward_host[start : start + cnt].copy_(self.reward[start : start + cnt], non_blocking=True)
+                    flags_host[start : start + cnt].copy_(self._flags[start : start + cnt], non_blocking=True)
+                self.launches += 1
+        _cabi.check(rc, "frl_trading_step (step_host)")
+        for st in self._host_streams:
+            cur.wait_stream(st)
+        cur.synchronize()
+
     def get_state(self):
         """Per-env state in the natural [N, ...] layout (host-friendly; holdings transposed)."""
         return {

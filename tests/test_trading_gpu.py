@@ -242,3 +242,23 @@ def test_output_buffers_have_no_out_of_bounds_writes():
         for big, val in ((big_obs, -7.25), (big_rew, -7.25), (big_fl, 99)):
             assert bool((big[:pad] == val).all()) and bool((big[-pad:] == val).all())
         assert not bool((obs == -7.25).any()) and not bool((big_fl[pad:-pad] == 99).any())
+
+
+def test_step_host_pipelined_equals_plain_step():
+    """The pipelined host-buffer step (env slices over 3 streams) must equal one plain step."""
+    from finrl_b200 import synthetic as syn
+
+    N, T, D = 5000, 30, 30
+    env, o = _make(N, T=T)
+    O = env.state_space
+    h_act = torch.empty((N, D), dtype=torch.float32).pin_memory()
+    h_obs = torch.empty((N, O), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(N, dtype=torch.float64).pin_memory()
+    h_fl = torch.empty(N, dtype=torch.uint8).pin_memory()
+    acts = syn.make_actions((T + 4, N, D), seed=12)
+    for s in range(acts.shape[0]):
+        h_act.copy_(torch.from_numpy(acts[s]))
+        env.step_host(h_act, h_obs, h_rew, h_fl, auto_reset=True, n_chunks=7)
+        oobs, orew, ofl = o.step(acts[s], auto_reset=True)
+        assert np.array_equal(h_obs.numpy(), oobs) and np.array_equal(h_rew.numpy(), orew) and np.array_equal(h_fl.numpy(), ofl)
+    _compare(env, o)
