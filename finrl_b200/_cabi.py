@@ -206,6 +206,10 @@ SIGNATURES = {
         [C.POINTER(CashPenaltyParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
          C.c_void_p],
     ),
+    "frl_rolling_cov": (
+        C.c_int32,
+        [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
 }
 
 _lib = None

@@ -281,6 +281,20 @@ FRL_API int32_t frl_cashpenalty_step(const frl_cashpenalty_params *p, const void
                                      double *rewards, uint8_t *flags, float *obs, int32_t auto_reset, double *stats,
                                      void *stream);
 
+/* =========================================================================================
+ * Table precompute: the pandas loops that feed the envs
+ * ========================================================================================= */
+/* Rolling sample covariance (ddof = 1) and mean of daily returns.
+ *   ret      [T][D] f64 daily returns (pct_change of close; row 0 is NaN and never read)
+ *   window w (0 <= w < n_out) covers rows [first_row + w, first_row + w + n_rows)
+ *   cov_out  [n_out][D][D] f64, mean_out [n_out][D] f64 (nullable)
+ * With first_row = 1, n_rows = lookback this is the tutorial's `cov_list`
+ * (tutorials/2-Advance/FinRL_PortfolioAllocation_Explainable_DRL.py:157-174: 253 closes -> 252 returns
+ * -> .cov()); with first_row = 1 .. and n_rows = 252 shifted one day back it is the history block of
+ * FeatureEngineer.calculate_turbulence (finrl/meta/preprocessor/preprocessors.py:215-267). */
+FRL_API int32_t frl_rolling_cov(const double *ret, int32_t n_days, int32_t stock_dim, int32_t first_row,
+                                int32_t n_rows, int32_t n_out, double *cov_out, double *mean_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
