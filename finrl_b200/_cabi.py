@@ -141,6 +141,7 @@ class CashPenaltyParams(C.Structure):
         ("obs_tmpl", C.c_void_p),
         ("cash", C.c_void_p),
         ("hold", C.c_void_p),
+        ("hold_alt", C.c_void_p),
         ("date_index", C.c_void_p),
         ("start", C.c_void_p),
         ("fresh", C.c_void_p),

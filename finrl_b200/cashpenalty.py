@@ -110,7 +110,8 @@ class BatchedStockTradingEnvCashpenalty:
         self.daily_information_cols = list(daily_information_cols)
         dev = self.device
         self.cash = torch.empty(N, dtype=torch.float64, device=dev)
-        self.hold = torch.empty((D, N), dtype=torch.float64, device=dev)  # stock-major
+        self.hold = torch.empty((D, N), dtype=torch.float64, device=dev)      # stock-major, buffer 0
+        self.hold_alt = torch.zeros((D, N), dtype=torch.float64, device=dev)  # buffer 1 (ping-pong, see the kernel)
         self.date_index = torch.empty(N, dtype=torch.int32, device=dev)
         self.starting_point = torch.empty(N, dtype=torch.int32, device=dev)
         self.fresh = torch.empty(N, dtype=torch.uint8, device=dev)
@@ -130,6 +131,7 @@ class BatchedStockTradingEnvCashpenalty:
         p.initial_amount, p.cash_penalty_proportion = float(initial_amount), float(cash_penalty_proportion)
         p.close, p.turb, p.obs_tmpl = tables.close.data_ptr(), tables.turb.data_ptr(), tables.obs_tmpl.data_ptr()
         p.cash, p.hold, p.date_index, p.start = self.cash.data_ptr(), self.hold.data_ptr(), self.date_index.data_ptr(), self.starting_point.data_ptr()
+        p.hold_alt = self.hold_alt.data_ptr()
         p.fresh, p.last_cash, p.last_total, p.sum_trades = self.fresh.data_ptr(), self.last_cash.data_ptr(), self.last_total.data_ptr(), self.sum_trades.data_ptr()
         self._p = p
         self.launches = 0
@@ -141,8 +143,9 @@ class BatchedStockTradingEnvCashpenalty:
 
     @property
     def holdings(self):
-        """Holdings in the natural [N, D] layout (a transposed view of the stock-major device array)."""
-        return self.hold.t()
+        """Holdings in the natural [N, D] layout: per env the current one of the two stock-major buffers."""
+        use_alt = (self.fresh & 2).bool()
+        return self._torch.where(use_alt[None, :], self.hold_alt, self.hold).t()
 
     def _as_actions(self, actions, ndim):
         torch = self._torch

@@ -3,13 +3,17 @@
 // Mapping: ONE THREAD PER ENV, one warp per 32-env tile (the layout of trading.cu).  A first version ran
 // one warp per env (lanes = assets, shuffle-reduced dot products): every scalar decision was replicated
 // in 32 lanes and it issued ~650-800 warp-instructions per env-step (43-47 % of the HBM roofline).  Per
-// thread the same work is two streaming passes over the D assets:
-//   pass 1  read holding (stock-major, coalesced), closing price (warp-uniform, L1), staged action;
-//           form the transaction and accumulate np.dot(holdings, closings), proceeds, spend, sum|a|
-//   decide  cash shortage -> terminate / patient (scalar, per lane)
-//   pass 2  re-form the transaction (same ops => same bits), update the holding, store it, and drop its
-//           float32 image into the lane's own staging row, which the observation writer then reads
-//           row-wise — the action staging buffer doubles as the transposition buffer.
+// thread the same work is ONE streaming pass over the D assets in the common case:
+//   pass    read holding (stock-major, coalesced), closing price (warp-uniform, L1), staged action; form
+//           the transaction; accumulate np.dot(holdings, closings), proceeds, spend, sum|a|; write the
+//           TENTATIVE new holding into the env's other holdings buffer (ping-pong) and its float32 image
+//           into the lane's own staging row, which the observation writer later reads row-wise — the
+//           action staging buffer doubles as the transposition buffer.
+//   decide  (scalar, per lane) normal: flip the env's current-buffer bit.  CASH SHORTAGE + terminate: do
+//           not flip — the state is unchanged by construction.  CASH SHORTAGE + patient: a cheap fix-up
+//           pass undoes the buys (new > old => keep old), then flip.
+// Holdings therefore live in two stock-major buffers and bit 1 of the per-env `fresh` byte says which one
+// is current; reads + writes per step are the same 2 x 8D bytes as an in-place update.
 // np.dot's order is BLAS-specific (tolerance 1e-9 in the tests); the sums here are sequential in asset
 // order, which happens to be the CPU oracle's order as well.
 #include "common.cuh"
@@ -173,8 +177,9 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
 
     double cash = p.cash[n], last_cash = p.last_cash[n], last_total = p.last_total[n], sum_trades = p.sum_trades[n];
     int di = p.date_index[n], start = p.start[n];
-    bool fresh = p.fresh[n] != 0;
-    double *hp = p.hold + n;  // hold[j][n] at hp[j * ld]
+    const int bits0 = p.fresh[n];
+    bool fresh = (bits0 & 1) != 0;
+    bool cur = (bits0 & 2) != 0;  // which holdings buffer is current: hold (0) or hold_alt (1)
     ActT *myrow = stage + (size_t)lane * P;
     double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_liq = 0.0, st_short = 0.0;
 
@@ -226,9 +231,10 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
             const double turbulence = fresh ? 0.0 : __ldg(p.turb + di);
             const bool liq = p.use_turbulence && turbulence >= p.turbulence_threshold;
             if (liq) flags |= FRL_FLAG_LIQUIDATE;
-            // ---- pass 1: np.sum(|actions|), np.dot(holdings, closings), proceeds, spend ----
+            // ---- the pass: np.sum(|actions|), np.dot(holdings, closings), proceeds, spend, tentative holdings ----
             double asum = 0.0, asset_value = 0.0, proceeds = 0.0, spend = 0.0;
-            const double *hq = hp;
+            const double *hq = (cur ? p.hold_alt : p.hold) + n;  // hold[j][n] at hq[j * ld]
+            double *hw = (cur ? p.hold : p.hold_alt) + n;
             for (int j0 = 0; j0 < D; j0 += 8) {
                 // 8 independent holding loads in flight per thread (the holdings stream is the DRAM-latency
                 // critical path of this pass)
@@ -250,7 +256,11 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
                         asset_value = dadd(asset_value, dmul(hb[u], cb[u]));
                         proceeds = dadd(proceeds, dmul(v < 0.0 ? -v : 0.0, cb[u]));
                         spend = dadd(spend, dmul(v > 0.0 ? v : 0.0, cb[u]));
+                        const double hn = dadd(hb[u], v);  // holdings_updated = holdings + transactions (:361)
+                        if (valid) *hw = hn;
+                        *reinterpret_cast<float *>(myrow + j) = (float)hn;  // observation image, lane-private slot
                     }
+                    hw += ld;
                 }
             }
             sum_trades += asum;  // (:302), logging only
@@ -276,32 +286,21 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
                 flags |= FRL_FLAG_DONE;
                 reset_now = auto_reset != 0;
             } else {
-                // ---- pass 2: apply the transactions (holdings_updated = holdings + transactions) ----
                 cash = dsub(dsub(coh, spend), costs);
-                double *hw = hp;
-                const double *hq2 = hp;
-                for (int j0 = 0; j0 < D; j0 += 8) {
-                    double hb[8], cb[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int j = j0 + u;
-                        hb[u] = j < D ? __ldcg(hq2) : 0.0;  // L2 hit: pass 1 just streamed it
-                        cb[u] = j < D ? __ldg(crow + j) : 1.0;
-                        hq2 += ld;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int j = j0 + u;
-                        if (j < D) {
-                            double v = cp_transaction<ActT>(p, myrow[j], cb[u], hb[u], liq);
-                            if (no_buys && v > 0.0) v = 0.0;
-                            const double hn = dadd(hb[u], v);
-                            if (valid) *hw = hn;
-                            *reinterpret_cast<float *>(myrow + j) = (float)hn;  // observation image, lane-private slot
+                if (no_buys) {
+                    // patient: transactions = where(transactions > 0, 0, transactions) (:346) — undo the buys
+                    // of the tentative update (a buy is exactly a slot whose new holding exceeds the old one)
+                    const double *ho = (cur ? p.hold_alt : p.hold) + n;
+                    double *hn_p = (cur ? p.hold : p.hold_alt) + n;
+                    for (int j = 0; j < D; ++j) {
+                        const double h = __ldcg(ho + (size_t)j * ld), hn = __ldcg(hn_p + (size_t)j * ld);
+                        if (hn > h) {
+                            if (valid) hn_p[(size_t)j * ld] = h;
+                            *reinterpret_cast<float *>(myrow + j) = (float)h;
                         }
-                        hw += ld;
                     }
                 }
+                cur = !cur;  // the tentative buffer becomes the state
                 moved = true;
                 di += 1;
                 if (p.use_turbulence) fresh = false;  // self.turbulence is refreshed only with a threshold
@@ -321,8 +320,9 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
         }
         if (reset_now) {  // DummyVecEnv.step_wait -> reset (:132-158), random_start=False
             cash = p.initial_amount;
+            double *hz = (cur ? p.hold_alt : p.hold) + n;
             for (int j = 0; j < D; ++j) {
-                if (valid) hp[(size_t)j * ld] = 0.0;
+                if (valid) hz[(size_t)j * ld] = 0.0;
                 *reinterpret_cast<float *>(myrow + j) = 0.0f;
             }
             moved = true;
@@ -335,7 +335,8 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
         }
         if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
             if (!moved) {  // terminal / terminated without reset: image of the unchanged holdings
-                for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = (float)hp[(size_t)j * ld];
+                const double *hc = (cur ? p.hold_alt : p.hold) + n;
+                for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = (float)__ldcg(hc + (size_t)j * ld);
             }
             cashf[lane] = (float)cash;
             di_s[lane] = di;
@@ -348,7 +349,7 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
         p.cash[n] = cash;
         p.date_index[n] = di;
         p.start[n] = start;
-        p.fresh[n] = fresh ? 1 : 0;
+        p.fresh[n] = (uint8_t)((fresh ? 1 : 0) | (cur ? 2 : 0));
         p.last_cash[n] = last_cash;
         p.last_total[n] = last_total;
         p.sum_trades[n] = sum_trades;
@@ -379,7 +380,7 @@ __global__ void cashpenalty_reset_kernel(const frl_cashpenalty_params p, const u
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= p.n_envs) return;
     if (mask && !mask[n]) return;
-    for (int j = 0; j < p.stock_dim; ++j) p.hold[(size_t)j * p.env_stride + n] = 0.0;
+    for (int j = 0; j < p.stock_dim; ++j) p.hold[(size_t)j * p.env_stride + n] = 0.0;  // buffer 0 becomes current
     const int sp = start_points ? start_points[n] : 0;
     p.cash[n] = p.initial_amount;
     p.date_index[n] = sp;
@@ -406,7 +407,8 @@ __global__ void __launch_bounds__(WARPS * 32) cashpenalty_observe_kernel(const f
     if (env0 >= N) return;
     const int nvalid = (int)min((long long)32, (long long)N - env0);
     const long long n = lane < nvalid ? env0 + lane : (long long)N - 1;
-    for (int j = 0; j < D; ++j) stage[(size_t)lane * P + j] = (float)p.hold[(size_t)j * p.env_stride + n];
+    const double *hc = ((p.fresh[n] & 2) ? p.hold_alt : p.hold) + n;
+    for (int j = 0; j < D; ++j) stage[(size_t)lane * P + j] = (float)hc[(size_t)j * p.env_stride];
     cashf[lane] = (float)p.cash[n];
     di_s[lane] = p.date_index[n];
     __syncwarp();
@@ -424,7 +426,8 @@ int32_t cp_validate(const frl_cashpenalty_params *p)
     FRL_REQUIRE(p->env_stride >= p->n_envs, "cashpenalty: env_stride %d < n_envs %d", p->env_stride, p->n_envs);
     FRL_REQUIRE(!p->discrete_actions || p->shares_increment >= 1, "cashpenalty: shares_increment must be >= 1");
     FRL_REQUIRE(p->close && p->obs_tmpl && (!p->use_turbulence || p->turb), "cashpenalty: table pointer is NULL");
-    FRL_REQUIRE(p->cash && p->hold && p->date_index && p->start && p->fresh && p->last_cash && p->last_total && p->sum_trades,
+    FRL_REQUIRE(p->cash && p->hold && p->hold_alt && p->date_index && p->start && p->fresh && p->last_cash && p->last_total &&
+                    p->sum_trades,
                 "cashpenalty: state pointer is NULL");
     return FRL_OK;
 }

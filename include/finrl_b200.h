@@ -257,9 +257,12 @@ typedef struct frl_cashpenalty_params {
     /* ---- per-env state ---- */
     double *cash;        /* [N] cash_on_hand */
     double *hold;        /* [D][env_stride] holdings, stock-major (fractional unless discrete_actions) */
+    double *hold_alt;    /* [D][env_stride] second holdings buffer: a step writes the new holdings into the
+                            buffer that is NOT current and flips the env's bit, so a CASH SHORTAGE termination
+                            leaves the state untouched without a second pass */
     int32_t *date_index; /* [N] */
     int32_t *start;      /* [N] starting_point */
-    uint8_t *fresh;      /* [N] 1 while self.turbulence is still the 0 set by reset */
+    uint8_t *fresh;      /* [N] bit 0: self.turbulence is still the 0 set by reset; bit 1: hold_alt is current */
     double *last_cash;   /* [N] account_information["cash"][-1] */
     double *last_total;  /* [N] account_information["total_assets"][-1] */
     double *sum_trades;  /* [N] */
