@@ -277,6 +277,9 @@ def main():
         # D=30, hmax=3: almost everything ties -> stresses the argsort tie rule; cash-starved
         gen_trading("trading_d30_ties", T=60, D=30, K=1, n_steps=70, seed=7, threshold=None, act_dtype=np.float32, hmax=3,
                     initial_amount=3_000)
+        # single-stock branch of the reference (len(df.tic.unique()) == 1, :415-422, :441-450, :469-476)
+        gen_trading("trading_d1_single", T=30, D=1, K=2, n_steps=70, seed=10, threshold=60, act_dtype=np.float32, hmax=50,
+                    initial_amount=3_000)
         # actions outside [-1,1] (the reference does not clip) and a high cost
         gen_trading("trading_d8_wide", T=30, D=8, K=2, n_steps=40, seed=9, threshold=50, act_dtype=np.float64, hmax=100,
                     initial_amount=100_000, cost=0.01, act_scale=3.0)
