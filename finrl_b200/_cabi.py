@@ -151,6 +151,34 @@ class CashPenaltyParams(C.Structure):
     ]
 
 
+class CryptoParams(C.Structure):
+    """frl_crypto_params (include/finrl_b200.h)."""
+
+    _fields_ = [
+        ("n_envs", C.c_int32),
+        ("stock_dim", C.c_int32),
+        ("tech_dim", C.c_int32),
+        ("n_days", C.c_int32),
+        ("lookback", C.c_int32),
+        ("obs_dim", C.c_int32),
+        ("env_stride", C.c_int32),
+        ("_pad0", C.c_int32),
+        ("initial_capital", C.c_double),
+        ("buy_cost_pct", C.c_double),
+        ("sell_cost_pct", C.c_double),
+        ("gamma", C.c_double),
+        ("price", C.c_void_p),
+        ("act_norm", C.c_void_p),
+        ("obs_tmpl", C.c_void_p),
+        ("cash", C.c_void_p),
+        ("stocks", C.c_void_p),
+        ("time", C.c_void_p),
+        ("total", C.c_void_p),
+        ("gamma_return", C.c_void_p),
+        ("episode_return", C.c_void_p),
+    ]
+
+
 KIND_PY, KIND_F32, KIND_F64 = 0, 1, 2
 NP_REWARD_KIND_SHIFT = 4
 
@@ -205,6 +233,18 @@ SIGNATURES = {
     "frl_cashpenalty_step": (
         C.c_int32,
         [C.POINTER(CashPenaltyParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+         C.c_void_p],
+    ),
+    "frl_crypto_reset": (C.c_int32, [C.POINTER(CryptoParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "frl_crypto_observe": (C.c_int32, [C.POINTER(CryptoParams), C.c_void_p, C.c_void_p]),
+    "frl_crypto_rollout": (
+        C.c_int32,
+        [C.POINTER(CryptoParams), C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
+    ),
+    "frl_crypto_step": (
+        C.c_int32,
+        [C.POINTER(CryptoParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
          C.c_void_p],
     ),
     "frl_rolling_cov": (

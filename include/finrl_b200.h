@@ -285,6 +285,42 @@ FRL_API int32_t frl_cashpenalty_step(const frl_cashpenalty_params *p, const void
                                      void *stream);
 
 /* =========================================================================================
+ * Sibling  CryptoEnv — finrl/meta/env_cryptocurrency_trading/env_multiple_crypto.py
+ * ========================================================================================= */
+typedef struct frl_crypto_params {
+    int32_t n_envs;     /* N */
+    int32_t stock_dim;  /* D = crypto_num, 1..32 */
+    int32_t tech_dim;   /* columns of tech_array */
+    int32_t n_days;     /* T; max_step = T - lookback - 1 */
+    int32_t lookback;
+    int32_t obs_dim;    /* O = 1 + D + tech_dim * lookback (what get_state really returns, :93-99) */
+    int32_t env_stride; /* leading dimension of stocks (>= N) */
+    int32_t _pad0;
+    double initial_capital, buy_cost_pct, sell_cost_pct, gamma;
+    /* ---- tables ---- */
+    const double *price;    /* [T][32] price_array (float64), rows zero-padded */
+    const double *act_norm; /* [32] action_norm_vector (:103-111) */
+    const float *obs_tmpl;  /* [T][O] get_state row of time t with the cash / stocks slots zeroed */
+    /* ---- per-env state ---- */
+    double *cash;           /* [N] */
+    float *stocks;          /* [D][env_stride] fractional positions (float32 like the reference) */
+    int32_t *time;          /* [N] */
+    double *total;          /* [N] total_asset */
+    double *gamma_return;   /* [N] (not cleared by reset, like the reference) */
+    double *episode_return; /* [N] written when done */
+} frl_crypto_params;
+
+FRL_API int32_t frl_crypto_reset(const frl_crypto_params *p, const uint8_t *mask, float *obs, void *stream);
+FRL_API int32_t frl_crypto_observe(const frl_crypto_params *p, float *obs, void *stream);
+/* n_steps fused CryptoEnv.step (:59-91); conventions as frl_trading_rollout (auto_reset = reset after done). */
+FRL_API int32_t frl_crypto_rollout(const frl_crypto_params *p, const void *actions, int32_t actions_f64,
+                                   int64_t act_step_stride, int64_t act_env_stride, int32_t n_steps, double *rewards,
+                                   uint8_t *flags, float *obs, int32_t obs_mode, int32_t auto_reset, double *stats,
+                                   void *stream);
+FRL_API int32_t frl_crypto_step(const frl_crypto_params *p, const void *actions, int32_t actions_f64, double *rewards,
+                                uint8_t *flags, float *obs, int32_t auto_reset, double *stats, void *stream);
+
+/* =========================================================================================
  * Table precompute: the pandas loops that feed the envs
  * ========================================================================================= */
 /* Rolling sample covariance (ddof = 1) and mean of daily returns.

@@ -774,3 +774,119 @@ void ora_cp_step(const ora_cp_cfg *c, ora_cp_state *s, const void *actions, int 
 #pragma omp parallel for schedule(static)
     for (int n = 0; n < c->n_envs; ++n) cp_step_one(c, s, n, actions, actions_f64, reward_out, flags_out, auto_reset);
 }
+
+/* ======================================================================================= */
+/* sibling: CryptoEnv — finrl/meta/env_cryptocurrency_trading/env_multiple_crypto.py         */
+/* ======================================================================================= */
+/* Fractional positions in a float32 `stocks` array against float64 prices and a float64 cash:
+ * every product with the price promotes to float64; min() keeps the dtype of whichever side wins. */
+
+static double crypto_total(const ora_crypto_cfg *c, const float *stocks, const double *price, double cash)
+{
+    double prod[MAXD];
+    for (int i = 0; i < c->stock_dim; ++i) prod[i] = (double)stocks[i] * price[i];
+    return cash + ora_pairwise_sum_f64(prod, c->stock_dim); /* cash + (stocks * price).sum() */
+}
+
+void ora_crypto_reset(const ora_crypto_cfg *c, ora_crypto_state *s, const uint8_t *mask)
+{
+    for (int n = 0; n < c->n_envs; ++n) { /* reset (:47-57); gamma_return is NOT reset by the reference */
+        if (mask && !mask[n]) continue;
+        s->time[n] = c->lookback - 1;
+        s->cash[n] = c->initial_capital;
+        for (int i = 0; i < c->stock_dim; ++i) s->stocks[(size_t)n * c->stock_dim + i] = 0.0f;
+        s->total[n] = crypto_total(c, s->stocks + (size_t)n * c->stock_dim, c->price + (size_t)s->time[n] * c->stock_dim,
+                                   s->cash[n]);
+    }
+}
+
+static void crypto_obs_one(const ora_crypto_cfg *c, const ora_crypto_state *s, int n, float *obs)
+{
+    /* get_state (:93-99): hstack((cash*2**-18, stocks*2**-3)) is float64, each tech row * 2**-15 is appended
+     * and the whole vector is cast to float32 */
+    const int D = c->stock_dim, TD = c->tech_dim;
+    obs[0] = (float)(s->cash[n] * 3.814697265625e-06);
+    for (int i = 0; i < D; ++i) obs[1 + i] = (float)((double)(s->stocks[(size_t)n * D + i] * 0.125f));
+    for (int l = 0; l < c->lookback; ++l) {
+        const double *row = c->tech + (size_t)(s->time[n] - l) * TD;
+        for (int i = 0; i < TD; ++i) obs[1 + D + l * TD + i] = (float)(row[i] * 3.0517578125e-05);
+    }
+}
+
+void ora_crypto_obs(const ora_crypto_cfg *c, const ora_crypto_state *s, float *obs)
+{
+    const int O = 1 + c->stock_dim + c->tech_dim * c->lookback;
+    for (int n = 0; n < c->n_envs; ++n) crypto_obs_one(c, s, n, obs + (size_t)n * O);
+}
+
+static void crypto_step_one(const ora_crypto_cfg *c, ora_crypto_state *s, int n, const void *actions, int actions_f64,
+                            double *reward_out, uint8_t *flags_out, float *obs)
+{
+    const int D = c->stock_dim, O = 1 + D + c->tech_dim * c->lookback;
+    float *stocks = s->stocks + (size_t)n * D;
+    const int max_step = c->n_days - c->lookback - 1;
+    if (s->time[n] >= c->n_days - 1) { /* past the data (the reference would raise IndexError): inert */
+        if (reward_out) reward_out[n] = 0.0;
+        if (flags_out) flags_out[n] = ORA_FLAG_DONE;
+        if (obs) crypto_obs_one(c, s, n, obs + (size_t)n * O);
+        return;
+    }
+    s->time[n] += 1;
+    const double *price = c->price + (size_t)s->time[n] * D;
+    /* actions[i] = actions[i] * norm_vector_i, in place, in the action dtype (:62-64) */
+    double a[MAXD];
+    for (int i = 0; i < D; ++i) {
+        if (actions_f64)
+            a[i] = ((const double *)actions)[(size_t)n * D + i] * c->act_norm[i];
+        else
+            a[i] = (double)(((const float *)actions)[(size_t)n * D + i] * (float)c->act_norm[i]);
+    }
+    double cash = s->cash[n];
+    for (int i = 0; i < D; ++i) { /* sells (:66-70) */
+        if (a[i] < 0 && price[i] > 0) {
+            double nsh; /* min(stocks, -action) -> -action iff it is smaller */
+            if (-a[i] < (double)stocks[i]) {
+                nsh = -a[i]; /* dtype of the action: f32 - f32 stays f32, f32 - f64 is f64 then cast back */
+                stocks[i] = actions_f64 ? (float)((double)stocks[i] - nsh) : (float)(stocks[i] - (float)nsh);
+            } else {
+                nsh = (double)stocks[i];
+                stocks[i] = stocks[i] - stocks[i];
+            }
+            cash += price[i] * nsh * (1 - c->sell_cost_pct);
+        }
+    }
+    for (int i = 0; i < D; ++i) { /* buys (:72-76) */
+        if (a[i] > 0 && price[i] > 0) {
+            const double avail = ora_floor_divide_f64(cash, price[i]);
+            double nsh;
+            if (a[i] < avail) { /* min(avail, action) -> the action */
+                nsh = a[i];
+                stocks[i] = actions_f64 ? (float)((double)stocks[i] + nsh) : (float)(stocks[i] + (float)nsh);
+            } else {
+                nsh = avail;
+                stocks[i] = (float)((double)stocks[i] + nsh);
+            }
+            cash -= price[i] * nsh * (1 + c->buy_cost_pct);
+        }
+    }
+    s->cash[n] = cash;
+    const int done = s->time[n] == max_step;
+    if (obs) crypto_obs_one(c, s, n, obs + (size_t)n * O);
+    const double next_total = crypto_total(c, stocks, price, cash);
+    double reward = (next_total - s->total[n]) * 1.52587890625e-05; /* 2 ** -16 */
+    s->total[n] = next_total;
+    s->gamma_return[n] = s->gamma_return[n] * c->gamma + reward;
+    if (done) {
+        reward = s->gamma_return[n];
+        s->episode_return[n] = s->total[n] / c->initial_capital;
+    }
+    if (reward_out) reward_out[n] = reward;
+    if (flags_out) flags_out[n] = done ? ORA_FLAG_DONE : 0;
+}
+
+void ora_crypto_step(const ora_crypto_cfg *c, ora_crypto_state *s, const void *actions, int actions_f64,
+                     double *reward_out, uint8_t *flags_out, float *obs)
+{
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < c->n_envs; ++n) crypto_step_one(c, s, n, actions, actions_f64, reward_out, flags_out, obs);
+}

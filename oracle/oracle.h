@@ -176,6 +176,29 @@ void ora_cp_obs(const ora_cp_cfg *c, const ora_cp_state *s, double *obs /*[N][1+
 void ora_cp_step(const ora_cp_cfg *c, ora_cp_state *s, const void *actions, int actions_f64, double *reward_out,
                  uint8_t *flags_out, int auto_reset);
 
+/* ---- sibling: CryptoEnv (env_cryptocurrency_trading/env_multiple_crypto.py) ---------------- */
+typedef struct {
+    int32_t n_envs, stock_dim, tech_dim, n_days, lookback;
+    double initial_capital, buy_cost_pct, sell_cost_pct, gamma;
+    const double *price;     /* [T][D] price_array (float64) */
+    const double *tech;      /* [T][tech_dim] tech_array */
+    const double *act_norm;  /* [D] action_norm_vector (:103-111) */
+} ora_crypto_cfg;
+
+typedef struct {
+    double *cash;         /* [N] */
+    float *stocks;        /* [N][D] */
+    int32_t *time;        /* [N] */
+    double *total;        /* [N] total_asset */
+    double *gamma_return; /* [N] */
+    double *episode_return; /* [N] */
+} ora_crypto_state;
+
+void ora_crypto_reset(const ora_crypto_cfg *c, ora_crypto_state *s, const uint8_t *mask);
+void ora_crypto_obs(const ora_crypto_cfg *c, const ora_crypto_state *s, float *obs /*[N][1+D+tech_dim*lookback]*/);
+void ora_crypto_step(const ora_crypto_cfg *c, ora_crypto_state *s, const void *actions, int actions_f64,
+                     double *reward_out, uint8_t *flags_out, float *obs);
+
 #ifdef __cplusplus
 }
 #endif

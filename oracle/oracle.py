@@ -382,3 +382,66 @@ class CashPenaltyOracle:
         lib().ora_cp_step(C.byref(self._cfg), C.byref(self._st), _p(a), C.c_int(a.dtype == np.float64), _p(reward),
                           _p(flags), C.c_int(int(auto_reset)))
         return reward, flags
+
+
+# --------------------------------------------------------------------------------------------
+# sibling: CryptoEnv
+# --------------------------------------------------------------------------------------------
+class _CryptoCfg(C.Structure):
+    _fields_ = [("n_envs", C.c_int32), ("stock_dim", C.c_int32), ("tech_dim", C.c_int32), ("n_days", C.c_int32),
+                ("lookback", C.c_int32), ("initial_capital", C.c_double), ("buy_cost_pct", C.c_double),
+                ("sell_cost_pct", C.c_double), ("gamma", C.c_double), ("price", C.c_void_p), ("tech", C.c_void_p),
+                ("act_norm", C.c_void_p)]
+
+
+class _CryptoState(C.Structure):
+    _fields_ = [("cash", C.c_void_p), ("stocks", C.c_void_p), ("time", C.c_void_p), ("total", C.c_void_p),
+                ("gamma_return", C.c_void_p), ("episode_return", C.c_void_p)]
+
+
+def crypto_action_norm(price_array):
+    """_generate_action_normalizer (env_multiple_crypto.py:103-111)."""
+    import math
+
+    return np.asarray([1 / (10 ** math.floor(math.log(p, 10))) for p in price_array[0]]) * 10000
+
+
+class CryptoOracle:
+    """N independent copies of the reference ``CryptoEnv``
+    (finrl/meta/env_cryptocurrency_trading/env_multiple_crypto.py), stepped on the CPU."""
+
+    def __init__(self, price_array, tech_array, n_envs, lookback=1, initial_capital=1e6, buy_cost_pct=1e-3,
+                 sell_cost_pct=1e-3, gamma=0.99):
+        self.price = np.ascontiguousarray(price_array, dtype=np.float64)
+        T, D = self.price.shape
+        self.tech = np.ascontiguousarray(tech_array, dtype=np.float64).reshape(T, -1)
+        self.norm = np.ascontiguousarray(crypto_action_norm(self.price), dtype=np.float64)
+        N = int(n_envs)
+        self.N, self.D, self.T, self.TD, self.lookback = N, D, T, self.tech.shape[1], int(lookback)
+        self.O = 1 + D + self.TD * self.lookback
+        self.cash = np.zeros(N); self.stocks = np.zeros((N, D), dtype=np.float32); self.time = np.zeros(N, dtype=np.int32)
+        self.total = np.zeros(N); self.gamma_return = np.zeros(N); self.episode_return = np.zeros(N)
+        self._cfg = _CryptoCfg(N, D, self.TD, T, self.lookback, float(initial_capital), float(buy_cost_pct),
+                               float(sell_cost_pct), float(gamma), _p(self.price), _p(self.tech), _p(self.norm))
+        self._st = _CryptoState(_p(self.cash), _p(self.stocks), _p(self.time), _p(self.total), _p(self.gamma_return),
+                                _p(self.episode_return))
+        self.reset()
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        lib().ora_crypto_reset(C.byref(self._cfg), C.byref(self._st), _p(m))
+        return self.obs()
+
+    def obs(self):
+        out = np.empty((self.N, self.O), dtype=np.float32)
+        lib().ora_crypto_obs(C.byref(self._cfg), C.byref(self._st), _p(out))
+        return out
+
+    def step(self, actions, want_obs=True):
+        a = np.ascontiguousarray(actions)
+        assert a.shape == (self.N, self.D) and a.dtype in (np.float32, np.float64)
+        reward = np.empty(self.N); flags = np.empty(self.N, dtype=np.uint8)
+        obs = np.empty((self.N, self.O), dtype=np.float32) if want_obs else None
+        lib().ora_crypto_step(C.byref(self._cfg), C.byref(self._st), _p(a), C.c_int(a.dtype == np.float64), _p(reward),
+                              _p(flags), _p(obs))
+        return obs, reward, flags

@@ -23,6 +23,7 @@ ENV_FILES = {
     "env_stocktrading_cashpenalty": "finrl/meta/env_stock_trading/env_stocktrading_cashpenalty.py",
     "env_portfolio": "finrl/meta/env_portfolio_allocation/env_portfolio.py",
     "env_nas100_wrds": "finrl/meta/env_stock_trading/env_nas100_wrds.py",
+    "env_multiple_crypto": "finrl/meta/env_cryptocurrency_trading/env_multiple_crypto.py",
 }
 
 
@@ -135,6 +136,21 @@ def _install_stubs():
         )
 
 
+def _install_finrl_stubs():
+    """env_multiple_crypto.py imports the agent adapters and DataProcessor at module level (unused by
+    the env class); give it inert namespaces instead of importing ray / elegantrl / alpaca."""
+    if "finrl" in sys.modules:
+        return
+    names = ["finrl", "finrl.agents", "finrl.agents.elegantrl", "finrl.agents.elegantrl.models",
+             "finrl.agents.stablebaselines3", "finrl.agents.stablebaselines3.models", "finrl.meta",
+             "finrl.meta.data_processor"]
+    for n in names:
+        sys.modules[n] = types.ModuleType(n)
+    sys.modules["finrl.agents.elegantrl.models"].DRLAgent = object
+    sys.modules["finrl.agents.stablebaselines3.models"].DRLAgent = object
+    sys.modules["finrl.meta.data_processor"].DataProcessor = object
+
+
 _cache: dict = {}
 
 
@@ -145,6 +161,8 @@ def load(name: str):
     if not available():
         raise RuntimeError(f"reference tree not present at {REF_ROOT}")
     _install_stubs()
+    if name == "env_multiple_crypto":
+        _install_finrl_stubs()
     path = os.path.join(REF_ROOT, ENV_FILES[name])
     spec = importlib.util.spec_from_file_location("_finrl_ref_" + name, path)
     mod = importlib.util.module_from_spec(spec)

@@ -254,6 +254,40 @@ def gen_cashpenalty(name, T, D, n_steps, seed, act_dtype, threshold=None, patien
           f"min cash={out['obs'][:, 0].min():.3f}")
 
 
+# ------------------------------------------------------------------------------------------
+# sibling  CryptoEnv  (env_cryptocurrency_trading/env_multiple_crypto.py)
+# ------------------------------------------------------------------------------------------
+def gen_crypto(name, T, D, K, n_steps, seed, act_dtype, lookback=1, initial_capital=1e6, scales=None):
+    mod = ref_loader.load("env_multiple_crypto")
+    close, tech, turb = syn.make_tables(T, D, K, seed=seed)
+    if scales is not None:  # coins span orders of magnitude, which is what the action normaliser is about
+        close = close * np.asarray(scales)[None, :] / 100.0
+    price_array, tech_array, _ = syn.make_np_arrays(close, tech, turb)
+    env = mod.CryptoEnv({"price_array": price_array, "tech_array": tech_array}, lookback=lookback,
+                        initial_capital=initial_capital)
+    obs0 = env.reset()
+    actions = syn.make_actions((n_steps, D), seed=seed + 1, dtype=np.float64).astype(act_dtype)
+    O = obs0.shape[0]
+    out = {k: np.zeros(n_steps) for k in ("cash", "total", "gamma_return", "reward", "episode_return")}
+    out["done"] = np.zeros(n_steps, dtype=np.uint8)
+    out["stocks"] = np.zeros((n_steps, D), dtype=np.float32)
+    out["obs"] = np.zeros((n_steps, O), dtype=np.float32)
+    out["time"] = np.zeros(n_steps, dtype=np.int64)
+    for s in range(n_steps):
+        state, reward, done, info = env.step(actions[s].copy())
+        assert info is None and state.dtype == np.float32
+        out["cash"][s], out["total"][s], out["gamma_return"][s] = env.cash, env.total_asset, env.gamma_return
+        out["reward"][s], out["done"][s], out["episode_return"][s] = reward, done, env.episode_return
+        out["stocks"][s], out["obs"][s], out["time"][s] = env.stocks, state, env.time
+        if done:
+            env.reset()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), price_array=price_array, tech_array=tech_array, actions=actions,
+                        obs0=obs0, lookback=np.array(lookback), initial_capital=np.array(float(initial_capital)),
+                        action_norm_vector=np.asarray(env.action_norm_vector), **out, **_meta())
+    print(f"{name}: {n_steps} steps, dones={int(out['done'].sum())}, min cash={out['cash'].min():.4f}, "
+          f"max stocks={out['stocks'].max():.3f}")
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     which = set(sys.argv[1:])
@@ -296,6 +330,11 @@ def main():
     if want("portfolio"):
         gen_portfolio("portfolio_d30_f64", T=252 + 24, D=30, K=4, n_steps=50, seed=21, act_dtype=np.float64)
         gen_portfolio("portfolio_d6_f32", T=40 + 12, D=6, K=2, n_steps=30, seed=22, act_dtype=np.float32, lookback=40)
+    if want("crypto"):
+        gen_crypto("crypto_d5_f32", T=45, D=5, K=3, n_steps=100, seed=41, act_dtype=np.float32, lookback=1,
+                   initial_capital=2e5, scales=[300.0, 1.5, 0.02, 45.0, 7000.0])
+        gen_crypto("crypto_d8_lb3_f64", T=40, D=8, K=2, n_steps=80, seed=42, act_dtype=np.float64, lookback=3,
+                   initial_capital=1e6, scales=[30000.0, 2000.0, 1.0, 0.5, 150.0, 20.0, 6.0, 0.08])
     if want("cashpenalty"):
         gen_cashpenalty("cashpen_d10", T=30, D=10, n_steps=65, seed=31, act_dtype=np.float32, hmax=5000)
         gen_cashpenalty("cashpen_d10_turb_patient", T=30, D=10, n_steps=65, seed=32, act_dtype=np.float64, threshold=70,

@@ -53,6 +53,7 @@ def test_struct_layouts_match_the_header():
         "frl_trading_params": (_cabi.TradingParams, ["n_envs", "hmax", "turbulence_threshold", "close", "cash", "episode", "asset_out"]),
         "frl_np_params": (_cabi.NpParams, ["gamma", "initial_capital", "obs_amount_floor", "price", "amount", "episode_return"]),
         "frl_portfolio_params": (_cabi.PortfolioParams, ["initial_amount", "ret", "reward"]),
+        "frl_crypto_params": (_cabi.CryptoParams, ["lookback", "env_stride", "initial_capital", "gamma", "price", "episode_return"]),
         "frl_cashpenalty_params": (_cabi.CashPenaltyParams, ["patient", "env_stride", "buy_cost_pct", "cash_penalty_proportion", "close", "hold_alt", "sum_trades"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "finrl_b200.h"', "int main(){"]

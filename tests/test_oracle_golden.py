@@ -228,3 +228,27 @@ def test_cashpenalty_oracle_vs_reference(path):
         assert o.date_index[0] == g["date_index"][s], ctx
         np.testing.assert_allclose(reward[0], g["reward"][s], rtol=1e-12, atol=1e-18, err_msg=ctx)
         np.testing.assert_allclose(o.obs()[0], g["obs"][s], rtol=1e-12, atol=1e-9, err_msg=ctx)
+
+
+# ---------------------------------------------------------------------------- sibling: CryptoEnv
+CRYPTO = sorted(glob.glob(os.path.join(GOLDEN, "crypto_*.npz")))
+
+
+@pytest.mark.parametrize("path", CRYPTO, ids=[os.path.basename(p)[:-4] for p in CRYPTO])
+def test_crypto_oracle_vs_reference(path):
+    g = np.load(path)
+    o = ora.CryptoOracle(g["price_array"], g["tech_array"], 1, lookback=int(g["lookback"]),
+                         initial_capital=float(g["initial_capital"]))
+    assert np.array_equal(o.norm, g["action_norm_vector"])
+    assert np.array_equal(o.obs()[0], g["obs0"])
+    acts = g["actions"]
+    for s in range(acts.shape[0]):
+        obs, reward, flags = o.step(acts[s][None, :])
+        ctx = f"step {s}"
+        assert bool(flags[0] & 1) == bool(g["done"][s]) and o.time[0] == g["time"][s], ctx
+        assert o.cash[0] == g["cash"][s] and np.array_equal(o.stocks[0], g["stocks"][s]), ctx
+        assert o.total[0] == g["total"][s] and o.gamma_return[0] == g["gamma_return"][s] and reward[0] == g["reward"][s], ctx
+        assert np.array_equal(obs[0], g["obs"][s]), ctx
+        if g["done"][s]:
+            assert o.episode_return[0] == g["episode_return"][s], ctx
+            o.reset()
