@@ -113,6 +113,8 @@ class PortfolioParams(C.Structure):
         ("pv", C.c_void_p),
         ("day", C.c_void_p),
         ("reward", C.c_void_p),
+        ("ret_out", C.c_void_p),
+        ("weights_out", C.c_void_p),
     ]
 
 

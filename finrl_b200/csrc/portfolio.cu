@@ -192,8 +192,14 @@ portfolio_rollout_kernel(const frl_portfolio_params p, const ActT *__restrict__ 
             // sum(((close_new / close_old) - 1) * weights): Python sum, sequential (:183-185)
             double pr = 0.0;
 #pragma unroll
-            for (int j = 0; j < SLOTS; ++j)
-                if (j < D) pr = dadd(pr, dmul(__ldg(rrow + j), (double)pf_div<ActT>(e[j], den)));
+            for (int j = 0; j < SLOTS; ++j) {
+                if (j < D) {
+                    const double w = (double)pf_div<ActT>(e[j], den);
+                    pr = dadd(pr, dmul(__ldg(rrow + j), w));
+                    if (p.weights_out && valid) p.weights_out[(size_t)n * D + j] = w;
+                }
+            }
+            if (p.ret_out && valid) p.ret_out[n] = pr;
             pv = dmul(pv, dadd(1.0, pr));
             reward = pv;  // reward = new portfolio value, unscaled (:196)
             last_reward = reward;

@@ -27,7 +27,8 @@ class StockPortfolioEnv:
         self.observation_space = Box(low=-np.inf, high=np.inf, shape=(state_space + len(tech_indicator_list), state_space))
         self._device = device
         self.engine = BatchedStockPortfolioEnv(df, stock_dim=stock_dim, initial_amount=initial_amount, state_space=state_space,
-                                               tech_indicator_list=tech_indicator_list, day=day, n_envs=1, device=device)
+                                               tech_indicator_list=tech_indicator_list, day=day, n_envs=1, device=device,
+                                               track_weights=True)
         self._dates = df.date.to_numpy().reshape(self.engine.n_days, stock_dim)[:, 0] if "date" in df.columns else None
         self.state = self.engine.tables.host_obs[self.day]
         self.covs = self.state[:stock_dim]
@@ -52,7 +53,6 @@ class StockPortfolioEnv:
         a = np.asarray(actions)
         if a.dtype not in (np.float32, np.float64):
             a = a.astype(np.float64)
-        prev = self.portfolio_value
         obs, reward, done, flags = self.engine.step(torch.as_tensor(a.reshape(1, -1)), want_obs=False)
         self.terminal = bool(done[0].item())
         if self.terminal:
@@ -69,8 +69,9 @@ class StockPortfolioEnv:
         self.covs = self.state[: self.stock_dim]
         self.portfolio_value = float(self.engine.portfolio_value[0].item())
         self.reward = float(reward[0].item())
-        self.portfolio_return_memory.append(self.portfolio_value / prev - 1)
-        self.actions_memory.append(self.softmax_normalization(a))
+        # logging memories straight from the kernel (portfolio_return and the softmax weights it used)
+        self.portfolio_return_memory.append(float(self.engine.last_return[0].item()))
+        self.actions_memory.append(self.engine.last_weights[0].cpu().numpy())
         self.date_memory.append(self._date())
         self.asset_memory.append(self.portfolio_value)
         return self.state, self.reward, self.terminal, {}
@@ -92,7 +93,8 @@ class StockPortfolioEnv:
         return self.state
 
     def softmax_normalization(self, actions):
-        # logging helper only (actions_memory); the weights used by step() are computed on the device
+        """The reference's public helper (:225-229).  ``step`` does not use it — the weights are computed
+        on the device — it is kept for callers that invoke it directly."""
         e = np.exp(actions)
         return e / np.sum(e)
 

@@ -74,7 +74,7 @@ class BatchedStockPortfolioEnv:
     def __init__(self, df=None, stock_dim=None, hmax=None, initial_amount=1_000_000, transaction_cost_pct=None,
                  reward_scaling=None, state_space=None, action_space=None, tech_indicator_list: Sequence[str] = (),
                  turbulence_threshold=None, lookback=252, day=0, *, n_envs=1, device="cuda",
-                 tables: Optional[PortfolioTables] = None):
+                 tables: Optional[PortfolioTables] = None, track_weights: bool = False):
         import torch
 
         self._torch = torch
@@ -112,6 +112,11 @@ class BatchedStockPortfolioEnv:
         p.initial_amount = float(initial_amount)
         p.ret, p.obs_table = tables.ret.data_ptr(), tables.obs_table.data_ptr()
         p.pv, p.day, p.reward = self.portfolio_value.data_ptr(), self.day.data_ptr(), self.reward.data_ptr()
+        # optional: the step's portfolio_return and softmax weights (the reference's logging memories)
+        self.last_return = torch.zeros(N, dtype=torch.float64, device=dev) if track_weights else None
+        self.last_weights = torch.zeros((N, D), dtype=torch.float64, device=dev) if track_weights else None
+        p.ret_out = self.last_return.data_ptr() if track_weights else None
+        p.weights_out = self.last_weights.data_ptr() if track_weights else None
         self._p = p
         self.launches = 0
         self.kernel_events = None

@@ -213,6 +213,9 @@ typedef struct frl_portfolio_params {
     double *pv;     /* [N] self.portfolio_value */
     int32_t *day;   /* [N] self.day */
     double *reward; /* [N] self.reward (returned again by the terminal step) */
+    /* ---- optional per-env outputs of the last step (NULL = skip) ---- */
+    double *ret_out;     /* [N] portfolio_return (portfolio_return_memory entry) */
+    double *weights_out; /* [N][D] softmax weights (actions_memory entry), float64 */
 } frl_portfolio_params;
 
 /* StockPortfolioEnv.reset (:202-220) for envs with mask[n] != 0 (NULL = all). obs nullable [N][obs_dim]. */

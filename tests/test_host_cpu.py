@@ -52,7 +52,7 @@ def test_struct_layouts_match_the_header():
     checks = {
         "frl_trading_params": (_cabi.TradingParams, ["n_envs", "hmax", "turbulence_threshold", "close", "cash", "episode", "asset_out"]),
         "frl_np_params": (_cabi.NpParams, ["gamma", "initial_capital", "obs_amount_floor", "price", "amount", "episode_return"]),
-        "frl_portfolio_params": (_cabi.PortfolioParams, ["initial_amount", "ret", "reward"]),
+        "frl_portfolio_params": (_cabi.PortfolioParams, ["initial_amount", "ret", "reward", "ret_out", "weights_out"]),
         "frl_crypto_params": (_cabi.CryptoParams, ["lookback", "env_stride", "initial_capital", "gamma", "price", "episode_return"]),
         "frl_cashpenalty_params": (_cabi.CashPenaltyParams, ["patient", "env_stride", "buy_cost_pct", "cash_penalty_proportion", "close", "hold_alt", "sum_trades"]),
     }
@@ -204,3 +204,15 @@ def test_two_rank_sharding_equals_single_process(tmp_path):
     for p in parts:
         np.testing.assert_allclose(p["stats"], tot, rtol=1e-12)
         assert p["stats"][2] == tot[2] and p["stats"][6] == tot[6]
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No silent fallback when the CUDA extension is absent: the first use raises EngineError."""
+    import subprocess
+
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from finrl_b200 import _cabi\n"
+            "try:\n    _cabi.lib()\nexcept _cabi.EngineError as e:\n    print('RAISED', 'no CPU fallback' in str(e))\n" % ROOT)
+    env = dict(os.environ, FINRL_B200_LIB=str(tmp_path / "missing.so"))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert "RAISED True" in out.stdout, out.stdout + out.stderr

@@ -105,6 +105,9 @@ def test_portfolio_gym_class_matches_reference():
                 state = env.reset()
             assert np.array_equal(state, g["obs"][s]) and env.day == g["day"][s], ctx
             assert abs(env.portfolio_value - g["pv"][s]) <= 1e-9 * g["pv"][s], ctx
+            if not g["done"][s]:
+                np.testing.assert_allclose(env.actions_memory[-1], g["weights"][s], rtol=1e-9)
+                assert abs(env.portfolio_return_memory[-1] - g["pret"][s]) <= 1e-9 * max(abs(g["pret"][s]), 1e-3), ctx
 
 
 def test_cashpenalty_gym_class_matches_reference():
