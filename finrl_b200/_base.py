@@ -1,0 +1,152 @@
+"""Shared host plumbing of the batched engines: device binding, action marshalling, and the two
+C-ABI call shapes (``*_step`` and ``*_rollout``) every env kind exposes with identical signatures."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+
+
+class BatchedEnvBase:
+    """Subclasses set ``_PREFIX`` (e.g. ``"frl_trading"``), build ``self._p`` (the params struct) and the
+    buffers ``self._obs`` / ``self._flags`` / ``self.stats`` and, unless the reward lives in the state
+    (StockTradingEnv), ``self._rew``."""
+
+    _PREFIX = ""
+    _ACTION_NAME = "stock_dim"
+
+    # ---- construction helpers ---------------------------------------------------------------
+    def _bind_device(self, device):
+        import torch
+
+        self._torch = torch
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _cabi.EngineError("finrl_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        _cabi.lib()  # fail loudly before any allocation if the extension is missing
+        self.launches = 0          # kernels launched through the C-ABI (bench.py reports it)
+        self.kernel_events = None  # set to a list to collect (start, end) CUDA events around each step launch
+        return torch
+
+    def _stream(self):
+        return _cabi.current_stream(self.device)
+
+    def _fn(self, name):
+        return getattr(_cabi.lib(), f"{self._PREFIX}_{name}")
+
+    def _as_actions(self, actions, ndim):
+        torch = self._torch
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions))
+        if actions.dtype not in (torch.float32, torch.float64):
+            actions = actions.to(torch.float32)
+        if actions.device != self.device:
+            actions = actions.to(self.device, non_blocking=True)
+        if actions.dim() != ndim or actions.shape[-1] != self.stock_dim:
+            raise ValueError(f"actions must have {ndim} dims ending in {self._ACTION_NAME}={self.stock_dim}, got {tuple(actions.shape)}")
+        return actions.contiguous()
+
+    def _obs_out(self):
+        return self._obs
+
+    def _reward_out(self):
+        return getattr(self, "_rew", None)
+
+    def _reward_result(self):
+        return self._rew
+
+    # ---- the two call shapes ----------------------------------------------------------------------
+    def step(self, actions, auto_reset: bool = False, want_obs: bool = True, accumulate_stats: bool = False,
+             want_done: bool = True):
+        """One ``step`` of every env.  Returns (obs, reward[N] f64, done[N] bool, flags[N] u8).  The tensors
+        are engine-owned buffers that the next call overwrites.  ``done`` is ``flags & FLAG_DONE`` (two tiny
+        torch kernels); pass ``want_done=False`` to get None instead."""
+        torch = self._torch
+        a = self._as_actions(actions, 2)
+        if a.shape[0] != self.n_envs:
+            raise ValueError(f"actions must have n_envs={self.n_envs} rows")
+        obs = self._obs_out() if want_obs else None
+        ev = self.kernel_events
+        with torch.cuda.device(self.device):
+            if ev is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            rc = self._fn("step")(
+                C.byref(self._p), _cabi.ptr(a), int(a.dtype == torch.float64), _cabi.ptr(self._reward_out()),
+                _cabi.ptr(self._flags), _cabi.ptr(obs), int(auto_reset),
+                _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
+            )
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
+        _cabi.check(rc, f"{self._PREFIX}_step")
+        self.launches += 1
+        done = (self._flags & _cabi.FLAG_DONE).bool() if want_done else None
+        return self._shape_obs(obs), self._reward_result(), done, self._flags
+
+    def _shape_obs(self, obs):
+        return obs
+
+    def rollout(self, actions, layout: str = "KND", obs_mode: str = "last", auto_reset: bool = True,
+                accumulate_stats: bool = True, rewards=None, flags=None, obs=None):
+        """Fused multi-step rollout: ``actions`` is [K, N, D] (layout "KND", time-major like SB3's rollout
+        buffer) or [N, K, D] ("NKD").  Returns (obs, rewards[K,N] f64, flags[K,N] u8) where obs is None /
+        [N,O] / [K,N,O] for obs_mode "none" / "last" / "all"."""
+        torch = self._torch
+        a = self._as_actions(actions, 3)
+        D, N = self.stock_dim, self.n_envs
+        if layout == "KND":
+            K, ok = a.shape[0], a.shape[1] == N
+        elif layout == "NKD":
+            K, ok = a.shape[1], a.shape[0] == N
+        else:
+            raise ValueError("layout must be 'KND' or 'NKD'")
+        if not ok:
+            raise ValueError(f"actions shape {tuple(a.shape)} does not match n_envs={N} for layout {layout}")
+        step_stride, env_stride = (N * D, D) if layout == "KND" else (D, K * D)
+        mode = {"none": _cabi.OBS_NONE, "last": _cabi.OBS_LAST, "all": _cabi.OBS_ALL}[obs_mode]
+        if rewards is None:
+            rewards = torch.empty((K, N), dtype=torch.float64, device=self.device)
+        if flags is None:
+            flags = torch.empty((K, N), dtype=torch.uint8, device=self.device)
+        if mode == _cabi.OBS_LAST and obs is None:
+            obs = self._obs_out()
+        elif mode == _cabi.OBS_ALL and obs is None:
+            obs = torch.empty((K, N, self._obs_out().shape[-1]), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(
+                self._fn("rollout")(
+                    C.byref(self._p), _cabi.ptr(a), int(a.dtype == torch.float64), step_stride, env_stride, int(K),
+                    _cabi.ptr(rewards), _cabi.ptr(flags), _cabi.ptr(obs) if mode else None, mode, int(auto_reset),
+                    _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
+                ),
+                f"{self._PREFIX}_rollout",
+            )
+        self.launches += 1
+        return (obs if mode else None), rewards, flags
+
+    def observe(self, out=None):
+        """float32 observation of every env, [N, O]."""
+        out = self._obs_out() if out is None else out
+        with self._torch.cuda.device(self.device):
+            _cabi.check(self._fn("observe")(C.byref(self._p), _cabi.ptr(out), self._stream()), f"{self._PREFIX}_observe")
+        self.launches += 1
+        return self._shape_obs(out)
+
+    def _mask(self, mask):
+        if mask is None:
+            return None
+        m = self._torch.as_tensor(mask, device=self.device).to(self._torch.uint8).contiguous()
+        if m.shape != (self.n_envs,):
+            raise ValueError("mask must have shape [n_envs]")
+        return m
+
+    def read_stats(self, reset: bool = False):
+        vals = self.stats.tolist()
+        if reset:
+            self.stats.zero_()
+        return dict(zip(_cabi.STAT_NAMES, vals))

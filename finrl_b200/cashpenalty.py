@@ -14,6 +14,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _cabi
+from ._base import BatchedEnvBase
 
 
 def frame_to_cashpenalty_arrays(df, daily_information_cols: Sequence[str], date_col_name="date", stock_col="tic"):
@@ -68,25 +69,21 @@ class CashPenaltyTables:
                                  turb=torch.from_numpy(turb).to(dev), obs_tmpl=torch.from_numpy(tmpl).to(dev))
 
 
-class BatchedStockTradingEnvCashpenalty:
+class BatchedStockTradingEnvCashpenalty(BatchedEnvBase):
     """Keywords mirror ``StockTradingEnvCashpenalty.__init__`` (:52-70); extra: ``n_envs``, ``device``,
     ``tables``.  ``random_start`` draws per-env starting points with Python's ``random`` like the
-    reference when N is small, on the device otherwise; parity runs use ``random_start=False``."""
+    reference when N is small, on the device otherwise; parity runs use ``random_start=False``.  ``step`` /
+    ``rollout`` / ``observe`` come from :class:`BatchedEnvBase`."""
+
+    _PREFIX = "frl_cashpenalty"
+    _ACTION_NAME = "n_assets"
 
     def __init__(self, df=None, buy_cost_pct=3e-3, sell_cost_pct=3e-3, date_col_name="date", hmax=10,
                  discrete_actions=False, shares_increment=1, turbulence_threshold=None, print_verbosity=10,
                  initial_amount=1e6, daily_information_cols=("open", "close", "high", "low", "volume"),
                  cache_indicator_data=True, cash_penalty_proportion=0.1, random_start=True, patient=False, currency="$",
                  *, n_envs=1, device="cuda", tables: Optional[CashPenaltyTables] = None):
-        import torch
-
-        self._torch = torch
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise _cabi.EngineError("finrl_b200 runs on CUDA devices only (no CPU fallback)")
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
-        _cabi.lib()
+        torch = self._bind_device(device)
         if not np.isscalar(hmax):
             raise NotImplementedError("per-asset hmax arrays are not supported yet (scalar hmax only)")
         self.df = df
@@ -134,30 +131,13 @@ class BatchedStockTradingEnvCashpenalty:
         p.hold_alt = self.hold_alt.data_ptr()
         p.fresh, p.last_cash, p.last_total, p.sum_trades = self.fresh.data_ptr(), self.last_cash.data_ptr(), self.last_total.data_ptr(), self.sum_trades.data_ptr()
         self._p = p
-        self.launches = 0
-        self.kernel_events = None
         self.reset()
-
-    def _stream(self):
-        return _cabi.current_stream(self.device)
 
     @property
     def holdings(self):
         """Holdings in the natural [N, D] layout: per env the current one of the two stock-major buffers."""
         use_alt = (self.fresh & 2).bool()
         return self._torch.where(use_alt[None, :], self.hold_alt, self.hold).t()
-
-    def _as_actions(self, actions, ndim):
-        torch = self._torch
-        if not isinstance(actions, torch.Tensor):
-            actions = torch.as_tensor(np.asarray(actions))
-        if actions.dtype not in (torch.float32, torch.float64):
-            actions = actions.to(torch.float32)
-        if actions.device != self.device:
-            actions = actions.to(self.device, non_blocking=True)
-        if actions.dim() != ndim or actions.shape[-1] != self.stock_dim:
-            raise ValueError(f"actions must have {ndim} dims ending in n_assets={self.stock_dim}, got {tuple(actions.shape)}")
-        return actions
 
     def reset(self, mask=None, start_points=None, out=None):
         torch = self._torch
@@ -173,8 +153,7 @@ class BatchedStockTradingEnvCashpenalty:
         sp = None
         if start_points is not None:
             sp = torch.as_tensor(start_points, device=self.device).to(torch.int32).contiguous()
-        if mask is not None:
-            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        mask = self._mask(mask)
         with torch.cuda.device(self.device):
             _cabi.check(
                 _cabi.lib().frl_cashpenalty_reset(C.byref(self._p), _cabi.ptr(mask), _cabi.ptr(sp), _cabi.ptr(out), self._stream()),
@@ -182,72 +161,6 @@ class BatchedStockTradingEnvCashpenalty:
             )
         self.launches += 2
         return out
-
-    def observe(self, out=None):
-        out = self._obs if out is None else out
-        with self._torch.cuda.device(self.device):
-            _cabi.check(_cabi.lib().frl_cashpenalty_observe(C.byref(self._p), _cabi.ptr(out), self._stream()), "frl_cashpenalty_observe")
-        self.launches += 1
-        return out
-
-    def step(self, actions, auto_reset=False, want_obs=True, accumulate_stats=False, want_done=True):
-        """One ``step`` -> (state[N,O] f32, reward[N] f64, done[N] bool, flags[N] u8)."""
-        a = self._as_actions(actions, 2)
-        if a.shape[0] != self.n_envs:
-            raise ValueError(f"actions must have n_envs={self.n_envs} rows")
-        a = a.contiguous()
-        obs = self._obs if want_obs else None
-        ev = self.kernel_events
-        with self._torch.cuda.device(self.device):
-            if ev is not None:
-                e0, e1 = self._torch.cuda.Event(enable_timing=True), self._torch.cuda.Event(enable_timing=True)
-                e0.record()
-            rc = _cabi.lib().frl_cashpenalty_step(
-                C.byref(self._p), _cabi.ptr(a), int(a.dtype == self._torch.float64), _cabi.ptr(self._rew),
-                _cabi.ptr(self._flags), _cabi.ptr(obs), int(auto_reset),
-                _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
-            )
-            if ev is not None:
-                e1.record()
-                ev.append((e0, e1))
-        _cabi.check(rc, "frl_cashpenalty_step")
-        self.launches += 1
-        done = (self._flags & _cabi.FLAG_DONE).bool() if want_done else None
-        return obs, self._rew, done, self._flags
-
-    def rollout(self, actions, layout="KND", obs_mode="last", auto_reset=True, accumulate_stats=True):
-        torch = self._torch
-        a = self._as_actions(actions, 3)
-        D, N = self.stock_dim, self.n_envs
-        if layout == "KND":
-            K, ok = a.shape[0], a.shape[1] == N
-        elif layout == "NKD":
-            K, ok = a.shape[1], a.shape[0] == N
-        else:
-            raise ValueError("layout must be 'KND' or 'NKD'")
-        if not ok:
-            raise ValueError(f"actions shape {tuple(a.shape)} does not match n_envs={N} for layout {layout}")
-        a = a.contiguous()
-        step_stride, env_stride = (N * D, D) if layout == "KND" else (D, K * D)
-        mode = {"none": _cabi.OBS_NONE, "last": _cabi.OBS_LAST, "all": _cabi.OBS_ALL}[obs_mode]
-        rewards = torch.empty((K, N), dtype=torch.float64, device=self.device)
-        flags = torch.empty((K, N), dtype=torch.uint8, device=self.device)
-        obs = None
-        if mode == _cabi.OBS_LAST:
-            obs = self._obs
-        elif mode == _cabi.OBS_ALL:
-            obs = torch.empty((K, N, self.state_space), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
-            _cabi.check(
-                _cabi.lib().frl_cashpenalty_rollout(
-                    C.byref(self._p), _cabi.ptr(a), int(a.dtype == torch.float64), step_stride, env_stride, int(K),
-                    _cabi.ptr(rewards), _cabi.ptr(flags), _cabi.ptr(obs), mode, int(auto_reset),
-                    _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
-                ),
-                "frl_cashpenalty_rollout",
-            )
-        self.launches += 1
-        return obs, rewards, flags
 
     def read_stats(self, reset=False):
         vals = self.stats.tolist()

@@ -12,22 +12,18 @@ import math
 import numpy as np
 
 from . import _cabi
+from ._base import BatchedEnvBase
 from .spaces import Box
 from .vec_env import BatchedVecEnv
 
 
-class BatchedCryptoEnv:
+class BatchedCryptoEnv(BatchedEnvBase):
+    _PREFIX = "frl_crypto"
+    _ACTION_NAME = "crypto_num"
+
     def __init__(self, config, lookback=1, initial_capital=1e6, buy_cost_pct=1e-3, sell_cost_pct=1e-3, gamma=0.99, *,
                  n_envs=1, device="cuda"):
-        import torch
-
-        self._torch = torch
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise _cabi.EngineError("finrl_b200 runs on CUDA devices only (no CPU fallback)")
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
-        _cabi.lib()
+        torch = self._bind_device(device)
         price = np.ascontiguousarray(config["price_array"], dtype=np.float64)
         T, D = price.shape
         if not 1 <= D <= 32:
@@ -76,74 +72,16 @@ class BatchedCryptoEnv:
         p.cash, p.stocks, p.time = self.cash.data_ptr(), self.stocks.data_ptr(), self.time.data_ptr()
         p.total, p.gamma_return, p.episode_return = self.total_asset.data_ptr(), self.gamma_return.data_ptr(), self.episode_return.data_ptr()
         self._p = p
-        self.launches = 0
         self.reset()
-
-    def _stream(self):
-        return _cabi.current_stream(self.device)
-
-    def _as_actions(self, actions, ndim):
-        torch = self._torch
-        if not isinstance(actions, torch.Tensor):
-            actions = torch.as_tensor(np.asarray(actions))
-        if actions.dtype not in (torch.float32, torch.float64):
-            actions = actions.to(torch.float32)
-        if actions.device != self.device:
-            actions = actions.to(self.device, non_blocking=True)
-        if actions.dim() != ndim or actions.shape[-1] != self.stock_dim:
-            raise ValueError(f"actions must have {ndim} dims ending in crypto_num={self.stock_dim}, got {tuple(actions.shape)}")
-        return actions.contiguous()
 
     def reset(self, mask=None, out=None):
         torch = self._torch
         out = self._obs if out is None else out
-        if mask is not None:
-            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        mask = self._mask(mask)
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().frl_crypto_reset(C.byref(self._p), _cabi.ptr(mask), _cabi.ptr(out), self._stream()), "frl_crypto_reset")
         self.launches += 2
         return out
-
-    def observe(self, out=None):
-        out = self._obs if out is None else out
-        with self._torch.cuda.device(self.device):
-            _cabi.check(_cabi.lib().frl_crypto_observe(C.byref(self._p), _cabi.ptr(out), self._stream()), "frl_crypto_observe")
-        self.launches += 1
-        return out
-
-    def step(self, actions, auto_reset=False, want_obs=True, accumulate_stats=False, want_done=True):
-        a = self._as_actions(actions, 2)
-        obs = self._obs if want_obs else None
-        with self._torch.cuda.device(self.device):
-            _cabi.check(
-                _cabi.lib().frl_crypto_step(C.byref(self._p), _cabi.ptr(a), int(a.dtype == self._torch.float64), _cabi.ptr(self._rew),
-                                            _cabi.ptr(self._flags), _cabi.ptr(obs), int(auto_reset),
-                                            _cabi.ptr(self.stats) if accumulate_stats else None, self._stream()),
-                "frl_crypto_step",
-            )
-        self.launches += 1
-        done = (self._flags & _cabi.FLAG_DONE).bool() if want_done else None
-        return obs, self._rew, done, self._flags
-
-    def rollout(self, actions, layout="KND", obs_mode="last", auto_reset=True, accumulate_stats=True):
-        torch = self._torch
-        a = self._as_actions(actions, 3)
-        D, N = self.stock_dim, self.n_envs
-        K = a.shape[0] if layout == "KND" else a.shape[1]
-        step_stride, env_stride = (N * D, D) if layout == "KND" else (D, K * D)
-        mode = {"none": _cabi.OBS_NONE, "last": _cabi.OBS_LAST, "all": _cabi.OBS_ALL}[obs_mode]
-        rewards = torch.empty((K, N), dtype=torch.float64, device=self.device)
-        flags = torch.empty((K, N), dtype=torch.uint8, device=self.device)
-        obs = self._obs if mode == _cabi.OBS_LAST else (torch.empty((K, N, self.obs_dim), dtype=torch.float32, device=self.device) if mode else None)
-        with torch.cuda.device(self.device):
-            _cabi.check(
-                _cabi.lib().frl_crypto_rollout(C.byref(self._p), _cabi.ptr(a), int(a.dtype == torch.float64), step_stride, env_stride,
-                                               int(K), _cabi.ptr(rewards), _cabi.ptr(flags), _cabi.ptr(obs), mode, int(auto_reset),
-                                               _cabi.ptr(self.stats) if accumulate_stats else None, self._stream()),
-                "frl_crypto_rollout",
-            )
-        self.launches += 1
-        return obs, rewards, flags
 
 
 class CryptoEnv:

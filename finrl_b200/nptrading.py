@@ -14,6 +14,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _cabi
+from ._base import BatchedEnvBase
 
 
 @dataclass
@@ -68,22 +69,18 @@ class NpTables:
         )
 
 
-class BatchedNpStockTradingEnv:
+class BatchedNpStockTradingEnv(BatchedEnvBase):
     """N numpy-env instances on one GPU.  Keywords mirror ``StockTradingEnv.__init__``
-    (env_stocktrading_np.py:9-22); extra: ``n_envs``, ``device``, ``tables``."""
+    (env_stocktrading_np.py:9-22); extra: ``n_envs``, ``device``, ``tables``.  ``step`` / ``rollout`` /
+    ``observe`` / ``read_stats`` come from :class:`BatchedEnvBase`; ``step`` returns (state[N,O] f32,
+    reward[N] f64, done[N] bool, flags[N] u8) with the reward's numpy kind in flag bits 4-5."""
+
+    _PREFIX = "frl_np"
 
     def __init__(self, config=None, initial_account=1e6, gamma=0.99, turbulence_thresh=99, min_stock_rate=0.1,
                  max_stock=1e2, initial_capital=1e6, buy_cost_pct=1e-3, sell_cost_pct=1e-3, reward_scaling=2**-11,
                  initial_stocks=None, *, n_envs=1, device="cuda", tables=None, if_train=None, obs_amount_floor=None):
-        import torch
-
-        self._torch = torch
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise _cabi.EngineError("finrl_b200 runs on CUDA devices only (no CPU fallback)")
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
-        _cabi.lib()
+        torch = self._bind_device(device)
         if tables is None:
             if config is None:
                 raise ValueError("either config or tables is required")
@@ -122,7 +119,7 @@ class BatchedNpStockTradingEnv:
         self.episode_return = torch.zeros(N, dtype=torch.float64, device=dev)
         self.stats = torch.zeros(_cabi.N_STATS, dtype=torch.float64, device=dev)
         self._obs = torch.empty((N, O), dtype=torch.float32, device=dev)
-        self._reward = torch.empty(N, dtype=torch.float64, device=dev)
+        self._rew = torch.empty(N, dtype=torch.float64, device=dev)
         self._flags = torch.empty(N, dtype=torch.uint8, device=dev)
         p = _cabi.NpParams()
         p.n_envs, p.stock_dim, p.tech_dim, p.n_days, p.obs_dim, p.env_stride = N, D, TD, T, O, N
@@ -137,24 +134,7 @@ class BatchedNpStockTradingEnv:
         p.day, p.total, p.gamma_reward = self.day.data_ptr(), self.total_asset.data_ptr(), self.gamma_reward.data_ptr()
         p.init_total, p.episode_return = self.initial_total_asset.data_ptr(), self.episode_return.data_ptr()
         self._p = p
-        self.launches = 0
-        self.kernel_events = None
         self.reset()
-
-    def _stream(self):
-        return _cabi.current_stream(self.device)
-
-    def _as_actions(self, actions, ndim):
-        torch = self._torch
-        if not isinstance(actions, torch.Tensor):
-            actions = torch.as_tensor(np.asarray(actions))
-        if actions.dtype not in (torch.float32, torch.float64):
-            actions = actions.to(torch.float32)
-        if actions.device != self.device:
-            actions = actions.to(self.device, non_blocking=True)
-        if actions.dim() != ndim or actions.shape[-1] != self.stock_dim:
-            raise ValueError(f"actions must have {ndim} dims ending in stock_dim={self.stock_dim}, got {tuple(actions.shape)}")
-        return actions
 
     # ------------------------------------------------------------------------------------------
     def draw_train_reset(self, rng=None):
@@ -186,8 +166,7 @@ class BatchedNpStockTradingEnv:
         if stocks0 is not None:
             s0 = torch.as_tensor(stocks0, device=self.device).to(torch.float32).reshape(self.n_envs, self.stock_dim).t().contiguous()
             f = torch.as_tensor(factor, device=self.device).to(torch.float64).reshape(self.n_envs).contiguous()
-        if mask is not None:
-            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        mask = self._mask(mask)
         with torch.cuda.device(self.device):
             _cabi.check(
                 _cabi.lib().frl_np_reset(C.byref(self._p), _cabi.ptr(mask), _cabi.ptr(s0), _cabi.ptr(f), _cabi.ptr(out), self._stream()),
@@ -195,76 +174,6 @@ class BatchedNpStockTradingEnv:
             )
         self.launches += 2
         return out
-
-    def observe(self, out=None):
-        out = self._obs if out is None else out
-        with self._torch.cuda.device(self.device):
-            _cabi.check(_cabi.lib().frl_np_observe(C.byref(self._p), _cabi.ptr(out), self._stream()), "frl_np_observe")
-        self.launches += 1
-        return out
-
-    def step(self, actions, auto_reset: bool = False, want_obs: bool = True, accumulate_stats: bool = False,
-             want_done: bool = True):
-        """One ``step`` of every env -> (state[N,O] f32, reward[N] f64, done[N] bool, flags[N] u8).
-        Buffers are engine-owned and overwritten by the next call."""
-        a = self._as_actions(actions, 2)
-        if a.shape[0] != self.n_envs:
-            raise ValueError(f"actions must have n_envs={self.n_envs} rows")
-        a = a.contiguous()
-        obs = self._obs if want_obs else None
-        ev = self.kernel_events
-        with self._torch.cuda.device(self.device):
-            if ev is not None:
-                e0, e1 = self._torch.cuda.Event(enable_timing=True), self._torch.cuda.Event(enable_timing=True)
-                e0.record()
-            rc = _cabi.lib().frl_np_step(
-                C.byref(self._p), _cabi.ptr(a), int(a.dtype == self._torch.float64), _cabi.ptr(self._reward),
-                _cabi.ptr(self._flags), _cabi.ptr(obs), int(auto_reset),
-                _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
-            )
-            if ev is not None:
-                e1.record()
-                ev.append((e0, e1))
-        _cabi.check(rc, "frl_np_step")
-        self.launches += 1
-        done = (self._flags & _cabi.FLAG_DONE).bool() if want_done else None
-        return obs, self._reward, done, self._flags
-
-    def rollout(self, actions, layout: str = "KND", obs_mode: str = "last", auto_reset: bool = True,
-                accumulate_stats: bool = True, rewards=None, flags=None, obs=None):
-        torch = self._torch
-        a = self._as_actions(actions, 3)
-        D, N = self.stock_dim, self.n_envs
-        if layout == "KND":
-            K, ok = a.shape[0], a.shape[1] == N
-        elif layout == "NKD":
-            K, ok = a.shape[1], a.shape[0] == N
-        else:
-            raise ValueError("layout must be 'KND' or 'NKD'")
-        if not ok:
-            raise ValueError(f"actions shape {tuple(a.shape)} does not match n_envs={N} for layout {layout}")
-        a = a.contiguous()
-        step_stride, env_stride = (N * D, D) if layout == "KND" else (D, K * D)
-        mode = {"none": _cabi.OBS_NONE, "last": _cabi.OBS_LAST, "all": _cabi.OBS_ALL}[obs_mode]
-        if rewards is None:
-            rewards = torch.empty((K, N), dtype=torch.float64, device=self.device)
-        if flags is None:
-            flags = torch.empty((K, N), dtype=torch.uint8, device=self.device)
-        if mode == _cabi.OBS_LAST and obs is None:
-            obs = self._obs
-        elif mode == _cabi.OBS_ALL and obs is None:
-            obs = torch.empty((K, N, self.state_dim), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
-            _cabi.check(
-                _cabi.lib().frl_np_rollout(
-                    C.byref(self._p), _cabi.ptr(a), int(a.dtype == torch.float64), step_stride, env_stride, int(K),
-                    _cabi.ptr(rewards), _cabi.ptr(flags), _cabi.ptr(obs) if mode else None, mode, int(auto_reset),
-                    _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
-                ),
-                "frl_np_rollout",
-            )
-        self.launches += 1
-        return (obs if mode else None), rewards, flags
 
     # ------------------------------------------------------------------------------------------
     def get_state(self):
@@ -275,9 +184,3 @@ class BatchedNpStockTradingEnv:
             "total_kind": (k >> 2) & 3, "gamma_reward": self.gamma_reward.clone(), "gr_kind": (k >> 4) & 3,
             "init_total": self.initial_total_asset.clone(), "episode_return": self.episode_return.clone(),
         }
-
-    def read_stats(self, reset: bool = False):
-        vals = self.stats.tolist()
-        if reset:
-            self.stats.zero_()
-        return dict(zip(_cabi.STAT_NAMES, vals))

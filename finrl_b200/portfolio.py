@@ -15,6 +15,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _cabi
+from ._base import BatchedEnvBase
 
 
 def frame_to_portfolio_arrays(df, stock_dim: int, tech_indicator_list: Sequence[str]):
@@ -66,24 +67,19 @@ class PortfolioTables:
         )
 
 
-class BatchedStockPortfolioEnv:
+class BatchedStockPortfolioEnv(BatchedEnvBase):
     """Keywords mirror ``StockPortfolioEnv.__init__`` (env_portfolio.py:66-80); ``hmax``,
     ``transaction_cost_pct``, ``reward_scaling``, ``turbulence_threshold`` and ``lookback`` are accepted
-    and unused, exactly as in the reference's ``step``."""
+    and unused, exactly as in the reference's ``step``.  ``step`` / ``rollout`` / ``read_stats`` come from
+    :class:`BatchedEnvBase`; observations are returned as [N, D+K, D] float32 (materialised lazily)."""
+
+    _PREFIX = "frl_portfolio"
 
     def __init__(self, df=None, stock_dim=None, hmax=None, initial_amount=1_000_000, transaction_cost_pct=None,
                  reward_scaling=None, state_space=None, action_space=None, tech_indicator_list: Sequence[str] = (),
                  turbulence_threshold=None, lookback=252, day=0, *, n_envs=1, device="cuda",
                  tables: Optional[PortfolioTables] = None, track_weights: bool = False):
-        import torch
-
-        self._torch = torch
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise _cabi.EngineError("finrl_b200 runs on CUDA devices only (no CPU fallback)")
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
-        _cabi.lib()
+        torch = self._bind_device(device)
         if tables is None:
             if df is None:
                 raise ValueError("either df or tables is required")
@@ -118,36 +114,17 @@ class BatchedStockPortfolioEnv:
         p.ret_out = self.last_return.data_ptr() if track_weights else None
         p.weights_out = self.last_weights.data_ptr() if track_weights else None
         self._p = p
-        self.launches = 0
-        self.kernel_events = None
-
-    def _stream(self):
-        return _cabi.current_stream(self.device)
 
     def _obs_buf(self):
         if self._obs is None:
             self._obs = self._torch.empty((self.n_envs, self.tables.obs_dim), dtype=self._torch.float32, device=self.device)
         return self._obs
 
-    def _as_actions(self, actions, ndim):
-        torch = self._torch
-        if not isinstance(actions, torch.Tensor):
-            actions = torch.as_tensor(np.asarray(actions))
-        if actions.dtype not in (torch.float32, torch.float64):
-            actions = actions.to(torch.float32)
-        if actions.device != self.device:
-            actions = actions.to(self.device, non_blocking=True)
-        if actions.dim() != ndim or actions.shape[-1] != self.stock_dim:
-            raise ValueError(f"actions must have {ndim} dims ending in stock_dim={self.stock_dim}, got {tuple(actions.shape)}")
-        return actions
+    def _obs_out(self):
+        return self._obs_buf()
 
-    def observe(self, out=None):
-        """Materialised observation [N, D+K, D] float32."""
-        out = self._obs_buf() if out is None else out
-        with self._torch.cuda.device(self.device):
-            _cabi.check(_cabi.lib().frl_portfolio_observe(C.byref(self._p), _cabi.ptr(out), self._stream()), "frl_portfolio_observe")
-        self.launches += 1
-        return out.view(self.n_envs, *self.obs_shape)
+    def _shape_obs(self, obs):
+        return None if obs is None else obs.view(self.n_envs, *self.obs_shape)
 
     def observe_view(self):
         """The same observation without per-env copies: a gather of the per-day table by ``day``
@@ -156,75 +133,15 @@ class BatchedStockPortfolioEnv:
 
     def reset(self, mask=None, want_obs=True):
         torch = self._torch
-        if mask is not None:
-            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        mask = self._mask(mask)
         out = self._obs_buf() if want_obs else None
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().frl_portfolio_reset(C.byref(self._p), _cabi.ptr(mask), _cabi.ptr(out), self._stream()), "frl_portfolio_reset")
         self.launches += 2 if want_obs else 1
         return out.view(self.n_envs, *self.obs_shape) if want_obs else None
 
-    def step(self, actions, auto_reset=False, want_obs=True, accumulate_stats=False, want_done=True):
-        """One ``step`` -> (obs [N, D+K, D] f32 or None, reward[N] f64, done[N] bool, flags[N] u8)."""
-        a = self._as_actions(actions, 2)
-        if a.shape[0] != self.n_envs:
-            raise ValueError(f"actions must have n_envs={self.n_envs} rows")
-        a = a.contiguous()
-        obs = self._obs_buf() if want_obs else None
-        ev = self.kernel_events
-        with self._torch.cuda.device(self.device):
-            if ev is not None:
-                e0, e1 = self._torch.cuda.Event(enable_timing=True), self._torch.cuda.Event(enable_timing=True)
-                e0.record()
-            rc = _cabi.lib().frl_portfolio_step(
-                C.byref(self._p), _cabi.ptr(a), int(a.dtype == self._torch.float64), _cabi.ptr(self._rew),
-                _cabi.ptr(self._flags), _cabi.ptr(obs), int(auto_reset),
-                _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
-            )
-            if ev is not None:
-                e1.record()
-                ev.append((e0, e1))
-        _cabi.check(rc, "frl_portfolio_step")
-        self.launches += 1
-        done = (self._flags & _cabi.FLAG_DONE).bool() if want_done else None
-        return (obs.view(self.n_envs, *self.obs_shape) if want_obs else None), self._rew, done, self._flags
-
-    def rollout(self, actions, layout="KND", obs_mode="none", auto_reset=True, accumulate_stats=True):
-        torch = self._torch
-        a = self._as_actions(actions, 3)
-        D, N = self.stock_dim, self.n_envs
-        if layout == "KND":
-            K, ok = a.shape[0], a.shape[1] == N
-        elif layout == "NKD":
-            K, ok = a.shape[1], a.shape[0] == N
-        else:
-            raise ValueError("layout must be 'KND' or 'NKD'")
-        if not ok:
-            raise ValueError(f"actions shape {tuple(a.shape)} does not match n_envs={N} for layout {layout}")
-        a = a.contiguous()
-        step_stride, env_stride = (N * D, D) if layout == "KND" else (D, K * D)
-        mode = {"none": _cabi.OBS_NONE, "last": _cabi.OBS_LAST, "all": _cabi.OBS_ALL}[obs_mode]
-        rewards = torch.empty((K, N), dtype=torch.float64, device=self.device)
-        flags = torch.empty((K, N), dtype=torch.uint8, device=self.device)
-        obs = None
-        if mode == _cabi.OBS_LAST:
-            obs = self._obs_buf()
-        elif mode == _cabi.OBS_ALL:
-            obs = torch.empty((K, N, self.tables.obs_dim), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
-            _cabi.check(
-                _cabi.lib().frl_portfolio_rollout(
-                    C.byref(self._p), _cabi.ptr(a), int(a.dtype == torch.float64), step_stride, env_stride, int(K),
-                    _cabi.ptr(rewards), _cabi.ptr(flags), _cabi.ptr(obs), mode, int(auto_reset),
-                    _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
-                ),
-                "frl_portfolio_rollout",
-            )
-        self.launches += 1
-        return obs, rewards, flags
-
-    def read_stats(self, reset=False):
-        vals = self.stats.tolist()
-        if reset:
-            self.stats.zero_()
-        return dict(zip(_cabi.STAT_NAMES, vals))
+    def rollout(self, actions, layout="KND", obs_mode="none", auto_reset=True, accumulate_stats=True, **kw):
+        """As :meth:`BatchedEnvBase.rollout`; the default is ``obs_mode="none"`` because the observation is a
+        pure per-day table row (``tables.obs_table[day]``)."""
+        return super().rollout(actions, layout=layout, obs_mode=obs_mode, auto_reset=auto_reset,
+                               accumulate_stats=accumulate_stats, **kw)

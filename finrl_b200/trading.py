@@ -13,6 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _cabi
+from ._base import BatchedEnvBase
 from .tables import TradingTables
 
 
@@ -27,12 +28,15 @@ def _scalar_cost(x, name):
     return float(arr[0])
 
 
-class BatchedStockTradingEnv:
+class BatchedStockTradingEnv(BatchedEnvBase):
     """N lock-stepped (or not) ``StockTradingEnv`` instances on one GPU.
 
     Parameters mirror ``StockTradingEnv.__init__`` (env_stocktrading.py:24-47); extra keywords:
     ``n_envs``, ``device`` and ``tables`` (pre-built :class:`TradingTables`, instead of ``df``).
+    ``step`` / ``rollout`` / ``observe`` / ``read_stats`` come from :class:`BatchedEnvBase`.
     """
+
+    _PREFIX = "frl_trading"
 
     def __init__(
         self,
@@ -58,15 +62,7 @@ class BatchedStockTradingEnv:
         tables: Optional[TradingTables] = None,
         track_asset: bool = False,
     ):
-        import torch
-
-        self._torch = torch
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise _cabi.EngineError("finrl_b200 runs on CUDA devices only (no CPU fallback)")
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
-        _cabi.lib()  # fail loudly before any allocation if the extension is missing
+        torch = self._bind_device(device)
         if tables is None:
             if df is None:
                 raise ValueError("either df or tables is required")
@@ -146,120 +142,25 @@ class BatchedStockTradingEnv:
         self.asset = torch.zeros(N, dtype=torch.float64, device=dev) if track_asset else None
         p.asset_out = self.asset.data_ptr() if track_asset else None
         self._p = p
-        self.launches = 0  # kernels launched through the C-ABI (bench.py reports it)
-        self.kernel_events = None  # set to a list to collect (start, end) CUDA events around each step launch
         with torch.cuda.device(dev):
             _cabi.check(_cabi.lib().frl_trading_init(C.byref(p), int(day), self._stream()), "frl_trading_init")
         self.launches += 1
 
     # ------------------------------------------------------------------------------------------
-    def _stream(self):
-        return _cabi.current_stream(self.device)
+    def _reward_out(self):
+        return None  # the reward lives in the state (self.reward), like the reference's self.reward
 
-    def _as_actions(self, actions, ndim):
-        torch = self._torch
-        if not isinstance(actions, torch.Tensor):
-            actions = torch.as_tensor(np.asarray(actions))
-        if actions.dtype not in (torch.float32, torch.float64):
-            actions = actions.to(torch.float32)
-        if actions.device != self.device:
-            actions = actions.to(self.device, non_blocking=True)
-        if actions.dim() != ndim or actions.shape[-1] != self.stock_dim:
-            raise ValueError(f"actions must have {ndim} dims ending in stock_dim={self.stock_dim}, got {tuple(actions.shape)}")
-        return actions
-
-    # ------------------------------------------------------------------------------------------
-    def observe(self, out=None):
-        """float32 image of every env's state list (``render()``), shape [N, O]."""
-        out = self._obs if out is None else out
-        with self._torch.cuda.device(self.device):
-            _cabi.check(_cabi.lib().frl_trading_observe(C.byref(self._p), _cabi.ptr(out), self._stream()), "frl_trading_observe")
-        self.launches += 1
-        return out
+    def _reward_result(self):
+        return self.reward
 
     def reset(self, mask=None, out=None):
         """``StockTradingEnv.reset`` for all envs (or those with ``mask[n] != 0``)."""
-        torch = self._torch
         out = self._obs if out is None else out
-        if mask is not None:
-            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
-            if mask.shape != (self.n_envs,):
-                raise ValueError("mask must have shape [n_envs]")
-        with torch.cuda.device(self.device):
-            _cabi.check(
-                _cabi.lib().frl_trading_reset(C.byref(self._p), _cabi.ptr(mask), _cabi.ptr(out), self._stream()),
-                "frl_trading_reset",
-            )
+        mask = self._mask(mask)
+        with self._torch.cuda.device(self.device):
+            _cabi.check(self._fn("reset")(C.byref(self._p), _cabi.ptr(mask), _cabi.ptr(out), self._stream()), "frl_trading_reset")
         self.launches += 2
         return out
-
-    def step(self, actions, auto_reset: bool = False, want_obs: bool = True, accumulate_stats: bool = False,
-             want_done: bool = True):
-        """One ``step`` of every env.  Returns (obs[N,O] f32, reward[N] f64, done[N] bool, flags[N] u8).
-        The returned tensors are engine-owned buffers that the next call overwrites.  ``done`` is
-        ``flags & FLAG_DONE`` (two tiny torch kernels); pass ``want_done=False`` to get None instead."""
-        a = self._as_actions(actions, 2)
-        if a.shape[0] != self.n_envs:
-            raise ValueError(f"actions must have n_envs={self.n_envs} rows")
-        a = a.contiguous()
-        obs = self._obs if want_obs else None
-        ev = self.kernel_events
-        with self._torch.cuda.device(self.device):
-            if ev is not None:
-                e0, e1 = self._torch.cuda.Event(enable_timing=True), self._torch.cuda.Event(enable_timing=True)
-                e0.record()
-            rc = _cabi.lib().frl_trading_step(
-                C.byref(self._p), _cabi.ptr(a), int(a.dtype == self._torch.float64), None, _cabi.ptr(self._flags),
-                _cabi.ptr(obs), int(auto_reset), _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
-            )
-            if ev is not None:
-                e1.record()
-                ev.append((e0, e1))
-        _cabi.check(rc, "frl_trading_step")
-        self.launches += 1
-        done = (self._flags & _cabi.FLAG_DONE).bool() if want_done else None
-        return obs, self.reward, done, self._flags
-
-    def rollout(self, actions, layout: str = "KND", obs_mode: str = "last", auto_reset: bool = True,
-                accumulate_stats: bool = True, rewards=None, flags=None, obs=None):
-        """Fused multi-step rollout: ``actions`` is [K, N, D] (layout "KND", time-major like SB3's
-        rollout buffer) or [N, K, D] ("NKD").  Returns (obs, rewards[K,N] f64, flags[K,N] u8) where
-        obs is None / [N,O] / [K,N,O] for obs_mode "none" / "last" / "all"."""
-        torch = self._torch
-        a = self._as_actions(actions, 3)
-        D, N = self.stock_dim, self.n_envs
-        if layout == "KND":
-            K = a.shape[0]
-            ok = a.shape[1] == N
-        elif layout == "NKD":
-            K = a.shape[1]
-            ok = a.shape[0] == N
-        else:
-            raise ValueError("layout must be 'KND' or 'NKD'")
-        if not ok:
-            raise ValueError(f"actions shape {tuple(a.shape)} does not match n_envs={N} for layout {layout}")
-        a = a.contiguous()
-        step_stride, env_stride = (N * D, D) if layout == "KND" else (D, K * D)
-        mode = {"none": _cabi.OBS_NONE, "last": _cabi.OBS_LAST, "all": _cabi.OBS_ALL}[obs_mode]
-        if rewards is None:
-            rewards = torch.empty((K, N), dtype=torch.float64, device=self.device)
-        if flags is None:
-            flags = torch.empty((K, N), dtype=torch.uint8, device=self.device)
-        if mode == _cabi.OBS_LAST and obs is None:
-            obs = self._obs
-        elif mode == _cabi.OBS_ALL and obs is None:
-            obs = torch.empty((K, N, self.state_space), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
-            _cabi.check(
-                _cabi.lib().frl_trading_rollout(
-                    C.byref(self._p), _cabi.ptr(a), int(a.dtype == torch.float64), step_stride, env_stride, int(K),
-                    _cabi.ptr(rewards), _cabi.ptr(flags), _cabi.ptr(obs) if mode else None, mode, int(auto_reset),
-                    _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
-                ),
-                "frl_trading_rollout",
-            )
-        self.launches += 1
-        return (obs if mode else None), rewards, flags
 
     # ------------------------------------------------------------------------------------------
     def _chunk_params(self, start: int, count: int):
@@ -349,9 +250,3 @@ class BatchedStockTradingEnv:
         sd = torch.where(self.sday < 0, -self.sday - 1, self.sday).long()
         prices = self.tables.close[sd, : self.stock_dim]  # [N, D]
         return self.cash + (prices * self.hold.t().double()).sum(dim=1)
-
-    def read_stats(self, reset: bool = False):
-        vals = self.stats.tolist()
-        if reset:
-            self.stats.zero_()
-        return dict(zip(_cabi.STAT_NAMES, vals))
