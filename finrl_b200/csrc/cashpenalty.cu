@@ -357,20 +357,7 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
     if (stats) {
         double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, valid ? last_total : 0.0, st_liq,
                                  valid ? (double)n_steps : 0.0, st_short};
-#pragma unroll
-        for (int w = 4; w >= 1; w >>= 1) {
-            const bool up = (lane & w) != 0;
-#pragma unroll
-            for (int i = 0; i < w; ++i) {
-                const double keep = up ? v[i + w] : v[i];
-                const double send = up ? v[i] : v[i + w];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-            }
-        }
-        double s = v[0];
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        if (lane < 8 && s != 0.0) atomicAdd(stats + lane, s);
+        reduce_stats8(v, lane, stats);
     }
 }
 

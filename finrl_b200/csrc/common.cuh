@@ -68,4 +68,49 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// ---- the 8-slot statistics vector -----------------------------------------------------------------
+// 8 values x 32 lanes: three halving exchanges leave lane l with the partial sum of value (l & 7) over 4
+// lanes, two more butterflies finish it — 9 shuffles instead of 40 — then one atomicAdd per slot and warp.
+__device__ __forceinline__ void reduce_stats8(double (&v)[FRL_N_STATS], int lane, double *__restrict__ stats)
+{
+#pragma unroll
+    for (int w = 4; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const double keep = up ? v[i + w] : v[i];
+            const double send = up ? v[i] : v[i + w];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+    double s = v[0];
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    if (lane < 8 && s != 0.0) atomicAdd(stats + lane, s);
+}
+
+// ---- action staging -------------------------------------------------------------------------------
+// Stage one step's actions of a 32-env tile into shared memory, flat [32 envs][D] exactly as they lie in
+// global memory.  With the default layout (act_env_stride == D) the tile is one contiguous run: D fully
+// coalesced, independent loads per lane are issued back to back, then parked.  Rows beyond the valid envs
+// are zero-filled.  Callers bracket this with __syncwarp().
+template <int SLOTS, typename ActT>
+__device__ __forceinline__ void stage_actions_flat(ActT *__restrict__ dst, const ActT *__restrict__ abase, long long env0,
+                                                   long long act_env_stride, int D, int nvalid, int lane)
+{
+    if (act_env_stride == D) {
+        const ActT *tile = abase + (size_t)env0 * D + lane;
+        const int cnt = nvalid * D - lane;
+        ActT av[SLOTS];
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i) av[i] = (i < D && 32 * i < cnt) ? __ldcs(tile + 32 * i) : ActT(0);
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i)
+            if (i < D) dst[lane + 32 * i] = av[i];
+    } else {
+        for (int r = 0; r < 32; ++r)
+            if (lane < D) dst[r * D + lane] = r < nvalid ? abase[(size_t)(env0 + r) * act_env_stride + lane] : ActT(0);
+    }
+}
+
 }  // namespace frl

@@ -150,20 +150,7 @@ portfolio_rollout_kernel(const frl_portfolio_params p, const ActT *__restrict__ 
     for (int k = 0; k < n_steps; ++k) {
         const ActT *abase = actions + (size_t)k * act_step_stride;
         __syncwarp();
-        if (act_env_stride == D) {
-            const ActT *tile = abase + (size_t)env0 * D + lane;
-            const int cnt = nvalid * D - lane;
-            ActT av[SLOTS];
-#pragma unroll
-            for (int i = 0; i < SLOTS; ++i) av[i] = (i < D && 32 * i < cnt) ? __ldcs(tile + 32 * i) : ActT(0);
-#pragma unroll
-            for (int i = 0; i < SLOTS; ++i)
-                if (i < D) sm.act[lane + 32 * i] = av[i];
-        } else {
-            for (int r = 0; r < 32; ++r)
-                if (lane < D)
-                    sm.act[r * D + lane] = r < nvalid ? abase[(size_t)(env0 + r) * act_env_stride + lane] : ActT(0);
-        }
+        stage_actions_flat<SLOTS, ActT>(sm.act, abase, env0, act_env_stride, D, nvalid, lane);
         __syncwarp();
 
         uint8_t flags = 0;
@@ -224,20 +211,7 @@ portfolio_rollout_kernel(const frl_portfolio_params p, const ActT *__restrict__ 
     }
     if (stats) {
         double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, valid ? pv : 0.0, 0.0, valid ? (double)n_steps : 0.0, 0.0};
-#pragma unroll
-        for (int w = 4; w >= 1; w >>= 1) {
-            const bool up = (lane & w) != 0;
-#pragma unroll
-            for (int i = 0; i < w; ++i) {
-                const double keep = up ? v[i + w] : v[i];
-                const double send = up ? v[i] : v[i + w];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-            }
-        }
-        double s = v[0];
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        if (lane < 8 && s != 0.0) atomicAdd(stats + lane, s);
+        reduce_stats8(v, lane, stats);
     }
 }
 

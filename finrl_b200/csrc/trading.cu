@@ -246,22 +246,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
         // ---- stage this step's actions for the tile (coalesced) ----
         const ActT *abase = actions + (size_t)k * act_step_stride;
         __syncwarp();
-        if (act_env_stride == D) {
-            // the tile's 32 x D actions are one contiguous run: D fully coalesced, independent loads
-            // per lane, parked flat in shared memory (rows beyond the valid envs are zero-filled)
-            const ActT *tile = abase + (size_t)env0 * D + lane;
-            const int cnt = nvalid * D - lane;
-            ActT av[SLOTS];
-#pragma unroll
-            for (int i = 0; i < SLOTS; ++i) av[i] = (i < D && 32 * i < cnt) ? ld_stream(tile + 32 * i) : ActT(0);
-#pragma unroll
-            for (int i = 0; i < SLOTS; ++i)
-                if (i < D) sm.act[lane + 32 * i] = av[i];
-        } else {
-            for (int r = 0; r < 32; ++r)
-                if (lane < D)
-                    sm.act[r * D + lane] = r < nvalid ? abase[(size_t)(env0 + r) * act_env_stride + lane] : ActT(0);
-        }
+        stage_actions_flat<SLOTS, ActT>(sm.act, abase, env0, act_env_stride, D, nvalid, lane);
         __syncwarp();
 
         uint8_t flags = 0;
@@ -424,24 +409,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
             steps = (double)n_steps;
         }
         double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, fin_asset, st_liq, steps, fin_trades};
-        // 8 values x 32 lanes: three halving exchanges leave lane l with the partial sum of value
-        // (l & 7) over 4 lanes, two more butterflies finish it — 9 shuffles instead of 40.
-#pragma unroll
-        for (int w = 4; w >= 1; w >>= 1) {
-            const bool up = (lane & w) != 0;
-#pragma unroll
-            for (int i = 0; i < w; ++i) {
-                const double keep = up ? v[i + w] : v[i];
-                const double send = up ? v[i] : v[i + w];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-            }
-        }
-        double s = v[0];
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        // lane l (< 8) now holds stat index bitrev3(l)... resolve the index the exchanges produced
-        const int idx = ((lane & 4) ? 4 : 0) + ((lane & 2) ? 2 : 0) + ((lane & 1) ? 1 : 0);
-        if (lane < 8 && s != 0.0) atomicAdd(stats + idx, s);
+        reduce_stats8(v, lane, stats);
     }
 }
 
