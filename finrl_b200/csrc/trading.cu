@@ -10,8 +10,12 @@
 // Bit-exactness: every product/sum on the cash path is an explicit __dmul_rn/__dadd_rn in the
 // reference's order; np.argsort's tie order is reproduced by running the same bitonic network
 //  on register-resident packed keys.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "sort_network.inc"
+#include "trading_common.cuh"
 
 // tuning knobs (A/B-tested on B200, see profiles/)
 #ifndef FRL_LD_STREAM
@@ -46,8 +50,6 @@ __device__ __forceinline__ void st_stream(T *p, T v)
 #endif
 }
 
-constexpr int kMaxAbsAction = (1 << 26) - 1;  // |int(action*hmax)| is clamped to this (key packing)
-
 // keys are (a << 5) | index; swap only on STRICT a[lo] > a[hi] — ties keep network order.
 #define FRL_CEX(lo, hi)                                                                            \
     {                                                                                              \
@@ -72,23 +74,6 @@ __device__ __forceinline__ void bitonic_network(int (&key)[SLOTS])
     }
 }
 
-template <typename ActT>
-__device__ __forceinline__ int action_to_shares(ActT a, double hmax);
-template <>
-__device__ __forceinline__ int action_to_shares<float>(float a, double hmax)
-{
-    // float32 array * python int -> float32 product, then astype(int) truncates toward zero.
-    // cvt.rzi.s32.f32 saturates, so |v| >= 2^31 lands on the clamp like the int64 cast would.
-    const int t = __float2int_rz(fmul(a, (float)hmax));
-    return max(-kMaxAbsAction, min(kMaxAbsAction, t));
-}
-template <>
-__device__ __forceinline__ int action_to_shares<double>(double a, double hmax)
-{
-    const int t = __double2int_rz(dmul(a, hmax));
-    return max(-kMaxAbsAction, min(kMaxAbsAction, t));
-}
-
 constexpr int kHoldPitch = 33;  // hold_s[j][lane]: conflict-free both per-lane (compute) and per-row (obs)
 
 template <int SLOTS, typename ActT, int WARPS>
@@ -102,7 +87,6 @@ struct alignas(16) WarpSmem {
     int sd[32];
 };
 
-__device__ __forceinline__ int state_day(int sday) { return sday < 0 ? -sday - 1 : sday; }
 
 // sequential Python sum() of price*holding over the D stocks, then cash + that (:311-314, :344-347)
 template <int SLOTS>
@@ -534,6 +518,21 @@ extern "C" int32_t frl_trading_rollout(const frl_trading_params *p, const void *
     FRL_REQUIRE(obs_mode == FRL_OBS_NONE || obs != nullptr, "trading_rollout: obs is NULL but obs_mode=%d", obs_mode);
     cudaStream_t st = (cudaStream_t)stream;
     const int D = p->stock_dim;
+    // Small batches are latency-bound in the thread-per-env kernel; below the measured crossover (~8K envs)
+    // the 8-lanes-per-env kernel of trading_small.cu is faster (table in its header).
+    // FRL_TRADING_KERNEL=tile|small forces one of them (tests run the whole parity suite under both).
+    static const int small_max = [] {
+        const char *f = getenv("FRL_TRADING_KERNEL");
+        if (f && !strcmp(f, "tile")) return 0;
+        if (f && !strcmp(f, "small")) return 0x7fffffff;
+        const char *m = getenv("FRL_TRADING_SMALL_MAX");
+        return m ? atoi(m) : 8192;
+    }();
+    if (p->n_envs <= small_max) {
+        launch_trading_small(*p, actions, actions_f64, act_step_stride, act_env_stride, n_steps, rewards, flags, obs,
+                             obs_mode, auto_reset, stats, st);
+        return check_launch("trading_rollout(small)");
+    }
 #define FRL_GO(SLOTS, DCT)                                                                                        \
     do {                                                                                                          \
         if (actions_f64)                                                                                          \

@@ -15,6 +15,13 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
+def test_both_kernels_are_exercised_by_this_suite():
+    """frl_trading_rollout picks the 8-lanes-per-env kernel for n_envs <= 8192 and the thread-per-env kernel
+    above (FRL_TRADING_KERNEL=tile|small forces one; CI runs this file under both).  The sizes used below
+    (1, 33, 70, 100, 4096 / 4103, 5000, 1M) cover both sides of the switch."""
+    assert os.environ.get("FRL_TRADING_KERNEL", "") in ("", "tile", "small")
+
+
 def _env_from_golden(g, n_envs=1):
     from finrl_b200 import BatchedStockTradingEnv, TradingTables
 
