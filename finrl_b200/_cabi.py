@@ -188,6 +188,7 @@ NP_REWARD_KIND_SHIFT = 4
 SIGNATURES = {
     "frl_abi_version": (C.c_int32, []),
     "frl_last_error": (C.c_char_p, []),
+    "frl_set_option": (C.c_int32, [C.c_char_p, C.c_int64]),
     "frl_trading_init": (C.c_int32, [C.POINTER(TradingParams), C.c_int32, C.c_void_p]),
     "frl_trading_reset": (C.c_int32, [C.POINTER(TradingParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "frl_trading_observe": (C.c_int32, [C.POINTER(TradingParams), C.c_void_p, C.c_void_p]),
@@ -282,6 +283,11 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = lib().frl_last_error().decode("utf-8", "replace")
         raise EngineError(f"{what} failed (status {rc}): {msg}")
+
+
+def set_option(name: str, value: int):
+    """frl_set_option: e.g. set_option("trading_small_max", 0) forces the thread-per-env trading kernel."""
+    check(lib().frl_set_option(name.encode(), int(value)), f"frl_set_option({name})")
 
 
 def ptr(t):

@@ -462,6 +462,24 @@ int32_t validate(const frl_trading_params *p)
     return FRL_OK;
 }
 
+// n_envs at or below which frl_trading_rollout uses the 8-lanes-per-env kernel; FRL_TRADING_KERNEL=tile|small
+// or FRL_TRADING_SMALL_MAX set the default, frl_set_option("trading_small_max", v) changes it at run time.
+int g_small_max = -1;
+int trading_small_max()
+{
+    if (g_small_max < 0) {
+        const char *f = getenv("FRL_TRADING_KERNEL");
+        const char *m = getenv("FRL_TRADING_SMALL_MAX");
+        if (f && !strcmp(f, "tile"))
+            g_small_max = 0;
+        else if (f && !strcmp(f, "small"))
+            g_small_max = 0x7fffffff;
+        else
+            g_small_max = m ? atoi(m) : 8192;
+    }
+    return g_small_max;
+}
+
 template <int SLOTS, int DCT, typename ActT, int WARPS>
 void launch_rollout(const frl_trading_params &p, const void *actions, long long sstride, long long estride, int n_steps,
                     double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats,
@@ -477,6 +495,18 @@ void launch_rollout(const frl_trading_params &p, const void *actions, long long 
 }  // namespace frl
 
 using namespace frl;
+
+extern "C" int32_t frl_set_option(const char *name, int64_t value)
+{
+    FRL_REQUIRE(name != nullptr, "set_option: name is NULL");
+    if (!strcmp(name, "trading_small_max")) {
+        FRL_REQUIRE(value >= 0, "set_option: trading_small_max must be >= 0");
+        g_small_max = value > 0x7fffffff ? 0x7fffffff : (int)value;
+        return FRL_OK;
+    }
+    set_error("set_option: unknown option '%s'", name);
+    return FRL_E_INVALID;
+}
 
 extern "C" int32_t frl_trading_init(const frl_trading_params *p, int32_t day0, void *stream)
 {
@@ -521,14 +551,7 @@ extern "C" int32_t frl_trading_rollout(const frl_trading_params *p, const void *
     // Small batches are latency-bound in the thread-per-env kernel; below the measured crossover (~8K envs)
     // the 8-lanes-per-env kernel of trading_small.cu is faster (table in its header).
     // FRL_TRADING_KERNEL=tile|small forces one of them (tests run the whole parity suite under both).
-    static const int small_max = [] {
-        const char *f = getenv("FRL_TRADING_KERNEL");
-        if (f && !strcmp(f, "tile")) return 0;
-        if (f && !strcmp(f, "small")) return 0x7fffffff;
-        const char *m = getenv("FRL_TRADING_SMALL_MAX");
-        return m ? atoi(m) : 8192;
-    }();
-    if (p->n_envs <= small_max) {
+    if (p->n_envs <= trading_small_max()) {
         launch_trading_small(*p, actions, actions_f64, act_step_stride, act_env_stride, n_steps, rewards, flags, obs,
                              obs_mode, auto_reset, stats, st);
         return check_launch("trading_rollout(small)");

@@ -60,6 +60,9 @@ extern "C" {
 #define FRL_N_STATS 8
 
 FRL_API int32_t frl_abi_version(void);
+/* Tuning knobs.  "trading_small_max": frl_trading_step/rollout use the low-latency 8-lanes-per-env kernel
+ * for n_envs <= value and the thread-per-env kernel above (default 8192, the measured crossover; 0 = never). */
+FRL_API int32_t frl_set_option(const char *name, int64_t value);
 /* thread-local, never NULL; valid until the next failing call on this thread */
 FRL_API const char *frl_last_error(void);
 

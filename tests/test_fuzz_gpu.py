@@ -8,10 +8,13 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
+@pytest.mark.parametrize("kernel", ["tile", "small"])
 @pytest.mark.parametrize("seed", range(14))
-def test_trading_fuzz(seed):
-    from finrl_b200 import BatchedStockTradingEnv, TradingTables, synthetic as syn
+def test_trading_fuzz(seed, kernel):
+    from finrl_b200 import BatchedStockTradingEnv, TradingTables, _cabi, synthetic as syn
     from oracle import oracle as ora
+
+    _cabi.set_option("trading_small_max", 0 if kernel == "tile" else 2**31 - 1)
 
     rng = np.random.default_rng(1000 + seed)
     D = int(rng.integers(1, 33))
@@ -46,6 +49,7 @@ def test_trading_fuzz(seed):
             assert np.array_equal(st[name].cpu().numpy(), ref), ctx + " " + name
         if not auto and s % 7 == 6:
             assert np.array_equal(env.reset().cpu().numpy(), o.reset()), ctx
+    _cabi.set_option("trading_small_max", 8192)
 
 
 @pytest.mark.parametrize("seed", range(10))

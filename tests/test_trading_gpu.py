@@ -15,11 +15,15 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-def test_both_kernels_are_exercised_by_this_suite():
-    """frl_trading_rollout picks the 8-lanes-per-env kernel for n_envs <= 8192 and the thread-per-env kernel
-    above (FRL_TRADING_KERNEL=tile|small forces one; CI runs this file under both).  The sizes used below
-    (1, 33, 70, 100, 4096 / 4103, 5000, 1M) cover both sides of the switch."""
-    assert os.environ.get("FRL_TRADING_KERNEL", "") in ("", "tile", "small")
+@pytest.fixture(autouse=True, params=["tile", "small"])
+def trading_kernel(request):
+    """Every test of this file runs twice: with the thread-per-env kernel (trading.cu) and with the
+    8-lanes-per-env low-latency kernel (trading_small.cu) forced for all batch sizes."""
+    from finrl_b200 import _cabi
+
+    _cabi.set_option("trading_small_max", 0 if request.param == "tile" else 2**31 - 1)
+    yield request.param
+    _cabi.set_option("trading_small_max", 8192)
 
 
 def _env_from_golden(g, n_envs=1):
@@ -202,7 +206,13 @@ def test_masked_reset_and_stale_day():
     _compare(env, o)
 
 
-def test_full_size_properties():
+def test_full_size_properties(trading_kernel):
+    if trading_kernel == "small":
+        pytest.skip("the 1M-env workload belongs to the thread-per-env kernel")
+    _full_size_properties()
+
+
+def _full_size_properties():
     """BASELINE size (1M envs/GPU): size-independent properties instead of a CPU replay.
     (1) every env fed the SAME actions must end bit-identical to env 0, which is checked against
     the oracle; (2) obs rows are consistent with the state arrays; (3) stats add up."""
