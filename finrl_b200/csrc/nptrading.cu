@@ -316,7 +316,10 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
                             const double am = amount.k == FRL_KIND_F64 ? amount.v : (double)(float)amount.v;
                             const bool plenty = am >= dmul((double)(aj + 1), (double)pj);
                             double avail = 0.0;
-                            if (!plenty)
+                            // 0 <= amount < price: the quotient is exactly 0 (the usual state of a cash-starved
+                            // env) — only the division is skipped, the zero-share update still runs (it can
+                            // change the numpy kind of `amount` and it resets the cool-down counter)
+                            if (!plenty && !(am >= 0.0 && am < (double)pj))
                                 avail = amount.k == FRL_KIND_F64 ? floor_div_f64(am, (double)pj)
                                                                   : (double)floor_div_f32((float)am, pj);
                             if (plenty) {  // min(avail, action) -> the int64

@@ -326,8 +326,13 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
                         const double pj = __ldg(prow + j);
                         const double unit = dmul(pj, one_plus_bc);
                         double nsh = (double)a;
-                        // min(cash // unit, a): the quotient only matters when cash < (a+1)*unit
+                        trades += 1;  // even when 0 shares end up bought (Q5)
+                        // min(cash // unit, a): the quotient only matters when cash < (a+1)*unit ...
                         if (!(cash >= dmul(nsh + 1.0, unit))) {
+                            // ... and when not even one share is affordable it is exactly 0: buying 0 shares
+                            // changes nothing (x - 0.0 and x + 0.0 are identities) — the common state of a
+                            // cash-starved env, which then skips the division and the whole update
+                            if (cash >= 0.0 && cash < unit) continue;
                             const double avail = floor_div_f64(cash, unit);
                             nsh = (nsh < avail) ? nsh : avail;
                         }
@@ -335,7 +340,6 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
                         cash = dsub(cash, dmul(pv, one_plus_bc));
                         sm.hold[j * kHoldPitch + lane] += (int)nsh;
                         cost = dadd(cost, dmul(pv, p.buy_cost_pct));
-                        trades += 1;  // even when nsh == 0 (Q5)
                     }
                 }
             }

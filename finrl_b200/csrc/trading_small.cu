@@ -304,13 +304,18 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
                             cost = dadd(cost, bc);
                             e.hold[j] = bh + a;
                         } else {
-                            const double avail = floor_div_f64(cash, dmul(pj, one_plus_bc));
-                            double nsh = (double)a;
-                            nsh = (nsh < avail) ? nsh : avail;
-                            const double pv = dmul(pj, nsh);
-                            cash = dsub(cash, dmul(pv, one_plus_bc));
-                            cost = dadd(cost, dmul(pv, p.buy_cost_pct));
-                            e.hold[j] = bh + (int)nsh;
+                            const double unit = dmul(pj, one_plus_bc);
+                            // not even one share affordable: cash // unit == 0 exactly and buying 0 shares is a
+                            // no-op (the common state of a cash-starved env) — skip the division
+                            if (!(cash >= 0.0 && cash < unit)) {
+                                const double avail = floor_div_f64(cash, unit);
+                                double nsh = (double)a;
+                                nsh = (nsh < avail) ? nsh : avail;
+                                const double pv = dmul(pj, nsh);
+                                cash = dsub(cash, dmul(pv, one_plus_bc));
+                                cost = dadd(cost, dmul(pv, p.buy_cost_pct));
+                                e.hold[j] = bh + (int)nsh;
+                            }
                         }
                         thr = thr_n; spend = spend_n; bc = bc_n; pj = pj_n; kk = kk_n; bh = bh_n;
                     }
