@@ -21,7 +21,7 @@ N_STATS = 8
 STAT_NAMES = ("reward_sum", "reward_sqsum", "done_count", "episode_asset_sum", "asset_sum", "liq_count", "env_steps",
               "trades_sum")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class EngineError(RuntimeError):
@@ -44,7 +44,7 @@ class TradingParams(C.Structure):
         ("sell_cost_pct", C.c_double),
         ("reward_scaling", C.c_double),
         ("use_turbulence", C.c_int32),
-        ("_pad0", C.c_int32),
+        ("close_pitch", C.c_int32),
         ("turbulence_threshold", C.c_double),
         ("close", C.c_void_p),
         ("disable_mask", C.c_void_p),

@@ -240,7 +240,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
             flags = FRL_FLAG_DONE;
             reward = last_reward;
             if (valid) {
-                const double *prow = p.close + (size_t)state_day(sday) * 32;
+                const double *prow = p.close + (size_t)state_day(sday) * p.close_pitch;
                 if (!asset_ok) asset = total_asset<SLOTS>(cash, prow, sm.hold, lane, D);
                 st_done += 1.0;
                 st_epi += asset;
@@ -263,7 +263,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
             const int sd = state_day(sday);
             const double turb = sday < 0 ? 0.0 : __ldg(p.risk + sd);
             const bool liq = p.use_turbulence && (turb >= p.turbulence_threshold);
-            const double *prow = p.close + (size_t)sd * 32;
+            const double *prow = p.close + (size_t)sd * p.close_pitch;
             const double begin = asset_ok ? asset : total_asset<SLOTS>(cash, prow, sm.hold, lane, D);
 
             if (liq) {
@@ -346,7 +346,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
             // ---- state: s -> s+1 (:335-352) ----
             day += 1;
             sday = day;
-            asset = total_asset<SLOTS>(cash, p.close + (size_t)day * 32, sm.hold, lane, D);
+            asset = total_asset<SLOTS>(cash, p.close + (size_t)day * p.close_pitch, sm.hold, lane, D);
             asset_ok = true;
             reward = dmul(dsub(asset, begin), p.reward_scaling);
             last_reward = reward;
@@ -382,7 +382,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
     }
     if (p.asset_out) {
         if (!asset_ok) {
-            asset = total_asset<SLOTS>(cash, p.close + (size_t)state_day(sday) * 32, sm.hold, lane, D);
+            asset = total_asset<SLOTS>(cash, p.close + (size_t)state_day(sday) * p.close_pitch, sm.hold, lane, D);
             asset_ok = true;
         }
         if (valid) p.asset_out[n] = asset;
@@ -391,7 +391,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
         double fin_asset = 0.0, fin_trades = 0.0, steps = 0.0;
         if (valid) {
             if (!asset_ok)
-                asset = total_asset<SLOTS>(cash, p.close + (size_t)state_day(sday) * 32, sm.hold, lane, D);
+                asset = total_asset<SLOTS>(cash, p.close + (size_t)state_day(sday) * p.close_pitch, sm.hold, lane, D);
             fin_asset = asset;
             fin_trades = (double)trades;
             steps = (double)n_steps;
@@ -449,16 +449,37 @@ __global__ void __launch_bounds__(WARPS * 32) trading_observe_kernel(const frl_t
     write_obs_tile<0>(p, sm, obs, env0, nvalid, lane);
 }
 
+// D > 32: one warp per env, holdings straight from the stock-major array (only used by observe/reset)
+__global__ void trading_observe_wide_kernel(const frl_trading_params p, float *__restrict__ obs)
+{
+    const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= p.n_envs) return;
+    const int O = p.obs_dim, D = p.stock_dim;
+    const float *trow = p.obs_tmpl + (size_t)state_day(p.sday[n]) * O;
+    float *orow = obs + (size_t)n * O;
+    for (int pos = lane; pos < O; pos += 32) {
+        float v = __ldg(trow + pos);
+        if (pos == 0)
+            v = (float)p.cash[n];
+        else if (pos > D && pos <= 2 * D)
+            v = (float)p.hold[(size_t)(pos - 1 - D) * p.env_stride + n];
+        orow[pos] = v;
+    }
+}
+
 int32_t validate(const frl_trading_params *p)
 {
     FRL_REQUIRE(p != nullptr, "trading: params is NULL");
     FRL_REQUIRE(p->n_envs >= 1, "trading: n_envs must be >= 1 (got %d)", p->n_envs);
-    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 32, "trading: stock_dim must be in 1..32 (got %d)", p->stock_dim);
+    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 128, "trading: stock_dim must be in 1..128 (got %d)", p->stock_dim);
+    FRL_REQUIRE((p->close_pitch == 32 || p->close_pitch == 128) && p->close_pitch >= p->stock_dim,
+                "trading: close_pitch must be 32 or 128 and >= stock_dim (got %d for D=%d)", p->close_pitch, p->stock_dim);
     FRL_REQUIRE(p->n_tech >= 0 && p->n_days >= 1, "trading: bad n_tech/n_days (%d, %d)", p->n_tech, p->n_days);
     FRL_REQUIRE(p->obs_dim == 1 + 2 * p->stock_dim + p->n_tech * p->stock_dim,
                 "trading: obs_dim %d != 1 + 2D + K*D = %d", p->obs_dim, 1 + 2 * p->stock_dim + p->n_tech * p->stock_dim);
     FRL_REQUIRE(p->env_stride >= p->n_envs, "trading: env_stride %d < n_envs %d", p->env_stride, p->n_envs);
-    FRL_REQUIRE((long long)p->env_stride * 32 < (1LL << 31), "trading: env_stride %d too large (32*stride must be < 2^31)",
+    FRL_REQUIRE((long long)p->env_stride * p->close_pitch < (1LL << 31), "trading: env_stride %d too large (pitch*stride must be < 2^31)",
                 p->env_stride);
     FRL_REQUIRE(p->close && p->risk && p->obs_tmpl, "trading: table pointer is NULL");
     FRL_REQUIRE(p->cash && p->hold && p->day && p->sday && p->cost && p->trades && p->reward && p->episode,
@@ -525,6 +546,11 @@ extern "C" int32_t frl_trading_observe(const frl_trading_params *p, float *obs, 
     if (int32_t rc = validate(p)) return rc;
     FRL_REQUIRE(obs != nullptr, "trading_observe: obs is NULL");
     constexpr int W = 4;
+    if (p->stock_dim > 32) {
+        const long long threads = (long long)p->n_envs * 32;
+        trading_observe_wide_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*p, obs);
+        return check_launch("trading_observe");
+    }
     const long long tiles = ((long long)p->n_envs + 31) / 32;
     trading_observe_kernel<W><<<(unsigned)((tiles + W - 1) / W), W * 32, 0, (cudaStream_t)stream>>>(*p, obs);
     return check_launch("trading_observe");
@@ -555,7 +581,7 @@ extern "C" int32_t frl_trading_rollout(const frl_trading_params *p, const void *
     // Small batches are latency-bound in the thread-per-env kernel; below the measured crossover (~8K envs)
     // the 8-lanes-per-env kernel of trading_small.cu is faster (table in its header).
     // FRL_TRADING_KERNEL=tile|small forces one of them (tests run the whole parity suite under both).
-    if (p->n_envs <= trading_small_max()) {
+    if (p->n_envs <= trading_small_max() || p->stock_dim > 32) {
         launch_trading_small(*p, actions, actions_f64, act_step_stride, act_env_stride, n_steps, rewards, flags, obs,
                              obs_mode, auto_reset, stats, st);
         return check_launch("trading_rollout(small)");

@@ -31,27 +31,39 @@ namespace {
 
 constexpr int kGroup = 8;  // lanes per env
 
-struct alignas(16) OctEnv {  // per-env scratch
-    double sell_cash[32], sell_cost[32];  // by sorted position (0.0 where nothing is sold)
+template <int S>
+struct alignas(16) OctEnv {  // per-env scratch, S = 8R slots
+    double sell_cash[S], sell_cost[S];  // by sorted position (0.0 where nothing is sold)
     // enabled buys, COMPACTED in execution order (largest action first): entry 0 is processed first
-    double buy_thr[32], buy_spend[32], buy_cost[32], buy_p[32];
-    double prod[32];  // by stock index: price * holding for the sequential asset sum
-    int buy_aj[32];   // (a << 5) | j
-    int buy_h[32];    // holding before the buy
-    int hold[32];     // by stock index
+    double buy_thr[S], buy_spend[S], buy_cost[S], buy_p[S];
+    double prod[S];  // by stock index: price * holding for the sequential asset sum
+    int buy_aj[S];   // (a << IB) | j
+    int buy_h[S];    // holding before the buy
+    int hold[S];     // by stock index
 };
 
-// strict-greater compare-exchange on packed keys (a << 5) | index: ties keep network order
+// packed keys (a << IB) | index with IB index bits (5 up to 32 slots, 7 up to 128)
+template <int R>
+struct KeyBits {
+    static constexpr int IB = (8 * R <= 32) ? 5 : 7;
+    static constexpr int MASK = (1 << IB) - 1;
+    static constexpr int AMAX = (1 << (31 - IB)) - 1;  // |int(action*hmax)| clamp that keeps the key in int32
+                                                       // (IB = 5: 2^26 - 1, the same clamp as trading.cu)
+};
+
+// strict-greater compare-exchange on packed keys: ties keep network order
+template <int MASK>
 __device__ __forceinline__ void cex_local(int &lo, int &hi)
 {
-    const bool sw = lo > (hi | 31);
+    const bool sw = lo > (hi | MASK);
     const int t = sw ? hi : lo;
     hi = sw ? lo : hi;
     lo = t;
 }
+template <int MASK>
 __device__ __forceinline__ int cex_remote(int mine, int other, bool i_am_lo)
 {
-    const bool sw = i_am_lo ? (mine > (other | 31)) : (other > (mine | 31));
+    const bool sw = i_am_lo ? (mine > (other | MASK)) : (other > (mine | MASK));
     return sw ? other : mine;
 }
 
@@ -61,6 +73,7 @@ template <int R>
 __device__ __forceinline__ void distributed_network(int (&key)[R], int l, unsigned gmask)
 {
     constexpr int SLOTS = kGroup * R;
+    constexpr int MASK = KeyBits<R>::MASK;
 #pragma unroll
     for (int blk = 2; blk <= SLOTS; blk <<= 1) {
         // ---- flip stage: pairs (b+i, b+blk-1-i) ----
@@ -68,7 +81,7 @@ __device__ __forceinline__ void distributed_network(int (&key)[R], int l, unsign
 #pragma unroll
             for (int b = 0; b < R; b += blk)
 #pragma unroll
-                for (int i = 0; i < blk / 2; ++i) cex_local(key[b + i], key[b + blk - 1 - i]);
+                for (int i = 0; i < blk / 2; ++i) cex_local<MASK>(key[b + i], key[b + blk - 1 - i]);
         } else {
             const int lanes = blk / R;                   // lanes spanned by one block
             const int partner_xor = lanes - 1;           // mirrored lane inside the block
@@ -77,7 +90,7 @@ __device__ __forceinline__ void distributed_network(int (&key)[R], int l, unsign
 #pragma unroll
             for (int r = 0; r < R; ++r) other[r] = __shfl_xor_sync(gmask, key[R - 1 - r], partner_xor);
 #pragma unroll
-            for (int r = 0; r < R; ++r) key[r] = cex_remote(key[r], other[r], i_am_lo);
+            for (int r = 0; r < R; ++r) key[r] = cex_remote<MASK>(key[r], other[r], i_am_lo);
         }
         // ---- half-cleaners: pairs (x, x+d), d = blk/4 ... 1 ----
 #pragma unroll
@@ -86,14 +99,14 @@ __device__ __forceinline__ void distributed_network(int (&key)[R], int l, unsign
 #pragma unroll
                 for (int b = 0; b < R; b += 2 * d)
 #pragma unroll
-                    for (int i = 0; i < d; ++i) cex_local(key[b + i], key[b + i + d]);
+                    for (int i = 0; i < d; ++i) cex_local<MASK>(key[b + i], key[b + i + d]);
             } else {
                 const int lx = d / R;
                 const bool i_am_lo = (l & lx) == 0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const int other = __shfl_xor_sync(gmask, key[r], lx);
-                    key[r] = cex_remote(key[r], other, i_am_lo);
+                    key[r] = cex_remote<MASK>(key[r], other, i_am_lo);
                 }
             }
         }
@@ -102,7 +115,7 @@ __device__ __forceinline__ void distributed_network(int (&key)[R], int l, unsign
 
 // sequential Python sum() of price*holding (lanes prepare the products, the leader adds them in order)
 template <int R>
-__device__ __forceinline__ double group_total_asset(OctEnv &e, double cash, const double *__restrict__ prow, int D, int l,
+__device__ __forceinline__ double group_total_asset(OctEnv<8 * R> &e, double cash, const double *__restrict__ prow, int D, int l,
                                                     unsigned gmask)
 {
 #pragma unroll
@@ -127,11 +140,14 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
                      long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
                      float *__restrict__ obs, int obs_mode, int auto_reset, double *__restrict__ stats)
 {
-    __shared__ OctEnv smem[WARPS * 4];
+    using Env = OctEnv<8 * R>;
+    constexpr int IB = KeyBits<R>::IB, IMASK = KeyBits<R>::MASK, AMAX = KeyBits<R>::AMAX;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Env *smem = reinterpret_cast<Env *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 3, l = lane & 7;
     const unsigned gmask = 0xffu << (8 * g);
-    OctEnv &e = smem[warp * 4 + g];
+    Env &e = smem[warp * 4 + g];
     const int N = p.n_envs, D = p.stock_dim, T = p.n_days, O = p.obs_dim;
     const long long n = ((long long)blockIdx.x * WARPS + warp) * 4 + g;
     if (n >= N) return;  // group-uniform: nothing below synchronises wider than the group
@@ -146,7 +162,7 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
     }
     __syncwarp(gmask);
     const double one_minus_sc = dsub(1.0, p.sell_cost_pct), one_plus_bc = dadd(1.0, p.buy_cost_pct);
-    const int hmax_i = (int)max(-(double)kMaxAbsAction, min((double)kMaxAbsAction, p.hmax));
+    const int hmax_i = (int)max(-(double)AMAX, min((double)AMAX, p.hmax));
     double asset = 0.0;
     bool asset_ok = false;
     double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_liq = 0.0;
@@ -166,7 +182,7 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
             flags = FRL_FLAG_DONE;
             reward = last_reward;
             if (!asset_ok) {
-                asset = __shfl_sync(gmask, group_total_asset<R>(e, cash, p.close + (size_t)state_day(sday) * 32, D, l, gmask), 8 * g);
+                asset = __shfl_sync(gmask, group_total_asset<R>(e, cash, p.close + (size_t)state_day(sday) * p.close_pitch, D, l, gmask), 8 * g);
                 asset_ok = true;
             }
             st_done += 1.0;
@@ -190,7 +206,7 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
             const int sd = state_day(sday);
             const double turb = sday < 0 ? 0.0 : __ldg(p.risk + sd);
             const bool liq = p.use_turbulence && (turb >= p.turbulence_threshold);
-            const double *prow = p.close + (size_t)sd * 32;
+            const double *prow = p.close + (size_t)sd * p.close_pitch;
             if (!asset_ok) asset = __shfl_sync(gmask, group_total_asset<R>(e, cash, prow, D, l, gmask), 8 * g);
             const double begin = asset;
 
@@ -199,14 +215,15 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int j = l * R + r;
-                const int a = liq ? -hmax_i : action_to_shares<ActT>(av[r], p.hmax);
-                key[r] = j < D ? a * 32 + j : 0x7fffffff;
+                const int a = liq ? -hmax_i : max(-AMAX, min(AMAX, action_to_shares<ActT>(av[r], p.hmax)));
+                key[r] = j < D ? (a << IB) + j : 0x7fffffff;
             }
             if (liq)
                 flags = FRL_FLAG_LIQUIDATE;  // all keys tie: the network never swaps, order = index order
             else
                 distributed_network<R>(key, l, gmask);
-            const uint32_t dis = (!liq && p.disable_mask) ? __ldg(p.disable_mask + sd) : 0u;
+            const uint32_t *dis_row = p.disable_mask + (size_t)sd * (p.close_pitch >> 5);
+            const bool use_dis = !liq && p.disable_mask != nullptr;
 
             // ---- everything that does not depend on the running cash, one sorted slot per (lane, r) ----
             int my_trades = 0, my_buys = 0;
@@ -221,12 +238,13 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
                 b_h[r] = 0;
                 if (pos < D) {
                     const int kk = key[r];
-                    const int a = kk >> 5, j = kk & 31;
+                    const int a = kk >> IB, j = kk & IMASK;
                     const double pj = __ldg(prow + j);
                     const int h = e.hold[j];
+                    const bool disabled = use_dis && ((__ldg(dis_row + (j >> 5)) >> (j & 31)) & 1u);
                     if (a < 0) {
                         // _sell_stock (:102-169): liquidation checks price > 0, normal mode the disable flag
-                        const bool ok = liq ? (pj > 0.0 && h > 0) : (!((dis >> j) & 1u) && h > 0);
+                        const bool ok = liq ? (pj > 0.0 && h > 0) : (!disabled && h > 0);
                         if (ok) {
                             const int m = liq ? h : min(-a, h);
                             const double pv = dmul(pj, (double)m);
@@ -235,7 +253,7 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
                             e.hold[j] = h - m;  // distinct stock per slot: no conflict
                             my_trades += 1;
                         }
-                    } else if (a > 0 && !liq && !((dis >> j) & 1u)) {
+                    } else if (a > 0 && !liq && !disabled) {
                         // _buy_stock (:171-201): the part that is independent of cash
                         const double unit = dmul(pj, one_plus_bc);
                         const double pv = dmul(pj, (double)a);
@@ -295,10 +313,10 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
                     double thr = e.buy_thr[0], spend = e.buy_spend[0], bc = e.buy_cost[0], pj = e.buy_p[0];
                     int kk = e.buy_aj[0], bh = e.buy_h[0];
                     for (int i = 0; i < total_buys; ++i) {
-                        const int nx = min(i + 1, 31);
+                        const int nx = min(i + 1, 8 * R - 1);
                         const double thr_n = e.buy_thr[nx], spend_n = e.buy_spend[nx], bc_n = e.buy_cost[nx], pj_n = e.buy_p[nx];
                         const int kk_n = e.buy_aj[nx], bh_n = e.buy_h[nx];
-                        const int a = kk >> 5, j = kk & 31;
+                        const int a = kk >> IB, j = kk & IMASK;
                         if (cash >= thr) {
                             cash = dsub(cash, spend);
                             cost = dadd(cost, bc);
@@ -328,7 +346,7 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
             // ---- state: s -> s+1 (:335-352) ----
             day += 1;
             sday = day;
-            asset = __shfl_sync(gmask, group_total_asset<R>(e, cash, p.close + (size_t)day * 32, D, l, gmask), 8 * g);
+            asset = __shfl_sync(gmask, group_total_asset<R>(e, cash, p.close + (size_t)day * p.close_pitch, D, l, gmask), 8 * g);
             asset_ok = true;
             reward = dmul(dsub(asset, begin), p.reward_scaling);
             last_reward = reward;
@@ -362,7 +380,7 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
     }
     if (p.asset_out || stats) {
         if (!asset_ok)
-            asset = __shfl_sync(gmask, group_total_asset<R>(e, cash, p.close + (size_t)state_day(sday) * 32, D, l, gmask), 8 * g);
+            asset = __shfl_sync(gmask, group_total_asset<R>(e, cash, p.close + (size_t)state_day(sday) * p.close_pitch, D, l, gmask), 8 * g);
     }
     if (l == 0) {
         p.cash[n] = cash;
@@ -386,11 +404,13 @@ template <int R, typename ActT>
 void launch_small_r(const frl_trading_params &p, const void *actions, long long sstride, long long estride, int n_steps,
                     double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
 {
-    constexpr int W = FRL_SMALL_WARPS;
+    constexpr int W = (R <= 4) ? FRL_SMALL_WARPS : 1;  // 4 envs x 2.2 KB (R = 4) ... 8.7 KB (R = 16) of scratch per warp
+    const size_t smem = sizeof(OctEnv<8 * R>) * W * 4;
+    static_assert(sizeof(OctEnv<8 * R>) * W * 4 <= 48 * 1024, "scratch must fit the default shared-memory limit");
     const long long groups = p.n_envs;
     const unsigned grid = (unsigned)((groups + W * 4 - 1) / (W * 4));
-    trading_small_kernel<R, ActT, W><<<grid, W * 32, 0, st>>>(p, (const ActT *)actions, sstride, estride, n_steps, rewards,
-                                                             flags, obs, obs_mode, auto_reset, stats);
+    trading_small_kernel<R, ActT, W><<<grid, W * 32, smem, st>>>(p, (const ActT *)actions, sstride, estride, n_steps, rewards,
+                                                                flags, obs, obs_mode, auto_reset, stats);
 }
 
 }  // namespace
@@ -411,8 +431,12 @@ void launch_trading_small(const frl_trading_params &p, const void *actions, int 
         FRL_GO(1);  // numpy pads to next_pow2(max(D, 8)) slots
     else if (D <= 16)
         FRL_GO(2);
-    else
+    else if (D <= 32)
         FRL_GO(4);
+    else if (D <= 64)
+        FRL_GO(8);
+    else
+        FRL_GO(16);
 #undef FRL_GO
 }
 

@@ -47,8 +47,8 @@ class TradingTables:
     n_days: int
     stock_dim: int
     n_tech: int
-    close: "torch.Tensor"         # [T, 32] f64, rows zero-padded
-    disable_mask: "torch.Tensor"  # [T] int32 bit mask (first indicator == 1.0)
+    close: "torch.Tensor"         # [T, pitch] f64, rows zero-padded (pitch 32 or 128)
+    disable_mask: "torch.Tensor"  # [T, pitch/32] int32 bit mask (first indicator == 1.0)
     risk: "torch.Tensor"          # [T] f64
     obs_tmpl: "torch.Tensor"      # [T, O] f32
     host_close: np.ndarray
@@ -65,20 +65,23 @@ class TradingTables:
 
         close = np.ascontiguousarray(close, dtype=np.float64)
         T, D = close.shape
-        if not 1 <= D <= 32:
-            raise ValueError(f"stock_dim must be in 1..32 for the StockTradingEnv kernel (got {D})")
+        if not 1 <= D <= 128:
+            raise ValueError(f"stock_dim must be in 1..128 for the StockTradingEnv kernels (got {D})")
         tech = np.ascontiguousarray(tech, dtype=np.float64).reshape(-1, T, D)
         K = tech.shape[0]
         risk = np.zeros(T) if risk is None else np.ascontiguousarray(risk, dtype=np.float64)
         if risk.shape != (T,):
             raise ValueError(f"risk must have shape ({T},), got {risk.shape}")
         O = 1 + 2 * D + K * D
-        close32 = np.zeros((T, 32), dtype=np.float64)
+        pitch = 32 if D <= 32 else 128
+        close32 = np.zeros((T, pitch), dtype=np.float64)
         close32[:, :D] = close
-        mask = np.zeros(T, dtype=np.uint32)
+        mask = np.zeros((T, pitch // 32), dtype=np.uint32)
         if K > 0:
-            bits = (tech[0] == 1.0).astype(np.uint32)  # `state[index + 2D + 1] != True`
-            mask = (bits << np.arange(D, dtype=np.uint32)[None, :]).sum(axis=1).astype(np.uint32)
+            bits = np.zeros((T, pitch), dtype=np.uint32)
+            bits[:, :D] = tech[0] == 1.0  # `state[index + 2D + 1] != True`
+            words = bits.reshape(T, pitch // 32, 32) << np.arange(32, dtype=np.uint32)[None, None, :]
+            mask = words.sum(axis=2).astype(np.uint32)
         tmpl = np.zeros((T, O), dtype=np.float32)
         tmpl[:, 1 : 1 + D] = close.astype(np.float32)
         if K > 0:
@@ -87,7 +90,7 @@ class TradingTables:
         return TradingTables(
             n_days=T, stock_dim=D, n_tech=K,
             close=torch.from_numpy(close32).to(dev),
-            disable_mask=torch.from_numpy(mask.view(np.int32)).to(dev),
+            disable_mask=torch.from_numpy(np.ascontiguousarray(mask).view(np.int32)).to(dev),
             risk=torch.from_numpy(risk).to(dev),
             obs_tmpl=torch.from_numpy(tmpl).to(dev),
             host_close=close, host_tech=tech, host_risk=risk,

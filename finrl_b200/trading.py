@@ -131,6 +131,7 @@ class BatchedStockTradingEnv(BatchedEnvBase):
         p.buy_cost_pct, p.sell_cost_pct = self.buy_cost_pct, self.sell_cost_pct
         p.reward_scaling = float(reward_scaling)
         p.use_turbulence = int(turbulence_threshold is not None)
+        p.close_pitch = int(tables.close.shape[1])
         p.turbulence_threshold = float(turbulence_threshold) if turbulence_threshold is not None else 0.0
         p.close, p.disable_mask = tables.close.data_ptr(), tables.disable_mask.data_ptr()
         p.risk, p.obs_tmpl = tables.risk.data_ptr(), tables.obs_tmpl.data_ptr()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FRL_ABI_VERSION 1
+#define FRL_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FRL_API __attribute__((visibility("default")))
@@ -71,7 +71,9 @@ FRL_API const char *frl_last_error(void);
  * ========================================================================================= */
 typedef struct frl_trading_params {
     int32_t n_envs;     /* N >= 1 */
-    int32_t stock_dim;  /* D, 1..32 (one sort slot per stock) */
+    int32_t stock_dim;  /* D, 1..128 (np.argsort's network rule is pinned for n <= 256).  D <= 32
+                           runs in the thread-per-env kernel (or the 8-lanes-per-env one for small batches),
+                           33..128 always in the 8-lanes-per-env kernel */
     int32_t n_tech;     /* K >= 0 */
     int32_t n_days;     /* T >= 1 = len(df.index.unique()) */
     int32_t obs_dim;    /* O = 1 + 2D + K*D (state_space) */
@@ -81,12 +83,12 @@ typedef struct frl_trading_params {
     double buy_cost_pct, sell_cost_pct;
     double reward_scaling;
     int32_t use_turbulence; /* turbulence_threshold is not None */
-    int32_t _pad0;
+    int32_t close_pitch;    /* row pitch of `close` in doubles: 32 for D <= 32, 128 for D <= 128 */
     double turbulence_threshold;
     /* ---- tables (read-only, replicated per GPU) ---- */
-    const double *close;          /* [T][32]  close price, rows zero-padded to 32 */
-    const uint32_t *disable_mask; /* [T] bit i set <=> first tech indicator of stock i == 1.0
-                                     (the "disable" flag of env_stocktrading.py:105,174) */
+    const double *close;          /* [T][close_pitch] close price, rows zero-padded */
+    const uint32_t *disable_mask; /* [T][close_pitch/32] bit i of the row set <=> first tech indicator of stock
+                                     i == 1.0 (the "disable" flag of env_stocktrading.py:105,174) */
     const double *risk;           /* [T] risk_indicator_col (turbulence / vix) */
     const float *obs_tmpl;        /* [T][O] float32 image of the state list of day t with the
                                      cash and holdings slots zeroed */

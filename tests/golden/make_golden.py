@@ -314,6 +314,11 @@ def main():
         # single-stock branch of the reference (len(df.tic.unique()) == 1, :415-422, :441-450, :469-476)
         gen_trading("trading_d1_single", T=30, D=1, K=2, n_steps=70, seed=10, threshold=60, act_dtype=np.float32, hmax=50,
                     initial_amount=3_000)
+        # wide universes (64- and 128-slot argsort networks): many ties, cash-starved
+        gen_trading("trading_d60_wide", T=25, D=60, K=2, n_steps=60, seed=61, threshold=90, act_dtype=np.float32, hmax=10,
+                    initial_amount=40_000, plant_disable=[(4, 33), (4, 59), (12, 0)])
+        gen_trading("trading_d100_nasdaq", T=20, D=100, K=1, n_steps=45, seed=62, threshold=None, act_dtype=np.float32,
+                    hmax=5, initial_amount=60_000, plant_disable=[(3, 64), (3, 99)])
         # actions outside [-1,1] (the reference does not clip) and a high cost
         gen_trading("trading_d8_wide", T=30, D=8, K=2, n_steps=40, seed=9, threshold=50, act_dtype=np.float64, hmax=100,
                     initial_amount=100_000, cost=0.01, act_scale=3.0)

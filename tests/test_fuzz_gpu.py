@@ -17,7 +17,7 @@ def test_trading_fuzz(seed, kernel):
     _cabi.set_option("trading_small_max", 0 if kernel == "tile" else 2**31 - 1)
 
     rng = np.random.default_rng(1000 + seed)
-    D = int(rng.integers(1, 33))
+    D = int(rng.integers(1, 33)) if seed < 10 else int(rng.integers(33, 129))  # > 32 always runs 8 lanes per env
     K = int(rng.integers(0, 5))
     T = int(rng.integers(4, 36))
     N = int(rng.choice([1, 31, 33, 100]))

@@ -64,7 +64,10 @@ def test_golden_single_env(path):
             assert st["cost"][0].item() == g["cost"][s], ctx
 
 
-@pytest.mark.parametrize("path", TRADING[:2], ids=[os.path.basename(p)[:-4] for p in TRADING[:2]])
+ROLL = [p for p in TRADING if any(t in p for t in ("d30_f32", "d30_starved", "d100_nasdaq"))]
+
+
+@pytest.mark.parametrize("path", ROLL, ids=[os.path.basename(p)[:-4] for p in ROLL])
 def test_golden_fused_rollout(path):
     """The whole golden trajectory in ONE fused rollout launch (obs after every step)."""
     g = np.load(path)
