@@ -11,5 +11,6 @@ from .trading import BatchedStockTradingEnv  # noqa: F401
 from .nptrading import BatchedNpStockTradingEnv, NpTables  # noqa: F401
 from .portfolio import BatchedStockPortfolioEnv, PortfolioTables  # noqa: F401
 from .cashpenalty import BatchedStockTradingEnvCashpenalty, CashPenaltyTables  # noqa: F401
+from .stoploss import BatchedStockTradingEnvStopLoss  # noqa: F401
 
 __version__ = "0.1.0"

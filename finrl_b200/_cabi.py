@@ -118,6 +118,47 @@ class PortfolioParams(C.Structure):
     ]
 
 
+class StopLossParams(C.Structure):
+    """frl_stoploss_params (include/finrl_b200.h)."""
+
+    _fields_ = [
+        ("n_envs", C.c_int32),
+        ("stock_dim", C.c_int32),
+        ("n_cols", C.c_int32),
+        ("n_days", C.c_int32),
+        ("obs_dim", C.c_int32),
+        ("discrete_actions", C.c_int32),
+        ("shares_increment", C.c_int32),
+        ("use_turbulence", C.c_int32),
+        ("patient", C.c_int32),
+        ("env_stride", C.c_int32),
+        ("buy_cost_pct", C.c_double),
+        ("sell_cost_pct", C.c_double),
+        ("hmax", C.c_double),
+        ("turbulence_threshold", C.c_double),
+        ("initial_amount", C.c_double),
+        ("cash_penalty_proportion", C.c_double),
+        ("stoploss_penalty", C.c_double),
+        ("min_profit_penalty", C.c_double),
+        ("close", C.c_void_p),
+        ("turb", C.c_void_p),
+        ("obs_tmpl", C.c_void_p),
+        ("cash", C.c_void_p),
+        ("hold", C.c_void_p),
+        ("prev_hold", C.c_void_p),
+        ("avg_buy", C.c_void_p),
+        ("n_buys", C.c_void_p),
+        ("cdiff", C.c_void_p),
+        ("pdiff", C.c_void_p),
+        ("date_index", C.c_void_p),
+        ("start", C.c_void_p),
+        ("fresh", C.c_void_p),
+        ("last_cash", C.c_void_p),
+        ("last_total", C.c_void_p),
+        ("sum_trades", C.c_void_p),
+    ]
+
+
 class CashPenaltyParams(C.Structure):
     """frl_cashpenalty_params (include/finrl_b200.h)."""
 
@@ -236,6 +277,18 @@ SIGNATURES = {
     "frl_cashpenalty_step": (
         C.c_int32,
         [C.POINTER(CashPenaltyParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+         C.c_void_p],
+    ),
+    "frl_stoploss_reset": (C.c_int32, [C.POINTER(StopLossParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "frl_stoploss_observe": (C.c_int32, [C.POINTER(StopLossParams), C.c_void_p, C.c_void_p]),
+    "frl_stoploss_rollout": (
+        C.c_int32,
+        [C.POINTER(StopLossParams), C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
+    ),
+    "frl_stoploss_step": (
+        C.c_int32,
+        [C.POINTER(StopLossParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
          C.c_void_p],
     ),
     "frl_crypto_reset": (C.c_int32, [C.POINTER(CryptoParams), C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,0 +1,442 @@
+// Sibling env — StockTradingEnvStopLoss (reference: finrl/meta/env_stock_trading/env_stocktrading_stoploss.py).
+//
+// The cash-penalty env plus per-asset average-buy-price tracking, stop-loss liquidation and three extra
+// dot products in the reward.  One thread per env, two streaming passes over the D <= 128 assets (the six
+// per-asset state arrays are stock-major, so every access is a coalesced warp access):
+//   pass 1  reward terms of the PREVIOUS step's penalty arrays, np.dot(holdings, closings), the new
+//           closing_diff_avg_buy, the transaction of every asset, proceeds and spend
+//   decide  cash shortage -> terminate (only closing_diff_avg_buy changes, as in the reference) / patient
+//   pass 2  re-form the transactions, update holdings / previous holdings / average buy price / buy counts /
+//           profit-sell diffs, and leave the float32 holdings in the staging rows for the observation writer.
+// np.dot's order is BLAS-specific (1e-9 tolerance); the sums here are sequential in asset order.
+#include "common.cuh"
+
+namespace frl {
+namespace {
+
+__device__ __forceinline__ long long sl_floordiv_ll(long long a, long long b)
+{
+    long long q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) q -= 1;
+    return q;
+}
+
+struct SlTx {
+    double v;      // transaction (shares, signed)
+    double cdiff;  // closing_diff_avg_buy of this step
+};
+
+// the action pipeline of step() for one asset (:321-361)
+template <typename ActT>
+__device__ __forceinline__ SlTx sl_transaction(const frl_stoploss_params &p, ActT a, double c, double h, double avg, bool liq,
+                                               bool stop_on)
+{
+    double v;
+    if (sizeof(ActT) == 4)
+        v = (double)fmul((float)a, (float)p.hmax);
+    else
+        v = dmul((double)a, p.hmax);
+    const bool pos = c > 0.0;
+    if (!pos) v = 0.0;                // np.where(closings > 0, actions, 0)
+    if (liq) v = -dmul(h, c);         // -(holdings * closings): currency, divided by the price again below
+    if (p.discrete_actions) {
+        long long q = pos ? (long long)floor_div_f64(v, c) : 0;
+        const long long inc = p.shares_increment;
+        q = (q >= 0) ? sl_floordiv_ll(q, inc) * inc : sl_floordiv_ll(q + inc, inc) * inc;
+        v = (double)q;
+    } else {
+        v = pos ? __ddiv_rn(v, c) : 0.0;
+    }
+    v = (v > -h) ? v : -h;            // np.maximum(actions, -holdings)
+    SlTx r;
+    r.cdiff = dsub(c, dmul(p.stoploss_penalty, avg));  // closings - stoploss_penalty * avg_buy_price
+    if (stop_on && r.cdiff < 0.0) v = -h;              // stop-loss: clear the position
+    r.v = v;
+    return r;
+}
+
+// get_reward (:255-290) from the logged (total_assets, cash) and the three penalty dot products
+__device__ __forceinline__ double sl_reward(const frl_stoploss_params &p, double total_assets, double cash, int current_step,
+                                            double dot_prev_negc, double dot_hold_negp, double dot_hold_posp)
+{
+    if (current_step == 0) return 0.0;
+    double cash_penalty = dsub(dmul(total_assets, p.cash_penalty_proportion), cash);
+    if (!(cash_penalty > 0.0)) cash_penalty = 0.0;
+    const double stop_loss_penalty = current_step > 1 ? -dot_prev_negc : 0.0;
+    const double low_profit_penalty = -dot_hold_negp;
+    const double total_penalty = dadd(dadd(cash_penalty, stop_loss_penalty), low_profit_penalty);
+    double r = dsub(__ddiv_rn(dadd(dsub(total_assets, total_penalty), dot_hold_posp), p.initial_amount), 1.0);
+    return __ddiv_rn(r, (double)current_step);
+}
+
+template <typename ActT>
+__device__ __forceinline__ void sl_write_obs_tile(const frl_stoploss_params &p, const ActT *stage, int P, const float *cashf,
+                                                  const int *di_s, float *__restrict__ obs, long long env0, int nvalid,
+                                                  int lane)
+{
+    const int O = p.obs_dim, D = p.stock_dim;
+    constexpr int step = sizeof(ActT) / sizeof(float);
+    for (int r = 0; r < nvalid; ++r) {
+        const float *hrow = reinterpret_cast<const float *>(stage + (size_t)r * P);
+        const float *trow = p.obs_tmpl + (size_t)di_s[r] * O;
+        float *orow = obs + (size_t)(env0 + r) * O;
+        for (int pos = lane; pos < O; pos += 32) {
+            float v;
+            if (pos == 0)
+                v = cashf[r];
+            else if (pos <= D)
+                v = hrow[(pos - 1) * step];
+            else
+                v = __ldg(trow + pos);
+            orow[pos] = v;
+        }
+    }
+}
+
+template <typename ActT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ actions, long long act_step_stride,
+                        long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
+                        float *__restrict__ obs, int obs_mode, int auto_reset, double *__restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;
+    const int P = D | 1;
+    const size_t warp_bytes = (size_t)32 * P * sizeof(ActT) + 32 * sizeof(float) + 32 * sizeof(int);
+    unsigned char *base = smem_raw + warp * ((warp_bytes + 15) & ~(size_t)15);
+    ActT *stage = reinterpret_cast<ActT *>(base);
+    float *cashf = reinterpret_cast<float *>(base + (size_t)32 * P * sizeof(ActT));
+    int *di_s = reinterpret_cast<int *>(cashf + 32);
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const bool valid = lane < nvalid;
+    const long long n = valid ? env0 + lane : (long long)N - 1;
+
+    double cash = p.cash[n], last_cash = p.last_cash[n], last_total = p.last_total[n], sum_trades = p.sum_trades[n];
+    int di = p.date_index[n], start = p.start[n];
+    bool fresh = p.fresh[n] != 0;
+    ActT *myrow = stage + (size_t)lane * P;
+    double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_liq = 0.0, st_short = 0.0;
+
+    for (int k = 0; k < n_steps; ++k) {
+        const ActT *abase = actions + (size_t)k * act_step_stride;
+        __syncwarp();
+        if (act_env_stride == D) {
+            const ActT *tile = abase + (size_t)env0 * D;
+            const int cnt = nvalid * D;
+            int row = 0, col = lane;
+            while (col >= D) { col -= D; ++row; }
+            for (int e = lane; e < 32 * D; e += 32) {
+                stage[row * P + col] = e < cnt ? __ldcs(tile + e) : ActT(0);
+                col += 32;
+                while (col >= D) { col -= D; ++row; }
+            }
+        } else {
+            for (int r = 0; r < 32; ++r)
+                for (int j = lane; j < D; j += 32)
+                    stage[r * P + j] = r < nvalid ? abase[(size_t)(env0 + r) * act_env_stride + j] : ActT(0);
+        }
+        __syncwarp();
+
+        int flags = 0;
+        double reward;
+        const int current_step = di - start;
+        bool reset_now = false, moved = false;
+        // dot products of get_reward over the arrays as they stand at the start of the step
+        double d_prev_negc = 0.0, d_hold_negp = 0.0, d_hold_posp = 0.0, asum = 0.0;
+        if (di == T - 1) {
+            for (int j = 0; j < D; ++j) {
+                const size_t o = (size_t)j * ld + n;
+                const double h = p.hold[o], pv = p.prev_hold[o], cd = p.cdiff[o], pd = p.pdiff[o];
+                d_prev_negc = dadd(d_prev_negc, dmul(pv, cd < 0.0 ? cd : 0.0));
+                d_hold_negp = dadd(d_hold_negp, dmul(h, pd < 0.0 ? pd : 0.0));
+                d_hold_posp = dadd(d_hold_posp, dmul(h, pd > 0.0 ? pd : 0.0));
+                asum += fabs((double)myrow[j]);
+            }
+            sum_trades += asum;
+            flags = FRL_FLAG_DONE;
+            reward = sl_reward(p, last_total, last_cash, current_step, d_prev_negc, d_hold_negp, d_hold_posp);
+            reset_now = auto_reset != 0;
+        } else {
+            const double *crow = p.close + (size_t)di * D;
+            const double turbulence = fresh ? 0.0 : __ldg(p.turb + di);
+            const bool liq = p.use_turbulence && turbulence >= p.turbulence_threshold;
+            if (liq) flags |= FRL_FLAG_LIQUIDATE;
+            const double begin_cash = cash;
+            const bool stop_on = begin_cash >= dmul(p.stoploss_penalty, p.initial_amount);
+            // ---- pass 1 ----
+            double asset_value = 0.0, proceeds = 0.0, spend = 0.0, d_prev_negc_new = 0.0;
+            for (int j = 0; j < D; ++j) {
+                const size_t o = (size_t)j * ld + n;
+                const double c = __ldg(crow + j);
+                const double h = p.hold[o], pv = p.prev_hold[o], avg = p.avg_buy[o], cd = p.cdiff[o], pd = p.pdiff[o];
+                const ActT a = myrow[j];
+                const SlTx t = sl_transaction<ActT>(p, a, c, h, avg, liq, stop_on);
+                asum += fabs((double)a);
+                asset_value = dadd(asset_value, dmul(h, c));
+                d_prev_negc = dadd(d_prev_negc, dmul(pv, cd < 0.0 ? cd : 0.0));
+                d_hold_negp = dadd(d_hold_negp, dmul(h, pd < 0.0 ? pd : 0.0));
+                d_hold_posp = dadd(d_hold_posp, dmul(h, pd > 0.0 ? pd : 0.0));
+                d_prev_negc_new = dadd(d_prev_negc_new, dmul(pv, t.cdiff < 0.0 ? t.cdiff : 0.0));
+                proceeds = dadd(proceeds, dmul(t.v < 0.0 ? -t.v : 0.0, c));
+                spend = dadd(spend, dmul(t.v > 0.0 ? t.v : 0.0, c));
+            }
+            sum_trades += asum;
+            // reward from the PREVIOUS log entry (:313), then this step's entry is logged (:315-319)
+            reward = sl_reward(p, last_total, last_cash, current_step, d_prev_negc, d_hold_negp, d_hold_posp);
+            last_cash = begin_cash;
+            last_total = dadd(begin_cash, asset_value);
+            double costs = dmul(proceeds, p.sell_cost_pct);
+            double coh = dadd(begin_cash, proceeds);
+            costs = dadd(costs, dmul(spend, p.buy_cost_pct));
+            bool terminate = false, no_buys = false;
+            if (dadd(spend, costs) > coh) {
+                flags |= FRL_FLAG_SHORTAGE;
+                if (p.patient) {
+                    no_buys = true;
+                    spend = 0.0;
+                    costs = 0.0;
+                } else {
+                    terminate = true;
+                }
+            }
+            if (terminate) {
+                // return_terminal(reward=self.get_reward()) (:383-386): this step's log entry and closing diff,
+                // the previous profit diffs and holdings; closing_diff_avg_buy is the only array that changed
+                flags |= FRL_FLAG_DONE;
+                reward = sl_reward(p, last_total, last_cash, current_step, d_prev_negc_new, d_hold_negp, d_hold_posp);
+                if (valid && !auto_reset) {
+                    for (int j = 0; j < D; ++j) {
+                        const size_t o = (size_t)j * ld + n;
+                        p.cdiff[o] = dsub(__ldg(crow + j), dmul(p.stoploss_penalty, p.avg_buy[o]));
+                    }
+                }
+                reset_now = auto_reset != 0;
+            } else {
+                // ---- pass 2 ----
+                cash = dsub(dsub(coh, spend), costs);
+                for (int j = 0; j < D; ++j) {
+                    const size_t o = (size_t)j * ld + n;
+                    const double c = __ldg(crow + j);
+                    const double h = p.hold[o], avg = p.avg_buy[o];
+                    double nb = p.n_buys[o];
+                    const SlTx t = sl_transaction<ActT>(p, myrow[j], c, h, avg, liq, stop_on);
+                    const double sell = -(t.v < 0.0 ? t.v : 0.0);   // PRE-patient vectors, like the reference
+                    const double buy = t.v > 0.0 ? t.v : 0.0;
+                    double v = t.v;
+                    if (no_buys && v > 0.0) v = 0.0;
+                    // profitable sells (:391-404)
+                    const double scp = sell > 0.0 ? c : 0.0;
+                    const double pdn = (dsub(scp, avg) > 0.0) ? dsub(c, dmul(p.min_profit_penalty, avg)) : 0.0;
+                    const double hn = dadd(h, v);
+                    // incremental average buy price (:416-428); np.sign(buys) of the pre-patient buys
+                    double avgn = avg;
+                    if (buy > 0.0) {
+                        nb = dadd(nb, 1.0);
+                        avgn = dadd(avg, __ddiv_rn(dsub(c, avg), nb));
+                    }
+                    if (!(hn > 0.0)) {
+                        nb = 0.0;
+                        avgn = 0.0;
+                    }
+                    if (valid) {
+                        p.prev_hold[o] = h;
+                        p.hold[o] = hn;
+                        p.avg_buy[o] = avgn;
+                        p.n_buys[o] = nb;
+                        p.cdiff[o] = t.cdiff;
+                        p.pdiff[o] = pdn;
+                    }
+                    *reinterpret_cast<float *>(myrow + j) = (float)hn;
+                }
+                moved = true;
+                di += 1;
+                if (p.use_turbulence) fresh = false;
+            }
+        }
+        if (valid) {
+            if (rewards) rewards[(size_t)k * N + n] = reward;
+            if (flags_out) flags_out[(size_t)k * N + n] = (uint8_t)flags;
+            st_r += reward;
+            st_r2 += reward * reward;
+            if (flags & FRL_FLAG_DONE) {
+                st_done += 1.0;
+                st_epi += last_total;
+            }
+            if (flags & FRL_FLAG_LIQUIDATE) st_liq += 1.0;
+            if (flags & FRL_FLAG_SHORTAGE) st_short += 1.0;
+        }
+        if (reset_now) {  // reset (:134-165), random_start=False
+            cash = p.initial_amount;
+            for (int j = 0; j < D; ++j) {
+                const size_t o = (size_t)j * ld + n;
+                if (valid) p.hold[o] = p.prev_hold[o] = p.avg_buy[o] = p.n_buys[o] = p.cdiff[o] = p.pdiff[o] = 0.0;
+                *reinterpret_cast<float *>(myrow + j) = 0.0f;
+            }
+            moved = true;
+            di = 0;
+            start = 0;
+            fresh = true;
+            sum_trades = 0.0;
+            last_cash = 0.0;
+            last_total = 0.0;
+        }
+        if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
+            if (!moved)
+                for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = (float)p.hold[(size_t)j * ld + n];
+            cashf[lane] = (float)cash;
+            di_s[lane] = di;
+            __syncwarp();
+            float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
+            sl_write_obs_tile<ActT>(p, stage, P, cashf, di_s, o, env0, nvalid, lane);
+        }
+    }
+    if (valid) {
+        p.cash[n] = cash;
+        p.date_index[n] = di;
+        p.start[n] = start;
+        p.fresh[n] = fresh ? 1 : 0;
+        p.last_cash[n] = last_cash;
+        p.last_total[n] = last_total;
+        p.sum_trades[n] = sum_trades;
+    }
+    if (stats) {
+        double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, valid ? last_total : 0.0, st_liq,
+                                 valid ? (double)n_steps : 0.0, st_short};
+        reduce_stats8(v, lane, stats);
+    }
+}
+
+__global__ void stoploss_reset_kernel(const frl_stoploss_params p, const uint8_t *__restrict__ mask,
+                                      const int32_t *__restrict__ start_points)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.n_envs) return;
+    if (mask && !mask[n]) return;
+    for (int j = 0; j < p.stock_dim; ++j) {
+        const size_t o = (size_t)j * p.env_stride + n;
+        p.hold[o] = p.prev_hold[o] = p.avg_buy[o] = p.n_buys[o] = p.cdiff[o] = p.pdiff[o] = 0.0;
+    }
+    const int sp = start_points ? start_points[n] : 0;
+    p.cash[n] = p.initial_amount;
+    p.date_index[n] = sp;
+    p.start[n] = sp;
+    p.fresh[n] = 1;
+    p.last_cash[n] = 0.0;
+    p.last_total[n] = 0.0;
+    p.sum_trades[n] = 0.0;
+}
+
+__global__ void stoploss_observe_kernel(const frl_stoploss_params p, float *__restrict__ obs)
+{
+    const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= p.n_envs) return;
+    const int O = p.obs_dim, D = p.stock_dim;
+    const float *trow = p.obs_tmpl + (size_t)p.date_index[n] * O;
+    float *orow = obs + (size_t)n * O;
+    for (int pos = lane; pos < O; pos += 32) {
+        float v;
+        if (pos == 0)
+            v = (float)p.cash[n];
+        else if (pos <= D)
+            v = (float)p.hold[(size_t)(pos - 1) * p.env_stride + n];
+        else
+            v = __ldg(trow + pos);
+        orow[pos] = v;
+    }
+}
+
+int32_t sl_validate(const frl_stoploss_params *p)
+{
+    FRL_REQUIRE(p != nullptr, "stoploss: params is NULL");
+    FRL_REQUIRE(p->n_envs >= 1, "stoploss: n_envs must be >= 1 (got %d)", p->n_envs);
+    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 128, "stoploss: stock_dim must be in 1..128 (got %d)", p->stock_dim);
+    FRL_REQUIRE(p->n_cols >= 0 && p->n_days >= 1, "stoploss: bad n_cols/n_days (%d, %d)", p->n_cols, p->n_days);
+    FRL_REQUIRE(p->obs_dim == 1 + p->stock_dim + p->stock_dim * p->n_cols, "stoploss: obs_dim %d != 1 + D + D*C = %d",
+                p->obs_dim, 1 + p->stock_dim + p->stock_dim * p->n_cols);
+    FRL_REQUIRE(p->env_stride >= p->n_envs, "stoploss: env_stride %d < n_envs %d", p->env_stride, p->n_envs);
+    FRL_REQUIRE(!p->discrete_actions || p->shares_increment >= 1, "stoploss: shares_increment must be >= 1");
+    FRL_REQUIRE(p->close && p->obs_tmpl && (!p->use_turbulence || p->turb), "stoploss: table pointer is NULL");
+    FRL_REQUIRE(p->cash && p->hold && p->prev_hold && p->avg_buy && p->n_buys && p->cdiff && p->pdiff && p->date_index &&
+                    p->start && p->fresh && p->last_cash && p->last_total && p->sum_trades,
+                "stoploss: state pointer is NULL");
+    return FRL_OK;
+}
+
+template <typename ActT, int WARPS>
+int32_t sl_launch(const frl_stoploss_params &p, const void *actions, long long sstride, long long estride, int n_steps,
+                  double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
+{
+    const int P = p.stock_dim | 1;
+    const size_t warp_bytes = (size_t)32 * P * sizeof(ActT) + 32 * sizeof(float) + 32 * sizeof(int);
+    const size_t smem = WARPS * ((warp_bytes + 15) & ~(size_t)15);
+    auto kern = stoploss_rollout_kernel<ActT, WARPS>;
+    if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("stoploss_rollout: cannot reserve %zu B of shared memory (%s)", smem, cudaGetErrorString(e));
+            return FRL_E_CUDA;
+        }
+    }
+    const long long tiles = ((long long)p.n_envs + 31) / 32;
+    kern<<<(unsigned)((tiles + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(p, (const ActT *)actions, sstride, estride, n_steps,
+                                                                           rewards, flags, obs, obs_mode, auto_reset, stats);
+    return check_launch("stoploss_rollout");
+}
+
+}  // namespace
+}  // namespace frl
+
+using namespace frl;
+
+extern "C" int32_t frl_stoploss_observe(const frl_stoploss_params *p, float *obs, void *stream)
+{
+    if (int32_t rc = sl_validate(p)) return rc;
+    FRL_REQUIRE(obs != nullptr, "stoploss_observe: obs is NULL");
+    const long long threads = (long long)p->n_envs * 32;
+    stoploss_observe_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*p, obs);
+    return check_launch("stoploss_observe");
+}
+
+extern "C" int32_t frl_stoploss_reset(const frl_stoploss_params *p, const uint8_t *mask, const int32_t *start_points,
+                                      float *obs, void *stream)
+{
+    if (int32_t rc = sl_validate(p)) return rc;
+    stoploss_reset_kernel<<<(p->n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p, mask, start_points);
+    if (int32_t rc = check_launch("stoploss_reset")) return rc;
+    if (obs) return frl_stoploss_observe(p, obs, stream);
+    return FRL_OK;
+}
+
+extern "C" int32_t frl_stoploss_rollout(const frl_stoploss_params *p, const void *actions, int32_t actions_f64,
+                                        int64_t act_step_stride, int64_t act_env_stride, int32_t n_steps, double *rewards,
+                                        uint8_t *flags, float *obs, int32_t obs_mode, int32_t auto_reset, double *stats,
+                                        void *stream)
+{
+    if (int32_t rc = sl_validate(p)) return rc;
+    FRL_REQUIRE(actions != nullptr, "stoploss_rollout: actions is NULL");
+    FRL_REQUIRE(n_steps >= 1, "stoploss_rollout: n_steps must be >= 1 (got %d)", n_steps);
+    FRL_REQUIRE(act_env_stride >= p->stock_dim, "stoploss_rollout: act_env_stride %lld < stock_dim", (long long)act_env_stride);
+    FRL_REQUIRE(obs_mode >= FRL_OBS_NONE && obs_mode <= FRL_OBS_ALL, "stoploss_rollout: bad obs_mode %d", obs_mode);
+    FRL_REQUIRE(obs_mode == FRL_OBS_NONE || obs != nullptr, "stoploss_rollout: obs is NULL but obs_mode=%d", obs_mode);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (actions_f64)
+        return sl_launch<double, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags, obs, obs_mode,
+                                    auto_reset, stats, st);
+    return sl_launch<float, 4>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags, obs, obs_mode, auto_reset,
+                               stats, st);
+}
+
+extern "C" int32_t frl_stoploss_step(const frl_stoploss_params *p, const void *actions, int32_t actions_f64, double *rewards,
+                                     uint8_t *flags, float *obs, int32_t auto_reset, double *stats, void *stream)
+{
+    if (p == nullptr) {
+        set_error("stoploss_step: params is NULL");
+        return FRL_E_INVALID;
+    }
+    return frl_stoploss_rollout(p, actions, actions_f64, (int64_t)p->n_envs * p->stock_dim, p->stock_dim, 1, rewards, flags, obs,
+                                obs ? FRL_OBS_LAST : FRL_OBS_NONE, auto_reset, stats, stream);
+}

@@ -293,6 +293,60 @@ FRL_API int32_t frl_cashpenalty_step(const frl_cashpenalty_params *p, const void
                                      void *stream);
 
 /* =========================================================================================
+ * Sibling  StockTradingEnvStopLoss — finrl/meta/env_stock_trading/env_stocktrading_stoploss.py
+ * (the cash-penalty env plus average-buy-price tracking, stop-loss liquidation and stop-loss /
+ * low-profit penalties in the reward)
+ * ========================================================================================= */
+typedef struct frl_stoploss_params {
+    int32_t n_envs;    /* N */
+    int32_t stock_dim; /* D, 1..128 */
+    int32_t n_cols;    /* C */
+    int32_t n_days;    /* T */
+    int32_t obs_dim;   /* O = 1 + D + D*C */
+    int32_t discrete_actions;
+    int32_t shares_increment;
+    int32_t use_turbulence;
+    int32_t patient;
+    int32_t env_stride; /* leading dimension of the six stock-major arrays (>= N) */
+    double buy_cost_pct, sell_cost_pct;
+    double hmax;
+    double turbulence_threshold;
+    double initial_amount;
+    double cash_penalty_proportion;
+    double stoploss_penalty;
+    double min_profit_penalty; /* 1 + profit_loss_ratio * (1 - stoploss_penalty) (:101) */
+    /* ---- tables ---- */
+    const double *close;   /* [T][D] */
+    const double *turb;    /* [T] */
+    const float *obs_tmpl; /* [T][O] */
+    /* ---- per-env state ---- */
+    double *cash;        /* [N] */
+    double *hold;        /* [D][env_stride] state_memory[-1] holdings */
+    double *prev_hold;   /* [D][env_stride] state_memory[-2] holdings */
+    double *avg_buy;     /* [D][env_stride] avg_buy_price */
+    double *n_buys;      /* [D][env_stride] */
+    double *cdiff;       /* [D][env_stride] closing_diff_avg_buy */
+    double *pdiff;       /* [D][env_stride] profit_sell_diff_avg_buy */
+    int32_t *date_index; /* [N] */
+    int32_t *start;      /* [N] */
+    uint8_t *fresh;      /* [N] 1 while self.turbulence is still the 0 set by reset */
+    double *last_cash;   /* [N] */
+    double *last_total;  /* [N] */
+    double *sum_trades;  /* [N] */
+} frl_stoploss_params;
+
+FRL_API int32_t frl_stoploss_reset(const frl_stoploss_params *p, const uint8_t *mask, const int32_t *start_points,
+                                   float *obs, void *stream);
+FRL_API int32_t frl_stoploss_observe(const frl_stoploss_params *p, float *obs, void *stream);
+/* n_steps fused step (:292-443) incl. get_reward (:255-290); conventions as frl_cashpenalty_rollout. */
+FRL_API int32_t frl_stoploss_rollout(const frl_stoploss_params *p, const void *actions, int32_t actions_f64,
+                                     int64_t act_step_stride, int64_t act_env_stride, int32_t n_steps, double *rewards,
+                                     uint8_t *flags, float *obs, int32_t obs_mode, int32_t auto_reset, double *stats,
+                                     void *stream);
+FRL_API int32_t frl_stoploss_step(const frl_stoploss_params *p, const void *actions, int32_t actions_f64, double *rewards,
+                                  uint8_t *flags, float *obs, int32_t auto_reset, double *stats, void *stream);
+
+/* =========================================================================================
  * Sibling  CryptoEnv — finrl/meta/env_cryptocurrency_trading/env_multiple_crypto.py
  * ========================================================================================= */
 typedef struct frl_crypto_params {

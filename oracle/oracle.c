@@ -890,3 +890,189 @@ void ora_crypto_step(const ora_crypto_cfg *c, ora_crypto_state *s, const void *a
 #pragma omp parallel for schedule(static)
     for (int n = 0; n < c->n_envs; ++n) crypto_step_one(c, s, n, actions, actions_f64, reward_out, flags_out, obs);
 }
+
+/* ======================================================================================= */
+/* sibling: StockTradingEnvStopLoss — finrl/meta/env_stock_trading/env_stocktrading_stoploss.py */
+/* ======================================================================================= */
+
+static void sl_reset_one(const ora_sl_cfg *c, ora_sl_state *s, int n, int32_t start)
+{
+    const int D = c->stock_dim; /* reset (:134-165) */
+    s->cash[n] = c->initial_amount;
+    for (int i = 0; i < D; ++i) {
+        const size_t k = (size_t)n * D + i;
+        s->hold[k] = s->prev_hold[k] = s->avg_buy[k] = s->n_buys[k] = s->cdiff[k] = s->pdiff[k] = 0.0;
+    }
+    s->date_index[n] = start;
+    s->start[n] = start;
+    s->fresh[n] = 1;
+    s->sum_trades[n] = 0.0;
+    s->last_cash[n] = 0.0;
+    s->last_total[n] = 0.0;
+}
+
+void ora_sl_reset(const ora_sl_cfg *c, ora_sl_state *s, const uint8_t *mask, const int32_t *start_points)
+{
+    for (int n = 0; n < c->n_envs; ++n)
+        if (!mask || mask[n]) sl_reset_one(c, s, n, start_points ? start_points[n] : 0);
+}
+
+void ora_sl_obs(const ora_sl_cfg *c, const ora_sl_state *s, double *obs)
+{
+    const int D = c->stock_dim, DC = D * c->n_cols, O = 1 + D + DC;
+    for (int n = 0; n < c->n_envs; ++n) {
+        double *o = obs + (size_t)n * O;
+        o[0] = s->cash[n];
+        for (int i = 0; i < D; ++i) o[1 + i] = s->hold[(size_t)n * D + i];
+        memcpy(o + 1 + D, c->info + (size_t)s->date_index[n] * DC, sizeof(double) * (size_t)DC);
+    }
+}
+
+/* get_reward (:255-290) with the arrays as they stand when it is called */
+static double sl_reward(const ora_sl_cfg *c, const ora_sl_state *s, int n, int current_step, const double *cdiff)
+{
+    if (current_step == 0) return 0.0;
+    const int D = c->stock_dim;
+    const double *hold = s->hold + (size_t)n * D, *prev = s->prev_hold + (size_t)n * D, *pdiff = s->pdiff + (size_t)n * D;
+    const double total_assets = s->last_total[n], cash = s->last_cash[n];
+    double cash_penalty = total_assets * c->cash_penalty_proportion - cash;
+    if (!(cash_penalty > 0.0)) cash_penalty = 0.0;
+    double stop_loss_penalty = 0.0;
+    if (current_step > 1) {
+        double d = 0.0;
+        for (int i = 0; i < D; ++i) d += prev[i] * (cdiff[i] < 0 ? cdiff[i] : 0.0);
+        stop_loss_penalty = -1 * d;
+    }
+    double lp = 0.0, ar = 0.0;
+    for (int i = 0; i < D; ++i) {
+        lp += hold[i] * (pdiff[i] < 0 ? pdiff[i] : 0.0);
+        ar += hold[i] * (pdiff[i] > 0 ? pdiff[i] : 0.0);
+    }
+    const double low_profit_penalty = -1 * lp;
+    const double total_penalty = cash_penalty + stop_loss_penalty + low_profit_penalty;
+    double reward = ((total_assets - total_penalty + ar) / c->initial_amount) - 1;
+    reward /= current_step;
+    return reward;
+}
+
+static void sl_step_one(const ora_sl_cfg *c, ora_sl_state *s, int n, const void *actions, int actions_f64,
+                        double *reward_out, uint8_t *flags_out, int auto_reset)
+{
+    const int D = c->stock_dim, T = c->n_days;
+    const size_t base = (size_t)n * D;
+    double *hold = s->hold + base, *prev = s->prev_hold + base, *avg = s->avg_buy + base, *nb = s->n_buys + base;
+    double *cdiff = s->cdiff + base, *pdiff = s->pdiff + base;
+    uint8_t flags = 0;
+    {   /* self.sum_trades += np.sum(np.abs(actions)) (:294) */
+        if (actions_f64) {
+            double tmp[MAXD];
+            for (int i = 0; i < D; ++i) tmp[i] = fabs(((const double *)actions)[base + i]);
+            s->sum_trades[n] += ora_pairwise_sum_f64(tmp, D);
+        } else {
+            float tmp[MAXD];
+            for (int i = 0; i < D; ++i) tmp[i] = fabsf(((const float *)actions)[base + i]);
+            s->sum_trades[n] += (double)ora_pairwise_sum_f32(tmp, D);
+        }
+    }
+    const int di = s->date_index[n];
+    const int current_step = di - s->start[n];
+    if (di == T - 1) { /* last date (:302-304) */
+        if (reward_out) reward_out[n] = sl_reward(c, s, n, current_step, cdiff);
+        if (flags_out) flags_out[n] = ORA_FLAG_DONE;
+        if (auto_reset) sl_reset_one(c, s, n, 0);
+        return;
+    }
+    const double *close = c->close + (size_t)di * D;
+    const double begin_cash = s->cash[n];
+    double asset_value = 0.0;
+    for (int i = 0; i < D; ++i) asset_value += hold[i] * close[i];
+    /* reward from the PREVIOUS log entry and the previous step's penalty arrays, then log (:313-319) */
+    const double reward = sl_reward(c, s, n, current_step, cdiff);
+    s->last_cash[n] = begin_cash;
+    s->last_total[n] = begin_cash + asset_value;
+
+    double tx[MAXD], new_cdiff[MAXD];
+    const double turbulence = s->fresh[n] ? 0.0 : c->turb[di];
+    const int liq = c->use_turbulence && turbulence >= c->turbulence_threshold;
+    if (liq) flags |= ORA_FLAG_LIQUIDATE;
+    const int stop_on = begin_cash >= c->stoploss_penalty * c->initial_amount;
+    for (int i = 0; i < D; ++i) {
+        double a;
+        if (actions_f64)
+            a = ((const double *)actions)[base + i] * c->hmax;
+        else
+            a = (double)(((const float *)actions)[base + i] * (float)c->hmax);
+        if (!(close[i] > 0)) a = 0.0;
+        if (liq) a = -(hold[i] * close[i]); /* currency, divided by the price again below (:331-334) */
+        if (c->discrete_actions) {
+            int64_t q = (close[i] > 0) ? (int64_t)ora_floor_divide_f64(a, close[i]) : 0;
+            const int64_t inc = c->shares_increment;
+            q = (q >= 0) ? cp_floordiv_i64(q, inc) * inc : cp_floordiv_i64(q + inc, inc) * inc;
+            a = (double)q;
+        } else {
+            a = (close[i] > 0) ? a / close[i] : 0.0;
+        }
+        a = (a > -hold[i]) ? a : -hold[i];
+        new_cdiff[i] = close[i] - (c->stoploss_penalty * avg[i]); /* closing_diff_avg_buy (:354-356) */
+        if (stop_on && new_cdiff[i] < 0) a = -hold[i];            /* stop-loss: clear the position (:357-361) */
+        tx[i] = a;
+    }
+    for (int i = 0; i < D; ++i) cdiff[i] = new_cdiff[i];
+    double proceeds = 0.0, spend = 0.0;
+    double sells[MAXD], buys[MAXD];
+    for (int i = 0; i < D; ++i) {
+        sells[i] = -(tx[i] < 0 ? tx[i] : 0.0);
+        buys[i] = tx[i] > 0 ? tx[i] : 0.0;
+    }
+    for (int i = 0; i < D; ++i) proceeds += sells[i] * close[i];
+    double costs = proceeds * c->sell_cost_pct;
+    double coh = begin_cash + proceeds;
+    for (int i = 0; i < D; ++i) spend += buys[i] * close[i];
+    costs += spend * c->buy_cost_pct;
+    if ((spend + costs) > coh) {
+        flags |= ORA_FLAG_SHORTAGE;
+        if (c->patient) {
+            for (int i = 0; i < D; ++i)
+                if (tx[i] > 0) tx[i] = 0.0;
+            spend = 0.0;
+            costs = 0.0;
+        } else { /* terminate (:383-386): get_reward() again, now with this step's log entry and closing diff */
+            flags |= ORA_FLAG_DONE;
+            if (reward_out) reward_out[n] = sl_reward(c, s, n, current_step, cdiff);
+            if (flags_out) flags_out[n] = flags;
+            if (auto_reset) sl_reset_one(c, s, n, 0);
+            return;
+        }
+    }
+    /* profitable sells (:391-404); `sells` and `buys` are the PRE-patient vectors */
+    for (int i = 0; i < D; ++i) {
+        const double scp = sells[i] > 0 ? close[i] : 0.0;
+        const int profit = (scp - avg[i]) > 0;
+        pdiff[i] = profit ? close[i] - ((1 + c->profit_loss_ratio * (1 - c->stoploss_penalty)) * avg[i]) : 0.0;
+    }
+    coh = coh - spend - costs;
+    for (int i = 0; i < D; ++i) {
+        const double hn = hold[i] + tx[i];
+        const double sg = buys[i] > 0 ? 1.0 : 0.0; /* np.sign(buys) */
+        nb[i] += sg;
+        if (sg > 0) avg[i] = avg[i] + ((close[i] - avg[i]) / nb[i]);
+        if (!(hn > 0)) {
+            nb[i] = 0.0;
+            avg[i] = 0.0;
+        }
+        prev[i] = hold[i];
+        hold[i] = hn;
+    }
+    s->cash[n] = coh;
+    s->date_index[n] = di + 1;
+    s->fresh[n] = c->use_turbulence ? 0 : 1;
+    if (reward_out) reward_out[n] = reward;
+    if (flags_out) flags_out[n] = flags;
+}
+
+void ora_sl_step(const ora_sl_cfg *c, ora_sl_state *s, const void *actions, int actions_f64, double *reward_out,
+                 uint8_t *flags_out, int auto_reset)
+{
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < c->n_envs; ++n) sl_step_one(c, s, n, actions, actions_f64, reward_out, flags_out, auto_reset);
+}

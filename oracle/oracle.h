@@ -176,6 +176,42 @@ void ora_cp_obs(const ora_cp_cfg *c, const ora_cp_state *s, double *obs /*[N][1+
 void ora_cp_step(const ora_cp_cfg *c, ora_cp_state *s, const void *actions, int actions_f64, double *reward_out,
                  uint8_t *flags_out, int auto_reset);
 
+/* ---- sibling: StockTradingEnvStopLoss (env_stocktrading_stoploss.py) ----------------------- */
+typedef struct {
+    int32_t n_envs, stock_dim, n_cols, n_days;
+    double buy_cost_pct, sell_cost_pct, hmax;
+    int32_t discrete_actions, shares_increment;
+    double stoploss_penalty, profit_loss_ratio;
+    int32_t use_turbulence;
+    double turbulence_threshold;
+    double initial_amount, cash_penalty_proportion;
+    int32_t patient;
+    const double *close; /* [T][D] */
+    const double *turb;  /* [T] */
+    const double *info;  /* [T][D*C] */
+} ora_sl_cfg;
+
+typedef struct {
+    double *cash;        /* [N] */
+    double *hold;        /* [N][D] state_memory[-1] holdings */
+    double *prev_hold;   /* [N][D] state_memory[-2] holdings */
+    double *avg_buy;     /* [N][D] avg_buy_price */
+    double *n_buys;      /* [N][D] */
+    double *cdiff;       /* [N][D] closing_diff_avg_buy */
+    double *pdiff;       /* [N][D] profit_sell_diff_avg_buy */
+    int32_t *date_index; /* [N] */
+    int32_t *start;      /* [N] */
+    uint8_t *fresh;      /* [N] */
+    double *last_cash;   /* [N] account_information["cash"][-1] */
+    double *last_total;  /* [N] account_information["total_assets"][-1] */
+    double *sum_trades;  /* [N] */
+} ora_sl_state;
+
+void ora_sl_reset(const ora_sl_cfg *c, ora_sl_state *s, const uint8_t *mask, const int32_t *start_points);
+void ora_sl_obs(const ora_sl_cfg *c, const ora_sl_state *s, double *obs /*[N][1+D+D*C]*/);
+void ora_sl_step(const ora_sl_cfg *c, ora_sl_state *s, const void *actions, int actions_f64, double *reward_out,
+                 uint8_t *flags_out, int auto_reset);
+
 /* ---- sibling: CryptoEnv (env_cryptocurrency_trading/env_multiple_crypto.py) ---------------- */
 typedef struct {
     int32_t n_envs, stock_dim, tech_dim, n_days, lookback;

@@ -445,3 +445,71 @@ class CryptoOracle:
         lib().ora_crypto_step(C.byref(self._cfg), C.byref(self._st), _p(a), C.c_int(a.dtype == np.float64), _p(reward),
                               _p(flags), _p(obs))
         return obs, reward, flags
+
+
+# --------------------------------------------------------------------------------------------
+# sibling: StockTradingEnvStopLoss
+# --------------------------------------------------------------------------------------------
+class _SlCfg(C.Structure):
+    _fields_ = [("n_envs", C.c_int32), ("stock_dim", C.c_int32), ("n_cols", C.c_int32), ("n_days", C.c_int32),
+                ("buy_cost_pct", C.c_double), ("sell_cost_pct", C.c_double), ("hmax", C.c_double),
+                ("discrete_actions", C.c_int32), ("shares_increment", C.c_int32),
+                ("stoploss_penalty", C.c_double), ("profit_loss_ratio", C.c_double), ("use_turbulence", C.c_int32),
+                ("turbulence_threshold", C.c_double), ("initial_amount", C.c_double),
+                ("cash_penalty_proportion", C.c_double), ("patient", C.c_int32),
+                ("close", C.c_void_p), ("turb", C.c_void_p), ("info", C.c_void_p)]
+
+
+class _SlState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("cash", "hold", "prev_hold", "avg_buy", "n_buys", "cdiff", "pdiff", "date_index",
+                                          "start", "fresh", "last_cash", "last_total", "sum_trades")]
+
+
+class StopLossOracle:
+    """N independent copies of the reference ``StockTradingEnvStopLoss``
+    (finrl/meta/env_stock_trading/env_stocktrading_stoploss.py), stepped on the CPU."""
+
+    def __init__(self, close, info, turb, n_envs, buy_cost_pct=3e-3, sell_cost_pct=3e-3, hmax=10, discrete_actions=False,
+                 shares_increment=1, stoploss_penalty=0.9, profit_loss_ratio=2, turbulence_threshold=None,
+                 initial_amount=1e6, cash_penalty_proportion=0.1, patient=False):
+        self.close = np.ascontiguousarray(close, dtype=np.float64)
+        T, D = self.close.shape
+        self.info = np.ascontiguousarray(info, dtype=np.float64).reshape(T, -1)
+        Cc = self.info.shape[1] // D
+        self.turb = np.ascontiguousarray(turb if turb is not None else np.zeros(T), dtype=np.float64)
+        N = int(n_envs)
+        self.N, self.D, self.C, self.T, self.O = N, D, Cc, T, 1 + D + D * Cc
+        z = lambda: np.zeros((N, D))
+        self.cash = np.zeros(N); self.hold = z(); self.prev_hold = z(); self.avg_buy = z(); self.n_buys = z()
+        self.cdiff = z(); self.pdiff = z()
+        self.date_index = np.zeros(N, dtype=np.int32); self.start = np.zeros(N, dtype=np.int32)
+        self.fresh = np.zeros(N, dtype=np.uint8)
+        self.last_cash = np.zeros(N); self.last_total = np.zeros(N); self.sum_trades = np.zeros(N)
+        self._cfg = _SlCfg(N, D, Cc, T, float(buy_cost_pct), float(sell_cost_pct), float(hmax), int(discrete_actions),
+                           int(shares_increment), float(stoploss_penalty), float(profit_loss_ratio),
+                           int(turbulence_threshold is not None),
+                           float(turbulence_threshold if turbulence_threshold is not None else 0.0), float(initial_amount),
+                           float(cash_penalty_proportion), int(patient), _p(self.close), _p(self.turb), _p(self.info))
+        self._st = _SlState(_p(self.cash), _p(self.hold), _p(self.prev_hold), _p(self.avg_buy), _p(self.n_buys),
+                            _p(self.cdiff), _p(self.pdiff), _p(self.date_index), _p(self.start), _p(self.fresh),
+                            _p(self.last_cash), _p(self.last_total), _p(self.sum_trades))
+        self.reset()
+
+    def reset(self, mask=None, start_points=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        sp = None if start_points is None else np.ascontiguousarray(start_points, dtype=np.int32)
+        lib().ora_sl_reset(C.byref(self._cfg), C.byref(self._st), _p(m), _p(sp))
+        return self.obs()
+
+    def obs(self):
+        out = np.empty((self.N, self.O))
+        lib().ora_sl_obs(C.byref(self._cfg), C.byref(self._st), _p(out))
+        return out
+
+    def step(self, actions, auto_reset=False):
+        a = np.ascontiguousarray(actions)
+        assert a.shape == (self.N, self.D) and a.dtype in (np.float32, np.float64)
+        reward = np.empty(self.N); flags = np.empty(self.N, dtype=np.uint8)
+        lib().ora_sl_step(C.byref(self._cfg), C.byref(self._st), _p(a), C.c_int(a.dtype == np.float64), _p(reward),
+                          _p(flags), C.c_int(int(auto_reset)))
+        return reward, flags

@@ -24,6 +24,7 @@ ENV_FILES = {
     "env_portfolio": "finrl/meta/env_portfolio_allocation/env_portfolio.py",
     "env_nas100_wrds": "finrl/meta/env_stock_trading/env_nas100_wrds.py",
     "env_multiple_crypto": "finrl/meta/env_cryptocurrency_trading/env_multiple_crypto.py",
+    "env_stocktrading_stoploss": "finrl/meta/env_stock_trading/env_stocktrading_stoploss.py",
 }
 
 

@@ -212,19 +212,22 @@ def gen_portfolio(name, T, D, K, n_steps, seed, act_dtype, lookback=252):
 # ------------------------------------------------------------------------------------------
 def gen_cashpenalty(name, T, D, n_steps, seed, act_dtype, threshold=None, patient=False, discrete=False, hmax=10,
                     initial_amount=1e6, shares_increment=1, cols=("open", "close", "high", "low", "volume"),
-                    cost=3e-3, penalty=0.1):
-    mod = ref_loader.load("env_stocktrading_cashpenalty")
+                    cost=3e-3, penalty=0.1, stoploss=None):
+    """``stoploss=(stoploss_penalty, profit_loss_ratio)`` generates from the sibling StockTradingEnvStopLoss."""
+    mod = ref_loader.load("env_stocktrading_stoploss" if stoploss else "env_stocktrading_cashpenalty")
     close, _tech, turb = syn.make_tables(T, D, 0, seed=seed)
     o, h, l, v = syn.make_ohlv(close, seed)
     df = syn.make_frame(close, np.zeros((0, T, D)), turb, tech_names=[], extra_cols={"open": o, "high": h, "low": l, "volume": v})
     df = df.reset_index(drop=True)
     with _quiet():
-        env = mod.StockTradingEnvCashpenalty(
-            df=df, buy_cost_pct=cost, sell_cost_pct=cost, hmax=hmax, discrete_actions=discrete,
-            shares_increment=shares_increment, turbulence_threshold=threshold, print_verbosity=10**9,
-            initial_amount=initial_amount, daily_information_cols=list(cols), cache_indicator_data=True,
-            cash_penalty_proportion=penalty, random_start=False, patient=patient,
-        )
+        kw = dict(df=df, buy_cost_pct=cost, sell_cost_pct=cost, hmax=hmax, discrete_actions=discrete,
+                  shares_increment=shares_increment, turbulence_threshold=threshold, print_verbosity=10**9,
+                  initial_amount=initial_amount, daily_information_cols=list(cols), cache_indicator_data=True,
+                  cash_penalty_proportion=penalty, random_start=False, patient=patient)
+        if stoploss:
+            env = mod.StockTradingEnvStopLoss(stoploss_penalty=stoploss[0], profit_loss_ratio=stoploss[1], **kw)
+        else:
+            env = mod.StockTradingEnvCashpenalty(**kw)
         obs0 = np.asarray(env.reset(), dtype=np.float64)
     actions = syn.make_actions((n_steps, D), seed=seed + 1, dtype=np.float64).astype(act_dtype)
     O = env.state_space
@@ -248,6 +251,7 @@ def gen_cashpenalty(name, T, D, n_steps, seed, act_dtype, threshold=None, patien
         os.path.join(HERE, name + ".npz"), actions=actions, obs0=obs0, cols=np.array(list(cols), dtype="U16"),
         cfg=np.array([cost, cost, hmax, float(discrete), shares_increment, -1.0 if threshold is None else 1.0,
                       0.0 if threshold is None else threshold, initial_amount, penalty, float(patient)]),
+        stoploss=np.array(stoploss if stoploss else [0.0, 0.0]),
         **tables, **out, **_meta(),
     )
     print(f"{name}: {n_steps} steps, dones={int(out['done'].sum())}, liq={int(out['liq'].sum())}, "
@@ -335,6 +339,14 @@ def main():
     if want("portfolio"):
         gen_portfolio("portfolio_d30_f64", T=252 + 24, D=30, K=4, n_steps=50, seed=21, act_dtype=np.float64)
         gen_portfolio("portfolio_d6_f32", T=40 + 12, D=6, K=2, n_steps=30, seed=22, act_dtype=np.float32, lookback=40)
+    if want("stoploss"):
+        gen_cashpenalty("stoploss_d10", T=40, D=10, n_steps=85, seed=51, act_dtype=np.float32, hmax=8000, stoploss=(0.9, 2))
+        gen_cashpenalty("stoploss_d10_turb_patient", T=40, D=10, n_steps=85, seed=52, act_dtype=np.float64, threshold=70,
+                        patient=True, hmax=30000, initial_amount=1e5, stoploss=(0.95, 3))
+        gen_cashpenalty("stoploss_d8_shortage", T=30, D=8, n_steps=45, seed=53, act_dtype=np.float32, hmax=25000,
+                        initial_amount=1e5, stoploss=(0.9, 2))
+        gen_cashpenalty("stoploss_d6_discrete", T=30, D=6, n_steps=62, seed=54, act_dtype=np.float32, hmax=4000,
+                        discrete=True, shares_increment=2, threshold=90, stoploss=(0.97, 1.5))
     if want("crypto"):
         gen_crypto("crypto_d5_f32", T=45, D=5, K=3, n_steps=100, seed=41, act_dtype=np.float32, lookback=1,
                    initial_capital=2e5, scales=[300.0, 1.5, 0.02, 45.0, 7000.0])

@@ -252,3 +252,30 @@ def test_crypto_oracle_vs_reference(path):
         if g["done"][s]:
             assert o.episode_return[0] == g["episode_return"][s], ctx
             o.reset()
+
+
+# ---------------------------------------------------------------------------- sibling: StockTradingEnvStopLoss
+SL = sorted(glob.glob(os.path.join(GOLDEN, "stoploss_*.npz")))
+
+
+def stoploss_args_from_golden(g):
+    close, info, turb, kw = cashpen_args_from_golden(g)
+    kw["stoploss_penalty"], kw["profit_loss_ratio"] = float(g["stoploss"][0]), float(g["stoploss"][1])
+    return close, info, turb, kw
+
+
+@pytest.mark.parametrize("path", SL, ids=[os.path.basename(p)[:-4] for p in SL])
+def test_stoploss_oracle_vs_reference(path):
+    g = np.load(path)
+    close, info, turb, kw = stoploss_args_from_golden(g)
+    o = ora.StopLossOracle(close, info, turb, 1, **kw)
+    np.testing.assert_allclose(o.obs()[0], g["obs0"], rtol=0, atol=0)
+    acts = g["actions"]
+    for s in range(acts.shape[0]):
+        reward, flags = o.step(acts[s][None, :], auto_reset=True)
+        ctx = f"step {s}"
+        assert bool(flags[0] & ora.FLAG_DONE) == bool(g["done"][s]), ctx
+        assert bool(flags[0] & ora.FLAG_LIQUIDATE) == bool(g["liq"][s]), ctx
+        assert o.date_index[0] == g["date_index"][s], ctx
+        np.testing.assert_allclose(reward[0], g["reward"][s], rtol=1e-11, atol=1e-16, err_msg=ctx)
+        np.testing.assert_allclose(o.obs()[0], g["obs"][s], rtol=1e-12, atol=1e-9, err_msg=ctx)
