@@ -54,7 +54,7 @@ class CashPenaltyTables:
     def from_arrays(close, info, turb, device) -> "CashPenaltyTables":
         import torch
 
-        close = np.ascontiguousarray(close, dtype=np.float64)
+        close = np.array(close, dtype=np.float64, order="C")  # own, writable copy
         T, D = close.shape
         if not 1 <= D <= 128:
             raise ValueError(f"number of assets must be in 1..128 for the cash-penalty kernel (got {D})")

@@ -74,7 +74,7 @@ def _compare_state(env, o, ctx):
     (512, 30, np.float32, dict(hmax=40000, initial_amount=1e5)),            # CASH SHORTAGE terminations
     (300, 128, np.float32, dict(discrete_actions=True, shares_increment=2, stoploss_penalty=0.98)),
     (300, 7, np.float32, dict(discrete_actions=True, shares_increment=1, turbulence_threshold=80, profit_loss_ratio=0.5)),
-    (400, 30, np.float32, dict(stoploss_penalty=0.995, profit_loss_ratio=1, hmax=20000)),  # stop-loss fires often
+    (400, 30, np.float32, dict(stoploss_penalty=0.999, profit_loss_ratio=1, hmax=1)),  # stop-loss fires often
 ])
 def test_step_vs_oracle(N, D, dtype, kw):
     from finrl_b200 import synthetic as syn
@@ -108,11 +108,12 @@ def test_step_vs_oracle(N, D, dtype, kw):
 
 def test_stoploss_actually_fires():
     """With a tight stop-loss the forced liquidation path must be hit: some env holds an asset at step s and
-    holds none of it at s+1 although its action was a buy."""
+    holds none of it at s+1 although its action was a buy.  The override is only armed while cash is at least
+    stoploss_penalty x initial_amount (:357), hence the tiny hmax."""
     from finrl_b200 import synthetic as syn
 
     N, D, T = 256, 10, 40
-    env, o = _make(N, T=T, D=D, stoploss_penalty=0.999, hmax=20000)
+    env, o = _make(N, T=T, D=D, stoploss_penalty=0.999, hmax=1)
     acts = np.abs(syn.make_actions((T - 1, N, D), seed=3))  # buys only
     fired = 0
     for s in range(T - 1):
