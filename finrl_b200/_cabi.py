@@ -21,7 +21,7 @@ N_STATS = 8
 STAT_NAMES = ("reward_sum", "reward_sqsum", "done_count", "episode_asset_sum", "asset_sum", "liq_count", "env_steps",
               "trades_sum")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class EngineError(RuntimeError):
@@ -60,6 +60,7 @@ class TradingParams(C.Structure):
         ("reward", C.c_void_p),
         ("episode", C.c_void_p),
         ("asset_out", C.c_void_p),
+        ("obs_tmpl4", C.c_void_p),
     ]
 
 

@@ -113,4 +113,23 @@ __device__ __forceinline__ void stage_actions_flat(ActT *__restrict__ dst, const
     }
 }
 
+// The two halves of the contiguous-layout fast path above, for kernels that want the action loads in flight
+// together with their state loads (one DRAM round trip instead of two).
+template <int SLOTS, typename ActT>
+__device__ __forceinline__ void stage_actions_load(ActT (&av)[SLOTS], const ActT *__restrict__ abase, long long env0, int D,
+                                                   int nvalid, int lane)
+{
+    const ActT *tile = abase + (size_t)env0 * D + lane;
+    const int cnt = nvalid * D - lane;
+#pragma unroll
+    for (int i = 0; i < SLOTS; ++i) av[i] = (i < D && 32 * i < cnt) ? __ldcs(tile + 32 * i) : ActT(0);
+}
+template <int SLOTS, typename ActT>
+__device__ __forceinline__ void stage_actions_store(ActT *__restrict__ dst, const ActT (&av)[SLOTS], int D, int lane)
+{
+#pragma unroll
+    for (int i = 0; i < SLOTS; ++i)
+        if (i < D) dst[lane + 32 * i] = av[i];
+}
+
 }  // namespace frl

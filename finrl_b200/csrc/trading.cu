@@ -76,16 +76,195 @@ __device__ __forceinline__ void bitonic_network(int (&key)[SLOTS])
 
 constexpr int kHoldPitch = 33;  // hold_s[j][lane]: conflict-free both per-lane (compute) and per-row (obs)
 
+#ifndef FRL_OBS_BULK
+#define FRL_OBS_BULK 1  // one-day tiles: 4-row template image loaded by the copy engine (TMA); rows leave as
+                        // 1 = bulk stores (A/B on B200: 0.306 ms), 2 = aligned 16-byte vector stores from the
+                        // patched image (0.320), 0 = off, per-row 4-byte stores (0.320)
+#endif
+#ifndef FRL_OBS_PARTS
+#define FRL_OBS_PARTS 1  // bulk stores per image: 1, 2 or 4
+#endif
+constexpr int kObsImgBytes = 4864;  // >= 16 * O for DOW-30 with 8 indicators (O = 301 -> 4816 B)
+
 template <int SLOTS, typename ActT, int WARPS>
 struct alignas(16) WarpSmem {
+    static constexpr int kActBytes = 32 * SLOTS * (int)sizeof(ActT);
+    static constexpr int kImgBytes = kActBytes > kObsImgBytes ? kActBytes : kObsImgBytes;
     // staged actions, flat [32 envs][D] exactly as they lie in global memory.  Once a lane has turned
     // ITS row into sort keys, the row is reused for that lane's sorted order (lane-private, so no
-    // cross-lane hazard and no barrier).
-    ActT act[32 * SLOTS];
+    // cross-lane hazard and no barrier).  After the trades the region is dead and becomes the 4-row
+    // observation image of the bulk-copy writer.
+    union alignas(16) {
+        ActT act[32 * SLOTS];
+        float img[kImgBytes / 4];
+    };
     int hold[SLOTS * kHoldPitch];
     float cashf[32];
     int sd[32];
+    unsigned long long mbar;  // completion barrier of the image load
 };
+
+// ---- bulk-copy (TMA) observation writer --------------------------------------------------------
+// The 32 observation rows of a tile are ONE contiguous, 16-byte-aligned block of 32*O floats, and all but
+// the cash / holdings slots of a row are the day's template.  So: bulk-load the day's 4-row template image
+// (16*O bytes, obs_tmpl4) into shared memory once, and per 4 rows patch the 4*(D+1) env-specific floats
+// and hand the image to the copy engine with one cp.async.bulk store — ~20 instructions per lane per four
+// rows instead of ~60 stores and selects.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_store_s2g(void *dst, unsigned src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
+
+// all 32 envs of the tile valid and on day sd0: start the image load (the action region must be dead)
+template <typename SM>
+__device__ __forceinline__ void obs_image_load(const frl_trading_params &p, SM &sm, int lane, int sd0)
+{
+    fence_proxy_async_smem();
+    __syncwarp();  // every lane is done with its action / order row; cashf and hold are visible
+    if (lane == 0) {
+        const unsigned bytes = 16u * (unsigned)p.obs_dim, mbar = smem_u32(&sm.mbar);
+        const float *src = p.obs_tmpl4 + (size_t)sd0 * 4 * p.obs_dim;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        bulk_copy_g2s(smem_u32(sm.img), src, bytes, mbar);
+    }
+}
+
+// ... and patch + store the 8 x 4 rows; otile = first row of the tile, 16-byte aligned
+template <int DCT, typename SM>
+__device__ __forceinline__ void write_obs_tile_bulk(const frl_trading_params &p, SM &sm, float *__restrict__ otile, int lane,
+                                                    int sd0, unsigned &phase)
+{
+    const int O = p.obs_dim, D = DCT > 0 ? DCT : p.stock_dim;
+    const unsigned bytes = 16u * (unsigned)O;
+    const unsigned mbar = smem_u32(&sm.mbar);
+    // the env-specific floats of the first four rows, fetched while the image is in flight
+    const int *hcol = sm.hold + lane * kHoldPitch;
+    float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, cq = 0.f;
+    if (lane < D) {
+        h0 = (float)hcol[0];
+        h1 = (float)hcol[1];
+        h2 = (float)hcol[2];
+        h3 = (float)hcol[3];
+    }
+    if (lane < 4) cq = sm.cashf[lane];
+    mbar_wait(mbar, phase);
+    phase ^= 1u;
+    float *pimg = sm.img + D + 1 + lane;
+#if FRL_OBS_BULK == 1
+    // Copy engine: the image leaves in FRL_OBS_PARTS pieces (whole rows each, cut at 16-byte boundaries just
+    // below a row start), one bulk store per piece, so a piece can be patched for the next four rows as soon
+    // as ITS last store has been read while the stores of the other pieces are still in flight.
+    constexpr int PARTS = FRL_OBS_PARTS, R = 4 / PARTS;
+    const char *img_b = reinterpret_cast<const char *>(sm.img);
+    char *out_b = reinterpret_cast<char *>(otile);
+#pragma unroll 1
+    for (int s = 0; s < 8; ++s) {
+        float hv[4] = {h0, h1, h2, h3};
+#pragma unroll
+        for (int q = 0; q < PARTS; ++q) {
+            if (s > 0) {
+                if (lane == 0) bulk_wait_read<PARTS - 1>();  // this piece's previous store has read the image
+                __syncwarp();
+            }
+            if (lane < D) {
+#pragma unroll
+                for (int r = q * R; r < (q + 1) * R; ++r) pimg[r * O] = hv[r];
+            }
+            if (lane >= q * R && lane < (q + 1) * R) sm.img[lane * O] = cq;
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned off = (unsigned)(q * R * O * 4) & ~15u;
+                const unsigned end = q + 1 == PARTS ? bytes : ((unsigned)((q + 1) * R * O * 4) & ~15u);
+                bulk_store_s2g(out_b + (size_t)s * bytes + off, smem_u32(img_b + off), end - off);
+            }
+        }
+        if (s < 7) {  // next four rows' values while the engine reads the image
+            if (lane < D) {
+                h0 = (float)hcol[4 * s + 4];
+                h1 = (float)hcol[4 * s + 5];
+                h2 = (float)hcol[4 * s + 6];
+                h3 = (float)hcol[4 * s + 7];
+            }
+            if (lane < 4) cq = sm.cashf[4 * s + 4 + lane];
+        }
+    }
+    if (lane == 0) bulk_wait_read<0>();  // the action region is restaged next
+    __syncwarp();
+#else
+#pragma unroll 1
+    for (int s = 0; s < 8; ++s) {
+        if (lane < D) {
+            pimg[0] = h0;
+            pimg[O] = h1;
+            pimg[2 * O] = h2;
+            pimg[3 * O] = h3;
+        }
+        if (lane < 4) sm.img[lane * O] = cq;
+        // the four rows are O aligned 16-byte vectors: LDS.128 -> STG.128, nothing to wait for
+        __syncwarp();
+        {
+            const float4 *iv = reinterpret_cast<const float4 *>(sm.img) + lane;
+            float4 *ov = reinterpret_cast<float4 *>(otile + (size_t)s * 4 * O) + lane;
+            constexpr int NV = DCT == 30 ? 10 : 16;  // ceil(O / 32) vectors per lane
+#pragma unroll
+            for (int c0 = 0; c0 < NV; c0 += 5) {
+                float4 v[5];
+#pragma unroll
+                for (int c = 0; c < 5; ++c)
+                    if (c0 + c < NV && lane + 32 * (c0 + c) < O) v[c] = iv[32 * (c0 + c)];
+#pragma unroll
+                for (int c = 0; c < 5; ++c)
+                    if (c0 + c < NV && lane + 32 * (c0 + c) < O) ov[32 * (c0 + c)] = v[c];
+            }
+        }
+        if (s < 7) {
+            if (lane < D) {
+                h0 = (float)hcol[4 * s + 4];
+                h1 = (float)hcol[4 * s + 5];
+                h2 = (float)hcol[4 * s + 6];
+                h3 = (float)hcol[4 * s + 7];
+            }
+            if (lane < 4) cq = sm.cashf[4 * s + 4 + lane];
+        }
+        __syncwarp();
+    }
+#endif
+}
 
 
 // sequential Python sum() of price*holding over the D stocks, then cash + that (:311-314, :344-347)
@@ -195,9 +374,9 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
                        double *__restrict__ stats)
 {
     using SM = WarpSmem<SLOTS, ActT, WARPS>;
-    __shared__ SM smem[WARPS];
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SM &sm = smem[warp];
+    SM &sm = reinterpret_cast<SM *>(smem_dyn)[warp];
     const int N = p.n_envs, D = DCT > 0 ? DCT : p.stock_dim, T = p.n_days;
     const int ld = p.env_stride;  // 32-bit index math: SLOTS * env_stride < 2^31 is validated on the host
     const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
@@ -205,16 +384,31 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
     const int nvalid = (int)min((long long)32, (long long)N - env0);
     const bool valid = lane < nvalid;
     const long long n = valid ? env0 + lane : (long long)N - 1;
+    unsigned img_phase = 0;
+#if FRL_OBS_BULK
+    const bool bulk_ok = p.obs_tmpl4 != nullptr && nvalid == 32 && 16 * p.obs_dim <= SM::kImgBytes && p.obs_dim <= 512 &&
+                         p.n_tech * D >= 4;  // a piece boundary never cuts through a row's cash / holdings slots
+    if (bulk_ok && lane == 0) mbar_init(smem_u32(&sm.mbar), 1);
+#else
+    const bool bulk_ok = false;
+#endif
 
     // ---- load state: one thread per env, stock-major holdings => coalesced ----
     double cash = p.cash[n], cost = p.cost[n], last_reward = p.reward[n];
     int day = p.day[n], sday = p.sday[n], trades = p.trades[n];
+    const bool act_flat = act_env_stride == D;
     {
-        // all D loads are issued back to back (independent), then parked in shared memory
+        // all D holdings loads and the first step's action loads are issued back to back (independent, one
+        // DRAM round trip), then parked in shared memory
         int hv[SLOTS];
         const int *hp = p.hold + n;
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) hv[j] = (j < D) ? ld_stream(hp + j * ld) : 0;
+        if (act_flat) {
+            ActT av[SLOTS];
+            stage_actions_load<SLOTS, ActT>(av, actions, env0, D, nvalid, lane);
+            stage_actions_store<SLOTS, ActT>(sm.act, av, D, lane);
+        }
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) sm.hold[j * kHoldPitch + lane] = hv[j];
     }
@@ -230,11 +424,13 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
         // ---- stage this step's actions for the tile (coalesced) ----
         const ActT *abase = actions + (size_t)k * act_step_stride;
         __syncwarp();
-        stage_actions_flat<SLOTS, ActT>(sm.act, abase, env0, act_env_stride, D, nvalid, lane);
+        if (k > 0 || !act_flat) stage_actions_flat<SLOTS, ActT>(sm.act, abase, env0, act_env_stride, D, nvalid, lane);
         __syncwarp();
 
         uint8_t flags = 0;
         double reward;
+        double begin = 0.0;
+        bool liq = false, stepped = false;
         if (day >= T - 1) {
             // ---- terminal branch (:221-301): no state change, previous scaled reward again (Q3) ----
             flags = FRL_FLAG_DONE;
@@ -262,9 +458,9 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
         } else {
             const int sd = state_day(sday);
             const double turb = sday < 0 ? 0.0 : __ldg(p.risk + sd);
-            const bool liq = p.use_turbulence && (turb >= p.turbulence_threshold);
+            liq = p.use_turbulence && (turb >= p.turbulence_threshold);
             const double *prow = p.close + (size_t)sd * p.close_pitch;
-            const double begin = asset_ok ? asset : total_asset<SLOTS>(cash, prow, sm.hold, lane, D);
+            begin = asset_ok ? asset : total_asset<SLOTS>(cash, prow, sm.hold, lane, D);
 
             if (liq) {
                 // actions = [-hmax]*D (:308-310): all keys tie, the network never swaps, so the sell
@@ -346,6 +542,23 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
             // ---- state: s -> s+1 (:335-352) ----
             day += 1;
             sday = day;
+            stepped = true;
+        }
+        // the action region is dead from here on: start the observation image load, then value the portfolio
+        const bool want_obs = obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1);
+        float *otile = nullptr;
+        bool bulk = false;
+        int sd0 = 0;
+        if (want_obs) {
+            const int sdn = state_day(sday);
+            sm.cashf[lane] = (float)cash;
+            sm.sd[lane] = sdn;
+            otile = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0) + (size_t)env0 * p.obs_dim;
+            sd0 = __shfl_sync(0xffffffffu, sdn, 0);
+            bulk = bulk_ok && (reinterpret_cast<uintptr_t>(otile) & 15) == 0 && __all_sync(0xffffffffu, sdn == sd0);
+            if (bulk) obs_image_load(p, sm, lane, sd0);
+        }
+        if (stepped) {
             asset = total_asset<SLOTS>(cash, p.close + (size_t)day * p.close_pitch, sm.hold, lane, D);
             asset_ok = true;
             reward = dmul(dsub(asset, begin), p.reward_scaling);
@@ -359,12 +572,13 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
             st_r += reward;
             st_r2 += reward * reward;
         }
-        if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
-            sm.cashf[lane] = (float)cash;
-            sm.sd[lane] = state_day(sday);
-            __syncwarp();
-            float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
-            write_obs_tile<DCT>(p, sm, o, env0, nvalid, lane);
+        if (want_obs) {
+            if (bulk) {
+                write_obs_tile_bulk<DCT>(p, sm, otile, lane, sd0, img_phase);
+            } else {
+                __syncwarp();
+                write_obs_tile<DCT>(p, sm, otile - (size_t)env0 * p.obs_dim, env0, nvalid, lane);
+            }
         }
     }
 
@@ -433,7 +647,11 @@ __global__ void trading_reset_kernel(const frl_trading_params p, const uint8_t *
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) trading_observe_kernel(const frl_trading_params p, float *__restrict__ obs)
 {
-    using SM = WarpSmem<32, float, WARPS>;
+    struct SM {  // what write_obs_tile reads
+        int hold[32 * kHoldPitch];
+        float cashf[32];
+        int sd[32];
+    };
     __shared__ SM smem[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SM &sm = smem[warp];
@@ -512,7 +730,14 @@ void launch_rollout(const frl_trading_params &p, const void *actions, long long 
 {
     const long long tiles = ((long long)p.n_envs + 31) / 32;
     const unsigned grid = (unsigned)((tiles + WARPS - 1) / WARPS);
-    trading_rollout_kernel<SLOTS, DCT, ActT, WARPS><<<grid, WARPS * 32, 0, st>>>(
+    auto kern = trading_rollout_kernel<SLOTS, DCT, ActT, WARPS>;
+    constexpr int smem = WARPS * (int)sizeof(WarpSmem<SLOTS, ActT, WARPS>);
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    kern<<<grid, WARPS * 32, smem, st>>>(
         p, (const ActT *)actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats);
 }
 

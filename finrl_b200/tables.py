@@ -51,6 +51,7 @@ class TradingTables:
     disable_mask: "torch.Tensor"  # [T, pitch/32] int32 bit mask (first indicator == 1.0)
     risk: "torch.Tensor"          # [T] f64
     obs_tmpl: "torch.Tensor"      # [T, O] f32
+    obs_tmpl4: Optional["torch.Tensor"]  # [T, 4*O] f32: every row four times (bulk-copy image), or None
     host_close: np.ndarray
     host_tech: np.ndarray
     host_risk: np.ndarray
@@ -87,12 +88,14 @@ class TradingTables:
         if K > 0:
             tmpl[:, 1 + 2 * D :] = np.transpose(tech, (1, 0, 2)).reshape(T, K * D).astype(np.float32)
         dev = torch.device(device)
+        # 4-row image for the bulk-copy observation writer (thread-per-env kernel, D <= 32, image <= 8 KB)
+        tmpl4 = torch.from_numpy(np.tile(tmpl, (1, 4))).to(dev) if (D <= 32 and 16 * O <= 8192) else None
         return TradingTables(
             n_days=T, stock_dim=D, n_tech=K,
             close=torch.from_numpy(close32).to(dev),
             disable_mask=torch.from_numpy(np.ascontiguousarray(mask).view(np.int32)).to(dev),
             risk=torch.from_numpy(risk).to(dev),
-            obs_tmpl=torch.from_numpy(tmpl).to(dev),
+            obs_tmpl=torch.from_numpy(tmpl).to(dev), obs_tmpl4=tmpl4,
             host_close=close, host_tech=tech, host_risk=risk,
         )
 

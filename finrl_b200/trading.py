@@ -142,6 +142,8 @@ class BatchedStockTradingEnv(BatchedEnvBase):
         # optional: the reference's end_total_asset of every env after each launch (asset_memory)
         self.asset = torch.zeros(N, dtype=torch.float64, device=dev) if track_asset else None
         p.asset_out = self.asset.data_ptr() if track_asset else None
+        tmpl4 = getattr(tables, "obs_tmpl4", None)
+        p.obs_tmpl4 = tmpl4.data_ptr() if tmpl4 is not None else None
         self._p = p
         with torch.cuda.device(dev):
             _cabi.check(_cabi.lib().frl_trading_init(C.byref(p), int(day), self._stream()), "frl_trading_init")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FRL_ABI_VERSION 2
+#define FRL_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define FRL_API __attribute__((visibility("default")))
@@ -107,6 +107,11 @@ typedef struct frl_trading_params {
     /* ---- optional per-env output ---- */
     double *asset_out; /* [N] or NULL: total asset (cash + sum price*holding, the reference's
                           end_total_asset / asset_memory entry) of the state after the last step */
+    /* ---- optional table ---- */
+    const float *obs_tmpl4; /* [T][4*O] or NULL: each obs_tmpl row repeated four times (16*O bytes, 16-byte
+                               aligned).  When present, a tile whose 32 envs sit on the same day gets its
+                               observation rows from this image through the bulk-copy engine (TMA): load the
+                               4-row image to shared memory, patch cash / holdings, one bulk store per 4 rows */
 } frl_trading_params;
 
 /* StockTradingEnv.__init__ (:24-100): day = day0, state built from day0, fresh. */

@@ -50,7 +50,7 @@ def test_struct_layouts_match_the_header():
     from finrl_b200 import _cabi
 
     checks = {
-        "frl_trading_params": (_cabi.TradingParams, ["n_envs", "hmax", "turbulence_threshold", "close", "cash", "episode", "asset_out"]),
+        "frl_trading_params": (_cabi.TradingParams, ["n_envs", "hmax", "turbulence_threshold", "close", "cash", "episode", "asset_out", "obs_tmpl4"]),
         "frl_np_params": (_cabi.NpParams, ["gamma", "initial_capital", "obs_amount_floor", "price", "amount", "episode_return"]),
         "frl_portfolio_params": (_cabi.PortfolioParams, ["initial_amount", "ret", "reward", "ret_out", "weights_out"]),
         "frl_crypto_params": (_cabi.CryptoParams, ["lookback", "env_stride", "initial_capital", "gamma", "price", "episode_return"]),

@@ -282,3 +282,42 @@ def test_step_host_pipelined_equals_plain_step():
         oobs, orew, ofl = o.step(acts[s], auto_reset=True)
         assert np.array_equal(h_obs.numpy(), oobs) and np.array_equal(h_rew.numpy(), orew) and np.array_equal(h_fl.numpy(), ofl)
     _compare(env, o)
+
+
+@pytest.mark.parametrize("N,D,K,dtype", [
+    (4096, 30, 8, np.float32),     # DOW-30 fast path, every tile full
+    (4096 + 36, 30, 8, np.float64),  # partial last tile -> row writer for that tile only
+    (2049, 32, 3, np.float32),     # odd N: every other step of an OBS_ALL rollout is misaligned for 16-byte copies
+    (1024, 7, 1, np.float32),
+    (1024, 5, 0, np.float32),      # no indicators: the image writer is not used
+])
+def test_image_obs_writer_equals_row_writer(trading_kernel, N, D, K, dtype):
+    """One-day tiles get their observation rows from the 4-row template image (bulk-copy engine); all other
+    tiles, and envs built without ``obs_tmpl4``, from the per-row writer.  Both must give identical bytes."""
+    if trading_kernel != "tile":
+        pytest.skip("the image writer belongs to the thread-per-env kernel")
+    from finrl_b200 import BatchedStockTradingEnv, TradingTables, synthetic as syn
+
+    T, S = 40, 12
+    close, tech, turb = syn.make_tables(T, D, K, seed=3)
+    args = dict(hmax=100, initial_amount=200_000, buy_cost_pct=0.001, sell_cost_pct=0.001, reward_scaling=1e-4,
+                turbulence_threshold=80)
+    tb = TradingTables.from_arrays(close, tech, turb, "cuda")
+    assert tb.obs_tmpl4 is not None and tb.obs_tmpl4.shape == (T, 4 * tb.obs_dim)
+    a = BatchedStockTradingEnv(tables=tb, n_envs=N, **args)
+    tr = TradingTables.from_arrays(close, tech, turb, "cuda")
+    tr.obs_tmpl4 = None
+    b = BatchedStockTradingEnv(tables=tr, n_envs=N, **args)
+    assert a._p.obs_tmpl4 and not b._p.obs_tmpl4
+    acts = torch.from_numpy(syn.make_actions((S, N, D), seed=9, dtype=dtype)).cuda()
+    oa, ra, fa = a.rollout(acts, obs_mode="all")
+    ob, rb, fb = b.rollout(acts, obs_mode="all")
+    assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(fa, fb)
+    # desynchronise the days inside tiles (masked reset), then single steps
+    m = (torch.arange(N, device="cuda") % 5 == 0)
+    a.reset(mask=m)
+    b.reset(mask=m)
+    for s in range(3):
+        xa = a.step(acts[s])[0].clone()
+        xb = b.step(acts[s])[0].clone()
+        assert torch.equal(xa, xb), s
