@@ -132,4 +132,50 @@ __device__ __forceinline__ void stage_actions_store(ActT *__restrict__ dst, cons
         if (i < D) dst[lane + 32 * i] = av[i];
 }
 
+// ---- bulk-copy engine (TMA, non-tensor form) ------------------------------------------------------
+// cp.async.bulk moves a contiguous, 16-byte-aligned run between global and shared memory without touching
+// the LSU/L1 path.  Loads complete on an mbarrier (expect_tx bytes), stores are tracked in bulk groups.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_store_s2g(void *dst, unsigned src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
+
 }  // namespace frl

@@ -15,7 +15,12 @@ template <int SLOTS, typename ActT>
 struct alignas(16) PfWarpSmem {
     ActT act[32 * SLOTS];
     int day[32];
+    unsigned long long mbar;  // completion barrier of the observation image load
 };
+
+#ifndef FRL_PF_IMG_ROWS
+#define FRL_PF_IMG_ROWS 1  // observation rows per shared-memory image (= rows per bulk store)
+#endif
 
 template <typename T>
 __device__ __forceinline__ T pf_exp(T x);
@@ -63,6 +68,31 @@ __device__ __forceinline__ T pf_pairwise_sum(const T (&x)[SLOTS], int D)
     for (int j = 8; j < SLOTS; ++j)
         if (j >= 8 * nb && j < D) res = pf_add(res, x[j]);
     return res;
+}
+
+// The observation of an env depends only on its day, so a tile whose 32 envs sit on one day writes 32 copies
+// of one table row: the copy engine (TMA) loads the row into shared memory (`rows` copies of it, back to
+// back) and stores it 32/rows times — no LSU store instructions, nothing to patch, all stores in flight at
+// once.  otile = first row of the tile; rows and tile are 16-byte aligned (checked by the caller).
+__device__ __forceinline__ void pf_write_obs_tile_bulk(const frl_portfolio_params &p, float *img, unsigned mbar, unsigned &phase,
+                                                       float *__restrict__ otile, int d0, int rows, int lane)
+{
+    const unsigned row_bytes = 4u * (unsigned)p.obs_dim;
+    __syncwarp();
+    if (lane == 0) {
+        const float *src = p.obs_table + (size_t)d0 * p.obs_dim;
+        mbar_expect_tx(mbar, row_bytes * rows);
+        for (int r = 0; r < rows; ++r) bulk_copy_g2s(smem_u32(img) + r * row_bytes, src, row_bytes, mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1u;
+    if (lane == 0) {
+        const unsigned chunk = row_bytes * rows;
+        char *dst = reinterpret_cast<char *>(otile);
+        for (int r = 0; r < 32; r += rows) bulk_store_s2g(dst + (size_t)r * row_bytes, smem_u32(img), chunk);
+        bulk_wait_read<0>();  // the image is reloaded by the next step / the block may retire
+    }
+    __syncwarp();
 }
 
 // broadcast the day's observation row to the tile's envs (obs[N][O] float32)
@@ -130,10 +160,11 @@ __global__ void __launch_bounds__(WARPS * 32)
 portfolio_rollout_kernel(const frl_portfolio_params p, const ActT *__restrict__ actions, long long act_step_stride,
                          long long act_env_stride, int n_steps, double *__restrict__ rewards,
                          uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode, int auto_reset,
-                         double *__restrict__ stats)
+                         double *__restrict__ stats, int img_rows)
 {
     using SM = PfWarpSmem<SLOTS, ActT>;
     __shared__ SM smem[WARPS];
+    extern __shared__ __align__(16) float pf_img[];  // [WARPS][img_rows * O] when the bulk writer is enabled
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SM &sm = smem[warp];
     const int N = p.n_envs, D = p.stock_dim, T = p.n_days;
@@ -142,6 +173,10 @@ portfolio_rollout_kernel(const frl_portfolio_params p, const ActT *__restrict__ 
     const int nvalid = (int)min((long long)32, (long long)N - env0);
     const bool valid = lane < nvalid;
     const long long n = valid ? env0 + lane : (long long)N - 1;
+    const bool bulk_ok = img_rows > 0 && nvalid == 32;
+    float *img = pf_img + (size_t)warp * img_rows * p.obs_dim;
+    unsigned img_phase = 0;
+    if (bulk_ok && lane == 0) mbar_init(smem_u32(&sm.mbar), 1);
 
     double pv = p.pv[n], last_reward = p.reward[n];
     int day = p.day[n];
@@ -199,9 +234,15 @@ portfolio_rollout_kernel(const frl_portfolio_params p, const ActT *__restrict__ 
         }
         if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
             sm.day[lane] = day;
-            __syncwarp();
             float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
-            pf_write_obs_tile(p, sm.day, o, env0, nvalid, lane);
+            float *otile = o + (size_t)env0 * p.obs_dim;
+            const int d0 = __shfl_sync(0xffffffffu, day, 0);
+            if (bulk_ok && (reinterpret_cast<uintptr_t>(otile) & 15) == 0 && __all_sync(0xffffffffu, day == d0)) {
+                pf_write_obs_tile_bulk(p, img, smem_u32(&sm.mbar), img_phase, otile, d0, img_rows, lane);
+            } else {
+                __syncwarp();
+                pf_write_obs_tile(p, sm.day, o, env0, nvalid, lane);
+            }
         }
     }
     if (valid) {
@@ -257,8 +298,21 @@ void pf_launch(const frl_portfolio_params &p, const void *actions, long long sst
 {
     const long long tiles = ((long long)p.n_envs + 31) / 32;
     const unsigned grid = (unsigned)((tiles + WARPS - 1) / WARPS);
-    portfolio_rollout_kernel<SLOTS, ActT, WARPS><<<grid, WARPS * 32, 0, st>>>(
-        p, (const ActT *)actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats);
+    auto kern = portfolio_rollout_kernel<SLOTS, ActT, WARPS>;
+    // bulk observation writer: rows must be 16-byte multiples on a 16-byte-aligned table, and the images of
+    // the block's warps must leave room for several blocks per SM
+    int img_rows = 0;
+    if (obs_mode != FRL_OBS_NONE && (p.obs_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(p.obs_table) & 15) == 0 &&
+        (size_t)FRL_PF_IMG_ROWS * p.obs_dim * 4 * WARPS <= 40 * 1024)
+        img_rows = FRL_PF_IMG_ROWS;
+    const size_t dyn = (size_t)img_rows * p.obs_dim * 4 * WARPS;
+    static bool configured = false;  // per instantiation: static + dynamic shared memory may exceed 48 KB
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024);
+        configured = true;
+    }
+    kern<<<grid, WARPS * 32, dyn, st>>>(p, (const ActT *)actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode,
+                                        auto_reset, stats, img_rows);
 }
 
 }  // namespace

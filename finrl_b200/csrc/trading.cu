@@ -110,45 +110,6 @@ struct alignas(16) WarpSmem {
 // (16*O bytes, obs_tmpl4) into shared memory once, and per 4 rows patch the 4*(D+1) env-specific floats
 // and hand the image to the copy engine with one cp.async.bulk store — ~20 instructions per lane per four
 // rows instead of ~60 stores and selects.
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(mbar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}" ::"r"(mbar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_store_s2g(void *dst, unsigned src, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int PENDING>
-__device__ __forceinline__ void bulk_wait_read()
-{
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
-}
-
 // all 32 envs of the tile valid and on day sd0: start the image load (the action region must be dead)
 template <typename SM>
 __device__ __forceinline__ void obs_image_load(const frl_trading_params &p, SM &sm, int lane, int sd0)
@@ -158,7 +119,7 @@ __device__ __forceinline__ void obs_image_load(const frl_trading_params &p, SM &
     if (lane == 0) {
         const unsigned bytes = 16u * (unsigned)p.obs_dim, mbar = smem_u32(&sm.mbar);
         const float *src = p.obs_tmpl4 + (size_t)sd0 * 4 * p.obs_dim;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        mbar_expect_tx(mbar, bytes);
         bulk_copy_g2s(smem_u32(sm.img), src, bytes, mbar);
     }
 }
