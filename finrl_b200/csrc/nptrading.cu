@@ -282,8 +282,8 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
 #pragma unroll
                 for (int j = 0; j < SLOTS; ++j) {
                     const int aj = (j < D) ? FRL_A(j) : 0;
+                    const float pj = (j < D) ? __ldg(prow + j) : 0.0f;  // unconditional: issued ahead of the chain
                     if (j < D && aj < -min_action) {
-                        const float pj = __ldg(prow + j);
                         if (pj > 0.0f) {
                             float st = stv[j];
                             NV x;
@@ -305,8 +305,8 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
 #pragma unroll
                 for (int j = 0; j < SLOTS; ++j) {
                     const int aj = (j < D) ? FRL_A(j) : 0;
+                    const float pj = (j < D) ? __ldg(prow + j) : 0.0f;
                     if (j < D && aj > min_action) {
-                        const float pj = __ldg(prow + j);
                         if (pj > 0.0f) {
                             float st = stv[j];
                             NV x;

@@ -24,6 +24,9 @@
 #ifndef FRL_ST_STREAM
 #define FRL_ST_STREAM 0  // st.global.cs for the state write-back
 #endif
+#ifndef FRL_LOOP_PIPE
+#define FRL_LOOP_PIPE 1  // software-pipelined sell / buy loops
+#endif
 #ifndef FRL_TRADING_MIN_BLOCKS
 #define FRL_TRADING_MIN_BLOCKS 4  // 128-thread blocks per SM the allocator must allow: 4 -> 128 regs, no remat (A/B: 6->0.43 ms, 5->0.39, 4->0.32, 3->0.37)
 #endif
@@ -459,6 +462,73 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
                     if (s < D) ord[s] = key[s];
                 const uint32_t dis = p.disable_mask ? __ldg(p.disable_mask + sd) : 0u;
 
+#if FRL_LOOP_PIPE
+                // Both loops are software-pipelined: the next order entry, its price (and holding) are fetched
+                // before the current trade's dependent fp64 chain, so the chain never waits for a load.
+                // ---- sells, most negative first (:321-324, _sell_stock :102-135) ----
+                {
+                    int kk = ord[0];
+                    double pj = __ldg(prow + (kk & 31));
+                    int h = sm.hold[(kk & 31) * kHoldPitch + lane];
+                    for (int s = 0; s < D; ++s) {
+                        if (kk >= 0) break;
+                        const int kn = ord[min(s + 1, D - 1)];
+                        const double pn = __ldg(prow + (kn & 31));
+                        const int hn = sm.hold[(kn & 31) * kHoldPitch + lane];  // another stock: not touched below
+                        const int a = kk >> 5, j = kk & 31;
+                        if (!((dis >> j) & 1u) && h > 0) {
+                            const int m = min(-a, h);
+                            const double pv = dmul(pj, (double)m);
+                            cash = dadd(cash, dmul(pv, one_minus_sc));
+                            sm.hold[j * kHoldPitch + lane] = h - m;
+                            cost = dadd(cost, dmul(pv, p.sell_cost_pct));
+                            trades += 1;
+                        }
+                        kk = kn;
+                        pj = pn;
+                        h = hn;
+                    }
+                }
+                // ---- buys, largest first, each limited by the cash left (:328-330, _buy_stock :171-201) ----
+                {
+                    int kk = ord[D - 1];
+                    double pj = __ldg(prow + (kk & 31));
+                    double unit = dmul(pj, one_plus_bc);
+                    for (int s = D - 1; s >= 0; --s) {
+                        if (kk < 32) break;
+                        const int kn = ord[max(s - 1, 0)];
+                        const double pn = __ldg(prow + (kn & 31));
+                        const double un = dmul(pn, one_plus_bc);
+                        const int a = kk >> 5, j = kk & 31;
+                        if (!((dis >> j) & 1u)) {
+                            double nsh = (double)a;
+                            trades += 1;  // even when 0 shares end up bought (Q5)
+                            bool buy = true;
+                            // min(cash // unit, a): the quotient only matters when cash < (a+1)*unit ...
+                            if (!(cash >= dmul(nsh + 1.0, unit))) {
+                                // ... and when not even one share is affordable it is exactly 0: buying 0 shares
+                                // changes nothing (x - 0.0 and x + 0.0 are identities) — the common state of a
+                                // cash-starved env, which then skips the division and the whole update
+                                if (cash >= 0.0 && cash < unit) {
+                                    buy = false;
+                                } else {
+                                    const double avail = floor_div_f64(cash, unit);
+                                    nsh = (nsh < avail) ? nsh : avail;
+                                }
+                            }
+                            if (buy) {
+                                const double pv = dmul(pj, nsh);
+                                cash = dsub(cash, dmul(pv, one_plus_bc));
+                                sm.hold[j * kHoldPitch + lane] += (int)nsh;
+                                cost = dadd(cost, dmul(pv, p.buy_cost_pct));
+                            }
+                        }
+                        kk = kn;
+                        pj = pn;
+                        unit = un;
+                    }
+                }
+#else
                 // ---- sells, most negative first (:321-324, _sell_stock :102-135) ----
                 for (int s = 0; s < D; ++s) {
                     const int kk = ord[s];
@@ -499,6 +569,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
                         cost = dadd(cost, dmul(pv, p.buy_cost_pct));
                     }
                 }
+#endif
             }
             // ---- state: s -> s+1 (:335-352) ----
             day += 1;
