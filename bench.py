@@ -211,7 +211,36 @@ class CashPenaltyStep(Workload):
         return step
 
 
-WORKLOADS = {w.name: w for w in (TradingStep, TradingRollout, NpStep, PortfolioStep, CashPenaltyStep)}
+class StopLossStep(CashPenaltyStep):
+    name = "stoploss_step"
+    # cash-penalty traffic + five more fp64 per-asset arrays read and written (previous holdings, average buy
+    # price, buy counts, closing / profit-sell diffs): 2404 obs + 400 actions + 12 x 800 state + ~60 scalars
+    bytes_per_env_step = 12464
+    kernel = "stoploss_rollout_kernel<float,4>"
+
+    def describe(self, envs):
+        return f"StockTradingEnvStopLoss NASDAQ-100 shape, {envs} envs/GPU, D=100 C=5 T=5000 O=601, random_start=False"
+
+    def make_env(self, dev, envs):
+        from finrl_b200 import BatchedStockTradingEnvStopLoss, CashPenaltyTables
+
+        return BatchedStockTradingEnvStopLoss(tables=CashPenaltyTables.from_arrays(*self.arrays(), dev), n_envs=envs,
+                                              device=dev, random_start=False, turbulence_threshold=99)
+
+    def make_cpu(self, envs):
+        from oracle import oracle as ora
+
+        close, info, turb = self.arrays()
+        o = ora.StopLossOracle(close, info, turb, envs, turbulence_threshold=99)
+
+        def step(a):
+            o.step(a, auto_reset=True)
+            o.obs()
+
+        return step
+
+
+WORKLOADS = {w.name: w for w in (TradingStep, TradingRollout, NpStep, PortfolioStep, CashPenaltyStep, StopLossStep)}
 
 
 def measured_peak():

@@ -145,12 +145,7 @@ class StopLossParams(C.Structure):
         ("turb", C.c_void_p),
         ("obs_tmpl", C.c_void_p),
         ("cash", C.c_void_p),
-        ("hold", C.c_void_p),
-        ("prev_hold", C.c_void_p),
-        ("avg_buy", C.c_void_p),
-        ("n_buys", C.c_void_p),
-        ("cdiff", C.c_void_p),
-        ("pdiff", C.c_void_p),
+        ("assets", C.c_void_p),
         ("date_index", C.c_void_p),
         ("start", C.c_void_p),
         ("fresh", C.c_void_p),

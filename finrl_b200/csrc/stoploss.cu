@@ -2,12 +2,14 @@
 //
 // The cash-penalty env plus per-asset average-buy-price tracking, stop-loss liquidation and three extra
 // dot products in the reward.  One thread per env, two streaming passes over the D <= 128 assets (the six
-// per-asset state arrays are stock-major, so every access is a coalesced warp access):
-//   pass 1  reward terms of the PREVIOUS step's penalty arrays, np.dot(holdings, closings), the new
-//           closing_diff_avg_buy, the transaction of every asset, proceeds and spend
-//   decide  cash shortage -> terminate (only closing_diff_avg_buy changes, as in the reference) / patient
-//   pass 2  re-form the transactions, update holdings / previous holdings / average buy price / buy counts /
-//           profit-sell diffs, and leave the float32 holdings in the staging rows for the observation writer.
+// per-asset state arrays are stock-major, so every access is a coalesced warp access), in ONE streaming pass
+// over double-buffered state:
+//   pass    reward terms of the PREVIOUS step's penalty arrays, np.dot(holdings, closings), the transaction
+//           of every asset, proceeds and spend, and the tentative new state (holdings / previous holdings /
+//           average buy price / buy counts / both diffs) written to the env's OTHER buffer; the float32
+//           holdings stay in the staging rows for the observation writer
+//   decide  cash shortage -> terminate (the buffer does not flip; only closing_diff_avg_buy changes, as in
+//           the reference) / patient (the buy slots are put back) / flip the buffer.
 // np.dot's order is BLAS-specific (1e-9 tolerance); the sums here are sequential in asset order.
 #include "common.cuh"
 
@@ -93,8 +95,24 @@ __device__ __forceinline__ void sl_write_obs_tile(const frl_stoploss_params &p, 
     }
 }
 
+// The six per-asset arrays live in ONE allocation, assets[2][6][D][env_stride]: two buffers of (holdings,
+// previous holdings, average buy price, buy counts, closing diff, profit-sell diff).  Bit 1 of an env's `fresh`
+// byte names its current buffer.  A step reads the current buffer and writes the other one, so the whole
+// update is ONE streaming pass (each array read once and written once); the buffer flips only when the step
+// goes through (no cash-shortage termination).
+enum { SL_HOLD = 0, SL_PREV = 1, SL_AVG = 2, SL_NB = 3, SL_CD = 4, SL_PD = 5, SL_ARRAYS = 6 };
+
+__device__ __forceinline__ double *sl_buf(const frl_stoploss_params &p, int which)
+{
+    return p.assets + (size_t)which * SL_ARRAYS * p.stock_dim * p.env_stride;
+}
+
+#ifndef FRL_SL_MIN_BLOCKS
+#define FRL_SL_MIN_BLOCKS 3  // 128-thread blocks per SM the register allocator must allow
+#endif
+
 template <typename ActT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, FRL_SL_MIN_BLOCKS * 128 / (WARPS * 32))
 stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ actions, long long act_step_stride,
                         long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
                         float *__restrict__ obs, int obs_mode, int auto_reset, double *__restrict__ stats)
@@ -102,6 +120,7 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;
+    const size_t arr = (size_t)D * ld;  // elements per array
     const int P = D | 1;
     const size_t warp_bytes = (size_t)32 * P * sizeof(ActT) + 32 * sizeof(float) + 32 * sizeof(int);
     unsigned char *base = smem_raw + warp * ((warp_bytes + 15) & ~(size_t)15);
@@ -116,7 +135,9 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
 
     double cash = p.cash[n], last_cash = p.last_cash[n], last_total = p.last_total[n], sum_trades = p.sum_trades[n];
     int di = p.date_index[n], start = p.start[n];
-    bool fresh = p.fresh[n] != 0;
+    const int fresh0 = p.fresh[n];
+    bool fresh = (fresh0 & 1) != 0;
+    int cur = (fresh0 >> 1) & 1;
     ActT *myrow = stage + (size_t)lane * P;
     double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_liq = 0.0, st_short = 0.0;
 
@@ -128,10 +149,19 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
             const int cnt = nvalid * D;
             int row = 0, col = lane;
             while (col >= D) { col -= D; ++row; }
-            for (int e = lane; e < 32 * D; e += 32) {
-                stage[row * P + col] = e < cnt ? __ldcs(tile + e) : ActT(0);
-                col += 32;
-                while (col >= D) { col -= D; ++row; }
+            for (int e0 = lane; e0 < 32 * D; e0 += 32 * 8) {
+                ActT v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + 32 * u;
+                    v[u] = e < cnt ? __ldcs(tile + e) : ActT(0);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (e0 + 32 * u < 32 * D) stage[row * P + col] = v[u];
+                    col += 32;
+                    while (col >= D) { col -= D; ++row; }
+                }
             }
         } else {
             for (int r = 0; r < 32; ++r)
@@ -144,12 +174,15 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
         double reward;
         const int current_step = di - start;
         bool reset_now = false, moved = false;
+        const double *rd = sl_buf(p, cur) + n;   // array a, asset j at rd[a * arr + j * ld]
+        double *wr = sl_buf(p, cur ^ 1) + n;
         // dot products of get_reward over the arrays as they stand at the start of the step
         double d_prev_negc = 0.0, d_hold_negp = 0.0, d_hold_posp = 0.0, asum = 0.0;
         if (di == T - 1) {
             for (int j = 0; j < D; ++j) {
-                const size_t o = (size_t)j * ld + n;
-                const double h = p.hold[o], pv = p.prev_hold[o], cd = p.cdiff[o], pd = p.pdiff[o];
+                const size_t o = (size_t)j * ld;
+                const double h = rd[SL_HOLD * arr + o], pv = rd[SL_PREV * arr + o], cd = rd[SL_CD * arr + o],
+                             pd = rd[SL_PD * arr + o];
                 d_prev_negc = dadd(d_prev_negc, dmul(pv, cd < 0.0 ? cd : 0.0));
                 d_hold_negp = dadd(d_hold_negp, dmul(h, pd < 0.0 ? pd : 0.0));
                 d_hold_posp = dadd(d_hold_posp, dmul(h, pd > 0.0 ? pd : 0.0));
@@ -166,22 +199,65 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
             if (liq) flags |= FRL_FLAG_LIQUIDATE;
             const double begin_cash = cash;
             const bool stop_on = begin_cash >= dmul(p.stoploss_penalty, p.initial_amount);
-            // ---- pass 1 ----
+            // ---- the pass: sums of the reward and of the trade, tentative new state into the other buffer ----
             double asset_value = 0.0, proceeds = 0.0, spend = 0.0, d_prev_negc_new = 0.0;
-            for (int j = 0; j < D; ++j) {
-                const size_t o = (size_t)j * ld + n;
-                const double c = __ldg(crow + j);
-                const double h = p.hold[o], pv = p.prev_hold[o], avg = p.avg_buy[o], cd = p.cdiff[o], pd = p.pdiff[o];
-                const ActT a = myrow[j];
-                const SlTx t = sl_transaction<ActT>(p, a, c, h, avg, liq, stop_on);
-                asum += fabs((double)a);
-                asset_value = dadd(asset_value, dmul(h, c));
-                d_prev_negc = dadd(d_prev_negc, dmul(pv, cd < 0.0 ? cd : 0.0));
-                d_hold_negp = dadd(d_hold_negp, dmul(h, pd < 0.0 ? pd : 0.0));
-                d_hold_posp = dadd(d_hold_posp, dmul(h, pd > 0.0 ? pd : 0.0));
-                d_prev_negc_new = dadd(d_prev_negc_new, dmul(pv, t.cdiff < 0.0 ? t.cdiff : 0.0));
-                proceeds = dadd(proceeds, dmul(t.v < 0.0 ? -t.v : 0.0, c));
-                spend = dadd(spend, dmul(t.v > 0.0 ? t.v : 0.0, c));
+            constexpr int U = 4;
+            for (int j0 = 0; j0 < D; j0 += U) {
+                double hb[U], pb[U], ab[U], nb_[U], cdb[U], pdb[U], cb[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {  // 6 x U independent loads in flight per thread
+                    const int j = j0 + u < D ? j0 + u : D - 1;
+                    const size_t o = (size_t)j * ld;
+                    hb[u] = __ldcs(rd + SL_HOLD * arr + o);
+                    pb[u] = __ldcs(rd + SL_PREV * arr + o);
+                    ab[u] = __ldcs(rd + SL_AVG * arr + o);
+                    nb_[u] = __ldcs(rd + SL_NB * arr + o);
+                    cdb[u] = __ldcs(rd + SL_CD * arr + o);
+                    pdb[u] = __ldcs(rd + SL_PD * arr + o);
+                    cb[u] = __ldg(crow + j);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u;
+                    if (j < D) {
+                        const double c = cb[u], h = hb[u], pv = pb[u], avg = ab[u], cd = cdb[u], pd = pdb[u];
+                        double nb = nb_[u];
+                        const ActT a = myrow[j];
+                        const SlTx t = sl_transaction<ActT>(p, a, c, h, avg, liq, stop_on);
+                        asum += fabs((double)a);
+                        asset_value = dadd(asset_value, dmul(h, c));
+                        d_prev_negc = dadd(d_prev_negc, dmul(pv, cd < 0.0 ? cd : 0.0));
+                        d_hold_negp = dadd(d_hold_negp, dmul(h, pd < 0.0 ? pd : 0.0));
+                        d_hold_posp = dadd(d_hold_posp, dmul(h, pd > 0.0 ? pd : 0.0));
+                        d_prev_negc_new = dadd(d_prev_negc_new, dmul(pv, t.cdiff < 0.0 ? t.cdiff : 0.0));
+                        const double sell = -(t.v < 0.0 ? t.v : 0.0), buy = t.v > 0.0 ? t.v : 0.0;
+                        proceeds = dadd(proceeds, dmul(sell, c));
+                        spend = dadd(spend, dmul(buy, c));
+                        // tentative update, as if the step goes through with its buys
+                        const double scp = sell > 0.0 ? c : 0.0;  // profitable sells (:391-404)
+                        const double pdn = (dsub(scp, avg) > 0.0) ? dsub(c, dmul(p.min_profit_penalty, avg)) : 0.0;
+                        const double hn = dadd(h, t.v);
+                        double avgn = avg;  // incremental average buy price (:416-428)
+                        if (buy > 0.0) {
+                            nb = dadd(nb, 1.0);
+                            avgn = dadd(avg, __ddiv_rn(dsub(c, avg), nb));
+                        }
+                        if (!(hn > 0.0)) {
+                            nb = 0.0;
+                            avgn = 0.0;
+                        }
+                        if (valid) {
+                            const size_t o = (size_t)j * ld;
+                            wr[SL_HOLD * arr + o] = hn;
+                            wr[SL_PREV * arr + o] = h;
+                            wr[SL_AVG * arr + o] = avgn;
+                            wr[SL_NB * arr + o] = nb;
+                            wr[SL_CD * arr + o] = t.cdiff;
+                            wr[SL_PD * arr + o] = pdn;
+                        }
+                        *reinterpret_cast<float *>(myrow + j) = (float)hn;
+                    }
+                }
             }
             sum_trades += asum;
             // reward from the PREVIOUS log entry (:313), then this step's entry is logged (:315-319)
@@ -204,53 +280,41 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
             }
             if (terminate) {
                 // return_terminal(reward=self.get_reward()) (:383-386): this step's log entry and closing diff,
-                // the previous profit diffs and holdings; closing_diff_avg_buy is the only array that changed
+                // the previous profit diffs and holdings; closing_diff_avg_buy is the only array that changed —
+                // it is written into the CURRENT buffer, the tentative one is dropped
                 flags |= FRL_FLAG_DONE;
                 reward = sl_reward(p, last_total, last_cash, current_step, d_prev_negc_new, d_hold_negp, d_hold_posp);
                 if (valid && !auto_reset) {
+                    double *cw = sl_buf(p, cur) + n;
                     for (int j = 0; j < D; ++j) {
-                        const size_t o = (size_t)j * ld + n;
-                        p.cdiff[o] = dsub(__ldg(crow + j), dmul(p.stoploss_penalty, p.avg_buy[o]));
+                        const size_t o = (size_t)j * ld;
+                        cw[SL_CD * arr + o] = dsub(__ldg(crow + j), dmul(p.stoploss_penalty, cw[SL_AVG * arr + o]));
                     }
                 }
                 reset_now = auto_reset != 0;
             } else {
-                // ---- pass 2 ----
                 cash = dsub(dsub(coh, spend), costs);
-                for (int j = 0; j < D; ++j) {
-                    const size_t o = (size_t)j * ld + n;
-                    const double c = __ldg(crow + j);
-                    const double h = p.hold[o], avg = p.avg_buy[o];
-                    double nb = p.n_buys[o];
-                    const SlTx t = sl_transaction<ActT>(p, myrow[j], c, h, avg, liq, stop_on);
-                    const double sell = -(t.v < 0.0 ? t.v : 0.0);   // PRE-patient vectors, like the reference
-                    const double buy = t.v > 0.0 ? t.v : 0.0;
-                    double v = t.v;
-                    if (no_buys && v > 0.0) v = 0.0;
-                    // profitable sells (:391-404)
-                    const double scp = sell > 0.0 ? c : 0.0;
-                    const double pdn = (dsub(scp, avg) > 0.0) ? dsub(c, dmul(p.min_profit_penalty, avg)) : 0.0;
-                    const double hn = dadd(h, v);
-                    // incremental average buy price (:416-428); np.sign(buys) of the pre-patient buys
-                    double avgn = avg;
-                    if (buy > 0.0) {
-                        nb = dadd(nb, 1.0);
-                        avgn = dadd(avg, __ddiv_rn(dsub(c, avg), nb));
+                if (no_buys) {
+                    // patient: the buys do not happen (:376-381).  Buy counts, average price and the profit diffs
+                    // were driven by the PRE-patient vectors (like the reference), so only the holdings of the buy
+                    // slots go back — and with them the "position closed" reset of count and average
+                    for (int j = 0; j < D; ++j) {
+                        const size_t o = (size_t)j * ld;
+                        const double h = rd[SL_HOLD * arr + o], hn = wr[SL_HOLD * arr + o];
+                        if (hn > h) {
+                            const double hk = dadd(h, 0.0);
+                            if (valid) {
+                                wr[SL_HOLD * arr + o] = hk;
+                                if (!(hk > 0.0)) {
+                                    wr[SL_AVG * arr + o] = 0.0;
+                                    wr[SL_NB * arr + o] = 0.0;
+                                }
+                            }
+                            *reinterpret_cast<float *>(myrow + j) = (float)hk;
+                        }
                     }
-                    if (!(hn > 0.0)) {
-                        nb = 0.0;
-                        avgn = 0.0;
-                    }
-                    if (valid) {
-                        p.prev_hold[o] = h;
-                        p.hold[o] = hn;
-                        p.avg_buy[o] = avgn;
-                        p.n_buys[o] = nb;
-                        p.cdiff[o] = t.cdiff;
-                        p.pdiff[o] = pdn;
-                    }
-                    *reinterpret_cast<float *>(myrow + j) = (float)hn;
                 }
+                cur ^= 1;
                 moved = true;
                 di += 1;
                 if (p.use_turbulence) fresh = false;
@@ -270,9 +334,13 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
         }
         if (reset_now) {  // reset (:134-165), random_start=False
             cash = p.initial_amount;
+            double *cw = sl_buf(p, cur) + n;
             for (int j = 0; j < D; ++j) {
-                const size_t o = (size_t)j * ld + n;
-                if (valid) p.hold[o] = p.prev_hold[o] = p.avg_buy[o] = p.n_buys[o] = p.cdiff[o] = p.pdiff[o] = 0.0;
+                const size_t o = (size_t)j * ld;
+                if (valid) {
+#pragma unroll
+                    for (int a = 0; a < SL_ARRAYS; ++a) cw[a * arr + o] = 0.0;
+                }
                 *reinterpret_cast<float *>(myrow + j) = 0.0f;
             }
             moved = true;
@@ -284,8 +352,10 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
             last_total = 0.0;
         }
         if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
-            if (!moved)
-                for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = (float)p.hold[(size_t)j * ld + n];
+            if (!moved) {
+                const double *cr = sl_buf(p, cur) + n;
+                for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = (float)cr[SL_HOLD * arr + (size_t)j * ld];
+            }
             cashf[lane] = (float)cash;
             di_s[lane] = di;
             __syncwarp();
@@ -297,7 +367,7 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
         p.cash[n] = cash;
         p.date_index[n] = di;
         p.start[n] = start;
-        p.fresh[n] = fresh ? 1 : 0;
+        p.fresh[n] = (uint8_t)((fresh ? 1 : 0) | (cur << 1));
         p.last_cash[n] = last_cash;
         p.last_total[n] = last_total;
         p.sum_trades[n] = sum_trades;
@@ -315,15 +385,15 @@ __global__ void stoploss_reset_kernel(const frl_stoploss_params p, const uint8_t
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= p.n_envs) return;
     if (mask && !mask[n]) return;
-    for (int j = 0; j < p.stock_dim; ++j) {
-        const size_t o = (size_t)j * p.env_stride + n;
-        p.hold[o] = p.prev_hold[o] = p.avg_buy[o] = p.n_buys[o] = p.cdiff[o] = p.pdiff[o] = 0.0;
-    }
+    const size_t arr = (size_t)p.stock_dim * p.env_stride;
+    double *b0 = sl_buf(p, 0) + n;
+    for (int j = 0; j < p.stock_dim; ++j)
+        for (int a = 0; a < SL_ARRAYS; ++a) b0[a * arr + (size_t)j * p.env_stride] = 0.0;
     const int sp = start_points ? start_points[n] : 0;
     p.cash[n] = p.initial_amount;
     p.date_index[n] = sp;
     p.start[n] = sp;
-    p.fresh[n] = 1;
+    p.fresh[n] = 1;  // fresh, current buffer 0
     p.last_cash[n] = 0.0;
     p.last_total[n] = 0.0;
     p.sum_trades[n] = 0.0;
@@ -336,13 +406,14 @@ __global__ void stoploss_observe_kernel(const frl_stoploss_params p, float *__re
     if (n >= p.n_envs) return;
     const int O = p.obs_dim, D = p.stock_dim;
     const float *trow = p.obs_tmpl + (size_t)p.date_index[n] * O;
+    const double *hold = sl_buf(p, (p.fresh[n] >> 1) & 1) + n;  // SL_HOLD is array 0
     float *orow = obs + (size_t)n * O;
     for (int pos = lane; pos < O; pos += 32) {
         float v;
         if (pos == 0)
             v = (float)p.cash[n];
         else if (pos <= D)
-            v = (float)p.hold[(size_t)(pos - 1) * p.env_stride + n];
+            v = (float)hold[(size_t)(pos - 1) * p.env_stride];
         else
             v = __ldg(trow + pos);
         orow[pos] = v;
@@ -360,8 +431,7 @@ int32_t sl_validate(const frl_stoploss_params *p)
     FRL_REQUIRE(p->env_stride >= p->n_envs, "stoploss: env_stride %d < n_envs %d", p->env_stride, p->n_envs);
     FRL_REQUIRE(!p->discrete_actions || p->shares_increment >= 1, "stoploss: shares_increment must be >= 1");
     FRL_REQUIRE(p->close && p->obs_tmpl && (!p->use_turbulence || p->turb), "stoploss: table pointer is NULL");
-    FRL_REQUIRE(p->cash && p->hold && p->prev_hold && p->avg_buy && p->n_buys && p->cdiff && p->pdiff && p->date_index &&
-                    p->start && p->fresh && p->last_cash && p->last_total && p->sum_trades,
+    FRL_REQUIRE(p->cash && p->assets && p->date_index && p->start && p->fresh && p->last_cash && p->last_total && p->sum_trades,
                 "stoploss: state pointer is NULL");
     return FRL_OK;
 }

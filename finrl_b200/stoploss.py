@@ -58,10 +58,9 @@ class BatchedStockTradingEnvStopLoss(BatchedEnvBase):
         dev = self.device
         f64 = dict(dtype=torch.float64, device=dev)
         self.cash = torch.empty(N, **f64)
-        # six stock-major per-asset arrays in one allocation: holdings, previous holdings, average buy price,
-        # buy counts, closing_diff_avg_buy, profit_sell_diff_avg_buy
-        self._assets = torch.zeros((6, D, N), **f64)
-        self.hold, self.prev_hold, self.avg_buy, self.n_buys, self.cdiff, self.pdiff = self._assets.unbind(0)
+        # two buffers of the six stock-major per-asset arrays (holdings, previous holdings, average buy price,
+        # buy counts, closing_diff_avg_buy, profit_sell_diff_avg_buy); bit 1 of `fresh` names an env's current one
+        self._assets = torch.zeros((2, 6, D, N), **f64)
         self.date_index = torch.empty(N, dtype=torch.int32, device=dev)
         self.starting_point = torch.empty(N, dtype=torch.int32, device=dev)
         self.fresh = torch.empty(N, dtype=torch.uint8, device=dev)
@@ -82,11 +81,22 @@ class BatchedStockTradingEnvStopLoss(BatchedEnvBase):
         p.stoploss_penalty, p.min_profit_penalty = float(stoploss_penalty), float(self.min_profit_penalty)
         p.close, p.turb, p.obs_tmpl = tables.close.data_ptr(), tables.turb.data_ptr(), tables.obs_tmpl.data_ptr()
         p.cash, p.date_index, p.start = self.cash.data_ptr(), self.date_index.data_ptr(), self.starting_point.data_ptr()
-        p.hold, p.prev_hold, p.avg_buy = self.hold.data_ptr(), self.prev_hold.data_ptr(), self.avg_buy.data_ptr()
-        p.n_buys, p.cdiff, p.pdiff = self.n_buys.data_ptr(), self.cdiff.data_ptr(), self.pdiff.data_ptr()
+        p.assets = self._assets.data_ptr()
         p.fresh, p.last_cash, p.last_total, p.sum_trades = self.fresh.data_ptr(), self.last_cash.data_ptr(), self.last_total.data_ptr(), self.sum_trades.data_ptr()
         self._p = p
         self.reset()
+
+    def _asset_array(self, idx):
+        """Array ``idx`` of every env's current buffer, stock-major [D, N]."""
+        use_alt = (self.fresh & 2).bool()
+        return self._torch.where(use_alt[None, :], self._assets[1, idx], self._assets[0, idx])
+
+    hold = property(lambda self: self._asset_array(0))
+    prev_hold = property(lambda self: self._asset_array(1))
+    avg_buy = property(lambda self: self._asset_array(2))
+    n_buys = property(lambda self: self._asset_array(3))
+    cdiff = property(lambda self: self._asset_array(4))
+    pdiff = property(lambda self: self._asset_array(5))
 
     @property
     def holdings(self):

@@ -312,7 +312,7 @@ typedef struct frl_stoploss_params {
     int32_t shares_increment;
     int32_t use_turbulence;
     int32_t patient;
-    int32_t env_stride; /* leading dimension of the six stock-major arrays (>= N) */
+    int32_t env_stride; /* leading dimension of the stock-major arrays (>= N) */
     double buy_cost_pct, sell_cost_pct;
     double hmax;
     double turbulence_threshold;
@@ -326,15 +326,13 @@ typedef struct frl_stoploss_params {
     const float *obs_tmpl; /* [T][O] */
     /* ---- per-env state ---- */
     double *cash;        /* [N] */
-    double *hold;        /* [D][env_stride] state_memory[-1] holdings */
-    double *prev_hold;   /* [D][env_stride] state_memory[-2] holdings */
-    double *avg_buy;     /* [D][env_stride] avg_buy_price */
-    double *n_buys;      /* [D][env_stride] */
-    double *cdiff;       /* [D][env_stride] closing_diff_avg_buy */
-    double *pdiff;       /* [D][env_stride] profit_sell_diff_avg_buy */
+    double *assets;      /* [2][6][D][env_stride]: two buffers of the six stock-major per-asset arrays, in the
+                            order holdings (state_memory[-1]), previous holdings (state_memory[-2]),
+                            avg_buy_price, n_buys, closing_diff_avg_buy, profit_sell_diff_avg_buy.  A step
+                            reads the env's current buffer and writes the other one (single streaming pass) */
     int32_t *date_index; /* [N] */
     int32_t *start;      /* [N] */
-    uint8_t *fresh;      /* [N] 1 while self.turbulence is still the 0 set by reset */
+    uint8_t *fresh;      /* [N] bit 0: self.turbulence is still the 0 set by reset; bit 1: current buffer */
     double *last_cash;   /* [N] */
     double *last_total;  /* [N] */
     double *sum_trades;  /* [N] */
