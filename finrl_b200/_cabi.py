@@ -152,6 +152,9 @@ class StopLossParams(C.Structure):
         ("last_cash", C.c_void_p),
         ("last_total", C.c_void_p),
         ("sum_trades", C.c_void_p),
+        ("hmax_vec", C.c_void_p),
+        ("hmax_vec_f32", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 
@@ -187,6 +190,9 @@ class CashPenaltyParams(C.Structure):
         ("last_cash", C.c_void_p),
         ("last_total", C.c_void_p),
         ("sum_trades", C.c_void_p),
+        ("hmax_vec", C.c_void_p),
+        ("hmax_vec_f32", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

@@ -47,13 +47,14 @@ __device__ __forceinline__ long long floordiv_ll(long long a, long long b)
 // not positive, shares = currency / price (or the discretised floor), never sell more than held,
 // turbulence clears the position.
 template <typename ActT>
-__device__ __forceinline__ double cp_transaction(const frl_cashpenalty_params &p, ActT a, double c, double h, bool liq)
+__device__ __forceinline__ double cp_transaction(const frl_cashpenalty_params &p, ActT a, double hmax, double c, double h,
+                                                 bool liq)
 {
     double v;
-    if (sizeof(ActT) == 4)
-        v = (double)fmul((float)a, (float)p.hmax);
+    if (sizeof(ActT) == 4 && !(p.hmax_vec && !p.hmax_vec_f32))
+        v = (double)fmul((float)a, (float)hmax);  // scalar (weak Python float) or float32 array: float32 product
     else
-        v = dmul((double)a, p.hmax);
+        v = dmul((double)a, hmax);
     if (!(c > 0.0)) v = 0.0;  // np.where(closings > 0, actions, 0)
     if (p.discrete_actions) {
         long long q = (long long)floor_div_f64(v, c);  // actions // closings, astype(int)
@@ -294,7 +295,7 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
                     const int j = j0 + u;
                     if (j < D) {
                         const ActT a = myrow[j];
-                        const double v = cp_transaction<ActT>(p, a, cb[u], hb[u], liq);
+                        const double v = cp_transaction<ActT>(p, a, p.hmax_vec ? __ldg(p.hmax_vec + j) : p.hmax, cb[u], hb[u], liq);
                         asum += fabs((double)a);
                         asset_value = dadd(asset_value, dmul(hb[u], cb[u]));
                         proceeds = dadd(proceeds, dmul(v < 0.0 ? -v : 0.0, cb[u]));

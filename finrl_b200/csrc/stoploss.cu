@@ -30,14 +30,14 @@ struct SlTx {
 
 // the action pipeline of step() for one asset (:321-361)
 template <typename ActT>
-__device__ __forceinline__ SlTx sl_transaction(const frl_stoploss_params &p, ActT a, double c, double h, double avg, bool liq,
+__device__ __forceinline__ SlTx sl_transaction(const frl_stoploss_params &p, ActT a, double hmax, double c, double h, double avg, bool liq,
                                                bool stop_on)
 {
     double v;
-    if (sizeof(ActT) == 4)
-        v = (double)fmul((float)a, (float)p.hmax);
+    if (sizeof(ActT) == 4 && !(p.hmax_vec && !p.hmax_vec_f32))
+        v = (double)fmul((float)a, (float)hmax);  // scalar (weak Python float) or float32 array: float32 product
     else
-        v = dmul((double)a, p.hmax);
+        v = dmul((double)a, hmax);
     const bool pos = c > 0.0;
     if (!pos) v = 0.0;                // np.where(closings > 0, actions, 0)
     if (liq) v = -dmul(h, c);         // -(holdings * closings): currency, divided by the price again below
@@ -248,7 +248,7 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
                                      cd = sb[SL_CD][u], pd = sb[SL_PD][u];
                         double nb = sb[SL_NB][u];
                         const ActT a = myrow[j];
-                        const SlTx t = sl_transaction<ActT>(p, a, c, h, avg, liq, stop_on);
+                        const SlTx t = sl_transaction<ActT>(p, a, p.hmax_vec ? __ldg(p.hmax_vec + j) : p.hmax, c, h, avg, liq, stop_on);
                         asum += fabs((double)a);
                         asset_value = dadd(asset_value, dmul(h, c));
                         d_prev_negc = dadd(d_prev_negc, dmul(pv, cd < 0.0 ? cd : 0.0));

@@ -32,8 +32,6 @@ class BatchedStockTradingEnvStopLoss(BatchedEnvBase):
                  cash_penalty_proportion=0.1, random_start=True, patient=False, currency="$",
                  *, n_envs=1, device="cuda", tables: Optional[CashPenaltyTables] = None):
         torch = self._bind_device(device)
-        if not np.isscalar(hmax):
-            raise NotImplementedError("per-asset hmax arrays are not supported yet (scalar hmax only)")
         self.df = df
         self.dates = self.assets = None
         if tables is None:
@@ -75,7 +73,18 @@ class BatchedStockTradingEnvStopLoss(BatchedEnvBase):
         p.n_envs, p.stock_dim, p.n_cols, p.n_days, p.obs_dim, p.env_stride = N, D, tables.n_cols, T, O, N
         p.discrete_actions, p.shares_increment = int(bool(discrete_actions)), int(shares_increment)
         p.use_turbulence, p.patient = int(turbulence_threshold is not None), int(bool(patient))
-        p.buy_cost_pct, p.sell_cost_pct, p.hmax = float(buy_cost_pct), float(sell_cost_pct), float(hmax)
+        p.buy_cost_pct, p.sell_cost_pct = float(buy_cost_pct), float(sell_cost_pct)
+        # scalar hmax (weak Python float: the product keeps the action dtype) or a per-asset array (numpy
+        # array-array promotion: float32 actions * float64 hmax -> float64) — `actions * self.hmax` (:268)
+        self._hmax_vec = None
+        if np.isscalar(hmax):
+            p.hmax = float(hmax)
+        else:
+            hv = np.asarray(hmax)
+            if hv.shape != (D,):
+                raise ValueError(f"hmax array must have shape ({D},), got {hv.shape}")
+            self._hmax_vec = torch.as_tensor(hv.astype(np.float64), device=dev)
+            p.hmax, p.hmax_vec, p.hmax_vec_f32 = 0.0, self._hmax_vec.data_ptr(), int(hv.dtype == np.float32)
         p.turbulence_threshold = float(turbulence_threshold) if turbulence_threshold is not None else 0.0
         p.initial_amount, p.cash_penalty_proportion = float(initial_amount), float(cash_penalty_proportion)
         p.stoploss_penalty, p.min_profit_penalty = float(stoploss_penalty), float(self.min_profit_penalty)

@@ -279,6 +279,11 @@ typedef struct frl_cashpenalty_params {
     double *last_cash;   /* [N] account_information["cash"][-1] */
     double *last_total;  /* [N] account_information["total_assets"][-1] */
     double *sum_trades;  /* [N] */
+    /* ---- optional ---- */
+    const double *hmax_vec; /* [D] or NULL: per-asset hmax array (`actions * self.hmax` broadcasts, :268); numpy
+                               array-array promotion then applies: float32 actions * float64 hmax -> float64 */
+    int32_t hmax_vec_f32;   /* the caller's array was float32: the product with float32 actions stays float32 */
+    int32_t reserved_;
 } frl_cashpenalty_params;
 
 /* reset (:132-158) for envs with mask[n] != 0 (NULL = all); start_points [N] (NULL = 0, i.e.
@@ -336,6 +341,10 @@ typedef struct frl_stoploss_params {
     double *last_cash;   /* [N] */
     double *last_total;  /* [N] */
     double *sum_trades;  /* [N] */
+    /* ---- optional ---- */
+    const double *hmax_vec; /* [D] or NULL: per-asset hmax array, as in frl_cashpenalty_params */
+    int32_t hmax_vec_f32;
+    int32_t reserved_;
 } frl_stoploss_params;
 
 FRL_API int32_t frl_stoploss_reset(const frl_stoploss_params *p, const uint8_t *mask, const int32_t *start_points,

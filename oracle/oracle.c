@@ -2,7 +2,7 @@
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC   (NO fused multiply-add, NO fast-math:
  * the reference's arithmetic is plain IEEE double/float, one rounding per operation).
- * Parity: pinned against the unmodified reference by tests/golden/*.npz.
+ * Parity: pinned against the unmodified reference by the npz fixtures under tests/golden.
  */
 #include "oracle.h"
 
@@ -711,10 +711,14 @@ static void cp_step_one(const ora_cp_cfg *c, ora_cp_state *s, int n, const void 
     const int liq = c->use_turbulence && turbulence >= c->turbulence_threshold;
     for (int i = 0; i < D; ++i) {
         double a; /* actions * hmax in the input dtype */
+        /* scalar hmax: weak Python float, the product stays in the action dtype; array hmax: numpy array-array
+           promotion (f32 * f64 -> f64, f32 * f32 -> f32) */
         if (actions_f64)
-            a = ((const double *)actions)[(size_t)n * D + i] * c->hmax;
+            a = ((const double *)actions)[(size_t)n * D + i] * (c->hmax_vec ? c->hmax_vec[i] : c->hmax);
+        else if (c->hmax_vec && !c->hmax_vec_f32)
+            a = (double)((const float *)actions)[(size_t)n * D + i] * c->hmax_vec[i];
         else
-            a = (double)(((const float *)actions)[(size_t)n * D + i] * (float)c->hmax);
+            a = (double)(((const float *)actions)[(size_t)n * D + i] * (float)(c->hmax_vec ? c->hmax_vec[i] : c->hmax));
         if (!(close[i] > 0)) a = 0.0; /* np.where(closings > 0, actions, 0) */
         if (c->discrete_actions) {
             /* actions // closings (float floor-div), astype(int), then toward-zero multiples of the increment */
@@ -999,9 +1003,11 @@ static void sl_step_one(const ora_sl_cfg *c, ora_sl_state *s, int n, const void 
     for (int i = 0; i < D; ++i) {
         double a;
         if (actions_f64)
-            a = ((const double *)actions)[base + i] * c->hmax;
+            a = ((const double *)actions)[base + i] * (c->hmax_vec ? c->hmax_vec[i] : c->hmax);
+        else if (c->hmax_vec && !c->hmax_vec_f32)
+            a = (double)((const float *)actions)[base + i] * c->hmax_vec[i];
         else
-            a = (double)(((const float *)actions)[base + i] * (float)c->hmax);
+            a = (double)(((const float *)actions)[base + i] * (float)(c->hmax_vec ? c->hmax_vec[i] : c->hmax));
         if (!(close[i] > 0)) a = 0.0;
         if (liq) a = -(hold[i] * close[i]); /* currency, divided by the price again below (:331-334) */
         if (c->discrete_actions) {

@@ -158,6 +158,8 @@ typedef struct {
     const double *close; /* [T][D] */
     const double *turb;  /* [T] "turbulence" column (only read when use_turbulence) */
     const double *info;  /* [T][D*C] get_date_vector(date): asset-major daily information */
+    const double *hmax_vec; /* [D] or NULL: per-asset hmax array (`actions * self.hmax` broadcasts, :268) */
+    int32_t hmax_vec_f32;   /* the array is float32: the product with float32 actions stays float32 */
 } ora_cp_cfg;
 
 typedef struct {
@@ -189,6 +191,8 @@ typedef struct {
     const double *close; /* [T][D] */
     const double *turb;  /* [T] */
     const double *info;  /* [T][D*C] */
+    const double *hmax_vec; /* [D] or NULL, as in ora_cp_cfg */
+    int32_t hmax_vec_f32;
 } ora_sl_cfg;
 
 typedef struct {

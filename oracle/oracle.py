@@ -330,7 +330,18 @@ class _CpCfg(C.Structure):
                 ("discrete_actions", C.c_int32), ("shares_increment", C.c_int32), ("use_turbulence", C.c_int32),
                 ("turbulence_threshold", C.c_double), ("initial_amount", C.c_double),
                 ("cash_penalty_proportion", C.c_double), ("patient", C.c_int32),
-                ("close", C.c_void_p), ("turb", C.c_void_p), ("info", C.c_void_p)]
+                ("close", C.c_void_p), ("turb", C.c_void_p), ("info", C.c_void_p),
+                ("hmax_vec", C.c_void_p), ("hmax_vec_f32", C.c_int32)]
+
+
+def _hmax_args(hmax, D):
+    """Scalar hmax -> (value, None, 0); per-asset array -> (0.0, float64 array [D], is_float32)."""
+    if np.isscalar(hmax):
+        return float(hmax), None, 0
+    arr = np.asarray(hmax)
+    if arr.shape != (D,):
+        raise ValueError(f"hmax array must have shape ({D},)")
+    return 0.0, np.ascontiguousarray(arr, dtype=np.float64), int(arr.dtype == np.float32)
 
 
 class _CpState(C.Structure):
@@ -356,10 +367,12 @@ class CashPenaltyOracle:
         self.cash = np.zeros(N); self.hold = np.zeros((N, D)); self.date_index = np.zeros(N, dtype=np.int32)
         self.start = np.zeros(N, dtype=np.int32); self.fresh = np.zeros(N, dtype=np.uint8)
         self.last_cash = np.zeros(N); self.last_total = np.zeros(N); self.sum_trades = np.zeros(N)
-        self._cfg = _CpCfg(N, D, Cc, T, float(buy_cost_pct), float(sell_cost_pct), float(hmax), int(discrete_actions),
+        hm, self._hmax_vec, hm32 = _hmax_args(hmax, D)
+        self._cfg = _CpCfg(N, D, Cc, T, float(buy_cost_pct), float(sell_cost_pct), hm, int(discrete_actions),
                            int(shares_increment), int(turbulence_threshold is not None),
                            float(turbulence_threshold if turbulence_threshold is not None else 0.0), float(initial_amount),
-                           float(cash_penalty_proportion), int(patient), _p(self.close), _p(self.turb), _p(self.info))
+                           float(cash_penalty_proportion), int(patient), _p(self.close), _p(self.turb), _p(self.info),
+                           _p(self._hmax_vec), hm32)
         self._st = _CpState(_p(self.cash), _p(self.hold), _p(self.date_index), _p(self.start), _p(self.fresh),
                             _p(self.last_cash), _p(self.last_total), _p(self.sum_trades))
         self.reset()
@@ -457,7 +470,8 @@ class _SlCfg(C.Structure):
                 ("stoploss_penalty", C.c_double), ("profit_loss_ratio", C.c_double), ("use_turbulence", C.c_int32),
                 ("turbulence_threshold", C.c_double), ("initial_amount", C.c_double),
                 ("cash_penalty_proportion", C.c_double), ("patient", C.c_int32),
-                ("close", C.c_void_p), ("turb", C.c_void_p), ("info", C.c_void_p)]
+                ("close", C.c_void_p), ("turb", C.c_void_p), ("info", C.c_void_p),
+                ("hmax_vec", C.c_void_p), ("hmax_vec_f32", C.c_int32)]
 
 
 class _SlState(C.Structure):
@@ -485,11 +499,13 @@ class StopLossOracle:
         self.date_index = np.zeros(N, dtype=np.int32); self.start = np.zeros(N, dtype=np.int32)
         self.fresh = np.zeros(N, dtype=np.uint8)
         self.last_cash = np.zeros(N); self.last_total = np.zeros(N); self.sum_trades = np.zeros(N)
-        self._cfg = _SlCfg(N, D, Cc, T, float(buy_cost_pct), float(sell_cost_pct), float(hmax), int(discrete_actions),
+        hm, self._hmax_vec, hm32 = _hmax_args(hmax, D)
+        self._cfg = _SlCfg(N, D, Cc, T, float(buy_cost_pct), float(sell_cost_pct), hm, int(discrete_actions),
                            int(shares_increment), float(stoploss_penalty), float(profit_loss_ratio),
                            int(turbulence_threshold is not None),
                            float(turbulence_threshold if turbulence_threshold is not None else 0.0), float(initial_amount),
-                           float(cash_penalty_proportion), int(patient), _p(self.close), _p(self.turb), _p(self.info))
+                           float(cash_penalty_proportion), int(patient), _p(self.close), _p(self.turb), _p(self.info),
+                           _p(self._hmax_vec), hm32)
         self._st = _SlState(_p(self.cash), _p(self.hold), _p(self.prev_hold), _p(self.avg_buy), _p(self.n_buys),
                             _p(self.cdiff), _p(self.pdiff), _p(self.date_index), _p(self.start), _p(self.fresh),
                             _p(self.last_cash), _p(self.last_total), _p(self.sum_trades))

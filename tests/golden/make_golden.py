@@ -249,8 +249,10 @@ def gen_cashpenalty(name, T, D, n_steps, seed, act_dtype, threshold=None, patien
     tables = {"close": close, "open": o, "high": h, "low": l, "volume": v, "turbulence": turb}
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"), actions=actions, obs0=obs0, cols=np.array(list(cols), dtype="U16"),
-        cfg=np.array([cost, cost, hmax, float(discrete), shares_increment, -1.0 if threshold is None else 1.0,
-                      0.0 if threshold is None else threshold, initial_amount, penalty, float(patient)]),
+        cfg=np.array([cost, cost, hmax if np.isscalar(hmax) else 0.0, float(discrete), shares_increment,
+                      -1.0 if threshold is None else 1.0, 0.0 if threshold is None else threshold, initial_amount, penalty,
+                      float(patient)]),
+        hmax_vec=np.zeros(0) if np.isscalar(hmax) else np.asarray(hmax),  # per-asset hmax array (dtype kept)
         stoploss=np.array(stoploss if stoploss else [0.0, 0.0]),
         **tables, **out, **_meta(),
     )
@@ -340,6 +342,8 @@ def main():
         gen_portfolio("portfolio_d30_f64", T=252 + 24, D=30, K=4, n_steps=50, seed=21, act_dtype=np.float64)
         gen_portfolio("portfolio_d6_f32", T=40 + 12, D=6, K=2, n_steps=30, seed=22, act_dtype=np.float32, lookback=40)
     if want("stoploss"):
+        gen_cashpenalty("stoploss_d7_hmaxvec", T=30, D=7, n_steps=50, seed=55, act_dtype=np.float32,
+                        hmax=np.linspace(3000.0, 9000.0, 7), stoploss=(0.92, 2))
         gen_cashpenalty("stoploss_d10", T=40, D=10, n_steps=85, seed=51, act_dtype=np.float32, hmax=8000, stoploss=(0.9, 2))
         gen_cashpenalty("stoploss_d10_turb_patient", T=40, D=10, n_steps=85, seed=52, act_dtype=np.float64, threshold=70,
                         patient=True, hmax=30000, initial_amount=1e5, stoploss=(0.95, 3))
@@ -353,6 +357,10 @@ def main():
         gen_crypto("crypto_d8_lb3_f64", T=40, D=8, K=2, n_steps=80, seed=42, act_dtype=np.float64, lookback=3,
                    initial_capital=1e6, scales=[30000.0, 2000.0, 1.0, 0.5, 150.0, 20.0, 6.0, 0.08])
     if want("cashpenalty"):
+        gen_cashpenalty("cashpen_d7_hmaxvec", T=30, D=7, n_steps=50, seed=35, act_dtype=np.float32,
+                        hmax=np.linspace(2000.0, 8000.0, 7))
+        gen_cashpenalty("cashpen_d5_hmaxvec_f32", T=24, D=5, n_steps=40, seed=36, act_dtype=np.float32,
+                        hmax=np.linspace(2000.0, 8000.0, 5).astype(np.float32), threshold=90)
         gen_cashpenalty("cashpen_d10", T=30, D=10, n_steps=65, seed=31, act_dtype=np.float32, hmax=5000)
         gen_cashpenalty("cashpen_d10_turb_patient", T=30, D=10, n_steps=65, seed=32, act_dtype=np.float64, threshold=70,
                         patient=True, hmax=20000, initial_amount=1e5)

@@ -206,6 +206,8 @@ def cashpen_args_from_golden(g):
     bc, sc, hmax, disc, inc, use_t, thr, init, pen, patient = g["cfg"]
     cols = [str(c) for c in g["cols"]]
     info = np.stack([g[c] for c in cols], axis=2)  # [T, D, C] asset-major like get_date_vector
+    if "hmax_vec" in g.files and g["hmax_vec"].size:
+        hmax = g["hmax_vec"]  # per-asset array, dtype as the reference received it
     kw = dict(buy_cost_pct=bc, sell_cost_pct=sc, hmax=hmax, discrete_actions=bool(disc), shares_increment=int(inc),
               turbulence_threshold=(thr if use_t > 0 else None), initial_amount=init, cash_penalty_proportion=pen,
               patient=bool(patient))
