@@ -509,6 +509,7 @@ def run_ours(args, wl):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8000": achieved / 8000.0,
                 "traffic": traffic, "peak_source": peak_src, "kernel": wl.kernel, "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_env_step": wl.bytes_per_env_step,
             },
