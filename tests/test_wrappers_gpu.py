@@ -213,3 +213,42 @@ def test_nas100_sibling_class_matches_reference():
     with pytest.raises(TypeError):
         StockEnvNAS100(cwd=None, price_ary=g["price_array"].astype(np.float64), tech_ary=g["tech_array"],
                        turbulence_ary=g["turbulence_array"])
+
+
+def test_stoploss_gym_class_and_vec_env_match_reference():
+    """The StockTradingEnvStopLoss drop-in on a frame vs the golden of the unmodified reference, and its
+    get_multiproc_env VecEnv (n GPU envs instead of n forked processes) vs the oracle."""
+    from finrl_b200 import synthetic as syn
+    from finrl_b200.env_stocktrading_stoploss import StockTradingEnvStopLoss
+    from oracle import oracle as ora
+    from test_oracle_golden import stoploss_args_from_golden
+
+    g = np.load(os.path.join(GOLDEN, "stoploss_d10_turb_patient.npz"))
+    close, info, turb, kw = stoploss_args_from_golden(g)
+    T, D = close.shape
+    df = syn.make_frame(close, np.zeros((0, T, D)), turb, tech_names=[],
+                        extra_cols={c: g[c] for c in ("open", "high", "low", "volume")}).reset_index(drop=True)
+    env = StockTradingEnvStopLoss(df=df, random_start=False, print_verbosity=10**9,
+                                  daily_information_cols=[str(c) for c in g["cols"]], **kw)
+    np.testing.assert_allclose(env.reset(), g["obs0"], rtol=1e-7)
+    acts = g["actions"]
+    for s in range(acts.shape[0]):
+        state, reward, done, info_ = env.step(acts[s])
+        ctx = f"step {s}"
+        assert done == bool(g["done"][s]), ctx
+        np.testing.assert_allclose(reward, g["reward"][s], rtol=1e-9, atol=1e-15, err_msg=ctx)
+        if done:
+            state = env.reset()
+        np.testing.assert_allclose(state[: 1 + D], g["obs"][s][: 1 + D], rtol=1e-9, atol=1e-7, err_msg=ctx)
+        assert env.date_index == g["date_index"][s], ctx
+    # VecEnv: 5 envs, numpy in/out, auto-reset
+    vec, obs = env.get_multiproc_env(n=5)
+    o = ora.StopLossOracle(close, info, turb, 5, **kw)
+    np.testing.assert_allclose(obs, o.obs().astype(np.float32), rtol=2e-7, atol=1e-6)
+    a = syn.make_actions((T + 5, 5, D), seed=77)
+    for s in range(a.shape[0]):
+        obs, rews, dones, infos = vec.step(a[s])
+        orew, ofl = o.step(a[s], auto_reset=True)
+        assert np.array_equal(dones, (ofl & 1).astype(bool)), s
+        np.testing.assert_allclose(rews, orew.astype(np.float32), rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(obs, o.obs().astype(np.float32), rtol=2e-7, atol=1e-6)
