@@ -318,6 +318,10 @@ def cpu_port_rate(wl, budget_s=12.0, envs=65536):
     threads, description).  This is the one place bench.py executes oracle/."""
     from oracle import oracle as ora
 
+    try:  # the GPU arm pins the process next to its GPU; the CPU baseline gets every host core back
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except OSError:
+        pass
     threads = ora.set_threads(os.cpu_count() or 1)  # all host threads, even under torchrun's OMP_NUM_THREADS=1
     step = wl.make_cpu(envs)
     pool = _cpu_actions(wl, envs)
@@ -374,6 +378,10 @@ def run_ours(args, wl):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from finrl_b200.dist import bind_cpu_affinity
+
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_cpu_affinity(local)  # pinned host buffers of the e2e leg land next to the GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N, D, KR = args.envs, wl.D, wl.rollout_k
@@ -518,6 +526,7 @@ def run_ours(args, wl):
                             f"memory, pipelined in {args.e2e_chunks} env slices over 3 streams") if use_pipelined else
                            "Batched*Env.step/rollout with pinned host actions in; obs + reward + flags copied back to host"},
             "gpu_launches": launches,
+            "host": {"cpus": len(all_cpus), "cpus_bound_to_gpu_numa": numa_cpus},
             "clocks": clocks,
             "stats": dict(zip(("reward_sum", "reward_sqsum", "done_count", "episode_asset_sum", "asset_sum", "liq_count",
                                "env_steps", "slot7"), stats_global.tolist())),

@@ -25,6 +25,30 @@ def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     return start, base + (1 if rank < extra else 0)
 
 
+def bind_cpu_affinity(device_index: int) -> Optional[int]:
+    """Pin this process to the CPU cores NVML reports as local to the GPU (same NUMA node / PCIe root), so
+    that pinned host buffers allocated afterwards are local to the GPU's link and the host-buffer step does
+    not cross sockets.  Returns the number of CPUs in the new affinity set, or None when NVML is unavailable.
+    ``FRL_NO_NUMA_BIND=1`` disables it."""
+    if os.environ.get("FRL_NO_NUMA_BIND") == "1":
+        return None
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        try:
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def init_from_env(backend: Optional[str] = None):
     """Read RANK / LOCAL_RANK / WORLD_SIZE (torchrun), bind the GPU, create the process group.
     Returns (rank, world, local_rank)."""
@@ -37,6 +61,7 @@ def init_from_env(backend: Optional[str] = None):
     use_cuda = torch.cuda.is_available()
     if use_cuda:
         torch.cuda.set_device(local)
+        bind_cpu_affinity(local)
     if world > 1 and not dist.is_initialized():
         backend = backend or ("nccl" if use_cuda else "gloo")
         kw = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}
