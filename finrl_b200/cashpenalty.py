@@ -3,7 +3,7 @@
 Reference: /root/reference/finrl/meta/env_stock_trading/env_stocktrading_cashpenalty.py.  Fractional
 (or discretised) share trading with ``hmax`` in currency, reward = cash-penalised gain per elapsed
 step computed BEFORE trading, CASH SHORTAGE termination or ``patient`` mode (incl. quirk Q9), and
-turbulence liquidation.  One thread per env, two streaming passes over the assets (finrl_b200/csrc/cashpenalty.cu).
+turbulence liquidation.  One thread per env, one streaming pass over the assets with ping-pong holdings buffers (finrl_b200/csrc/cashpenalty.cu).
 """
 from __future__ import annotations
 

@@ -1,7 +1,7 @@
 // Sibling env — StockTradingEnvStopLoss (reference: finrl/meta/env_stock_trading/env_stocktrading_stoploss.py).
 //
 // The cash-penalty env plus per-asset average-buy-price tracking, stop-loss liquidation and three extra
-// dot products in the reward.  One thread per env, two streaming passes over the D <= 128 assets (the six
+// dot products in the reward.  One thread per env over the D <= 128 assets (the six
 // per-asset state arrays are stock-major, so every access is a coalesced warp access), in ONE streaming pass
 // over double-buffered state:
 //   pass    reward terms of the PREVIOUS step's penalty arrays, np.dot(holdings, closings), the transaction
