@@ -95,6 +95,8 @@ class NpParams(C.Structure):
         ("gamma_reward", C.c_void_p),
         ("init_total", C.c_void_p),
         ("episode_return", C.c_void_p),
+        ("price_pitch", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

@@ -1,0 +1,59 @@
+// Shared pieces of the numpy-env kernels (nptrading.cu: D <= 32, state in registers; np_wide.cu: D <= 128,
+// state streamed): the NEP-50 scalar with its kind, the action cast and the amount slot of the observation.
+#pragma once
+
+#include "common.cuh"
+
+namespace frl {
+
+struct NV {  // a numpy / Python scalar: value + NEP-50 kind
+    double v;
+    int k;
+};
+__device__ __forceinline__ NV nv(double v, int k) { return NV{v, k}; }
+__device__ __forceinline__ NV nv_add(NV x, NV y)
+{
+    if (x.k == FRL_KIND_PY && y.k == FRL_KIND_PY) return nv(dadd(x.v, y.v), FRL_KIND_PY);
+    if (x.k == FRL_KIND_F64 || y.k == FRL_KIND_F64) return nv(dadd(x.v, y.v), FRL_KIND_F64);
+    return nv((double)fadd((float)x.v, (float)y.v), FRL_KIND_F32);  // f32 (a weak Python float adopts it)
+}
+__device__ __forceinline__ NV nv_sub(NV x, NV y)
+{
+    if (x.k == FRL_KIND_PY && y.k == FRL_KIND_PY) return nv(dsub(x.v, y.v), FRL_KIND_PY);
+    if (x.k == FRL_KIND_F64 || y.k == FRL_KIND_F64) return nv(dsub(x.v, y.v), FRL_KIND_F64);
+    return nv((double)fsub((float)x.v, (float)y.v), FRL_KIND_F32);
+}
+__device__ __forceinline__ NV nv_mul(NV x, NV y)
+{
+    if (x.k == FRL_KIND_PY && y.k == FRL_KIND_PY) return nv(dmul(x.v, y.v), FRL_KIND_PY);
+    if (x.k == FRL_KIND_F64 || y.k == FRL_KIND_F64) return nv(dmul(x.v, y.v), FRL_KIND_F64);
+    return nv((double)fmul((float)x.v, (float)y.v), FRL_KIND_F32);
+}
+
+template <typename ActT>
+__device__ __forceinline__ int np_action_to_shares(ActT a, double max_stock);
+template <>
+__device__ __forceinline__ int np_action_to_shares<float>(float a, double max_stock)
+{
+    return __float2int_rz(fmul(a, (float)max_stock));  // f32 array * Python float -> f32; astype(int)
+}
+template <>
+__device__ __forceinline__ int np_action_to_shares<double>(double a, double max_stock)
+{
+    return __double2int_rz(dmul(a, max_stock));
+}
+
+// np.array(self.amount * 2**-12, dtype=np.float32): the power-of-two scale commutes with the cast
+// (StockEnvNAS100 shows max(amount, 1e4): Python's max returns the float floor only when it is larger)
+__device__ __forceinline__ float np_amount_obs(NV amount, double floor_)
+{
+    const double a = floor_ > amount.v ? floor_ : amount.v;
+    return fmul((float)a, 0.000244140625f);
+}
+
+// np_wide.cu
+void launch_np_wide(const frl_np_params &p, const void *actions, int actions_f64, long long sstride, long long estride, int n_steps,
+                    double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st);
+void launch_np_observe_wide(const frl_np_params &p, float *obs, cudaStream_t st);
+
+}  // namespace frl

@@ -1,0 +1,416 @@
+// A2 wide — numpy / ElegantRL StockTradingEnv for 33..128 stocks (NASDAQ-100: StockEnvNAS100 at its natural
+// size; reference: finrl/meta/env_stock_trading/env_stocktrading_np.py, env_nas100_wrds.py).
+//
+// nptrading.cu keeps stocks / cool-down counters of <= 32 stocks in registers.  Here they stay in the
+// stock-major global arrays and are STREAMED, one thread per env, in the order the reference walks them —
+// sells and buys both run in ascending stock index (:112,:120), so the step is two passes of blocks of 8
+// stocks (loads of a block issued together), the second of which also accumulates numpy's pairwise
+// float32 sum of stocks*price (8 accumulators over the full blocks, then the tail) and leaves the float32
+// stocks image in the lane's own action-staging row for the observation writer.  Same NEP-50 scalar
+// arithmetic (np_common.cuh) as the register kernel: bit-identical results (the whole numpy-env parity suite
+// runs under both kernels).
+#include "np_common.cuh"
+
+namespace frl {
+namespace {
+
+#ifndef FRL_NPW_MIN_BLOCKS
+#define FRL_NPW_MIN_BLOCKS 3
+#endif
+
+__device__ __forceinline__ void npw_cp_async(float *dst, const float *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void npw_cp_async(double *dst, const double *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+// numpy pairwise float32 sum for n <= 128, fed one block of 8 products at a time in index order
+struct Pairwise8 {
+    float r[8];
+    float res;
+    __device__ __forceinline__ void init()
+    {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = 0.0f;
+        res = 0.0f;
+    }
+    // x: the products of stocks j0..j0+7 (entries >= D ignored); nb = D >> 3 full blocks
+    __device__ __forceinline__ void block(const float (&x)[8], int j0, int D)
+    {
+        const int nb = D >> 3;
+        const int b = j0 >> 3;
+        if (b < nb) {
+            if (b == 0) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = x[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = fadd(r[u], x[u]);
+            }
+            if (b == nb - 1) res = fadd(fadd(fadd(r[0], r[1]), fadd(r[2], r[3])), fadd(fadd(r[4], r[5]), fadd(r[6], r[7])));
+        } else {  // the tail (or everything when D < 8): sequential
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (j0 + u < D) res = fadd(res, x[u]);
+        }
+    }
+};
+
+template <typename ActT>
+__device__ __forceinline__ void npw_write_obs_range(const frl_np_params &p, const ActT *stage, int P, const float *amountf,
+                                                    const int *day_s, float *__restrict__ obs, long long env0, int nvalid, int lane,
+                                                    int beg, int end, int img_beg, float img_mul)
+{
+    // positions [beg, end) of every row; [img_beg, img_beg + D) come from the staged image (times img_mul)
+    const int O = p.obs_dim, D = p.stock_dim;
+    constexpr int step = sizeof(ActT) / sizeof(float);
+    for (int r = 0; r < nvalid; ++r) {
+        const float *irow = reinterpret_cast<const float *>(stage + (size_t)r * P);
+        const float *trow = p.obs_tmpl + (size_t)day_s[r] * O;
+        float *orow = obs + (size_t)(env0 + r) * O;
+        for (int pos = beg + lane; pos < end; pos += 32) {
+            float v;
+            if (pos == 0)
+                v = amountf[r];
+            else if (pos >= img_beg && pos < img_beg + D)
+                v = fmul(irow[(pos - img_beg) * step], img_mul);
+            else
+                v = __ldg(trow + pos);
+            orow[pos] = v;
+        }
+    }
+}
+
+template <typename ActT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, FRL_NPW_MIN_BLOCKS * 128 / (WARPS * 32))
+np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long long act_step_stride, long long act_env_stride,
+               int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode,
+               int auto_reset, double *__restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;
+    const int P = D | 1;  // odd row pitch: conflict-free per-lane row walks
+    const size_t warp_bytes = (size_t)32 * P * sizeof(ActT) + 32 * sizeof(float) + 32 * sizeof(int);
+    unsigned char *base = smem_raw + warp * ((warp_bytes + 15) & ~(size_t)15);
+    ActT *stage = reinterpret_cast<ActT *>(base);  // [32 envs][P]
+    float *amountf = reinterpret_cast<float *>(base + (size_t)32 * P * sizeof(ActT));
+    int *day_s = reinterpret_cast<int *>(amountf + 32);
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const bool valid = lane < nvalid;
+    const long long n = valid ? env0 + lane : (long long)N - 1;
+
+    const int kinds = p.kinds[n];
+    NV amount = nv(p.amount[n], kinds & 3);
+    NV total = nv(p.total[n], (kinds >> 2) & 3);
+    NV gr = nv(p.gamma_reward[n], (kinds >> 4) & 3);
+    int day = p.day[n];
+    double init_total = 0.0;
+    bool init_total_loaded = false;
+    float *sp = p.stocks + n, *cp = p.cool + n;  // stock j at [j * ld]
+    ActT *myrow = stage + (size_t)lane * P;
+    const NV one_minus_sc = nv(dsub(1.0, p.sell_cost_pct), FRL_KIND_PY);
+    const NV one_plus_bc = nv(dadd(1.0, p.buy_cost_pct), FRL_KIND_PY);
+    const int min_action = (int)dmul(p.max_stock, p.min_stock_rate);  // int(max_stock * min_stock_rate) (:111)
+    double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_liq = 0.0;
+
+    for (int k = 0; k < n_steps; ++k) {
+        // ---- stage this step's actions into [env][P] rows (cp.async: the whole tile in flight at once) ----
+        const ActT *abase = actions + (size_t)k * act_step_stride;
+        __syncwarp();
+        if (act_env_stride == D) {
+            const ActT *tile = abase + (size_t)env0 * D;
+            const int cnt = nvalid * D;
+            int row = 0, col = lane;
+            while (col >= D) { col -= D; ++row; }
+            for (int e = lane; e < 32 * D; e += 32) {
+                ActT *dst = stage + row * P + col;
+                if (e < cnt)
+                    npw_cp_async(dst, tile + e);
+                else
+                    *dst = ActT(0);
+                col += 32;
+                while (col >= D) { col -= D; ++row; }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        } else {
+            for (int r = 0; r < 32; ++r)
+                for (int j = lane; j < D; j += 32)
+                    stage[r * P + j] = r < nvalid ? abase[(size_t)(env0 + r) * act_env_stride + j] : ActT(0);
+        }
+        __syncwarp();
+
+        int flags = 0;
+        NV reward = nv(0.0, FRL_KIND_PY);
+        bool image_ok = false;  // the staging row holds the float32 stocks of the current state
+        if (day >= T - 1) {
+            flags = FRL_FLAG_DONE;  // past the last day: inert, done again
+        } else {
+            day += 1;  // trades happen at the NEW day's prices (:106-107)
+            const float *prow = p.price + (size_t)day * p.price_pitch;
+            Pairwise8 acc;
+            acc.init();
+            if (__ldg(p.turb_bool + day) == 0.0f) {
+                // ---- pass 1: cool_down += 1, sells in ascending index (:108-119) ----
+                for (int j0 = 0; j0 < D; j0 += 8) {
+                    float st[8], cl[8], pr[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = j0 + u < D ? j0 + u : D - 1;
+                        st[u] = sp[(size_t)j * ld];
+                        cl[u] = cp[(size_t)j * ld];
+                        pr[u] = __ldg(prow + j);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = j0 + u;
+                        if (j < D) {
+                            const int aj = np_action_to_shares<ActT>(myrow[j], p.max_stock);
+                            float c = fadd(cl[u], 1.0f);
+                            if (aj < -min_action && pr[u] > 0.0f) {
+                                float s = st[u];
+                                NV x;
+                                if ((double)(-aj) < (double)s) {  // min(stocks, -action) -> the int64
+                                    const double nsh = (double)(-aj);
+                                    s = (float)dsub((double)s, nsh);
+                                    x = nv_mul(nv(dmul((double)pr[u], nsh), FRL_KIND_F64), one_minus_sc);
+                                } else {  // -> the float32 holding
+                                    x = nv_mul(nv((double)fmul(pr[u], s), FRL_KIND_F32), one_minus_sc);
+                                    s = fsub(s, s);
+                                }
+                                amount = nv_add(amount, x);
+                                c = 0.0f;
+                                if (valid) sp[(size_t)j * ld] = s;
+                            }
+                            if (valid) cp[(size_t)j * ld] = c;
+                        }
+                    }
+                }
+                // ---- pass 2: buys in ascending index (:120-129, quirk Q6), asset sum, stocks image ----
+                for (int j0 = 0; j0 < D; j0 += 8) {
+                    float st[8], pr[8], x8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = j0 + u < D ? j0 + u : D - 1;
+                        st[u] = sp[(size_t)j * ld];  // this thread's own pass-1 stores
+                        pr[u] = __ldg(prow + j);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = j0 + u;
+                        x8[u] = 0.0f;
+                        if (j < D) {
+                            const int aj = np_action_to_shares<ActT>(myrow[j], p.max_stock);
+                            const float pj = pr[u];
+                            float s = st[u];
+                            if (aj > min_action && pj > 0.0f) {
+                                NV x;
+                                const double am = amount.k == FRL_KIND_F64 ? amount.v : (double)(float)amount.v;
+                                const bool plenty = am >= dmul((double)(aj + 1), (double)pj);
+                                double avail = 0.0;
+                                if (!plenty && !(am >= 0.0 && am < (double)pj))
+                                    avail = amount.k == FRL_KIND_F64 ? floor_div_f64(am, (double)pj)
+                                                                      : (double)floor_div_f32((float)am, pj);
+                                if (plenty) {  // min(avail, action) -> the int64
+                                    const double nsh = (double)aj;
+                                    s = (float)dadd((double)s, nsh);
+                                    x = nv_mul(nv(dmul((double)pj, nsh), FRL_KIND_F64), one_plus_bc);
+                                } else if (amount.k == FRL_KIND_F64) {
+                                    s = (float)dadd((double)s, avail);
+                                    x = nv_mul(nv(dmul((double)pj, avail), FRL_KIND_F64), one_plus_bc);
+                                } else {
+                                    const float nsh = (float)avail;
+                                    s = fadd(s, nsh);
+                                    x = nv_mul(nv((double)fmul(pj, nsh), FRL_KIND_F32), one_plus_bc);
+                                }
+                                amount = nv_sub(amount, x);
+                                if (valid) {
+                                    sp[(size_t)j * ld] = s;
+                                    cp[(size_t)j * ld] = 0.0f;
+                                }
+                            }
+                            x8[u] = fmul(s, pj);
+                            *reinterpret_cast<float *>(myrow + j) = s;  // action j is consumed: the slot takes the image
+                        }
+                    }
+                    acc.block(x8, j0, D);
+                }
+            } else {
+                // ---- sell everything when turbulence (:131-134) ----
+                flags |= FRL_FLAG_LIQUIDATE;
+                for (int j0 = 0; j0 < D; j0 += 8) {
+                    float x8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = j0 + u;
+                        x8[u] = j < D ? fmul(sp[(size_t)j * ld], __ldg(prow + j)) : 0.0f;
+                    }
+                    acc.block(x8, j0, D);
+                }
+                amount = nv_add(amount, nv_mul(nv((double)acc.res, FRL_KIND_F32), one_minus_sc));
+                for (int j = 0; j < D; ++j) {
+                    if (valid) {
+                        sp[(size_t)j * ld] = 0.0f;
+                        cp[(size_t)j * ld] = 0.0f;
+                    }
+                    *reinterpret_cast<float *>(myrow + j) = 0.0f;
+                }
+                acc.init();  // (stocks * price).sum() of the emptied book: +0.0f
+                if (valid) st_liq += 1.0;
+            }
+            image_ok = true;
+            // ---- reward bookkeeping (:136-145) ----
+            const NV tot = nv_add(amount, nv((double)acc.res, FRL_KIND_F32));
+            reward = nv_mul(nv_sub(tot, total), nv(p.reward_scaling, FRL_KIND_PY));
+            total = tot;
+            gr = nv_add(nv_mul(gr, nv(p.gamma, FRL_KIND_PY)), reward);
+            if (day == T - 1) {
+                flags |= FRL_FLAG_DONE;
+                reward = gr;
+                if (!init_total_loaded) {
+                    init_total = p.init_total[n];
+                    init_total_loaded = true;
+                }
+                const double er = (total.k == FRL_KIND_F64) ? __ddiv_rn(total.v, init_total)
+                                                             : (double)__fdiv_rn((float)total.v, (float)init_total);
+                if (valid) {
+                    p.episode_return[n] = er;
+                    st_done += 1.0;
+                    st_epi += total.v;
+                }
+            }
+        }
+        if (valid) {
+            if (rewards) rewards[(size_t)k * N + n] = reward.v;
+            if (flags_out) flags_out[(size_t)k * N + n] = (uint8_t)(flags | (reward.k << FRL_NP_REWARD_KIND_SHIFT));
+            st_r += reward.v;
+            st_r2 += reward.v * reward.v;
+        }
+        if ((flags & FRL_FLAG_DONE) && auto_reset) {
+            // reset (:80-101), deterministic branch
+            Pairwise8 acc;
+            acc.init();
+            for (int j0 = 0; j0 < D; j0 += 8) {
+                float x8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = j0 + u;
+                    x8[u] = 0.0f;
+                    if (j < D) {
+                        const float s0 = p.init_stocks ? __ldg(p.init_stocks + j) : 0.0f;
+                        if (valid) {
+                            sp[(size_t)j * ld] = s0;
+                            cp[(size_t)j * ld] = 0.0f;
+                        }
+                        *reinterpret_cast<float *>(myrow + j) = s0;
+                        x8[u] = fmul(s0, __ldg(p.price + j));
+                    }
+                }
+                acc.block(x8, j0, D);
+            }
+            day = 0;
+            amount = nv(p.initial_capital, FRL_KIND_PY);
+            total = nv_add(amount, nv((double)acc.res, FRL_KIND_F32));
+            init_total = total.v;
+            init_total_loaded = true;
+            gr = nv(0.0, FRL_KIND_PY);
+            if (valid) p.init_total[n] = init_total;
+            image_ok = true;
+        }
+        if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
+            if (!image_ok)
+                for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = sp[(size_t)j * ld];
+            amountf[lane] = np_amount_obs(amount, p.obs_amount_floor);
+            day_s[lane] = day;
+            __syncwarp();
+            float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
+            const int s_beg = 3 + D, c_beg = 3 + 2 * D;
+            // [amount, turb, turb_bool, price, stocks * 2**-6 | cool-down, tech]: two phases through the one image
+            npw_write_obs_range<ActT>(p, stage, P, amountf, day_s, o, env0, nvalid, lane, 0, c_beg, s_beg, 0.015625f);
+            __syncwarp();
+            for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = cp[(size_t)j * ld];
+            __syncwarp();
+            npw_write_obs_range<ActT>(p, stage, P, amountf, day_s, o, env0, nvalid, lane, c_beg, p.obs_dim, c_beg, 1.0f);
+        }
+    }
+    if (valid) {
+        p.amount[n] = amount.v;
+        p.total[n] = total.v;
+        p.gamma_reward[n] = gr.v;
+        p.kinds[n] = (uint8_t)(amount.k | (total.k << 2) | (gr.k << 4));
+        p.day[n] = day;
+    }
+    if (stats) {
+        double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, valid ? total.v : 0.0, st_liq,
+                                 valid ? (double)n_steps : 0.0, 0.0};
+        reduce_stats8(v, lane, stats);
+    }
+}
+
+// one warp per env, stocks / cool-down straight from the stock-major arrays (observe / reset only)
+__global__ void np_observe_wide_kernel(const frl_np_params p, float *__restrict__ obs)
+{
+    const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= p.n_envs) return;
+    const int O = p.obs_dim, D = p.stock_dim;
+    const int s_beg = 3 + D, c_beg = 3 + 2 * D, sp_end = 3 + 3 * D;
+    const float *trow = p.obs_tmpl + (size_t)p.day[n] * O;
+    float *orow = obs + (size_t)n * O;
+    for (int pos = lane; pos < O; pos += 32) {
+        float v;
+        if (pos == 0)
+            v = np_amount_obs(nv(p.amount[n], p.kinds[n] & 3), p.obs_amount_floor);
+        else if (pos >= s_beg && pos < c_beg)
+            v = fmul(p.stocks[n + (size_t)(pos - s_beg) * p.env_stride], 0.015625f);
+        else if (pos >= c_beg && pos < sp_end)
+            v = p.cool[n + (size_t)(pos - c_beg) * p.env_stride];
+        else
+            v = __ldg(trow + pos);
+        orow[pos] = v;
+    }
+}
+
+template <typename ActT, int WARPS>
+void npw_launch(const frl_np_params &p, const void *actions, long long sstride, long long estride, int n_steps, double *rewards,
+                uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
+{
+    const int P = p.stock_dim | 1;
+    const size_t warp_bytes = (size_t)32 * P * sizeof(ActT) + 32 * sizeof(float) + 32 * sizeof(int);
+    const size_t smem = WARPS * ((warp_bytes + 15) & ~(size_t)15);
+    auto kern = np_wide_kernel<ActT, WARPS>;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            set_error("np_rollout(wide): cannot reserve %zu B of shared memory", smem);
+            return;
+        }
+    }
+    const long long tiles = ((long long)p.n_envs + 31) / 32;
+    kern<<<(unsigned)((tiles + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(p, (const ActT *)actions, sstride, estride, n_steps,
+                                                                           rewards, flags, obs, obs_mode, auto_reset, stats);
+}
+
+}  // namespace
+
+void launch_np_wide(const frl_np_params &p, const void *actions, int actions_f64, long long sstride, long long estride, int n_steps,
+                    double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
+{
+    if (actions_f64)
+        npw_launch<double, 2>(p, actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats, st);
+    else
+        npw_launch<float, 4>(p, actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats, st);
+}
+
+void launch_np_observe_wide(const frl_np_params &p, float *obs, cudaStream_t st)
+{
+    const long long threads = (long long)p.n_envs * 32;
+    np_observe_wide_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, obs);
+}
+
+}  // namespace frl

@@ -9,7 +9,11 @@
 // (SURVEY.md H3).  Each of those is carried as (double value, 2-bit kind) and every operation is done
 // in the precision numpy would pick, with explicit round-to-nearest intrinsics (no FMA contraction).
 // (stocks*price).sum() is numpy's pairwise float32 summation.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
+#include "np_common.cuh"
 
 #ifndef FRL_NP_MIN_BLOCKS
 #define FRL_NP_MIN_BLOCKS 8  // 64-thread units per SM the register allocator must allow (8 -> 128 regs)
@@ -20,30 +24,6 @@
 
 namespace frl {
 namespace {
-
-struct NV {  // a numpy / Python scalar: value + NEP-50 kind
-    double v;
-    int k;
-};
-__device__ __forceinline__ NV nv(double v, int k) { return NV{v, k}; }
-__device__ __forceinline__ NV nv_add(NV x, NV y)
-{
-    if (x.k == FRL_KIND_PY && y.k == FRL_KIND_PY) return nv(dadd(x.v, y.v), FRL_KIND_PY);
-    if (x.k == FRL_KIND_F64 || y.k == FRL_KIND_F64) return nv(dadd(x.v, y.v), FRL_KIND_F64);
-    return nv((double)fadd((float)x.v, (float)y.v), FRL_KIND_F32);  // f32 (a weak Python float adopts it)
-}
-__device__ __forceinline__ NV nv_sub(NV x, NV y)
-{
-    if (x.k == FRL_KIND_PY && y.k == FRL_KIND_PY) return nv(dsub(x.v, y.v), FRL_KIND_PY);
-    if (x.k == FRL_KIND_F64 || y.k == FRL_KIND_F64) return nv(dsub(x.v, y.v), FRL_KIND_F64);
-    return nv((double)fsub((float)x.v, (float)y.v), FRL_KIND_F32);
-}
-__device__ __forceinline__ NV nv_mul(NV x, NV y)
-{
-    if (x.k == FRL_KIND_PY && y.k == FRL_KIND_PY) return nv(dmul(x.v, y.v), FRL_KIND_PY);
-    if (x.k == FRL_KIND_F64 || y.k == FRL_KIND_F64) return nv(dmul(x.v, y.v), FRL_KIND_F64);
-    return nv((double)fmul((float)x.v, (float)y.v), FRL_KIND_F32);
-}
 
 constexpr int kPitch = 33;
 
@@ -58,19 +38,6 @@ struct alignas(16) NpWarpSmem {
     float amountf[32];
     int day[32];
 };
-
-template <typename ActT>
-__device__ __forceinline__ int np_action_to_shares(ActT a, double max_stock);
-template <>
-__device__ __forceinline__ int np_action_to_shares<float>(float a, double max_stock)
-{
-    return __float2int_rz(fmul(a, (float)max_stock));  // f32 array * Python float -> f32; astype(int)
-}
-template <>
-__device__ __forceinline__ int np_action_to_shares<double>(double a, double max_stock)
-{
-    return __double2int_rz(dmul(a, max_stock));
-}
 
 // (self.stocks * price).sum(): float32 products, numpy pairwise summation (n < 8 sequential; else 8
 // accumulators over the full blocks of 8, tree-combined, then the tail sequentially).
@@ -103,14 +70,6 @@ __device__ __forceinline__ float np_asset_f32(const float (&stv)[SLOTS], const f
     for (int j = 8; j < SLOTS; ++j)
         if (j >= 8 * nb && j < D) res = fadd(res, x[j]);
     return res;
-}
-
-// np.array(self.amount * 2**-12, dtype=np.float32): the power-of-two scale commutes with the cast
-// (StockEnvNAS100 shows max(amount, 1e4): Python's max returns the float floor only when it is larger)
-__device__ __forceinline__ float np_amount_obs(NV amount, double floor_)
-{
-    const double a = floor_ > amount.v ? floor_ : amount.v;
-    return fmul((float)a, 0.000244140625f);
 }
 
 // ---- observation rows: [amount, turb, turb_bool, price*2^-6 x D, stocks*2^-6 x D, cool x D, tech] ----
@@ -273,7 +232,7 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
 #define FRL_A(j) np_action_to_shares<ActT>(arow[j], p.max_stock)
 
             day += 1;  // trades happen at the NEW day's prices (:106-107)
-            const float *prow = p.price + (size_t)day * 32;
+            const float *prow = p.price + (size_t)day * p.price_pitch;
 #pragma unroll
             for (int j = 0; j < SLOTS; ++j) clv[j] = fadd(clv[j], 1.0f);  // cool_down += 1
 
@@ -433,8 +392,8 @@ __global__ void np_reset_kernel(const frl_np_params p, const uint8_t *__restrict
     if (mask && !mask[n]) return;
     const int D = p.stock_dim, ld = p.env_stride;
     // (stocks * price[0]).sum() with numpy's pairwise order, from a thread-private copy
-    float x[32];
-    for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+    float x[128];
+    for (int j = 0; j < 128; ++j) x[j] = 0.0f;
     for (int j = 0; j < D; ++j) {
         const float st = (stocks0 && factor) ? stocks0[n + (size_t)j * ld] : (p.init_stocks ? p.init_stocks[j] : 0.0f);
         p.stocks[n + (size_t)j * ld] = st;
@@ -494,17 +453,32 @@ int32_t np_validate(const frl_np_params *p)
 {
     FRL_REQUIRE(p != nullptr, "np: params is NULL");
     FRL_REQUIRE(p->n_envs >= 1, "np: n_envs must be >= 1 (got %d)", p->n_envs);
-    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 32, "np: stock_dim must be in 1..32 (got %d)", p->stock_dim);
+    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 128, "np: stock_dim must be in 1..128 (got %d)", p->stock_dim);
+    FRL_REQUIRE((p->price_pitch == 32 || p->price_pitch == 128) && p->price_pitch >= p->stock_dim,
+                "np: price_pitch must be 32 or 128 and >= stock_dim (got %d for D=%d)", p->price_pitch, p->stock_dim);
     FRL_REQUIRE(p->tech_dim >= 0 && p->n_days >= 2, "np: bad tech_dim/n_days (%d, %d)", p->tech_dim, p->n_days);
     FRL_REQUIRE(p->obs_dim == 3 + 3 * p->stock_dim + p->tech_dim, "np: obs_dim %d != 1 + 2 + 3D + tech_dim = %d",
                 p->obs_dim, 3 + 3 * p->stock_dim + p->tech_dim);
     FRL_REQUIRE(p->env_stride >= p->n_envs, "np: env_stride %d < n_envs %d", p->env_stride, p->n_envs);
-    FRL_REQUIRE((long long)p->env_stride * 32 < (1LL << 31), "np: env_stride %d too large", p->env_stride);
+    FRL_REQUIRE((long long)p->env_stride * p->price_pitch < (1LL << 31), "np: env_stride %d too large", p->env_stride);
     FRL_REQUIRE(p->price && p->turb_bool && p->obs_tmpl, "np: table pointer is NULL");
     FRL_REQUIRE(p->amount && p->kinds && p->stocks && p->cool && p->day && p->total && p->gamma_reward &&
                     p->init_total && p->episode_return,
                 "np: state pointer is NULL");
     return FRL_OK;
+}
+
+// stock counts from which frl_np_* use the streaming kernel of np_wide.cu (always above 32);
+// frl_set_option("np_wide_min_d", v) / FRL_NP_WIDE_MIN_D lower it so that tests can run every shape through it
+int g_np_wide_min_d = -1;
+int np_wide_min_d()
+{
+    if (g_np_wide_min_d < 0) {
+        const char *m = getenv("FRL_NP_WIDE_MIN_D");
+        g_np_wide_min_d = m ? atoi(m) : 33;
+        if (g_np_wide_min_d < 1 || g_np_wide_min_d > 33) g_np_wide_min_d = 33;
+    }
+    return g_np_wide_min_d;
 }
 
 template <int SLOTS, int DCT, typename ActT, int WARPS>
@@ -518,6 +492,14 @@ void np_launch(const frl_np_params &p, const void *actions, long long sstride, l
 }
 
 }  // namespace
+
+int32_t np_set_option(const char *name, int64_t value)
+{
+    if (strcmp(name, "np_wide_min_d")) return 1;  // not ours
+    g_np_wide_min_d = value < 1 ? 1 : (value > 33 ? 33 : (int)value);
+    return FRL_OK;
+}
+
 }  // namespace frl
 
 using namespace frl;
@@ -526,6 +508,10 @@ extern "C" int32_t frl_np_observe(const frl_np_params *p, float *obs, void *stre
 {
     if (int32_t rc = np_validate(p)) return rc;
     FRL_REQUIRE(obs != nullptr, "np_observe: obs is NULL");
+    if (p->stock_dim >= np_wide_min_d()) {
+        launch_np_observe_wide(*p, obs, (cudaStream_t)stream);
+        return check_launch("np_observe(wide)");
+    }
     constexpr int W = 2;
     const long long tiles = ((long long)p->n_envs + 31) / 32;
     np_observe_kernel<W><<<(unsigned)((tiles + W - 1) / W), W * 32, 0, (cudaStream_t)stream>>>(*p, obs);
@@ -555,6 +541,11 @@ extern "C" int32_t frl_np_rollout(const frl_np_params *p, const void *actions, i
     FRL_REQUIRE(obs_mode == FRL_OBS_NONE || obs != nullptr, "np_rollout: obs is NULL but obs_mode=%d", obs_mode);
     cudaStream_t st = (cudaStream_t)stream;
     const int D = p->stock_dim;
+    if (D >= np_wide_min_d()) {
+        launch_np_wide(*p, actions, actions_f64, act_step_stride, act_env_stride, n_steps, rewards, flags, obs, obs_mode,
+                       auto_reset, stats, st);
+        return check_launch("np_rollout(wide)");
+    }
 #define FRL_GO(SLOTS, DCT)                                                                                        \
     do {                                                                                                          \
         if (actions_f64)                                                                                          \

@@ -776,6 +776,10 @@ void launch_rollout(const frl_trading_params &p, const void *actions, long long 
 }  // namespace
 }  // namespace frl
 
+namespace frl {
+int32_t np_set_option(const char *name, int64_t value);  // nptrading.cu
+}
+
 using namespace frl;
 
 extern "C" int32_t frl_set_option(const char *name, int64_t value)
@@ -786,6 +790,7 @@ extern "C" int32_t frl_set_option(const char *name, int64_t value)
         g_small_max = value > 0x7fffffff ? 0x7fffffff : (int)value;
         return FRL_OK;
     }
+    if (np_set_option(name, value) == FRL_OK) return FRL_OK;
     set_error("set_option: unknown option '%s'", name);
     return FRL_E_INVALID;
 }

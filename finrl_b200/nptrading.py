@@ -24,7 +24,7 @@ class NpTables:
     n_days: int
     stock_dim: int
     tech_dim: int
-    price: "torch.Tensor"      # [T, 32] f32
+    price: "torch.Tensor"      # [T, pitch] f32 (pitch 32 for D <= 32, else 128)
     turb_bool: "torch.Tensor"  # [T] f32
     obs_tmpl: "torch.Tensor"   # [T, O] f32
     host_price: np.ndarray     # price_ary  [T, D] f32
@@ -44,8 +44,8 @@ class NpTables:
 
         price = np.ascontiguousarray(np.asarray(price_array).astype(np.float32))
         T, D = price.shape
-        if not 1 <= D <= 32:
-            raise ValueError(f"stock_dim must be in 1..32 for the numpy-env kernel (got {D})")
+        if not 1 <= D <= 128:
+            raise ValueError(f"stock_dim must be in 1..128 for the numpy-env kernels (got {D})")
         tech = np.ascontiguousarray(np.asarray(tech_array).astype(np.float32) * 2**-7).reshape(T, -1)
         turb = np.asarray(turbulence_array)
         turb_bool = (turb > turbulence_thresh).astype(np.float32)
@@ -53,7 +53,7 @@ class NpTables:
         turb_ary = (sig * turbulence_thresh * 2**-5).astype(np.float32)
         TD = tech.shape[1]
         O = 3 + 3 * D + TD
-        price32 = np.zeros((T, 32), dtype=np.float32)
+        price32 = np.zeros((T, 32 if D <= 32 else 128), dtype=np.float32)
         price32[:, :D] = price
         tmpl = np.zeros((T, O), dtype=np.float32)
         tmpl[:, 1] = turb_ary
@@ -129,6 +129,7 @@ class BatchedNpStockTradingEnv(BatchedEnvBase):
         # StockEnvNAS100's get_state shows max(amount, 1e4) (env_nas100_wrds.py:157)
         p.obs_amount_floor = float("-inf") if obs_amount_floor is None else float(obs_amount_floor)
         p.price, p.turb_bool, p.obs_tmpl = tables.price.data_ptr(), tables.turb_bool.data_ptr(), tables.obs_tmpl.data_ptr()
+        p.price_pitch = int(tables.price.shape[1])
         p.init_stocks = self._init_stocks.data_ptr()
         p.amount, p.kinds, p.stocks, p.cool = self.amount.data_ptr(), self.kinds.data_ptr(), self.stocks.data_ptr(), self.cool.data_ptr()
         p.day, p.total, p.gamma_reward = self.day.data_ptr(), self.total_asset.data_ptr(), self.gamma_reward.data_ptr()

@@ -158,7 +158,8 @@ FRL_API int32_t frl_trading_step(const frl_trading_params *p, const void *action
 
 typedef struct frl_np_params {
     int32_t n_envs;     /* N */
-    int32_t stock_dim;  /* D, 1..32 */
+    int32_t stock_dim;  /* D, 1..128: D <= 32 keeps stocks / cool-down in registers (nptrading.cu), 33..128 streams
+                           them (np_wide.cu; NASDAQ-100) */
     int32_t tech_dim;   /* columns of tech_array (= D*K, stock-major) */
     int32_t n_days;     /* T; max_step = T-1 */
     int32_t obs_dim;    /* O = state_dim = 1 + 2 + 3D + tech_dim (:63) */
@@ -169,7 +170,7 @@ typedef struct frl_np_params {
     double obs_amount_floor; /* get_state shows max(amount, floor): 1e4 for the sibling StockEnvNAS100
                                 (env_nas100_wrds.py:157), -inf for env_stocktrading_np */
     /* ---- tables ---- */
-    const float *price;       /* [T][32] price_ary = f32(price_array), rows zero-padded (:27) */
+    const float *price;       /* [T][price_pitch] price_ary = f32(price_array), rows zero-padded (:27) */
     const float *turb_bool;   /* [T] f32(turbulence_array > thresh) (:32) */
     const float *obs_tmpl;    /* [T][O] get_state() row of day t with amount/stocks/cool-down zeroed:
                                  [0, turbulence_ary[t], turbulence_bool[t], price*2^-6, 0.., 0.., tech_ary[t]] */
@@ -184,6 +185,8 @@ typedef struct frl_np_params {
     double *gamma_reward;   /* [N] */
     double *init_total;     /* [N] self.initial_total_asset */
     double *episode_return; /* [N] self.episode_return (written when done) */
+    int32_t price_pitch;    /* row pitch of `price` in floats: 32 for D <= 32, 128 for D <= 128 */
+    int32_t reserved_;
 } frl_np_params;
 
 /* StockTradingEnv.reset (:80-101) for envs with mask[n] != 0 (NULL = all).  stocks0 ([D][env_stride]

@@ -336,6 +336,11 @@ def main():
         gen_np("np_d30_kinds", T=40, D=30, K=8, n_steps=90, seed=14, if_train=True, thresh=99, quiet_steps=6)
         gen_np("np_nas100_d20", T=45, D=20, K=4, n_steps=100, seed=16, if_train=True, thresh=60, nas100=True,
                initial_capital=6e4, gamma=0.999)
+        # D > 32: the streaming kernel (np_wide.cu); StockEnvNAS100 at its natural size
+        gen_np("np_nas100_d100", T=40, D=100, K=2, n_steps=90, seed=17, if_train=True, thresh=60, nas100=True,
+               initial_capital=5e5, gamma=0.999)
+        gen_np("np_d50_train", T=36, D=50, K=3, n_steps=80, seed=18, if_train=True, thresh=70)
+        gen_np("np_d128_eval", T=30, D=128, K=1, n_steps=65, seed=19, if_train=False, thresh=80, initial_capital=3e5)
         gen_np("np_d12_kinds_eval", T=40, D=12, K=3, n_steps=90, seed=15, if_train=False, thresh=70, quiet_steps=5,
                initial_stocks=np.arange(12, dtype=np.float32))
     if want("portfolio"):

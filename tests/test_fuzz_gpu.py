@@ -52,13 +52,16 @@ def test_trading_fuzz(seed, kernel):
     _cabi.set_option("trading_small_max", 8192)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(16))
 def test_np_fuzz(seed):
-    from finrl_b200 import BatchedNpStockTradingEnv, synthetic as syn
+    """Seeds 0-9: D in 1..32 (register kernel; odd seeds forced through the streaming kernel as well);
+    seeds 10-15: D in 33..128 (streaming kernel, np_wide.cu)."""
+    from finrl_b200 import BatchedNpStockTradingEnv, _cabi, synthetic as syn
     from oracle import oracle as ora
 
     rng = np.random.default_rng(2000 + seed)
-    D = int(rng.integers(1, 33))
+    D = int(rng.integers(1, 33)) if seed < 10 else int(rng.integers(33, 129))
+    _cabi.set_option("np_wide_min_d", 1 if seed % 2 else 33)
     K = int(rng.integers(0, 4))
     T = int(rng.integers(4, 40))
     N = int(rng.choice([1, 31, 65]))
@@ -97,3 +100,4 @@ def test_np_fuzz(seed):
             assert np.array_equal(st[name].cpu().numpy(), ref), ctx + " " + name
         if done.all():
             reset_both()
+    _cabi.set_option("np_wide_min_d", 33)

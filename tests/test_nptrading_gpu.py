@@ -17,6 +17,17 @@ torch = pytest.importorskip("torch")
 NP = sorted(glob.glob(os.path.join(GOLDEN, "np_*.npz")))
 
 
+@pytest.fixture(autouse=True, params=["regs", "wide"])
+def np_kernel(request):
+    """Every test of this file runs twice: with the register kernel for D <= 32 (nptrading.cu) and with the
+    streaming kernel (np_wide.cu, the one D > 32 always uses) forced for every stock count."""
+    from finrl_b200 import _cabi
+
+    _cabi.set_option("np_wide_min_d", 33 if request.param == "regs" else 1)
+    yield request.param
+    _cabi.set_option("np_wide_min_d", 33)
+
+
 @pytest.mark.parametrize("path", NP, ids=[os.path.basename(p)[:-4] for p in NP])
 def test_golden_single_env(path):
     from finrl_b200 import BatchedNpStockTradingEnv
