@@ -137,6 +137,26 @@ class NpStep(Workload):
         return step
 
 
+class NpNas100Step(NpStep):
+    name = "np_nas100_step"
+    D = 100
+    K_TECH = 2
+    default_envs = 1 << 18
+    # actions 400 + state 2*(8 amount + 1 kind + 400 stocks + 400 cool-down + 4 day + 8 total + 8 gamma_reward + 8 init_total)
+    # + obs 4*503 + reward 8 + done 1
+    bytes_per_env_step = 4095
+    kernel = "np_wide_kernel<float,4>"
+
+    def describe(self, envs):
+        return (f"env_stocktrading_np at NASDAQ-100 size (streaming kernel), {envs} envs/GPU, D=100 K=2 T=2500 O=503, "
+                "turbulence_thresh 99")
+
+    def arrays(self):
+        from finrl_b200 import synthetic as syn
+
+        return syn.make_np_arrays(*syn.make_tables(T_DAYS, self.D, self.K_TECH, seed=0))
+
+
 class PortfolioStep(Workload):
     name = "portfolio_step"
     act_low, act_high = 0.0, 1.0
@@ -240,7 +260,7 @@ class StopLossStep(CashPenaltyStep):
         return step
 
 
-WORKLOADS = {w.name: w for w in (TradingStep, TradingRollout, NpStep, PortfolioStep, CashPenaltyStep, StopLossStep)}
+WORKLOADS = {w.name: w for w in (TradingStep, TradingRollout, NpStep, NpNas100Step, PortfolioStep, CashPenaltyStep, StopLossStep)}
 
 
 def measured_peak():

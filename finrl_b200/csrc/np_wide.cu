@@ -84,6 +84,67 @@ __device__ __forceinline__ void npw_write_obs_range(const frl_np_params &p, cons
     }
 }
 
+// Same range, all rows on one day and at most 16 chunks wide: the template values are loaded once into
+// registers and every row costs one (patched) store per chunk.
+template <typename ActT>
+__device__ __forceinline__ void npw_write_obs_range_uniform(const frl_np_params &p, const ActT *stage, int P, const float *amountf,
+                                                            int day0, float *__restrict__ obs, long long env0, int nvalid, int lane,
+                                                            int beg, int end, int img_beg, float img_mul)
+{
+    constexpr int MAXC = 16;
+    const int O = p.obs_dim, D = p.stock_dim;
+    constexpr int step = sizeof(ActT) / sizeof(float);
+    const float *trow = p.obs_tmpl + (size_t)day0 * O;
+    float t[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int pos = beg + lane + 32 * c;
+        t[c] = pos < end ? __ldg(trow + pos) : 0.0f;
+    }
+    // row-invariant per-chunk facts: is the position written at all, and where in the image does it come from
+    unsigned okmask = 0, imgmask = 0;
+    int ioff0 = 0;  // image offset of chunk 0's position (chunk c adds 32 * step * c)
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int pos = beg + lane + 32 * c;
+        if (pos < end) okmask |= 1u << c;
+        if (pos >= img_beg && pos < img_beg + D) imgmask |= 1u << c;
+    }
+    ioff0 = (beg + lane - img_beg) * step;
+    const bool first = (beg + lane) == 0;
+    float *orow = obs + (size_t)env0 * O + beg + lane;
+    const float *irow = reinterpret_cast<const float *>(stage) + ioff0;
+    for (int r = 0; r < nvalid; ++r) {
+        const float am = amountf[r];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            if ((okmask >> c) & 1u) {
+                float v = t[c];
+                if ((imgmask >> c) & 1u) v = fmul(irow[32 * step * c], img_mul);
+                if (c == 0 && first) v = am;
+                orow[32 * c] = v;
+            }
+        }
+        orow += O;
+        irow += (size_t)P * step;
+    }
+}
+
+template <typename ActT>
+__device__ __forceinline__ void npw_write_obs(const frl_np_params &p, const ActT *stage, int P, const float *amountf, const int *day_s,
+                                              float *__restrict__ obs, long long env0, int nvalid, int lane, int beg, int end,
+                                              int img_beg, float img_mul)
+{
+    const int day0 = day_s[0];
+    bool uniform = true;
+    if (lane < nvalid) uniform = day_s[lane] == day0;
+    uniform = __all_sync(0xffffffffu, uniform);
+    if (uniform && end - beg <= 512)
+        npw_write_obs_range_uniform<ActT>(p, stage, P, amountf, day0, obs, env0, nvalid, lane, beg, end, img_beg, img_mul);
+    else
+        npw_write_obs_range<ActT>(p, stage, P, amountf, day_s, obs, env0, nvalid, lane, beg, end, img_beg, img_mul);
+}
+
 template <typename ActT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, FRL_NPW_MIN_BLOCKS * 128 / (WARPS * 32))
 np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long long act_step_stride, long long act_env_stride,
@@ -158,14 +219,23 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
             acc.init();
             if (__ldg(p.turb_bool + day) == 0.0f) {
                 // ---- pass 1: cool_down += 1, sells in ascending index (:108-119) ----
+                // (both passes are software-pipelined: the next block's loads fly while this one is traded)
+                float st[8], cl[8], pr[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = u < D ? u : D - 1;
+                    st[u] = sp[(size_t)j * ld];
+                    cl[u] = cp[(size_t)j * ld];
+                    pr[u] = __ldg(prow + j);
+                }
                 for (int j0 = 0; j0 < D; j0 += 8) {
-                    float st[8], cl[8], pr[8];
+                    float stn[8], cln[8], prn[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int j = j0 + u < D ? j0 + u : D - 1;
-                        st[u] = sp[(size_t)j * ld];
-                        cl[u] = cp[(size_t)j * ld];
-                        pr[u] = __ldg(prow + j);
+                        const int j = j0 + 8 + u < D ? j0 + 8 + u : D - 1;
+                        stn[u] = sp[(size_t)j * ld];
+                        cln[u] = cp[(size_t)j * ld];
+                        prn[u] = __ldg(prow + j);
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
@@ -191,15 +261,28 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
                             if (valid) cp[(size_t)j * ld] = c;
                         }
                     }
-                }
-                // ---- pass 2: buys in ascending index (:120-129, quirk Q6), asset sum, stocks image ----
-                for (int j0 = 0; j0 < D; j0 += 8) {
-                    float st[8], pr[8], x8[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int j = j0 + u < D ? j0 + u : D - 1;
-                        st[u] = sp[(size_t)j * ld];  // this thread's own pass-1 stores
-                        pr[u] = __ldg(prow + j);
+                        st[u] = stn[u];
+                        cl[u] = cln[u];
+                        pr[u] = prn[u];
+                    }
+                }
+                // ---- pass 2: buys in ascending index (:120-129, quirk Q6), asset sum, stocks image ----
+                // (the prefetch of block b+1 reads stocks that block b never writes: different indices)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = u < D ? u : D - 1;
+                    st[u] = sp[(size_t)j * ld];  // this thread's own pass-1 stores
+                    pr[u] = __ldg(prow + j);
+                }
+                for (int j0 = 0; j0 < D; j0 += 8) {
+                    float stn[8], prn[8], x8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = j0 + 8 + u < D ? j0 + 8 + u : D - 1;
+                        stn[u] = sp[(size_t)j * ld];
+                        prn[u] = __ldg(prow + j);
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
@@ -240,6 +323,11 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
                         }
                     }
                     acc.block(x8, j0, D);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        st[u] = stn[u];
+                        pr[u] = prn[u];
+                    }
                 }
             } else {
                 // ---- sell everything when turbulence (:131-134) ----
@@ -332,11 +420,11 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
             float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
             const int s_beg = 3 + D, c_beg = 3 + 2 * D;
             // [amount, turb, turb_bool, price, stocks * 2**-6 | cool-down, tech]: two phases through the one image
-            npw_write_obs_range<ActT>(p, stage, P, amountf, day_s, o, env0, nvalid, lane, 0, c_beg, s_beg, 0.015625f);
+            npw_write_obs<ActT>(p, stage, P, amountf, day_s, o, env0, nvalid, lane, 0, c_beg, s_beg, 0.015625f);
             __syncwarp();
             for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = cp[(size_t)j * ld];
             __syncwarp();
-            npw_write_obs_range<ActT>(p, stage, P, amountf, day_s, o, env0, nvalid, lane, c_beg, p.obs_dim, c_beg, 1.0f);
+            npw_write_obs<ActT>(p, stage, P, amountf, day_s, o, env0, nvalid, lane, c_beg, p.obs_dim, c_beg, 1.0f);
         }
     }
     if (valid) {
