@@ -11,6 +11,30 @@ struct NV {  // a numpy / Python scalar: value + NEP-50 kind
     int k;
 };
 __device__ __forceinline__ NV nv(double v, int k) { return NV{v, k}; }
+// NEP-50 binary op: the result kind is max(kind_x, kind_y) with PY(0) < F32(1) < F64(2) — two Python floats
+// stay a Python float, a weak Python float adopts float32, float64 wins — and the arithmetic is float32 only
+// when the result is.  Written select-style (both candidates are cheap) so that the unrolled trade loops stay
+// branch-light.
+#ifndef FRL_NV_SELECT
+#define FRL_NV_SELECT 1
+#endif
+#if FRL_NV_SELECT
+__device__ __forceinline__ NV nv_add(NV x, NV y)
+{
+    const int k = max(x.k, y.k);
+    return nv(k == FRL_KIND_F32 ? (double)fadd((float)x.v, (float)y.v) : dadd(x.v, y.v), k);
+}
+__device__ __forceinline__ NV nv_sub(NV x, NV y)
+{
+    const int k = max(x.k, y.k);
+    return nv(k == FRL_KIND_F32 ? (double)fsub((float)x.v, (float)y.v) : dsub(x.v, y.v), k);
+}
+__device__ __forceinline__ NV nv_mul(NV x, NV y)
+{
+    const int k = max(x.k, y.k);
+    return nv(k == FRL_KIND_F32 ? (double)fmul((float)x.v, (float)y.v) : dmul(x.v, y.v), k);
+}
+#else
 __device__ __forceinline__ NV nv_add(NV x, NV y)
 {
     if (x.k == FRL_KIND_PY && y.k == FRL_KIND_PY) return nv(dadd(x.v, y.v), FRL_KIND_PY);
@@ -29,6 +53,7 @@ __device__ __forceinline__ NV nv_mul(NV x, NV y)
     if (x.k == FRL_KIND_F64 || y.k == FRL_KIND_F64) return nv(dmul(x.v, y.v), FRL_KIND_F64);
     return nv((double)fmul((float)x.v, (float)y.v), FRL_KIND_F32);
 }
+#endif
 
 template <typename ActT>
 __device__ __forceinline__ int np_action_to_shares(ActT a, double max_stock);
