@@ -61,7 +61,9 @@ extern "C" {
 
 FRL_API int32_t frl_abi_version(void);
 /* Tuning knobs.  "trading_small_max": frl_trading_step/rollout use the low-latency 8-lanes-per-env kernel
- * for n_envs <= value and the thread-per-env kernel above (default 8192, the measured crossover; 0 = never). */
+ * for n_envs <= value and the thread-per-env kernel above (default 8192, the measured crossover; 0 = never).
+ * "np_wide_min_d": frl_np_* stream stocks / cool-down from global memory (np_wide.cu) for stock_dim >= value
+ * and keep them in registers below (1..33, default 33: the register kernel holds at most 32 stocks). */
 FRL_API int32_t frl_set_option(const char *name, int64_t value);
 /* thread-local, never NULL; valid until the next failing call on this thread */
 FRL_API const char *frl_last_error(void);
