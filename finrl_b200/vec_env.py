@@ -85,21 +85,47 @@ class BatchedVecEnv(_Base):
             return obs.reshape(self.num_envs, *self.obs_shape), reward, done, {"flags": flags}
         import torch
 
+        # numpy in / numpy out like DummyVecEnv, through persistent PINNED host buffers: one async upload, one
+        # batch of async downloads and a single stream synchronisation per step (two when an env finished)
         a = self._actions
-        if not isinstance(a, torch.Tensor):
-            a = torch.as_tensor(np.ascontiguousarray(a))
-        obs, reward, done, flags = eng.step(a, auto_reset=False)
-        dones = done.cpu().numpy()
-        rewards = reward.cpu().numpy().astype(np.float32)
+        if isinstance(a, torch.Tensor):
+            d_act = a
+        else:
+            a = np.asarray(a)
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            h = self._pinned("act_" + a.dtype.name, (self.num_envs, self.action_dim), torch.from_numpy(a[:0].copy()).dtype)
+            np.copyto(h.numpy(), a.reshape(self.num_envs, self.action_dim))
+            d_act = h.to(eng.device, non_blocking=True)
+        obs, reward, done, flags = eng.step(d_act, auto_reset=False)
+        obs_h = self._pinned("obs", (self.num_envs, *self.obs_shape), torch.float32)
+        rew_h = self._pinned("rew", (self.num_envs,), reward.dtype)
+        flg_h = self._pinned("flags", (self.num_envs,), torch.uint8)
+        flg_h.copy_(flags, non_blocking=True)
+        rew_h.copy_(reward, non_blocking=True)
+        obs_h.copy_(obs.reshape(obs_h.shape), non_blocking=True)
+        torch.cuda.current_stream(eng.device).synchronize()
+        self._flags = flg_h.numpy().copy()
+        dones = (self._flags & _cabi.FLAG_DONE).astype(bool)
+        rewards = rew_h.numpy().astype(np.float32)
         terminal = {}
         if dones.any():
             idx = np.nonzero(dones)[0]
-            term = obs[torch.as_tensor(idx, device=obs.device)].cpu().numpy().reshape(len(idx), *self.obs_shape)
+            term = obs_h.numpy()[idx].copy()
             terminal = {int(i): term[k] for k, i in enumerate(idx)}
             obs = eng.reset(mask=done)  # DummyVecEnv.step_wait: obs = env.reset() for the done envs
-        out = obs.reshape(self.num_envs, *self.obs_shape).cpu().numpy()
-        self._flags = flags.cpu().numpy()
-        return out, rewards, dones, _LazyInfos(self.num_envs, terminal)
+            obs_h.copy_(obs.reshape(obs_h.shape), non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+        return obs_h.numpy().copy(), rewards, dones, _LazyInfos(self.num_envs, terminal)
+
+    def _pinned(self, name, shape, dtype):
+        import torch
+
+        bufs = self.__dict__.setdefault("_pinned_bufs", {})
+        b = bufs.get(name)
+        if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
+            b = bufs[name] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        return b
 
     def step(self, actions):
         self.step_async(actions)
