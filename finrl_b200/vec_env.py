@@ -43,8 +43,12 @@ class _LazyInfos:
 
 
 class BatchedVecEnv(_Base):
-    def __init__(self, engine, action_low=-1.0, action_high=1.0, tensor_mode: bool = False, obs_shape=None):
+    def __init__(self, engine, action_low=-1.0, action_high=1.0, tensor_mode: bool = False, obs_shape=None,
+                 copy_outputs: bool = True):
         self.engine = engine
+        # numpy mode: True returns fresh arrays like DummyVecEnv; False returns views of the pinned host buffers
+        # (valid until the next step) and saves one host memcpy of the observation batch
+        self.copy_outputs = copy_outputs
         self.num_envs = self.env_num = engine.n_envs
         self.tensor_mode = tensor_mode
         D = engine.stock_dim
@@ -116,7 +120,8 @@ class BatchedVecEnv(_Base):
             obs = eng.reset(mask=done)  # DummyVecEnv.step_wait: obs = env.reset() for the done envs
             obs_h.copy_(obs.reshape(obs_h.shape), non_blocking=True)
             torch.cuda.current_stream(eng.device).synchronize()
-        return obs_h.numpy().copy(), rewards, dones, _LazyInfos(self.num_envs, terminal)
+        out = obs_h.numpy()
+        return (out.copy() if self.copy_outputs else out), rewards, dones, _LazyInfos(self.num_envs, terminal)
 
     def _pinned(self, name, shape, dtype):
         import torch
