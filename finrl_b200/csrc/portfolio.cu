@@ -306,11 +306,9 @@ void pf_launch(const frl_portfolio_params &p, const void *actions, long long sst
         (size_t)FRL_PF_IMG_ROWS * p.obs_dim * 4 * WARPS <= 40 * 1024)
         img_rows = FRL_PF_IMG_ROWS;
     const size_t dyn = (size_t)img_rows * p.obs_dim * 4 * WARPS;
-    static bool configured = false;  // per instantiation: static + dynamic shared memory may exceed 48 KB
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024);
-        configured = true;
-    }
+    // static + dynamic shared memory above 48 KB needs the opt-in (per device, so it is not cached here)
+    if (dyn + WARPS * sizeof(PfWarpSmem<SLOTS, ActT>) > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     kern<<<grid, WARPS * 32, dyn, st>>>(p, (const ActT *)actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode,
                                         auto_reset, stats, img_rows);
 }

@@ -764,11 +764,7 @@ void launch_rollout(const frl_trading_params &p, const void *actions, long long 
     const unsigned grid = (unsigned)((tiles + WARPS - 1) / WARPS);
     auto kern = trading_rollout_kernel<SLOTS, DCT, ActT, WARPS>;
     constexpr int smem = WARPS * (int)sizeof(WarpSmem<SLOTS, ActT, WARPS>);
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = true;
-    }
+    static_assert(smem <= 48 * 1024, "the tile kernel's shared memory must stay within the default limit");
     kern<<<grid, WARPS * 32, smem, st>>>(
         p, (const ActT *)actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats);
 }
