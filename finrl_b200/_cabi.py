@@ -118,6 +118,8 @@ class PortfolioParams(C.Structure):
         ("reward", C.c_void_p),
         ("ret_out", C.c_void_p),
         ("weights_out", C.c_void_p),
+        ("ret_pitch", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

@@ -210,7 +210,7 @@ portfolio_rollout_kernel(const frl_portfolio_params p, const ActT *__restrict__ 
             for (int j = 0; j < SLOTS; ++j) e[j] = (j < D) ? pf_exp<ActT>(arow[j]) : ActT(0);
             const ActT den = pf_pairwise_sum<SLOTS, ActT>(e, D);
             day += 1;
-            const double *rrow = p.ret + (size_t)day * 32;
+            const double *rrow = p.ret + (size_t)day * p.ret_pitch;
             // sum(((close_new / close_old) - 1) * weights): Python sum, sequential (:183-185)
             double pr = 0.0;
 #pragma unroll
@@ -256,6 +256,163 @@ portfolio_rollout_kernel(const frl_portfolio_params p, const ActT *__restrict__ 
     }
 }
 
+// ---- D = 33..128 (e.g. a NASDAQ-100 portfolio): the exp values do not fit in registers, so the step makes two
+// sweeps over the lane's own staged action row — exp in place + numpy's pairwise sum fed in blocks of 8, then
+// weights and the sequential weighted return.  Same arithmetic and order as the register kernel.
+template <typename T>
+struct PfPairwise {
+    T r[8];
+    T res;
+    __device__ __forceinline__ void init()
+    {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = T(0);
+        res = T(0);
+    }
+    __device__ __forceinline__ void block(const T (&x)[8], int j0, int D)
+    {
+        const int nb = D >> 3, b = j0 >> 3;
+        if (b < nb) {
+            if (b == 0) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = x[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = pf_add(r[u], x[u]);
+            }
+            if (b == nb - 1)
+                res = pf_add(pf_add(pf_add(r[0], r[1]), pf_add(r[2], r[3])), pf_add(pf_add(r[4], r[5]), pf_add(r[6], r[7])));
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (j0 + u < D) res = pf_add(res, x[u]);
+        }
+    }
+};
+
+template <typename ActT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+portfolio_wide_kernel(const frl_portfolio_params p, const ActT *__restrict__ actions, long long act_step_stride,
+                      long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
+                      float *__restrict__ obs, int obs_mode, int auto_reset, double *__restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char pfw_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = p.n_envs, D = p.stock_dim, T = p.n_days;
+    const int P = D | 1;  // odd row pitch: conflict-free per-lane row walks
+    const size_t warp_bytes = (((size_t)32 * P * sizeof(ActT) + 32 * sizeof(int)) + 15) & ~(size_t)15;
+    ActT *stage = reinterpret_cast<ActT *>(pfw_smem + warp * warp_bytes);
+    int *day_s = reinterpret_cast<int *>(stage + (size_t)32 * P);
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const bool valid = lane < nvalid;
+    const long long n = valid ? env0 + lane : (long long)N - 1;
+    ActT *myrow = stage + (size_t)lane * P;
+
+    double pv = p.pv[n], last_reward = p.reward[n];
+    int day = p.day[n];
+    double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0;
+
+    for (int k = 0; k < n_steps; ++k) {
+        const ActT *abase = actions + (size_t)k * act_step_stride;
+        __syncwarp();
+        if (act_env_stride == D) {
+            const ActT *tile = abase + (size_t)env0 * D;
+            const int cnt = nvalid * D;
+            int row = 0, col = lane;
+            while (col >= D) { col -= D; ++row; }
+            for (int e = lane; e < 32 * D; e += 32) {
+                stage[row * P + col] = e < cnt ? __ldcs(tile + e) : ActT(0);
+                col += 32;
+                while (col >= D) { col -= D; ++row; }
+            }
+        } else {
+            for (int r = 0; r < 32; ++r)
+                for (int j = lane; j < D; j += 32)
+                    stage[r * P + j] = r < nvalid ? abase[(size_t)(env0 + r) * act_env_stride + j] : ActT(0);
+        }
+        __syncwarp();
+
+        uint8_t flags = 0;
+        double reward;
+        if (day >= T - 1) {
+            flags = FRL_FLAG_DONE;
+            reward = last_reward;
+            if (valid) {
+                st_done += 1.0;
+                st_epi += pv;
+            }
+            if (auto_reset) {
+                pv = p.initial_amount;
+                day = 0;
+            }
+        } else {
+            PfPairwise<ActT> acc;
+            acc.init();
+            for (int j0 = 0; j0 < D; j0 += 8) {
+                ActT e8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    e8[u] = ActT(0);
+                    if (j0 + u < D) {
+                        e8[u] = pf_exp<ActT>(myrow[j0 + u]);
+                        myrow[j0 + u] = e8[u];
+                    }
+                }
+                acc.block(e8, j0, D);
+            }
+            const ActT den = acc.res;
+            day += 1;
+            const double *rrow = p.ret + (size_t)day * p.ret_pitch;
+            double pr = 0.0;
+            for (int j = 0; j < D; ++j) {
+                const double w = (double)pf_div<ActT>(myrow[j], den);
+                pr = dadd(pr, dmul(__ldg(rrow + j), w));
+                if (p.weights_out && valid) p.weights_out[(size_t)n * D + j] = w;
+            }
+            if (p.ret_out && valid) p.ret_out[n] = pr;
+            pv = dmul(pv, dadd(1.0, pr));
+            reward = pv;
+            last_reward = reward;
+        }
+        if (valid) {
+            if (rewards) rewards[(size_t)k * N + n] = reward;
+            if (flags_out) flags_out[(size_t)k * N + n] = flags;
+            st_r += reward;
+            st_r2 += reward * reward;
+        }
+        if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
+            day_s[lane] = day;
+            __syncwarp();
+            float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
+            pf_write_obs_tile(p, day_s, o, env0, nvalid, lane);
+        }
+    }
+    if (valid) {
+        p.pv[n] = pv;
+        p.day[n] = day;
+        p.reward[n] = last_reward;
+    }
+    if (stats) {
+        double v[FRL_N_STATS] = {st_r, st_r2, st_done, st_epi, valid ? pv : 0.0, 0.0, valid ? (double)n_steps : 0.0, 0.0};
+        reduce_stats8(v, lane, stats);
+    }
+}
+
+template <typename ActT, int WARPS>
+void pf_launch_wide(const frl_portfolio_params &p, const void *actions, long long sstride, long long estride, int n_steps,
+                    double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
+{
+    const int P = p.stock_dim | 1;
+    const size_t smem = WARPS * ((((size_t)32 * P * sizeof(ActT) + 32 * sizeof(int)) + 15) & ~(size_t)15);
+    auto kern = portfolio_wide_kernel<ActT, WARPS>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long tiles = ((long long)p.n_envs + 31) / 32;
+    kern<<<(unsigned)((tiles + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(p, (const ActT *)actions, sstride, estride, n_steps,
+                                                                           rewards, flags, obs, obs_mode, auto_reset, stats);
+}
+
 __global__ void portfolio_reset_kernel(const frl_portfolio_params p, const uint8_t *__restrict__ mask)
 {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,7 +440,9 @@ int32_t pf_validate(const frl_portfolio_params *p)
 {
     FRL_REQUIRE(p != nullptr, "portfolio: params is NULL");
     FRL_REQUIRE(p->n_envs >= 1, "portfolio: n_envs must be >= 1 (got %d)", p->n_envs);
-    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 32, "portfolio: stock_dim must be in 1..32 (got %d)", p->stock_dim);
+    FRL_REQUIRE(p->stock_dim >= 1 && p->stock_dim <= 128, "portfolio: stock_dim must be in 1..128 (got %d)", p->stock_dim);
+    FRL_REQUIRE((p->ret_pitch == 32 || p->ret_pitch == 128) && p->ret_pitch >= p->stock_dim,
+                "portfolio: ret_pitch must be 32 or 128 and >= stock_dim (got %d for D=%d)", p->ret_pitch, p->stock_dim);
     FRL_REQUIRE(p->n_tech >= 0 && p->n_days >= 1, "portfolio: bad n_tech/n_days (%d, %d)", p->n_tech, p->n_days);
     FRL_REQUIRE(p->obs_dim == (p->stock_dim + p->n_tech) * p->stock_dim, "portfolio: obs_dim %d != (D+K)*D = %d",
                 p->obs_dim, (p->stock_dim + p->n_tech) * p->stock_dim);
@@ -359,7 +518,14 @@ extern "C" int32_t frl_portfolio_rollout(const frl_portfolio_params *p, const vo
             pf_launch<SLOTS, float, 4>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags,     \
                                        obs, obs_mode, auto_reset, stats, st);                                     \
     } while (0)
-    if (D <= 8)
+    if (D > 32) {
+        if (actions_f64)
+            pf_launch_wide<double, 2>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags, obs, obs_mode,
+                                      auto_reset, stats, st);
+        else
+            pf_launch_wide<float, 4>(*p, actions, act_step_stride, act_env_stride, n_steps, rewards, flags, obs, obs_mode,
+                                     auto_reset, stats, st);
+    } else if (D <= 8)
         FRL_GO(8);
     else if (D <= 16)
         FRL_GO(16);

@@ -38,7 +38,7 @@ class PortfolioTables:
     n_days: int
     stock_dim: int
     n_tech: int
-    ret: "torch.Tensor"        # [T, 32] f64
+    ret: "torch.Tensor"        # [T, pitch] f64 (pitch 32 for D <= 32, else 128)
     obs_table: "torch.Tensor"  # [T, (D+K)*D] f32
     host_obs: np.ndarray       # [T, D+K, D] f64 (the reference's state matrices)
 
@@ -52,12 +52,12 @@ class PortfolioTables:
 
         close = np.ascontiguousarray(close, dtype=np.float64)
         T, D = close.shape
-        if not 1 <= D <= 32:
-            raise ValueError(f"stock_dim must be in 1..32 for the portfolio kernel (got {D})")
+        if not 1 <= D <= 128:
+            raise ValueError(f"stock_dim must be in 1..128 for the portfolio kernels (got {D})")
         cov = np.ascontiguousarray(cov, dtype=np.float64).reshape(T, D, D)
         tech = np.ascontiguousarray(tech, dtype=np.float64).reshape(-1, T, D)
         K = tech.shape[0]
-        ret = np.zeros((T, 32), dtype=np.float64)
+        ret = np.zeros((T, 32 if D <= 32 else 128), dtype=np.float64)
         ret[1:, :D] = (close[1:] / close[:-1]) - 1  # (self.data.close.values / last_day_memory.close.values) - 1
         state = np.concatenate([cov, np.transpose(tech, (1, 0, 2))], axis=1)  # np.append(cov, tech rows, axis=0)
         dev = torch.device(device)
@@ -107,6 +107,7 @@ class BatchedStockPortfolioEnv(BatchedEnvBase):
         p.n_envs, p.stock_dim, p.n_tech, p.n_days, p.obs_dim = N, D, K, T, tables.obs_dim
         p.initial_amount = float(initial_amount)
         p.ret, p.obs_table = tables.ret.data_ptr(), tables.obs_table.data_ptr()
+        p.ret_pitch = int(tables.ret.shape[1])
         p.pv, p.day, p.reward = self.portfolio_value.data_ptr(), self.day.data_ptr(), self.reward.data_ptr()
         # optional: the step's portfolio_return and softmax weights (the reference's logging memories)
         self.last_return = torch.zeros(N, dtype=torch.float64, device=dev) if track_weights else None

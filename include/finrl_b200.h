@@ -214,14 +214,14 @@ FRL_API int32_t frl_np_step(const frl_np_params *p, const void *actions, int32_t
  * ========================================================================================= */
 typedef struct frl_portfolio_params {
     int32_t n_envs;    /* N */
-    int32_t stock_dim; /* D, 1..32 */
+    int32_t stock_dim; /* D, 1..128 (D <= 32: exp values in registers; above: two sweeps over the staged row) */
     int32_t n_tech;    /* K */
     int32_t n_days;    /* T */
     int32_t obs_dim;   /* (D + K) * D : np.append(cov (D x D), tech rows (K x D), axis=0) flattened */
     int32_t _pad0;
     double initial_amount;
     /* ---- tables ---- */
-    const double *ret;      /* [T][32] ret[t][j] = close[t][j] / close[t-1][j] - 1 (row 0 unused), the
+    const double *ret;      /* [T][ret_pitch] ret[t][j] = close[t][j] / close[t-1][j] - 1 (row 0 unused), the
                                env-independent factor of the weighted return (:183-185) */
     const float *obs_table; /* [T][obs_dim] float32 image of the day's state matrix */
     /* ---- per-env state ---- */
@@ -231,6 +231,8 @@ typedef struct frl_portfolio_params {
     /* ---- optional per-env outputs of the last step (NULL = skip) ---- */
     double *ret_out;     /* [N] portfolio_return (portfolio_return_memory entry) */
     double *weights_out; /* [N][D] softmax weights (actions_memory entry), float64 */
+    int32_t ret_pitch; /* row pitch of `ret` in doubles: 32 for D <= 32, 128 for D <= 128 */
+    int32_t reserved_;
 } frl_portfolio_params;
 
 /* StockPortfolioEnv.reset (:202-220) for envs with mask[n] != 0 (NULL = all). obs nullable [N][obs_dim]. */

@@ -346,6 +346,9 @@ def main():
     if want("portfolio"):
         gen_portfolio("portfolio_d30_f64", T=252 + 24, D=30, K=4, n_steps=50, seed=21, act_dtype=np.float64)
         gen_portfolio("portfolio_d6_f32", T=40 + 12, D=6, K=2, n_steps=30, seed=22, act_dtype=np.float32, lookback=40)
+        # D > 32: the two-sweep kernel
+        gen_portfolio("portfolio_d50_f64", T=60 + 16, D=50, K=2, n_steps=36, seed=23, act_dtype=np.float64, lookback=60)
+        gen_portfolio("portfolio_d72_f32", T=80 + 8, D=72, K=1, n_steps=18, seed=24, act_dtype=np.float32, lookback=80)
     if want("stoploss"):
         gen_cashpenalty("stoploss_d7_hmaxvec", T=30, D=7, n_steps=50, seed=55, act_dtype=np.float32,
                         hmax=np.linspace(3000.0, 9000.0, 7), stoploss=(0.92, 2))

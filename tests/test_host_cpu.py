@@ -51,8 +51,8 @@ def test_struct_layouts_match_the_header():
 
     checks = {
         "frl_trading_params": (_cabi.TradingParams, ["n_envs", "hmax", "turbulence_threshold", "close", "cash", "episode", "asset_out", "obs_tmpl4"]),
-        "frl_np_params": (_cabi.NpParams, ["gamma", "initial_capital", "obs_amount_floor", "price", "amount", "episode_return"]),
-        "frl_portfolio_params": (_cabi.PortfolioParams, ["initial_amount", "ret", "reward", "ret_out", "weights_out"]),
+        "frl_np_params": (_cabi.NpParams, ["gamma", "initial_capital", "obs_amount_floor", "price", "amount", "episode_return", "price_pitch"]),
+        "frl_portfolio_params": (_cabi.PortfolioParams, ["initial_amount", "ret", "reward", "ret_out", "weights_out", "ret_pitch"]),
         "frl_crypto_params": (_cabi.CryptoParams, ["lookback", "env_stride", "initial_capital", "gamma", "price", "episode_return"]),
         "frl_stoploss_params": (_cabi.StopLossParams, ["patient", "env_stride", "buy_cost_pct", "stoploss_penalty", "min_profit_penalty", "close", "assets", "fresh", "sum_trades", "hmax_vec", "hmax_vec_f32"]),
         "frl_cashpenalty_params": (_cabi.CashPenaltyParams, ["patient", "env_stride", "buy_cost_pct", "cash_penalty_proportion", "close", "hold_alt", "sum_trades", "hmax_vec", "hmax_vec_f32"]),

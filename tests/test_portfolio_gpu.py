@@ -50,7 +50,8 @@ def _make(N, T=40, D=30, K=4, seed=0):
     return env, ora.PortfolioOracle(close, cov, tech, N)
 
 
-@pytest.mark.parametrize("N,D,dtype", [(1, 30, np.float64), (4096 + 3, 30, np.float64), (500, 6, np.float32), (500, 13, np.float64)])
+@pytest.mark.parametrize("N,D,dtype", [(1, 30, np.float64), (4096 + 3, 30, np.float64), (500, 6, np.float32), (500, 13, np.float64),
+                                           (700, 100, np.float64), (333, 128, np.float32), (64, 33, np.float64)])
 def test_step_vs_oracle(N, D, dtype):
     from finrl_b200 import synthetic as syn
 
