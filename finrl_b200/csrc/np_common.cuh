@@ -55,6 +55,48 @@ __device__ __forceinline__ NV nv_mul(NV x, NV y)
 }
 #endif
 
+// Exact widening conversions WITHOUT the conversion unit (XU, 16 lanes/clk/SM — the busiest pipe of these
+// kernels, which convert between float32, float64 and int64 on every trade): float -> double by re-biasing
+// the exponent with integer ops (zero handled inline; denormals / inf / nan fall back to the converter), and a
+// non-negative int -> double with the 2**52 magic-number trick (one DADD).  Both are exact, like the casts.
+#ifndef FRL_NP_ALU_CONVERT
+#define FRL_NP_ALU_CONVERT 0  // A/B on B200: 1 grows the unrolled trade loops past the instruction cache (0.44 -> 0.76 ms)
+#endif
+__device__ __forceinline__ double np_f2d(float f)
+{
+#if FRL_NP_ALU_CONVERT
+    const unsigned b = __float_as_uint(f);
+    const unsigned e = b & 0x7f800000u;
+    if (e - 0x00800000u < 0x7f000000u)  // normal number
+        return __hiloint2double((int)((b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u)), (int)(b << 29));
+    if ((b & 0x7fffffffu) == 0u) return __hiloint2double((int)b, 0);  // +-0
+#endif
+    return (double)f;
+}
+__device__ __forceinline__ double np_u2d(int x)  // x >= 0
+{
+#if FRL_NP_ALU_CONVERT
+    return __hiloint2double(0x43300000, x) - 4503599627370496.0;
+#else
+    return (double)x;
+#endif
+}
+
+// The cash-limited buy needs numpy's floor division, a ~40-instruction sequence that the unrolled trade loops
+// would inline once per stock slot; it is rare at run time, so it lives out of line and the hot path of the
+// loops stays compact (instruction-cache footprint is what limits these kernels' issue rate).
+#ifndef FRL_NP_OUTLINE_DIV
+#define FRL_NP_OUTLINE_DIV 1
+#endif
+#if FRL_NP_OUTLINE_DIV
+static __device__ __noinline__ double np_floor_div(double a, double b, int f64)
+#else
+__device__ __forceinline__ double np_floor_div(double a, double b, int f64)
+#endif
+{
+    return f64 ? floor_div_f64(a, b) : (double)floor_div_f32((float)a, (float)b);
+}
+
 template <typename ActT>
 __device__ __forceinline__ int np_action_to_shares(ActT a, double max_stock);
 template <>

@@ -298,8 +298,7 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
                                 const bool plenty = am >= dmul((double)(aj + 1), (double)pj);
                                 double avail = 0.0;
                                 if (!plenty && !(am >= 0.0 && am < (double)pj))
-                                    avail = amount.k == FRL_KIND_F64 ? floor_div_f64(am, (double)pj)
-                                                                      : (double)floor_div_f32((float)am, pj);
+                                    avail = np_floor_div(am, (double)pj, amount.k == FRL_KIND_F64);
                                 if (plenty) {  // min(avail, action) -> the int64
                                     const double nsh = (double)aj;
                                     s = (float)dadd((double)s, nsh);

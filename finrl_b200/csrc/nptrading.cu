@@ -246,14 +246,15 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
                         if (pj > 0.0f) {
                             float st = stv[j];
                             NV x;
-                            if ((double)(-aj) < (double)st) {  // min(stocks, -action) -> the int64
-                                const double nsh = (double)(-aj);
-                                st = (float)dsub((double)st, nsh);
-                                x = nv_mul(nv(dmul((double)pj, nsh), FRL_KIND_F64), one_minus_sc);
+                            const double nsh = np_u2d(-aj), std_ = np_f2d(st);
+                            if (nsh < std_) {  // min(stocks, -action) -> the int64
+                                st = (float)dsub(std_, nsh);
+                                x = nv_mul(nv(dmul(np_f2d(pj), nsh), FRL_KIND_F64), one_minus_sc);
                             } else {  // -> the float32 holding
                                 x = nv_mul(nv((double)fmul(pj, st), FRL_KIND_F32), one_minus_sc);
                                 st = fsub(st, st);
                             }
+                            // (common code after the divergent branches: executed once per warp, not once per branch)
                             stv[j] = st;
                             amount = nv_add(amount, x);
                             clv[j] = 0.0f;
@@ -272,22 +273,24 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
                             // avail = amount // price is an exact floor, so `action < avail` <=> amount >=
                             // (action+1)*price, which is exact in fp64 (24-bit price x small int): the
                             // division only runs for the cash-limited buys
-                            const double am = amount.k == FRL_KIND_F64 ? amount.v : (double)(float)amount.v;
-                            const bool plenty = am >= dmul((double)(aj + 1), (double)pj);
+                            // amount // price is a float32 operation unless amount is float64; a float32 amount is
+                            // already float32-valued, only a (weak) Python float has to be rounded first
+                            const double am = amount.k == FRL_KIND_PY ? (double)(float)amount.v : amount.v;
+                            const double pjd = np_f2d(pj);
+                            const bool plenty = am >= dmul(np_u2d(aj + 1), pjd);
                             double avail = 0.0;
                             // 0 <= amount < price: the quotient is exactly 0 (the usual state of a cash-starved
                             // env) — only the division is skipped, the zero-share update still runs (it can
                             // change the numpy kind of `amount` and it resets the cool-down counter)
-                            if (!plenty && !(am >= 0.0 && am < (double)pj))
-                                avail = amount.k == FRL_KIND_F64 ? floor_div_f64(am, (double)pj)
-                                                                  : (double)floor_div_f32((float)am, pj);
+                            if (!plenty && !(am >= 0.0 && am < pjd))
+                                avail = np_floor_div(am, pjd, amount.k == FRL_KIND_F64);
                             if (plenty) {  // min(avail, action) -> the int64
-                                const double nsh = (double)aj;
-                                st = (float)dadd((double)st, nsh);
-                                x = nv_mul(nv(dmul((double)pj, nsh), FRL_KIND_F64), one_plus_bc);
+                                const double nsh = np_u2d(aj);
+                                st = (float)dadd(np_f2d(st), nsh);
+                                x = nv_mul(nv(dmul(pjd, nsh), FRL_KIND_F64), one_plus_bc);
                             } else if (amount.k == FRL_KIND_F64) {
-                                st = (float)dadd((double)st, avail);
-                                x = nv_mul(nv(dmul((double)pj, avail), FRL_KIND_F64), one_plus_bc);
+                                st = (float)dadd(np_f2d(st), avail);
+                                x = nv_mul(nv(dmul(pjd, avail), FRL_KIND_F64), one_plus_bc);
                             } else {
                                 const float nsh = (float)avail;
                                 st = fadd(st, nsh);
