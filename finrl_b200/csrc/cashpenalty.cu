@@ -46,12 +46,13 @@ __device__ __forceinline__ long long floordiv_ll(long long a, long long b)
 // get_transactions (:258-298) for one asset: actions*hmax in the input dtype, zero where the price is
 // not positive, shares = currency / price (or the discretised floor), never sell more than held,
 // turbulence clears the position.
-template <typename ActT>
+// HVEC: hmax is the per-asset array (its own instantiation, so the scalar path carries no checks)
+template <typename ActT, bool HVEC>
 __device__ __forceinline__ double cp_transaction(const frl_cashpenalty_params &p, ActT a, double hmax, double c, double h,
                                                  bool liq)
 {
     double v;
-    if (sizeof(ActT) == 4 && !(p.hmax_vec && !p.hmax_vec_f32))
+    if (sizeof(ActT) == 4 && !(HVEC && !p.hmax_vec_f32))
         v = (double)fmul((float)a, (float)hmax);  // scalar (weak Python float) or float32 array: float32 product
     else
         v = dmul((double)a, hmax);
@@ -170,7 +171,7 @@ __device__ __forceinline__ void cp_async_elem(double *dst, const double *src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-template <typename ActT, int WARPS>
+template <typename ActT, int WARPS, bool HVEC>
 __global__ void __launch_bounds__(WARPS * 32, FRL_CP_MIN_BLOCKS * 128 / (WARPS * 32))
 cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restrict__ actions, long long act_step_stride,
                            long long act_env_stride, int n_steps, double *__restrict__ rewards,
@@ -295,7 +296,7 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
                     const int j = j0 + u;
                     if (j < D) {
                         const ActT a = myrow[j];
-                        const double v = cp_transaction<ActT>(p, a, p.hmax_vec ? __ldg(p.hmax_vec + j) : p.hmax, cb[u], hb[u], liq);
+                        const double v = cp_transaction<ActT, HVEC>(p, a, HVEC ? __ldg(p.hmax_vec + j) : p.hmax, cb[u], hb[u], liq);
                         asum += fabs((double)a);
                         asset_value = dadd(asset_value, dmul(hb[u], cb[u]));
                         proceeds = dadd(proceeds, dmul(v < 0.0 ? -v : 0.0, cb[u]));
@@ -480,7 +481,7 @@ int32_t cp_launch(const frl_cashpenalty_params &p, const void *actions, long lon
                   double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
 {
     const size_t smem = cp_smem_bytes(p.stock_dim, sizeof(ActT), WARPS);
-    auto kern = cashpenalty_rollout_kernel<ActT, WARPS>;
+    auto kern = p.hmax_vec ? cashpenalty_rollout_kernel<ActT, WARPS, true> : cashpenalty_rollout_kernel<ActT, WARPS, false>;
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {

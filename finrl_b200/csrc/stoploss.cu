@@ -29,12 +29,12 @@ struct SlTx {
 };
 
 // the action pipeline of step() for one asset (:321-361)
-template <typename ActT>
+template <typename ActT, bool HVEC>
 __device__ __forceinline__ SlTx sl_transaction(const frl_stoploss_params &p, ActT a, double hmax, double c, double h, double avg, bool liq,
                                                bool stop_on)
 {
     double v;
-    if (sizeof(ActT) == 4 && !(p.hmax_vec && !p.hmax_vec_f32))
+    if (sizeof(ActT) == 4 && !(HVEC && !p.hmax_vec_f32))
         v = (double)fmul((float)a, (float)hmax);  // scalar (weak Python float) or float32 array: float32 product
     else
         v = dmul((double)a, hmax);
@@ -130,7 +130,7 @@ __device__ __forceinline__ void sl_cp_async(double *dst, const double *src)
 #define FRL_SL_MIN_BLOCKS 3  // 128-thread blocks per SM the register allocator must allow
 #endif
 
-template <typename ActT, int WARPS>
+template <typename ActT, int WARPS, bool HVEC>
 __global__ void __launch_bounds__(WARPS * 32, FRL_SL_MIN_BLOCKS * 128 / (WARPS * 32))
 stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ actions, long long act_step_stride,
                         long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
@@ -248,7 +248,7 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
                                      cd = sb[SL_CD][u], pd = sb[SL_PD][u];
                         double nb = sb[SL_NB][u];
                         const ActT a = myrow[j];
-                        const SlTx t = sl_transaction<ActT>(p, a, p.hmax_vec ? __ldg(p.hmax_vec + j) : p.hmax, c, h, avg, liq, stop_on);
+                        const SlTx t = sl_transaction<ActT, HVEC>(p, a, HVEC ? __ldg(p.hmax_vec + j) : p.hmax, c, h, avg, liq, stop_on);
                         asum += fabs((double)a);
                         asset_value = dadd(asset_value, dmul(h, c));
                         d_prev_negc = dadd(d_prev_negc, dmul(pv, cd < 0.0 ? cd : 0.0));
@@ -476,7 +476,7 @@ int32_t sl_launch(const frl_stoploss_params &p, const void *actions, long long s
     const int P = p.stock_dim | 1;
     const size_t warp_bytes = (size_t)32 * P * sizeof(ActT) + 32 * sizeof(float) + 32 * sizeof(int);
     const size_t smem = WARPS * ((warp_bytes + 15) & ~(size_t)15);
-    auto kern = stoploss_rollout_kernel<ActT, WARPS>;
+    auto kern = p.hmax_vec ? stoploss_rollout_kernel<ActT, WARPS, true> : stoploss_rollout_kernel<ActT, WARPS, false>;
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
