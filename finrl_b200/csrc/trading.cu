@@ -5,7 +5,9 @@
 // lock-step instead of 32 lanes idling behind one chain — and ONE WARP PER 32-ENV TILE for the
 // memory traffic: actions are staged through shared memory with coalesced loads, the stock-major
 // state arrays are read/written coalesced straight from registers, and the observation rows (74 %
-// of the bytes of a step) are written by the whole warp, 128 B per store instruction.
+// of the bytes of a step) leave through the bulk-copy engine (TMA): a 4-row template image per day is
+// bulk-loaded into shared memory, patched with the envs' cash / holdings and bulk-stored, four rows per
+// cp.async.bulk (tiles that are partial, unaligned or not on one day fall back to 128-B warp stores).
 //
 // Bit-exactness: every product/sum on the cash path is an explicit __dmul_rn/__dadd_rn in the
 // reference's order; np.argsort's tie order is reproduced by running the same bitonic network
@@ -113,6 +115,7 @@ struct alignas(16) WarpSmem {
 // (16*O bytes, obs_tmpl4) into shared memory once, and per 4 rows patch the 4*(D+1) env-specific floats
 // and hand the image to the copy engine with one cp.async.bulk store — ~20 instructions per lane per four
 // rows instead of ~60 stores and selects.
+
 // all 32 envs of the tile valid and on day sd0: start the image load (the action region must be dead)
 template <typename SM>
 __device__ __forceinline__ void obs_image_load(const frl_trading_params &p, SM &sm, int lane, int sd0)
