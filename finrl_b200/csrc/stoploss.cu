@@ -12,6 +12,7 @@
 //           the reference) / patient (the buy slots are put back) / flip the buffer.
 // np.dot's order is BLAS-specific (1e-9 tolerance); the sums here are sequential in asset order.
 #include "common.cuh"
+#include "cp_obs.cuh"
 
 namespace frl {
 namespace {
@@ -69,30 +70,6 @@ __device__ __forceinline__ double sl_reward(const frl_stoploss_params &p, double
     const double total_penalty = dadd(dadd(cash_penalty, stop_loss_penalty), low_profit_penalty);
     double r = dsub(__ddiv_rn(dadd(dsub(total_assets, total_penalty), dot_hold_posp), p.initial_amount), 1.0);
     return __ddiv_rn(r, (double)current_step);
-}
-
-template <typename ActT>
-__device__ __forceinline__ void sl_write_obs_tile(const frl_stoploss_params &p, const ActT *stage, int P, const float *cashf,
-                                                  const int *di_s, float *__restrict__ obs, long long env0, int nvalid,
-                                                  int lane)
-{
-    const int O = p.obs_dim, D = p.stock_dim;
-    constexpr int step = sizeof(ActT) / sizeof(float);
-    for (int r = 0; r < nvalid; ++r) {
-        const float *hrow = reinterpret_cast<const float *>(stage + (size_t)r * P);
-        const float *trow = p.obs_tmpl + (size_t)di_s[r] * O;
-        float *orow = obs + (size_t)(env0 + r) * O;
-        for (int pos = lane; pos < O; pos += 32) {
-            float v;
-            if (pos == 0)
-                v = cashf[r];
-            else if (pos <= D)
-                v = hrow[(pos - 1) * step];
-            else
-                v = __ldg(trow + pos);
-            orow[pos] = v;
-        }
-    }
 }
 
 // The six per-asset arrays live in ONE allocation, assets[2][6][D][env_stride]: two buffers of (holdings,
@@ -391,7 +368,7 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
             di_s[lane] = di;
             __syncwarp();
             float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
-            sl_write_obs_tile<ActT>(p, stage, P, cashf, di_s, o, env0, nvalid, lane);
+            cp_write_obs_tile<ActT>(p, stage, P, cashf, di_s, o, env0, nvalid, lane);
         }
     }
     if (valid) {
