@@ -104,6 +104,19 @@ class TradingRollout(TradingStep):
         return f"StockTradingEnv DOW-30 fused K=64 rollout (obs after the last step), {envs} envs/GPU, D=30 K=8 T=2500"
 
 
+class TradingNas100Step(TradingStep):
+    name = "trading_nas100_step"
+    D = 100
+    K_TECH = 2
+    default_envs = 1 << 18
+    # actions 400 + state 2*(8 cash + 400 hold + 4 day + 4 sday + 8 cost + 4 trades + 8 reward) + obs 4*401 + reward 8 + done 1
+    bytes_per_env_step = 2885
+    kernel = "trading_small_kernel<16,float,1> (D > 32 always runs in the 8-lanes-per-env kernel)"
+
+    def describe(self, envs):
+        return f"StockTradingEnv at NASDAQ-100 size, {envs} envs/GPU, D=100 K=2 T=2500 O=401, f32 actions, f32 obs"
+
+
 class NpStep(Workload):
     name = "np_step"
     bytes_per_env_step = 2015  # config 3
@@ -260,7 +273,7 @@ class StopLossStep(CashPenaltyStep):
         return step
 
 
-WORKLOADS = {w.name: w for w in (TradingStep, TradingRollout, NpStep, NpNas100Step, PortfolioStep, CashPenaltyStep, StopLossStep)}
+WORKLOADS = {w.name: w for w in (TradingStep, TradingRollout, TradingNas100Step, NpStep, NpNas100Step, PortfolioStep, CashPenaltyStep, StopLossStep)}
 
 
 def measured_peak():

@@ -1,6 +1,6 @@
 #!/bin/bash
 # every bench workload once, short, kernel time + roofline fraction per line
-for w in trading_step trading_rollout np_step np_nas100_step portfolio_step cashpenalty_step stoploss_step; do
+for w in trading_step trading_rollout trading_nas100_step np_step np_nas100_step portfolio_step cashpenalty_step stoploss_step; do
   python bench.py --workload $w --steps ${STEPS:-300} --warmup 10 --no-cpu --e2e-steps 3 2>&1 | tail -1 | python -c "
 import json,sys
 try:
