@@ -111,7 +111,7 @@ class TradingNas100Step(TradingStep):
     default_envs = 1 << 18
     # actions 400 + state 2*(8 cash + 400 hold + 4 day + 4 sday + 8 cost + 4 trades + 8 reward) + obs 4*401 + reward 8 + done 1
     bytes_per_env_step = 2885
-    kernel = "trading_small_kernel<16,float,1> (D > 32 always runs in the 8-lanes-per-env kernel)"
+    kernel = "trading_wide_kernel<float,2>"
 
     def describe(self, envs):
         return f"StockTradingEnv at NASDAQ-100 size, {envs} envs/GPU, D=100 K=2 T=2500 O=401, f32 actions, f32 obs"

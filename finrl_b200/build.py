@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libfinrl_b200.so")
-SOURCES = ["abi.cu", "trading.cu", "trading_small.cu", "nptrading.cu", "np_wide.cu", "portfolio.cu", "cashpenalty.cu", "preprocess.cu", "crypto.cu", "stoploss.cu"]
+SOURCES = ["abi.cu", "trading.cu", "trading_small.cu", "trading_wide.cu", "nptrading.cu", "np_wide.cu", "portfolio.cu", "cashpenalty.cu", "preprocess.cu", "crypto.cu", "stoploss.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static",

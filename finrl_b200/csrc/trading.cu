@@ -758,6 +758,18 @@ int trading_small_max()
     return g_small_max;
 }
 
+// D > 32: batches above this many envs run in the thread-per-env kernel of trading_wide.cu (keys and holdings in
+// shared memory), smaller ones in the 8-lanes-per-env kernel; frl_set_option("trading_wide_min_envs", v)
+int g_wide_min_envs = -1;
+int trading_wide_min_envs()
+{
+    if (g_wide_min_envs < 0) {
+        const char *m = getenv("FRL_TRADING_WIDE_MIN_ENVS");
+        g_wide_min_envs = m ? atoi(m) : 3072;  // measured crossover at D=100: 2048 -> 0.053 vs 0.070 ms, 4096 -> 0.108 vs 0.070
+    }
+    return g_wide_min_envs;
+}
+
 template <int SLOTS, int DCT, typename ActT, int WARPS>
 void launch_rollout(const frl_trading_params &p, const void *actions, long long sstride, long long estride, int n_steps,
                     double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats,
@@ -784,6 +796,11 @@ using namespace frl;
 extern "C" int32_t frl_set_option(const char *name, int64_t value)
 {
     FRL_REQUIRE(name != nullptr, "set_option: name is NULL");
+    if (!strcmp(name, "trading_wide_min_envs")) {
+        FRL_REQUIRE(value >= 0, "set_option: trading_wide_min_envs must be >= 0");
+        g_wide_min_envs = value > 0x7fffffff ? 0x7fffffff : (int)value;
+        return FRL_OK;
+    }
     if (!strcmp(name, "trading_small_max")) {
         FRL_REQUIRE(value >= 0, "set_option: trading_small_max must be >= 0");
         g_small_max = value > 0x7fffffff ? 0x7fffffff : (int)value;
@@ -842,6 +859,12 @@ extern "C" int32_t frl_trading_rollout(const frl_trading_params *p, const void *
     // Small batches are latency-bound in the thread-per-env kernel; below the measured crossover (~8K envs)
     // the 8-lanes-per-env kernel of trading_small.cu is faster (table in its header).
     // FRL_TRADING_KERNEL=tile|small forces one of them (tests run the whole parity suite under both).
+    if (p->stock_dim > 32 && p->n_envs > trading_wide_min_envs()) {
+        if (int32_t rc = launch_trading_wide(*p, actions, actions_f64, act_step_stride, act_env_stride, n_steps, rewards, flags,
+                                             obs, obs_mode, auto_reset, stats, st))
+            return rc;
+        return check_launch("trading_rollout(wide)");
+    }
     if (p->n_envs <= trading_small_max() || p->stock_dim > 32) {
         launch_trading_small(*p, actions, actions_f64, act_step_stride, act_env_stride, n_steps, rewards, flags, obs,
                              obs_mode, auto_reset, stats, st);

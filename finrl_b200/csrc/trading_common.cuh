@@ -31,4 +31,9 @@ void launch_trading_small(const frl_trading_params &p, const void *actions, int 
                           long long act_env_stride, int n_steps, double *rewards, uint8_t *flags, float *obs, int obs_mode,
                           int auto_reset, double *stats, cudaStream_t st);
 
+// host: the thread-per-env kernel for 33..128 stocks at large batches (defined in trading_wide.cu)
+int32_t launch_trading_wide(const frl_trading_params &p, const void *actions, int actions_f64, long long act_step_stride,
+                            long long act_env_stride, int n_steps, double *rewards, uint8_t *flags, float *obs, int obs_mode,
+                            int auto_reset, double *stats, cudaStream_t st);
+
 }  // namespace frl

@@ -62,6 +62,9 @@ extern "C" {
 FRL_API int32_t frl_abi_version(void);
 /* Tuning knobs.  "trading_small_max": frl_trading_step/rollout use the low-latency 8-lanes-per-env kernel
  * for n_envs <= value and the thread-per-env kernel above (default 8192, the measured crossover; 0 = never).
+ * "trading_wide_min_envs": for stock_dim > 32, batches above this many envs run in the thread-per-env kernel with
+ * keys / holdings in shared memory (trading_wide.cu), smaller ones in the 8-lanes-per-env kernel (default 3072,
+ * the measured crossover at D = 100).
  * "np_wide_min_d": frl_np_* stream stocks / cool-down from global memory (np_wide.cu) for stock_dim >= value
  * and keep them in registers below (1..33, default 33: the register kernel holds at most 32 stocks). */
 FRL_API int32_t frl_set_option(const char *name, int64_t value);
@@ -75,7 +78,8 @@ typedef struct frl_trading_params {
     int32_t n_envs;     /* N >= 1 */
     int32_t stock_dim;  /* D, 1..128 (np.argsort's network rule is pinned for n <= 256).  D <= 32
                            runs in the thread-per-env kernel (or the 8-lanes-per-env one for small batches),
-                           33..128 always in the 8-lanes-per-env kernel */
+                           33..128 in the 8-lanes-per-env kernel for small batches and in the thread-per-env
+                           kernel with shared-memory keys (trading_wide.cu) for large ones */
     int32_t n_tech;     /* K >= 0 */
     int32_t n_days;     /* T >= 1 = len(df.index.unique()) */
     int32_t obs_dim;    /* O = 1 + 2D + K*D (state_space) */

@@ -15,9 +15,10 @@ def test_trading_fuzz(seed, kernel):
     from oracle import oracle as ora
 
     _cabi.set_option("trading_small_max", 0 if kernel == "tile" else 2**31 - 1)
+    _cabi.set_option("trading_wide_min_envs", 0 if kernel == "tile" else 2**31 - 1)  # D > 32: wide vs 8 lanes
 
     rng = np.random.default_rng(1000 + seed)
-    D = int(rng.integers(1, 33)) if seed < 10 else int(rng.integers(33, 129))  # > 32 always runs 8 lanes per env
+    D = int(rng.integers(1, 33)) if seed < 10 else int(rng.integers(33, 129))  # > 32: thread-per-env wide kernel ("tile") or 8 lanes per env ("small")
     K = int(rng.integers(0, 5))
     T = int(rng.integers(4, 36))
     N = int(rng.choice([1, 31, 33, 100]))
@@ -50,6 +51,7 @@ def test_trading_fuzz(seed, kernel):
         if not auto and s % 7 == 6:
             assert np.array_equal(env.reset().cpu().numpy(), o.reset()), ctx
     _cabi.set_option("trading_small_max", 8192)
+    _cabi.set_option("trading_wide_min_envs", 3072)
 
 
 @pytest.mark.parametrize("seed", range(16))

@@ -15,15 +15,18 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-@pytest.fixture(autouse=True, params=["tile", "small"])
+@pytest.fixture(autouse=True, params=["tile", "small", "wide"])
 def trading_kernel(request):
-    """Every test of this file runs twice: with the thread-per-env kernel (trading.cu) and with the
-    8-lanes-per-env low-latency kernel (trading_small.cu) forced for all batch sizes."""
+    """Every test of this file runs three times: with the thread-per-env kernel (trading.cu; D > 32 falls to the
+    8-lanes-per-env one), with the 8-lanes-per-env low-latency kernel (trading_small.cu) forced for all batch
+    sizes, and with the thread-per-env kernels only (trading.cu for D <= 32, trading_wide.cu for D > 32)."""
     from finrl_b200 import _cabi
 
-    _cabi.set_option("trading_small_max", 0 if request.param == "tile" else 2**31 - 1)
-    yield request.param
+    _cabi.set_option("trading_small_max", 2**31 - 1 if request.param == "small" else 0)
+    _cabi.set_option("trading_wide_min_envs", 0 if request.param == "wide" else 2**31 - 1)
+    yield "tile" if request.param == "wide" else request.param
     _cabi.set_option("trading_small_max", 8192)
+    _cabi.set_option("trading_wide_min_envs", 3072)
 
 
 def _env_from_golden(g, n_envs=1):
