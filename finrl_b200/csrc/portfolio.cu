@@ -290,6 +290,15 @@ struct PfPairwise {
     }
 };
 
+__device__ __forceinline__ void pfw_cp_async(float *dst, const float *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pfw_cp_async(double *dst, const double *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 template <typename ActT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 portfolio_wide_kernel(const frl_portfolio_params p, const ActT *__restrict__ actions, long long act_step_stride,
@@ -322,11 +331,16 @@ portfolio_wide_kernel(const frl_portfolio_params p, const ActT *__restrict__ act
             const int cnt = nvalid * D;
             int row = 0, col = lane;
             while (col >= D) { col -= D; ++row; }
-            for (int e = lane; e < 32 * D; e += 32) {
-                stage[row * P + col] = e < cnt ? __ldcs(tile + e) : ActT(0);
+            for (int e = lane; e < 32 * D; e += 32) {  // cp.async: the whole tile in flight at once
+                ActT *dst = stage + row * P + col;
+                if (e < cnt)
+                    pfw_cp_async(dst, tile + e);
+                else
+                    *dst = ActT(0);
                 col += 32;
                 while (col >= D) { col -= D; ++row; }
             }
+            asm volatile("cp.async.commit_group;\ncp.async.wait_all;" ::: "memory");
         } else {
             for (int r = 0; r < 32; ++r)
                 for (int j = lane; j < D; j += 32)
