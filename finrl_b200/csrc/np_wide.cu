@@ -411,8 +411,10 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
             image_ok = true;
         }
         if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
-            if (!image_ok)
-                for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = sp[(size_t)j * ld];
+            if (!image_ok) {
+                for (int j = 0; j < D; ++j) npw_cp_async(reinterpret_cast<float *>(myrow + j), sp + (size_t)j * ld);
+                asm volatile("cp.async.commit_group;\ncp.async.wait_all;" ::: "memory");
+            }
             amountf[lane] = np_amount_obs(amount, p.obs_amount_floor);
             day_s[lane] = day;
             __syncwarp();
@@ -421,7 +423,9 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
             // [amount, turb, turb_bool, price, stocks * 2**-6 | cool-down, tech]: two phases through the one image
             npw_write_obs<ActT>(p, stage, P, amountf, day_s, o, env0, nvalid, lane, 0, c_beg, s_beg, 0.015625f);
             __syncwarp();
-            for (int j = 0; j < D; ++j) *reinterpret_cast<float *>(myrow + j) = cp[(size_t)j * ld];
+            // (cp.async: all D cool-down lines of the tile in flight at once instead of D dependent load+store pairs)
+            for (int j = 0; j < D; ++j) npw_cp_async(reinterpret_cast<float *>(myrow + j), cp + (size_t)j * ld);
+            asm volatile("cp.async.commit_group;\ncp.async.wait_all;" ::: "memory");
             __syncwarp();
             npw_write_obs<ActT>(p, stage, P, amountf, day_s, o, env0, nvalid, lane, c_beg, p.obs_dim, c_beg, 1.0f);
         }
