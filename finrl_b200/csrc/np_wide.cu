@@ -86,12 +86,11 @@ __device__ __forceinline__ void npw_write_obs_range(const frl_np_params &p, cons
 
 // Same range, all rows on one day and at most 16 chunks wide: the template values are loaded once into
 // registers and every row costs one (patched) store per chunk.
-template <typename ActT>
+template <typename ActT, int MAXC>
 __device__ __forceinline__ void npw_write_obs_range_uniform(const frl_np_params &p, const ActT *stage, int P, const float *amountf,
                                                             int day0, float *__restrict__ obs, long long env0, int nvalid, int lane,
                                                             int beg, int end, int img_beg, float img_mul)
 {
-    constexpr int MAXC = 16;
     const int O = p.obs_dim, D = p.stock_dim;
     constexpr int step = sizeof(ActT) / sizeof(float);
     const float *trow = p.obs_tmpl + (size_t)day0 * O;
@@ -139,8 +138,15 @@ __device__ __forceinline__ void npw_write_obs(const frl_np_params &p, const ActT
     bool uniform = true;
     if (lane < nvalid) uniform = day_s[lane] == day0;
     uniform = __all_sync(0xffffffffu, uniform);
-    if (uniform && end - beg <= 512)
-        npw_write_obs_range_uniform<ActT>(p, stage, P, amountf, day0, obs, env0, nvalid, lane, beg, end, img_beg, img_mul);
+    const int nch = (end - beg + 31) >> 5;  // chunk count compiled in (rounded up to 4 / 8 / 12 / 16)
+    if (uniform && nch <= 4)
+        npw_write_obs_range_uniform<ActT, 4>(p, stage, P, amountf, day0, obs, env0, nvalid, lane, beg, end, img_beg, img_mul);
+    else if (uniform && nch <= 8)
+        npw_write_obs_range_uniform<ActT, 8>(p, stage, P, amountf, day0, obs, env0, nvalid, lane, beg, end, img_beg, img_mul);
+    else if (uniform && nch <= 12)
+        npw_write_obs_range_uniform<ActT, 12>(p, stage, P, amountf, day0, obs, env0, nvalid, lane, beg, end, img_beg, img_mul);
+    else if (uniform && nch <= 16)
+        npw_write_obs_range_uniform<ActT, 16>(p, stage, P, amountf, day0, obs, env0, nvalid, lane, beg, end, img_beg, img_mul);
     else
         npw_write_obs_range<ActT>(p, stage, P, amountf, day_s, obs, env0, nvalid, lane, beg, end, img_beg, img_mul);
 }
