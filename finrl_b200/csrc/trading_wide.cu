@@ -48,32 +48,39 @@ __device__ __forceinline__ void cex_w(int *col, int lo, int hi)
 // sizes 2..16 are exactly the 16-slot network per group); only the flip stages of block size >= 32 and the
 // half-cleaners of distance >= 16 exchange through shared memory — 22 of the 28 stages of a 128-slot network
 // stay in registers.
-__device__ __forceinline__ void network_w(int *col, int slots)
+//
+// Pad slots (index >= D, key INT_MAX) never move: every compare-exchange is ascending (lo < hi, swap on strict
+// greater), a pad is never smaller than anything, and the pads start on top — so no real key ever enters a slot
+// >= D and any exchange whose upper slot is a pad is a no-op.  The column therefore only holds D keys.
+__device__ __forceinline__ void network_w(int *col, int slots, int D)
 {
-    for (int g = 0; g < slots; g += 16) {
+    for (int g = 0; g < D; g += 16) {
         int k[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) k[i] = col[(g + i) * kPitchW];
+        for (int i = 0; i < 16; ++i) k[i] = g + i < D ? col[(g + i) * kPitchW] : 0x7fffffff;
         FRL_SORT_NETWORK_16(FRL_CEXW, k)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) col[(g + i) * kPitchW] = k[i];
+        for (int i = 0; i < 16; ++i)
+            if (g + i < D) col[(g + i) * kPitchW] = k[i];
     }
     for (int blk = 32; blk <= slots; blk <<= 1) {
         const int half = blk >> 1;
-        for (int b = 0; b < slots; b += blk) {
+        for (int b = 0; b < D; b += blk) {
 #pragma unroll 4
-            for (int i = 0; i < half; ++i) cex_w(col, b + i, b + blk - 1 - i);
+            for (int i = 0; i < half; ++i)
+                if (b + blk - 1 - i < D) cex_w(col, b + i, b + blk - 1 - i);
         }
         for (int d = blk >> 2; d >= 16; d >>= 1) {
-            for (int b = 0; b < slots; b += 2 * d) {
+            for (int b = 0; b < D; b += 2 * d) {
 #pragma unroll 4
-                for (int i = 0; i < d; ++i) cex_w(col, b + i, b + i + d);
+                for (int i = 0; i < d; ++i)
+                    if (b + i + d < D) cex_w(col, b + i, b + i + d);
             }
         }
-        for (int g = 0; g < slots; g += 16) {
+        for (int g = 0; g < D; g += 16) {
             int k[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) k[i] = col[(g + i) * kPitchW];
+            for (int i = 0; i < 16; ++i) k[i] = g + i < D ? col[(g + i) * kPitchW] : 0x7fffffff;
 #pragma unroll
             for (int d = 8; d >= 1; d >>= 1) {
 #pragma unroll
@@ -81,7 +88,8 @@ __device__ __forceinline__ void network_w(int *col, int slots)
                     if ((i & d) == 0) FRL_CEXW(k[i], k[i + d])
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) col[(g + i) * kPitchW] = k[i];
+            for (int i = 0; i < 16; ++i)
+                if (g + i < D) col[(g + i) * kPitchW] = k[i];
         }
     }
 }
@@ -170,9 +178,9 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;
     const int slots = D <= 64 ? 64 : 128;
-    const size_t warp_ints = (size_t)(slots + D) * kPitchW + 64;
-    int *key = reinterpret_cast<int *>(tw_smem) + warp * warp_ints;  // [slots][33]
-    int *hold = key + (size_t)slots * kPitchW;                       // [D][33]
+    const size_t warp_ints = (size_t)(2 * D) * kPitchW + 64;
+    int *key = reinterpret_cast<int *>(tw_smem) + warp * warp_ints;  // [D][33] (pad slots are never stored)
+    int *hold = key + (size_t)D * kPitchW;                           // [D][33]
     float *cashf = reinterpret_cast<float *>(hold + (size_t)D * kPitchW);
     int *sd_s = reinterpret_cast<int *>(cashf + 32);
     const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
@@ -285,8 +293,7 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
                         kcol[j * kPitchW] = (sh << IBW) + j;
                     }
                 }
-                for (int j = D; j < slots; ++j) kcol[j * kPitchW] = 0x7fffffff;
-                network_w(kcol, slots);
+                network_w(kcol, slots, D);
                 const uint32_t *dis_row = p.disable_mask ? p.disable_mask + (size_t)sd * mask_words : nullptr;
 
                 // ---- sells, most negative first (:321-324, _sell_stock :102-135) ----
@@ -376,8 +383,7 @@ template <typename ActT, int WARPS>
 int32_t tw_launch(const frl_trading_params &p, const void *actions, long long sstride, long long estride, int n_steps, double *rewards,
                   uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
 {
-    const int slots = p.stock_dim <= 64 ? 64 : 128;
-    const size_t smem = (size_t)WARPS * ((size_t)(slots + p.stock_dim) * kPitchW + 64) * sizeof(int);
+    const size_t smem = (size_t)WARPS * ((size_t)(2 * p.stock_dim) * kPitchW + 64) * sizeof(int);
     auto kern = trading_wide_kernel<ActT, WARPS>;
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
