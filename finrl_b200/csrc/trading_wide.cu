@@ -296,42 +296,78 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
                 network_w(kcol, slots, D);
                 const uint32_t *dis_row = p.disable_mask ? p.disable_mask + (size_t)sd * mask_words : nullptr;
 
+                // Both loops are software-pipelined: the next order entry with its price, holding and disable bit is
+                // fetched before the current trade's dependent fp64 chain.
+                const int IM = (1 << IBW) - 1;
                 // ---- sells, most negative first (:321-324, _sell_stock :102-135) ----
-                for (int s = 0; s < D; ++s) {
-                    const int kk = kcol[s * kPitchW];
-                    if (kk >= 0) break;
-                    const int a = kk >> IBW, j = kk & ((1 << IBW) - 1);
-                    const int h = hcol[j * kPitchW];
-                    const bool dis = dis_row && ((__ldg(dis_row + (j >> 5)) >> (j & 31)) & 1u);
-                    if (!dis && h > 0) {
-                        const int m = min(-a, h);
-                        const double pv = dmul(__ldg(prow + j), (double)m);
-                        cash = dadd(cash, dmul(pv, one_minus_sc));
-                        hcol[j * kPitchW] = h - m;
-                        cost = dadd(cost, dmul(pv, p.sell_cost_pct));
-                        trades += 1;
+                {
+                    int kk = kcol[0];
+                    int j = kk & IM;
+                    double pj = __ldg(prow + j);
+                    int h = hcol[j * kPitchW];
+                    bool dis = dis_row && ((__ldg(dis_row + (j >> 5)) >> (j & 31)) & 1u);
+                    for (int s = 0; s < D; ++s) {
+                        if (kk >= 0) break;
+                        const int kn = kcol[min(s + 1, D - 1) * kPitchW];
+                        const int jn = kn & IM;
+                        const double pn = __ldg(prow + jn);
+                        const int hn = hcol[jn * kPitchW];  // another stock: not touched below
+                        const bool dn = dis_row && ((__ldg(dis_row + (jn >> 5)) >> (jn & 31)) & 1u);
+                        const int a = kk >> IBW;
+                        if (!dis && h > 0) {
+                            const int m = min(-a, h);
+                            const double pv = dmul(pj, (double)m);
+                            cash = dadd(cash, dmul(pv, one_minus_sc));
+                            hcol[j * kPitchW] = h - m;
+                            cost = dadd(cost, dmul(pv, p.sell_cost_pct));
+                            trades += 1;
+                        }
+                        kk = kn;
+                        j = jn;
+                        pj = pn;
+                        h = hn;
+                        dis = dn;
                     }
                 }
                 // ---- buys, largest first, each limited by the cash left (:328-330, _buy_stock :171-201) ----
-                for (int s = D - 1; s >= 0; --s) {
-                    const int kk = kcol[s * kPitchW];
-                    if (kk < (1 << IBW)) break;
-                    const int a = kk >> IBW, j = kk & ((1 << IBW) - 1);
-                    const bool dis = dis_row && ((__ldg(dis_row + (j >> 5)) >> (j & 31)) & 1u);
-                    if (!dis) {
-                        const double pj = __ldg(prow + j);
-                        const double unit = dmul(pj, one_plus_bc);
-                        double nsh = (double)a;
-                        trades += 1;  // even when 0 shares end up bought (Q5)
-                        if (!(cash >= dmul(nsh + 1.0, unit))) {
-                            if (cash >= 0.0 && cash < unit) continue;  // 0 shares: nothing changes
-                            const double avail = floor_div_f64(cash, unit);
-                            nsh = (nsh < avail) ? nsh : avail;
+                {
+                    int kk = kcol[(D - 1) * kPitchW];
+                    int j = kk & IM;
+                    double pj = __ldg(prow + j);
+                    double unit = dmul(pj, one_plus_bc);
+                    bool dis = dis_row && ((__ldg(dis_row + (j >> 5)) >> (j & 31)) & 1u);
+                    for (int s = D - 1; s >= 0; --s) {
+                        if (kk < (1 << IBW)) break;
+                        const int kn = kcol[max(s - 1, 0) * kPitchW];
+                        const int jn = kn & IM;
+                        const double pn = __ldg(prow + jn);
+                        const double un = dmul(pn, one_plus_bc);
+                        const bool dn = dis_row && ((__ldg(dis_row + (jn >> 5)) >> (jn & 31)) & 1u);
+                        const int a = kk >> IBW;
+                        if (!dis) {
+                            double nsh = (double)a;
+                            trades += 1;  // even when 0 shares end up bought (Q5)
+                            bool buy = true;
+                            if (!(cash >= dmul(nsh + 1.0, unit))) {
+                                if (cash >= 0.0 && cash < unit) {
+                                    buy = false;  // 0 shares: nothing changes
+                                } else {
+                                    const double avail = floor_div_f64(cash, unit);
+                                    nsh = (nsh < avail) ? nsh : avail;
+                                }
+                            }
+                            if (buy) {
+                                const double pv = dmul(pj, nsh);
+                                cash = dsub(cash, dmul(pv, one_plus_bc));
+                                hcol[j * kPitchW] += (int)nsh;
+                                cost = dadd(cost, dmul(pv, p.buy_cost_pct));
+                            }
                         }
-                        const double pv = dmul(pj, nsh);
-                        cash = dsub(cash, dmul(pv, one_plus_bc));
-                        hcol[j * kPitchW] += (int)nsh;
-                        cost = dadd(cost, dmul(pv, p.buy_cost_pct));
+                        kk = kn;
+                        j = jn;
+                        pj = pn;
+                        unit = un;
+                        dis = dn;
                     }
                 }
             }
