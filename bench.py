@@ -585,7 +585,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e through plain step() + copies instead of step_host()")
-    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--e2e-chunks", type=int, default=8)  # measured: 1 -> 42.2, 4 -> 45.2, 8 -> 45.6, 16 -> 45.7 M env-steps/s
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]()
     args.envs = args.envs or wl.default_envs
