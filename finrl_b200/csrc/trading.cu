@@ -30,7 +30,7 @@
 #define FRL_LOOP_PIPE 1  // software-pipelined sell / buy loops
 #endif
 #ifndef FRL_TRADING_MIN_BLOCKS
-#define FRL_TRADING_MIN_BLOCKS 4  // 128-thread blocks per SM the allocator must allow: 4 -> 128 regs, no remat (A/B: 6->0.43 ms, 5->0.39, 4->0.32, 3->0.37)
+#define FRL_TRADING_MIN_BLOCKS 5  // 128-thread blocks per SM the allocator must allow: 5 -> 96 regs, no spills.  A/B with the copy-engine obs writer: 3 -> 0.354 ms, 4 -> 0.297, 5 -> 0.290, 6 -> 0.301 (before it, 4 was best: the register template of the row writer spilled at 96)
 #endif
 
 namespace frl {
