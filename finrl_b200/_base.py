@@ -137,6 +137,20 @@ class BatchedEnvBase:
         self.launches += 1
         return self._shape_obs(out)
 
+    def clone_state_into(self, other):
+        """Copy every per-env state array of this engine into ``other`` (an engine of the same class and size
+        built on the same tables) — the device half of ``copy.deepcopy(env)`` that the reference's
+        ``get_sb_env`` performs (env_stocktrading_cashpenalty.py:374-380)."""
+        torch = self._torch
+        if type(other) is not type(self) or other.n_envs != self.n_envs:
+            raise ValueError("clone_state_into needs an engine of the same class and n_envs")
+        for name, v in vars(self).items():
+            w = vars(other).get(name)
+            if isinstance(v, torch.Tensor) and isinstance(w, torch.Tensor) and w.shape == v.shape \
+                    and w.dtype == v.dtype and w.data_ptr() != v.data_ptr():
+                w.copy_(v)
+        return other
+
     def _mask(self, mask):
         if mask is None:
             return None

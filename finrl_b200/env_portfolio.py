@@ -10,11 +10,11 @@ from __future__ import annotations
 import numpy as np
 
 from .portfolio import BatchedStockPortfolioEnv
-from .spaces import Box
-from .vec_env import BatchedVecEnv
+from .spaces import Box, gym_env_base
+from .vec_env import BatchedVecEnv, dummy_vec_env
 
 
-class StockPortfolioEnv:
+class StockPortfolioEnv(gym_env_base()):
     metadata = {"render.modes": ["human"]}
 
     def __init__(self, df, stock_dim, hmax, initial_amount, transaction_cost_pct, reward_scaling, state_space,
@@ -116,8 +116,10 @@ class StockPortfolioEnv:
         return [seed]
 
     def get_sb_env(self):
-        e = self.get_vec_env(1)
-        return e, e.reset()
+        """``DummyVecEnv([lambda: self])`` + first observation, as the reference (env_portfolio.py:258-261)."""
+        e = dummy_vec_env([lambda: self])
+        obs = e.reset()
+        return e, obs
 
     def get_vec_env(self, n_envs, tensor_mode=False):
         eng = BatchedStockPortfolioEnv(tables=self.engine.tables, n_envs=n_envs, device=self._device,

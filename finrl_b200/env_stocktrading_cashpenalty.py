@@ -3,18 +3,19 @@
 Same constructor and gym protocol as the reference class
 (/root/reference/finrl/meta/env_stock_trading/env_stocktrading_cashpenalty.py:19-409); ``step`` / ``reset``
 run on the GPU through a 1-env :class:`finrl_b200.cashpenalty.BatchedStockTradingEnvCashpenalty`.
-``get_sb_env`` / ``get_multiproc_env(n)`` return batched GPU VecEnvs instead of forking n processes.
+``get_sb_env`` is the reference's ``DummyVecEnv`` over a deep copy of this object; ``get_multiproc_env(n)``
+returns a batched GPU VecEnv of n envs instead of forking n processes.
 """
 from __future__ import annotations
 
 import numpy as np
 
 from .cashpenalty import BatchedStockTradingEnvCashpenalty
-from .spaces import Box
-from .vec_env import BatchedVecEnv
+from .spaces import Box, gym_env_base
+from .vec_env import BatchedVecEnv, _DeepCopyVecMixin
 
 
-class StockTradingEnvCashpenalty:
+class StockTradingEnvCashpenalty(_DeepCopyVecMixin, gym_env_base()):
     metadata = {"render.modes": ["human"]}
 
     def __init__(self, df, buy_cost_pct=3e-3, sell_cost_pct=3e-3, date_col_name="date", hmax=10, discrete_actions=False,
@@ -27,9 +28,10 @@ class StockTradingEnvCashpenalty:
                         initial_amount=initial_amount, daily_information_cols=list(daily_information_cols),
                         cache_indicator_data=cache_indicator_data, cash_penalty_proportion=cash_penalty_proportion,
                         random_start=random_start, patient=patient, currency=currency)
-        self.df, self._device = df, device
+        self._device = device
         self.engine = e = BatchedStockTradingEnvCashpenalty(df, n_envs=1, device=device, **self._kw)
         self.assets, self.dates = e.assets, e.dates
+        self.df = df.set_index(date_col_name)  # like the reference (:79): DRL_prediction counts df.index.unique()
         self.random_start, self.discrete_actions, self.patient, self.currency = random_start, discrete_actions, patient, currency
         self.shares_increment, self.hmax, self.initial_amount = shares_increment, hmax, initial_amount
         self.print_verbosity = print_verbosity
@@ -110,18 +112,16 @@ class StockTradingEnvCashpenalty:
         self.state_memory.append(state)
         return state, reward, False, {}
 
-    def get_sb_env(self):
-        e = self.get_vec_env(1)
-        return e, e.reset()
-
     def get_multiproc_env(self, n=10):
         e = self.get_vec_env(n)
         return e, e.reset()
 
     def get_vec_env(self, n_envs, tensor_mode=False):
+        return BatchedVecEnv(self._make_engine(n_envs), tensor_mode=tensor_mode)
+
+    def _make_engine(self, n_envs):
         kw = {k: v for k, v in self._kw.items() if k not in ("date_col_name",)}
-        eng = BatchedStockTradingEnvCashpenalty(tables=self.engine.tables, n_envs=n_envs, device=self._device, **kw)
-        return BatchedVecEnv(eng, tensor_mode=tensor_mode)
+        return BatchedStockTradingEnvCashpenalty(tables=self.engine.tables, n_envs=n_envs, device=self._device, **kw)
 
     def save_asset_memory(self):
         import pandas as pd

@@ -56,3 +56,14 @@ def vec_env_base():
         return VecEnv
     except Exception:
         return object
+
+
+def gym_env_base():
+    """``gym.Env`` (or gymnasium's) when importable, so the drop-in classes are real ``Env`` subclasses for
+    SB3's wrappers and type checks; ``object`` otherwise (none of them is installed in the build image)."""
+    for mod in ("gym", "gymnasium"):
+        try:
+            return __import__(mod).Env
+        except Exception:
+            continue
+    return object

@@ -248,8 +248,12 @@ class BatchedStockTradingEnv(BatchedEnvBase):
             dst.copy_(v.to(dst.dtype).reshape(dst.shape) if k != "hold" else v)
 
     def total_asset(self):
-        """cash + sum(price * holdings) with the prices currently in the state list (fp64, torch)."""
+        """cash + sum(price * holdings) with the prices currently in the state list, in the reference's order
+        (``state[0] + sum(prices * holdings)``: a sequential sum from 0, then the cash; fp64, exact per env)."""
         torch = self._torch
         sd = torch.where(self.sday < 0, -self.sday - 1, self.sday).long()
         prices = self.tables.close[sd, : self.stock_dim]  # [N, D]
-        return self.cash + (prices * self.hold.t().double()).sum(dim=1)
+        acc = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
+        for j in range(self.stock_dim):
+            acc = acc + prices[:, j] * self.hold[j].double()
+        return self.cash + acc

@@ -73,11 +73,11 @@ class _StubDummyVecEnv:
             infos.append(info)
         return self.buf_obs.copy(), rews, dones, infos
 
-    def env_method(self, name, *a, **k):
-        return [getattr(e, name)(*a, **k) for e in self.envs]
+    def env_method(self, method_name, *a, indices=None, **k):
+        return [getattr(e, method_name)(*a, **k) for e in self.envs]
 
-    def render(self):
-        return self.envs[0].render()
+    def render(self, mode="human"):
+        return self.envs[0].render(mode=mode)
 
 
 def _install_stubs():

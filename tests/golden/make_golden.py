@@ -294,6 +294,126 @@ def gen_crypto(name, T, D, K, n_steps, seed, act_dtype, lookback=1, initial_capi
           f"max stocks={out['stocks'].max():.3f}")
 
 
+# ------------------------------------------------------------------------------------------
+# adapter flows  (finrl/agents/stablebaselines3/models.py: DRL_prediction :110-130, ensemble :278-325)
+# ------------------------------------------------------------------------------------------
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import adapter_loops  # noqa: E402
+
+
+def _trading_env_kwargs(D, K, hmax, initial_amount, cost, threshold, risk_col):
+    return dict(stock_dim=D, hmax=hmax, initial_amount=initial_amount, num_stock_shares=[0] * D, buy_cost_pct=cost,
+                sell_cost_pct=cost, reward_scaling=1e-4, state_space=1 + 2 * D + K * D, action_space=D,
+                tech_indicator_list=syn.INDICATORS[:K], turbulence_threshold=threshold, risk_indicator_col=risk_col,
+                print_verbosity=10**9)
+
+
+def gen_adapter_trading_prediction(name, T, D, K, seed, threshold=70, hmax=100, initial_amount=200_000, cost=0.001):
+    """DRLAgent.DRL_prediction over the reference StockTradingEnv with a replayed action table."""
+    mod = ref_loader.load("env_stocktrading")
+    close, tech, turb = syn.make_tables(T, D, K, seed=seed)
+    df = syn.make_frame(close, tech, turb, risk_col="vix")
+    env = mod.StockTradingEnv(df=df, **_trading_env_kwargs(D, K, hmax, initial_amount, cost, threshold, "vix"))
+    actions = syn.make_actions((T, D), seed=seed + 1)
+    with _quiet():
+        df_account, df_actions = adapter_loops.drl_prediction(adapter_loops.ReplayModel(actions), env)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), close=close, tech=tech, risk=turb, actions=actions,
+        cfg=np.array([hmax, initial_amount, cost, threshold]),
+        account_date=np.array(df_account["date"].tolist(), dtype="U16"), account_value=df_account["account_value"].to_numpy(np.float64),
+        action_date=np.array(df_actions.index.tolist(), dtype="U16"), action_cols=np.array(list(df_actions.columns), dtype="U16"),
+        executed=df_actions.to_numpy(np.int64), **_meta())
+    print(f"{name}: account rows={len(df_account)}, action rows={df_actions.shape}, final={df_account['account_value'].iloc[-1]:.4f}")
+
+
+def gen_adapter_ensemble(name, W, D, K, seed, threshold=80, hmax=100, initial_amount=150_000, cost=0.001):
+    """Two consecutive trade windows of the ensemble agent: window 2 resumes from window 1's rendered state
+    (initial=False, previous_state=last_state).  The terminal branch writes its three CSVs into results/."""
+    import tempfile
+
+    mod = ref_loader.load("env_stocktrading")
+    close, tech, turb = syn.make_tables(2 * W, D, K, seed=seed)
+    kw = _trading_env_kwargs(D, K, hmax, initial_amount, cost, threshold, "turbulence")
+    actions = syn.make_actions((2 * W, D), seed=seed + 1)
+    out = {}
+    last_state, cwd = [], os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "results"))
+        os.chdir(tmp)
+        try:
+            for w in range(2):
+                sl = slice(w * W, (w + 1) * W)
+                df = syn.make_frame(close[sl], tech[:, sl], turb[sl])  # data_split re-indexes each window from 0
+                trace = {}
+                with _quiet():
+                    last_state = adapter_loops.ensemble_trade_window(
+                        sys.modules["stable_baselines3.common.vec_env"].DummyVecEnv, mod.StockTradingEnv, df,
+                        adapter_loops.ReplayModel(actions[sl]), last_state, w == 0, kw, "ens", 100 + w, trace)
+                out[f"w{w}_obs0"] = trace["obs0"]
+                out[f"w{w}_obs"] = np.asarray(trace["obs"], dtype=np.float32)
+                out[f"w{w}_rewards"] = np.asarray(trace["rewards"], dtype=np.float32)
+                out[f"w{w}_dones"] = np.asarray(trace["dones"], dtype=np.uint8)
+                out[f"w{w}_last_state"] = np.asarray(last_state, dtype=np.float64)
+                av = pd.read_csv(f"results/account_value_trade_ens_{100 + w}.csv")
+                rw = pd.read_csv(f"results/account_rewards_trade_ens_{100 + w}.csv")
+                ac = pd.read_csv(f"results/actions_trade_ens_{100 + w}.csv")
+                out[f"w{w}_csv_account_value"] = av["account_value"].to_numpy(np.float64)
+                out[f"w{w}_csv_daily_return"] = av["daily_return"].to_numpy(np.float64)
+                out[f"w{w}_csv_rewards"] = rw["account_rewards"].to_numpy(np.float64)
+                out[f"w{w}_csv_actions"] = ac.iloc[:, 1:].to_numpy(np.int64)
+                out[f"w{w}_csv_dates"] = np.array(av["date"].tolist(), dtype="U16")
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), close=close, tech=tech, risk=turb, actions=actions,
+                        cfg=np.array([hmax, initial_amount, cost, threshold, W]), **out, **_meta())
+    print(f"{name}: 2 windows x {W} days; w0 end cash={out['w0_last_state'][0]:.3f}, w1 first account value="
+          f"{out['w1_csv_account_value'][0]:.3f}, w1 last={out['w1_csv_account_value'][-1]:.3f}")
+
+
+def gen_adapter_portfolio_prediction(name, T, D, K, seed, lookback=60):
+    mod = ref_loader.load("env_portfolio")
+    close, tech, turb = syn.make_tables(T, D, K, seed=seed)
+    cov, first = syn.make_cov_table(close, lookback)
+    Te = T - first
+    df = syn.make_frame(close[first:], tech[:, first:], turb[first:])
+    df["cov_list"] = [cov[t] for t in range(Te) for _ in range(D)]
+    env = mod.StockPortfolioEnv(df=df, stock_dim=D, hmax=100, initial_amount=1_000_000, transaction_cost_pct=0.001,
+                                reward_scaling=1e-4, state_space=D, action_space=D, tech_indicator_list=syn.INDICATORS[:K])
+    actions = syn.make_actions((Te, D), seed=seed + 1, low=0.0, high=1.0)
+    os.makedirs("results", exist_ok=True)
+    with _quiet():
+        df_ret, df_w = adapter_loops.drl_prediction(adapter_loops.ReplayModel(actions), env)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), close=close[first:], tech=tech[:, first:], cov=cov, actions=actions,
+        ret_date=np.array(df_ret["date"].tolist(), dtype="U16"), daily_return=df_ret["daily_return"].to_numpy(np.float64),
+        weight_date=np.array(df_w.index.tolist(), dtype="U16"), weight_cols=np.array(list(df_w.columns), dtype="U16"),
+        weights=df_w.to_numpy(np.float64), **_meta())
+    print(f"{name}: return rows={len(df_ret)}, weights={df_w.shape}")
+
+
+def gen_adapter_cashpenalty_prediction(name, T, D, seed, hmax=5000, threshold=None):
+    mod = ref_loader.load("env_stocktrading_cashpenalty")
+    close, _tech, turb = syn.make_tables(T, D, 0, seed=seed)
+    o, h, l, v = syn.make_ohlv(close, seed)
+    df = syn.make_frame(close, np.zeros((0, T, D)), turb, tech_names=[], extra_cols={"open": o, "high": h, "low": l, "volume": v})
+    df = df.reset_index(drop=True)
+    actions = syn.make_actions((T, D), seed=seed + 1)
+    with _quiet():
+        env = mod.StockTradingEnvCashpenalty(df=df, hmax=hmax, turbulence_threshold=threshold, print_verbosity=10**9,
+                                             random_start=False, cache_indicator_data=True)
+        df_account, df_actions = adapter_loops.drl_prediction(adapter_loops.ReplayModel(actions), env)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), close=close, open=o, high=h, low=l, volume=v, turbulence=turb, actions=actions,
+        cfg=np.array([hmax, -1.0 if threshold is None else threshold]),
+        account_cols=np.array(list(df_account.columns), dtype="U16"),
+        account=df_account[["cash", "asset_value", "total_assets", "reward"]].to_numpy(np.float64),
+        account_date=np.array(df_account["date"].tolist(), dtype="U16"),
+        action_date=np.array(df_actions["date"].tolist(), dtype="U16"),
+        logged_actions=np.stack(df_actions["actions"].tolist()), transactions=np.stack(df_actions["transactions"].tolist()),
+        **_meta())
+    print(f"{name}: account rows={len(df_account)}, action rows={len(df_actions)}")
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     which = set(sys.argv[1:])
@@ -364,7 +484,15 @@ def main():
                    initial_capital=2e5, scales=[300.0, 1.5, 0.02, 45.0, 7000.0])
         gen_crypto("crypto_d8_lb3_f64", T=40, D=8, K=2, n_steps=80, seed=42, act_dtype=np.float64, lookback=3,
                    initial_capital=1e6, scales=[30000.0, 2000.0, 1.0, 0.5, 150.0, 20.0, 6.0, 0.08])
+    if want("adapter"):
+        gen_adapter_trading_prediction("adapter_trading_prediction", T=36, D=30, K=8, seed=71)
+        gen_adapter_ensemble("adapter_ensemble_two_windows", W=21, D=30, K=8, seed=72)
+        gen_adapter_portfolio_prediction("adapter_portfolio_prediction", T=60 + 20, D=12, K=3, seed=73)
+        gen_adapter_cashpenalty_prediction("adapter_cashpen_prediction", T=26, D=8, seed=74, threshold=85)
     if want("cashpenalty"):
+        # the BASELINE shape (config 5): 100 assets -> np.dot takes the blocked BLAS path
+        gen_cashpenalty("cashpen_d100_nasdaq", T=40, D=100, n_steps=85, seed=37, act_dtype=np.float32, hmax=2000,
+                        threshold=95)
         gen_cashpenalty("cashpen_d7_hmaxvec", T=30, D=7, n_steps=50, seed=35, act_dtype=np.float32,
                         hmax=np.linspace(2000.0, 8000.0, 7))
         gen_cashpenalty("cashpen_d5_hmaxvec_f32", T=24, D=5, n_steps=40, seed=36, act_dtype=np.float32,

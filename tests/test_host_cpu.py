@@ -142,6 +142,51 @@ def test_spaces_and_lazy_infos():
     assert [bool(i) for i in infos] == [False, False, False, True, False]
 
 
+def test_gym_vec_env_is_dummy_vec_env_protocol():
+    """GymVecEnv = SB3's DummyVecEnv over env OBJECTS: sequential stepping, float32 buffer, auto-reset with
+    terminal_observation, env_method/get_attr/render reaching the objects themselves (one entry per env)."""
+    from finrl_b200.spaces import Box
+    from finrl_b200.vec_env import GymVecEnv
+
+    class Counter:
+        def __init__(self, horizon):
+            self.observation_space, self.action_space = Box(-np.inf, np.inf, (3,)), Box(-1, 1, (2,))
+            self.horizon, self.t, self.log = horizon, 0, []
+
+        def reset(self):
+            self.t, self.log = 0, []
+            return [0.0, 0.0, float(self.horizon)]
+
+        def step(self, a):
+            self.t += 1
+            self.log.append(float(a[0]))
+            return [float(self.t), float(a[1]), float(self.horizon)], 0.5 * self.t, self.t >= self.horizon, {}
+
+        def render(self, mode="human"):
+            return ["state", self.t]
+
+        def memory(self, scale=1):
+            return [scale * x for x in self.log]
+
+    envs = [Counter(3), Counter(5)]
+    vec = GymVecEnv([lambda e=e: e for e in envs])
+    assert vec.num_envs == 2 and vec.envs[0] is envs[0]
+    obs = vec.reset()
+    assert obs.dtype == np.float32 and obs.shape == (2, 3)
+    for s in range(3):
+        obs, rews, dones, infos = vec.step(np.full((2, 2), s + 1.0, dtype=np.float32))
+    assert dones.tolist() == [True, False] and rews.dtype == np.float32 and rews.tolist() == [1.5, 1.5]
+    assert infos[0]["terminal_observation"] == [3.0, 3.0, 3.0] and infos[1] == {}
+    assert obs[0].tolist() == [0.0, 0.0, 3.0] and obs[1].tolist() == [3.0, 3.0, 5.0]  # env 0 was reset at once
+    assert vec.env_method("memory", scale=2) == [[], [2.0, 4.0, 6.0]]
+    assert vec.env_method(method_name="memory", indices=[1]) == [[1.0, 2.0, 3.0]]
+    assert vec.get_attr("horizon") == [3, 5] and vec.get_attr("t", indices=1) == [3]
+    vec.set_attr("horizon", 9, indices=[0])
+    assert envs[0].horizon == 9 and envs[1].horizon == 5
+    assert vec.render() == [["state", 0], ["state", 3]]
+    assert GymVecEnv([lambda: envs[1]]).render() == ["state", 3]  # one env: its own render(), as DummyVecEnv does
+
+
 def test_shard_range_partitions_exactly():
     from finrl_b200.dist import shard_range
 
