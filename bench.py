@@ -346,7 +346,7 @@ def _cpu_actions(wl, envs, n=4):
             for i in range(n)]
 
 
-def cpu_port_rate(wl, budget_s=12.0, envs=65536):
+def cpu_port_rate(wl, budget_s=12.0, envs=65536):  # callers pass the GPU arm's full per-GPU batch
     """Time the CPU oracle port on a bounded sample of the same workload.  Returns (env-steps/s,
     threads, description).  This is the one place bench.py executes oracle/."""
     from oracle import oracle as ora
@@ -370,6 +370,16 @@ def cpu_port_rate(wl, budget_s=12.0, envs=65536):
     return envs * steps / el, threads, f"{envs} envs x {steps} steps ({el:.1f} s), obs written, OpenMP static over envs"
 
 
+def workload_config(wl, envs, world):
+    """The `config` object both arms print: it names the workload and nothing arm-specific."""
+    big = wl.bytes_per_env_step * envs * wl.rollout_k > 2.5e8
+    return {
+        "workload": wl.describe(envs), "envs_per_gpu": envs, "env_steps_per_launch": envs * wl.rollout_k, "auto_reset": True,
+        "l2": ("per-step traffic exceeds the 126 MB L2 and consecutive steps use different action buffers; no explicit flush")
+              if big else "working set fits in L2 (latency-bound configuration); the roofline is quoted on the 1M-env workload",
+    }
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -377,199 +387,285 @@ def run_reference(args, wl):
     from oracle import oracle as ora
 
     threads = ora.set_threads(os.cpu_count() or 1)  # all host threads, even under torchrun's OMP_NUM_THREADS=1
-    envs = args.ref_envs
+    envs = args.ref_envs or args.envs  # by default the FULL per-GPU batch of the GPU arm (same config)
     step = wl.make_cpu(envs)
     pool = _cpu_actions(wl, envs)
-    # each "step" is one pass of the CPU port over a bounded sample of the workload
     for i in range(args.warmup):
         step(pool[i % 4])
     t0 = time.perf_counter()
     for i in range(args.steps):
         step(pool[i % 4])
     el = time.perf_counter() - t0
-    v = envs * args.steps / el
-    sample = f"{envs} envs per step (bounded sample of the {args.envs} envs/GPU workload), obs written"
+    v = envs * args.steps * wl.rollout_k / el
+    sample = (f"{envs} envs per step" + (" (the full per-GPU batch of the GPU arm)" if envs == args.envs else
+              f" (bounded sample of the {args.envs} envs/GPU workload)") + ", obs written")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl.describe(args.envs), "cpu_sample_envs": envs},
+        "config": workload_config(wl, args.envs, args.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "arm": {"cpu_envs_per_step": envs, "host_threads": threads},
+        "python_reference": PY_REFERENCE,
         "note": "the reference is pure Python (pandas/numpy) and cannot travel to the GPU box; this arm is its C "
-                "restatement (oracle/oracle.c) on all host threads. Survey-time numbers of the reference itself "
-                "(1 core): StockTradingEnv ~159, numpy env ~5.4k, portfolio ~930, cash-penalty ~4 env-steps/s.",
+                "restatement (oracle/oracle.c, pinned to the reference by tests/golden) on all host threads, on ONE GPU's "
+                "batch. `python_reference` holds the rates of the unmodified Python classes measured in the build container.",
     }))
+
+
+# the unmodified Python reference, measured in the build container (tools/time_reference_cpu.py ->
+# profiles/r02_reference_cpu_timing.txt); it cannot run on the GPU box (no /root/reference there)
+PY_REFERENCE = {
+    "where": "build container, 1 core per env", "unit": UNIT,
+    "StockTradingEnv_single_env": 159.0, "StockTradingEnv_DummyVecEnv_x8": None,
+    "env_stocktrading_np_single_env": 5400.0, "StockPortfolioEnv_single_env": 930.0, "Cashpenalty_single_env": 4.0,
+}
+_pyref = os.path.join(ROOT, "profiles", "python_reference_rates.json")
+if os.path.exists(_pyref):
+    try:
+        PY_REFERENCE.update(json.load(open(_pyref)))
+    except Exception:
+        pass
+
+
+def time_device(env, wl, pool, steps, warmup, world, ex, dist, torch, sampler=None):
+    """W warm-up launches, then K timed ones bracketed by CUDA events on the launching stream.  The ranks'
+    GPU timelines are aligned by a DEVICE-side collective enqueued right before the start event (a host
+    barrier leaves them up to a millisecond apart); nothing inside the timed loop waits for a peer."""
+    KR = wl.rollout_k
+    ev = []
+
+    def one(i):
+        if KR == 1:  # env.kernel_events: CUDA events recorded right around the C-ABI launch, on the launching stream
+            env.step(pool[i % len(pool)], auto_reset=True, want_obs=True, accumulate_stats=True, want_done=False)
+            return None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env.rollout(pool[i % len(pool)], obs_mode="last", auto_reset=True, accumulate_stats=True)
+        e1.record()
+        return e0, e1
+
+    for i in range(warmup):
+        one(i)
+    ex.flush()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.start()
+    launches0 = env.launches
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tick = torch.zeros(1, device=env.device)
+    if world > 1:
+        dist.all_reduce(tick)  # completes on all GPUs within microseconds of each other
+    if KR == 1:
+        env.kernel_events = ev
+    t_start.record()
+    for i in range(steps):
+        e = one(i)
+        if e is not None:
+            ev.append(e)
+        if (i + 1) % 16 == 0:
+            ex.flush()  # no-op with the fused peer exchange; side-stream all-reduce in the NCCL fallback
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler is not None else None
+    el = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=env.device)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    env.kernel_events = None
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    return float(el.item()), kernel_ms, env.launches - launches0, clocks
+
+
+def make_pool(wl, N, dev, torch, rank, n=3):
+    tdt = torch.float32 if wl.act_dtype == "float32" else torch.float64
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)  # every rank owns different envs, hence different actions
+    shape = (N, wl.D) if wl.rollout_k == 1 else (wl.rollout_k, N, wl.D)
+    span = wl.act_high - wl.act_low
+    return [(torch.rand(shape, generator=g, device=dev, dtype=tdt) * span + wl.act_low) for _ in range(n)], shape, tdt
 
 
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    from finrl_b200.dist import bind_cpu_affinity
+    from finrl_b200.dist import StatsExchange, init_from_env, shard_range
 
     all_cpus = os.sched_getaffinity(0)
-    numa_cpus = bind_cpu_affinity(local)  # pinned host buffers of the e2e leg land next to the GPU's PCIe root
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    N, D, KR = args.envs, wl.D, wl.rollout_k
-    env = wl.make_env(dev, N)  # tables replicated per GPU, envs sharded by index
-    tdt = torch.float32 if wl.act_dtype == "float32" else torch.float64
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)  # every rank owns different envs, hence different actions
-    POOL = 3
-    shape = (N, D) if KR == 1 else (KR, N, D)
-    span = wl.act_high - wl.act_low
-    pool = [(torch.rand(shape, generator=g, device=dev, dtype=tdt) * span + wl.act_low) for _ in range(POOL)]
-    stats_global = torch.zeros_like(env.stats)
-    ev_list = []
+    rank, world, local = init_from_env()  # binds the GPU and its NUMA-local CPUs, creates the NCCL group
+    numa_cpus = len(os.sched_getaffinity(0))
+    dev = torch.device("cuda", local)
+    start, N = shard_range(args.envs * world, rank, world)  # env-index sharding: this rank owns [start, start+N)
+    KR = wl.rollout_k
+    env = wl.make_env(dev, N)  # tables replicated per GPU
+    ex = StatsExchange(dev)    # the only exchange on the path: 64 B of statistics, pushed by the kernels' epilogue
+    ex.attach(env)
+    pool, shape, tdt = make_pool(wl, N, dev, torch, rank)
+    POOL = len(pool)
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
 
-    if KR == 1:
-        def one_step(i):
-            env.step(pool[i % POOL], auto_reset=True, want_obs=True, accumulate_stats=True, want_done=False)
-    else:
-        def one_step(i):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            env.rollout(pool[i % POOL], obs_mode="last", auto_reset=True, accumulate_stats=True)
-            e1.record()
-            ev_list.append((e0, e1))
-
-    def reduce_stats():
-        # the only collective on the path: 64 B of episode-return / asset statistics over NVLink
-        stats_global.copy_(env.stats)
-        if world > 1:
-            dist.all_reduce(stats_global)
-
-    for i in range(args.warmup):
-        one_step(i)
-    reduce_stats()
-    barrier()
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = env.launches
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if KR == 1:
-        env.kernel_events = []  # CUDA events right around every kernel launch, on the launching stream
-    ev_list.clear()
-    barrier()
-    t_start.record()
-    for i in range(args.steps):
-        one_step(i)
-        if (i + 1) % 16 == 0 or i == args.steps - 1:
-            reduce_stats()
-    t_end.record()
-    barrier()
-    clocks = sampler.stop()
-    elapsed_ms = t_start.elapsed_time(t_end)
-    events = env.kernel_events if KR == 1 else ev_list
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in events]))
-    env.kernel_events = None
-    launches = env.launches - launches0
-    el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(el.item())
+    elapsed_ms, kernel_ms, launches, clocks = time_device(env, wl, pool, args.steps, args.warmup, world, ex, dist, torch,
+                                                          ClockSampler(local))
     value = N * world * args.steps * KR / (elapsed_ms * 1e-3)
+    totals = ex.totals()
 
-    # ---- end to end through the numpy-facing call: host actions in, host obs/reward/flags out ----
-    OBS = wl.obs_numel(env)
-    h_act = [torch.empty(shape, dtype=tdt).pin_memory() for _ in range(POOL)]
-    for h, d in zip(h_act, pool):
+    # ---- end to end through the host-buffer call: pinned host actions in, host obs/reward/flags out -------
+    e2e = {}
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    h_act_pool = [torch.empty(shape, dtype=tdt).pin_memory() for _ in range(POOL)]
+    for h, d in zip(h_act_pool, pool):
         h.copy_(d)
-    h_obs = torch.empty((N, OBS), dtype=torch.float32).pin_memory()
-    rshape = (N,) if KR == 1 else (KR, N)
-    h_rew = torch.empty(rshape, dtype=torch.float64).pin_memory()
-    h_flag = torch.empty(rshape, dtype=torch.uint8).pin_memory()
-    d_act = torch.empty(shape, dtype=tdt, device=dev)
-
     use_pipelined = hasattr(env, "step_host") and KR == 1 and not args.no_pipeline
 
-    def e2e_step(i):
-        if use_pipelined:  # chunked H2D / kernel / D2H over three streams (BatchedStockTradingEnv.step_host)
-            env.step_host(h_act[i % POOL], h_obs, h_rew, h_flag, auto_reset=True, n_chunks=args.e2e_chunks)
-            return
-        d_act.copy_(h_act[i % POOL], non_blocking=True)
-        if KR == 1:
-            obs, rew, _, fl = env.step(d_act, auto_reset=True, want_obs=True, want_done=False)
-        else:
-            obs, rew, fl = env.rollout(d_act, obs_mode="last", auto_reset=True, accumulate_stats=False)
-        h_obs.copy_(obs.reshape(N, OBS), non_blocking=True)
-        h_rew.copy_(rew, non_blocking=True)
-        h_flag.copy_(fl, non_blocking=True)
-        torch.cuda.synchronize()  # the caller reads numpy arrays after every step
+    def time_e2e(fn):
+        for i in range(3):
+            fn(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            fn(i)
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return N * world * e2e_steps * KR / float(t.item())
 
-    e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    barrier()
-    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = N * world * e2e_steps * KR / float(e2e_t.item())
-    h2d = d_act.numel() * d_act.element_size()
-    d2h = h_obs.numel() * 4 + h_rew.numel() * 8 + h_flag.numel()
+    if use_pipelined:
+        _, h_obs, h_rew, h_flag = env.make_host_buffers("dense", tdt)
+        dense = time_e2e(lambda i: env.step_host(h_act_pool[i % POOL], h_obs, h_rew, h_flag, auto_reset=True,
+                                                 n_chunks=args.e2e_chunks))
+        h2d = h_act_pool[0].numel() * h_act_pool[0].element_size()
+        e2e = {"value": dense, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": h_obs.numel() * 4 + h_rew.numel() * 8 + h_flag.numel(), "steps": e2e_steps,
+               "layout": "dense",
+               "api": ("BatchedStockTradingEnv.step_host: pinned host actions in, dense obs[N,O] + reward + flags back to "
+                       f"pinned host memory, pipelined in {args.e2e_chunks} env slices over 3 streams")}
+        del h_obs
+        _, f_obs, h_rew, h_flag = env.make_host_buffers("factored", tdt)
+        fact = time_e2e(lambda i: env.step_host(h_act_pool[i % POOL], f_obs, h_rew, h_flag, auto_reset=True,
+                                                n_chunks=args.e2e_chunks))
+        d2h_f = f_obs.env_part.numel() * 4 + f_obs.state_day.numel() * 4 + h_rew.numel() * 8 + h_flag.numel()
+        e2e["factored"] = {
+            "value": fact, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_f,
+            "api": "step_host(obs=FactoredObs): env_part[N,1+D] f32 + state_day[N] i32 + reward + flags come back; the "
+                   "[T,O] per-day template stays pinned on the host (FactoredObs[n] / .dense() rebuild rows bit-exactly)"}
+        if args.e2e_expand:
+            dense_out = np.empty((N, env.state_space), dtype=np.float32)
+
+            def fexp(i):
+                env.step_host(h_act_pool[i % POOL], f_obs, h_rew, h_flag, auto_reset=True, n_chunks=args.e2e_chunks)
+                f_obs.dense(out=dense_out)
+
+            e2e["factored_expanded_on_host"] = {
+                "value": time_e2e(fexp), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_f,
+                "api": "factored transfer + FactoredObs.dense(out) on all host threads: a dense [N,O] host array again"}
+    else:
+        OBS = wl.obs_numel(env)
+        h_obs = torch.empty((N, OBS), dtype=torch.float32).pin_memory()
+        rshape = (N,) if KR == 1 else (KR, N)
+        h_rew = torch.empty(rshape, dtype=torch.float64).pin_memory()
+        h_flag = torch.empty(rshape, dtype=torch.uint8).pin_memory()
+        d_act = torch.empty(shape, dtype=tdt, device=dev)
+
+        def plain(i):
+            d_act.copy_(h_act_pool[i % POOL], non_blocking=True)
+            if KR == 1:
+                obs, rew, _, fl = env.step(d_act, auto_reset=True, want_obs=True, want_done=False)
+            else:
+                obs, rew, fl = env.rollout(d_act, obs_mode="last", auto_reset=True, accumulate_stats=False)
+            h_obs.copy_(obs.reshape(N, OBS), non_blocking=True)
+            h_rew.copy_(rew, non_blocking=True)
+            h_flag.copy_(fl, non_blocking=True)
+            torch.cuda.synchronize()  # the caller reads numpy arrays after every step
+
+        e2e = {"value": time_e2e(plain), "unit": UNIT, "h2d_bytes_per_step": d_act.numel() * d_act.element_size(),
+               "d2h_bytes_per_step": h_obs.numel() * 4 + h_rew.numel() * 8 + h_flag.numel(), "steps": e2e_steps,
+               "layout": "dense",
+               "api": "Batched*Env.step/rollout with pinned host actions in; obs + reward + flags copied back to host"}
+
+    # ---- the other BASELINE configs, short runs in the same process (every N, so SCALE sees them) ---------
+    peak, peak_src = measured_peak()
+    workloads = {}
+    if args.workload == "trading_step" and not args.no_extra:
+        del env, pool, h_act_pool
+        torch.cuda.empty_cache()
+        for name in EXTRA_WORKLOADS:
+            w2 = WORKLOADS[name]()
+            n2 = w2.default_envs
+            env2 = w2.make_env(dev, n2)
+            ex.attach(env2)
+            pool2, _, _ = make_pool(w2, n2, dev, torch, rank)
+            ms, kms, _, _ = time_device(env2, w2, pool2, args.extra_steps, 5, world, ex, dist, torch)
+            ach = w2.bytes_per_env_step * n2 * w2.rollout_k / (kms * 1e-3) / 1e9
+            workloads[name] = {
+                "value": n2 * world * args.extra_steps * w2.rollout_k / (ms * 1e-3), "unit": UNIT, "envs_per_gpu": n2,
+                "steps": args.extra_steps, "kernel_ms": kms, "ms_per_step": ms / args.extra_steps,
+                "algorithmic_bytes": w2.bytes_per_env_step * n2 * w2.rollout_k, "achieved_gbs": ach, "frac": ach / peak,
+                "kernel": w2.kernel, "workload": w2.describe(n2)}
+            del env2, pool2
+            torch.cuda.empty_cache()
+        ex.totals(reset=True)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         achieved = wl.bytes_per_env_step * N * KR / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
                 traffic = json.load(open(tp)).get(wl.name + "_dram_bytes_per_launch")
+                traffic_src = "ncu --set full capture (profiles/roofline_traffic.json), not measured in this run"
             except Exception:
                 traffic = None
-        big = wl.bytes_per_env_step * N * KR > 2.5e8
+        cfg = workload_config(wl, N, world)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": wl.describe(N), "envs_per_gpu": N, "total_envs": N * world, "env_steps_per_launch": N * KR,
-                "l2": ("per-step traffic exceeds the 126 MB L2 and consecutive steps use different action buffers; "
-                       "no explicit flush") if big else
-                      "working set fits in L2 (latency-bound configuration); the roofline is quoted on the 1M-env workload",
-                "parallelism": f"env-index sharding x{world}, tables replicated, NCCL all-reduce of 64 B stats every 16 steps",
-                "auto_reset": True,
-            },
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "arm": {"total_envs": N * world,
+                    "parallelism": f"env-index sharding x{world} (finrl_b200.dist.shard_range), tables replicated; statistics "
+                                   f"exchange: {ex.mode}" + (" (fused into the step kernel's epilogue: fp64 atomics into every "
+                                   "rank's peer-mapped totals, no collective launch)" if ex.mode == "p2p" else
+                                   f" (fallback: {getattr(ex, 'fallback_reason', None)})"),
+                    "timeline_alignment": "device-side all-reduce right before the start event" if world > 1 else "single GPU"},
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8000": achieved / 8000.0,
-                "traffic": traffic, "peak_source": peak_src, "kernel": wl.kernel, "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_env_step": wl.bytes_per_env_step,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": wl.kernel,
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": wl.bytes_per_env_step,
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": ("BatchedStockTradingEnv.step_host: pinned host actions in, obs + reward + flags back to pinned host "
-                            f"memory, pipelined in {args.e2e_chunks} env slices over 3 streams") if use_pipelined else
-                           "Batched*Env.step/rollout with pinned host actions in; obs + reward + flags copied back to host"},
+            "e2e": e2e,
             "gpu_launches": launches,
             "host": {"cpus": len(all_cpus), "cpus_bound_to_gpu_numa": numa_cpus},
             "clocks": clocks,
             "stats": dict(zip(("reward_sum", "reward_sqsum", "done_count", "episode_asset_sum", "asset_sum", "liq_count",
-                               "env_steps", "slot7"), stats_global.tolist())),
+                               "env_steps", "trades_sum"), totals)),
         }
+        if workloads:
+            out["workloads"] = workloads
         if world == 1 and not args.no_cpu:
-            v, cores, sample = cpu_port_rate(wl, args.cpu_seconds)
+            v, cores, sample = cpu_port_rate(wl, args.cpu_seconds, args.ref_envs or args.envs)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            out["python_reference"] = PY_REFERENCE
         print(json.dumps(out))
+    ex.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+EXTRA_WORKLOADS = ("trading_rollout", "np_step", "portfolio_step", "cashpenalty_step")
 
 
 def main():
@@ -580,7 +676,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="trading_step", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU")
-    ap.add_argument("--ref-envs", type=int, default=65536, help="envs per step of the CPU reference arm")
+    ap.add_argument("--ref-envs", type=int, default=None, help="envs per step of the CPU arms (default: the GPU arm's envs per GPU)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--extra-steps", type=int, default=20)
+    ap.add_argument("--e2e-expand", action="store_true", help="also time factored transfer + host-side expansion to dense")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
@@ -591,7 +690,7 @@ def main():
     args.envs = args.envs or wl.default_envs
     args.warmup = max(args.warmup, 3)
     if args.steps is None:
-        args.steps = 200 if args.impl == "reference" else 2000
+        args.steps = 25 if args.impl == "reference" else 2000
     if args.impl == "reference":
         run_reference(args, wl)
     else:

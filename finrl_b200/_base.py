@@ -78,7 +78,7 @@ class BatchedEnvBase:
             rc = self._fn("step")(
                 C.byref(self._p), _cabi.ptr(a), int(a.dtype == torch.float64), _cabi.ptr(self._reward_out()),
                 _cabi.ptr(self._flags), _cabi.ptr(obs), int(auto_reset),
-                _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
+                self._stats_arg() if accumulate_stats else None, self._stream(),
             )
             if ev is not None:
                 e1.record()
@@ -122,7 +122,7 @@ class BatchedEnvBase:
                 self._fn("rollout")(
                     C.byref(self._p), _cabi.ptr(a), int(a.dtype == torch.float64), step_stride, env_stride, int(K),
                     _cabi.ptr(rewards), _cabi.ptr(flags), _cabi.ptr(obs) if mode else None, mode, int(auto_reset),
-                    _cabi.ptr(self.stats) if accumulate_stats else None, self._stream(),
+                    self._stats_arg() if accumulate_stats else None, self._stream(),
                 ),
                 f"{self._PREFIX}_rollout",
             )
@@ -145,6 +145,8 @@ class BatchedEnvBase:
         if type(other) is not type(self) or other.n_envs != self.n_envs:
             raise ValueError("clone_state_into needs an engine of the same class and n_envs")
         for name, v in vars(self).items():
+            if name in ("stats", "_stats_block", "_stats_total"):
+                continue  # statistics (and a peer binding) belong to the engine they were attached to
             w = vars(other).get(name)
             if isinstance(v, torch.Tensor) and isinstance(w, torch.Tensor) and w.shape == v.shape \
                     and w.dtype == v.dtype and w.data_ptr() != v.data_ptr():
@@ -159,8 +161,37 @@ class BatchedEnvBase:
             raise ValueError("mask must have shape [n_envs]")
         return m
 
+    _STAT7_NAME = _cabi.STAT_NAMES[7]
+
+    def use_stats_block(self, block, alternate: bool = False):
+        """Accumulate into ``block`` (a 48-double frl_stats_block on this device) instead of the engine's own;
+        :class:`finrl_b200.dist.StatsExchange` hands every rank's engine a peer-mapped block this way, with
+        ``alternate=True``: consecutive launches then use the block's two accumulators in turn and each launch
+        pushes the previous one's sums to the peers (frl_stats_block in the header)."""
+        if block.numel() != _cabi.STATS_BLOCK_DOUBLES or block.dtype != self._torch.float64 or not block.is_cuda \
+                or block.data_ptr() % 128:
+            raise ValueError("use_stats_block needs a 128-byte-aligned float64 CUDA tensor of 48 elements")
+        self._stats_block = block
+        self.stats = block[: _cabi.N_STATS]
+        self._stats_alternate = alternate
+        self._stats_turn = 0
+
+    def _stats_arg(self):
+        """The accumulator this launch adds into: sum[0], or sum[0] / sum[1] in turn under an exchange."""
+        if not getattr(self, "_stats_alternate", False):
+            return _cabi.ptr(self.stats)
+        t = self._stats_turn
+        self._stats_turn = t ^ 1
+        return C.c_void_p(self._stats_block.data_ptr() + 64 * t)
+
     def read_stats(self, reset: bool = False):
-        vals = self.stats.tolist()
+        """The statistics accumulated in this engine's block as a dict: both accumulators plus, under an exchange,
+        the totals that already arrived (all ranks' launches); ``StatsExchange.totals()`` is the synchronised read."""
+        n = _cabi.N_STATS
+        blk = self._stats_block
+        vals = (blk[:n] + blk[n : 2 * n] + blk[2 * n : 3 * n]).tolist()
         if reset:
-            self.stats.zero_()
-        return dict(zip(_cabi.STAT_NAMES, vals))
+            blk[: 3 * n].zero_()
+        names = list(_cabi.STAT_NAMES)
+        names[7] = self._STAT7_NAME
+        return dict(zip(names, vals))

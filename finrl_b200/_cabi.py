@@ -21,7 +21,8 @@ N_STATS = 8
 STAT_NAMES = ("reward_sum", "reward_sqsum", "done_count", "episode_asset_sum", "asset_sum", "liq_count", "env_steps",
               "trades_sum")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
+STATS_BLOCK_DOUBLES = 48  # frl_stats_block: 384 bytes = sum[2][8], total[8], peer_total[8], n_peers, reserved
 
 
 class EngineError(RuntimeError):
@@ -239,6 +240,9 @@ SIGNATURES = {
     "frl_trading_init": (C.c_int32, [C.POINTER(TradingParams), C.c_int32, C.c_void_p]),
     "frl_trading_reset": (C.c_int32, [C.POINTER(TradingParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "frl_trading_observe": (C.c_int32, [C.POINTER(TradingParams), C.c_void_p, C.c_void_p]),
+    "frl_trading_observe_factored": (C.c_int32, [C.POINTER(TradingParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "frl_expand_obs_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_void_p, C.c_int32]),
     "frl_trading_rollout": (
         C.c_int32,
         [C.POINTER(TradingParams), C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
@@ -309,6 +313,13 @@ SIGNATURES = {
         [C.POINTER(CryptoParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
          C.c_void_p],
     ),
+    "frl_exchange_alloc": (C.c_int32, [C.POINTER(C.c_void_p)]),
+    "frl_exchange_free": (C.c_int32, [C.c_void_p]),
+    "frl_exchange_export": (C.c_int32, [C.c_void_p, C.c_char_p]),
+    "frl_exchange_open": (C.c_int32, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "frl_exchange_close": (C.c_int32, [C.c_void_p]),
+    "frl_exchange_bind": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    "frl_exchange_flush": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "frl_rolling_cov": (
         C.c_int32,
         [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -358,3 +369,18 @@ def current_stream(device):
     import torch
 
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def new_stats_block(torch, device):
+    """A zeroed frl_stats_block (48 doubles, its own 512-byte-aligned torch allocation): ``block[:8]`` and
+    ``block[8:16]`` are the two accumulators the kernels add into, ``block[16:24]`` the exchange totals."""
+    return torch.zeros(STATS_BLOCK_DOUBLES, dtype=torch.float64, device=device)
+
+
+class _DevicePointerView:
+    """``__cuda_array_interface__`` over a raw device pointer, so torch can view memory this library
+    allocated with cudaMalloc (the IPC-exportable statistics blocks)."""
+
+    def __init__(self, pointer: int, n_doubles: int):
+        self.__cuda_array_interface__ = {"shape": (n_doubles,), "typestr": "<f8", "data": (int(pointer), False),
+                                         "version": 2, "strides": None}

@@ -76,6 +76,7 @@ class BatchedStockTradingEnvCashpenalty(BatchedEnvBase):
     ``rollout`` / ``observe`` come from :class:`BatchedEnvBase`."""
 
     _PREFIX = "frl_cashpenalty"
+    _STAT7_NAME = "shortage_count"
     _ACTION_NAME = "n_assets"
 
     def __init__(self, df=None, buy_cost_pct=3e-3, sell_cost_pct=3e-3, date_col_name="date", hmax=10,
@@ -113,7 +114,8 @@ class BatchedStockTradingEnvCashpenalty(BatchedEnvBase):
         self.last_cash = torch.empty(N, dtype=torch.float64, device=dev)
         self.last_total = torch.empty(N, dtype=torch.float64, device=dev)
         self.sum_trades = torch.empty(N, dtype=torch.float64, device=dev)
-        self.stats = torch.zeros(_cabi.N_STATS, dtype=torch.float64, device=dev)
+        self._stats_block = _cabi.new_stats_block(torch, dev)
+        self.stats = self._stats_block[:_cabi.N_STATS]
         self._obs = torch.empty((N, O), dtype=torch.float32, device=dev)
         self._rew = torch.empty(N, dtype=torch.float64, device=dev)
         self._flags = torch.empty(N, dtype=torch.uint8, device=dev)
@@ -170,11 +172,3 @@ class BatchedStockTradingEnvCashpenalty(BatchedEnvBase):
             )
         self.launches += 2
         return out
-
-    def read_stats(self, reset=False):
-        vals = self.stats.tolist()
-        if reset:
-            self.stats.zero_()
-        names = list(_cabi.STAT_NAMES)
-        names[7] = "shortage_count"
-        return dict(zip(names, vals))

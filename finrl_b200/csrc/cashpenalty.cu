@@ -95,6 +95,7 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
                            uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode, int auto_reset,
                            double *__restrict__ stats)
 {
+    stats_exchange_previous(stats);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;

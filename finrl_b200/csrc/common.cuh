@@ -89,6 +89,35 @@ __device__ __forceinline__ void reduce_stats8(double (&v)[FRL_N_STATS], int lane
     if (lane < 8 && s != 0.0) atomicAdd(stats + lane, s);
 }
 
+// One-sided multi-GPU exchange fused into the step kernels (frl_stats_block in the header).  `stats` is one of
+// the block's two accumulators; the caller alternates them launch by launch, so the OTHER one holds the previous
+// launch's sums, complete by stream order.  The first thread of the grid adds those to total[] of every rank over
+// NVLink (fp64 atomics on peer-mapped memory, fire and forget) and clears them.  No counter, no fence, no
+// rendezvous: measured cost on the 1M-env StockTradingEnv step: none (a completion ticket per warp or per block,
+// the textbook last-block pattern, cost 4-8 % there — the kernel is latency-bound and every fence + atomic round
+// trip sits on a warp's critical path; tools/ab_stats_tail.sh, profiles/r02_ab_stats_exchange.txt).
+__device__ __forceinline__ void stats_push_accumulator(frl_stats_block *b, int which)
+{
+    const unsigned n_peers = b->n_peers;
+    if (n_peers == 0) return;
+#pragma unroll
+    for (int s = 0; s < FRL_N_STATS; ++s) {
+        const double v = __longlong_as_double(
+            (long long)atomicExch(reinterpret_cast<unsigned long long *>(&b->sum[which][s]), 0ull));
+        if (v != 0.0)
+            for (unsigned r = 0; r < n_peers; ++r) atomicAdd_system(b->peer_total[r] + s, v);
+    }
+}
+
+// Called by every thread at the top of a step / rollout kernel (before any early return).
+__device__ __forceinline__ void stats_exchange_previous(double *__restrict__ stats)
+{
+    if (stats == nullptr || blockIdx.x != 0 || threadIdx.x != 0) return;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(stats);
+    const int which = (int)((a >> 6) & 1);  // blocks are 128-byte aligned: sum[0] at +0, sum[1] at +64
+    stats_push_accumulator(reinterpret_cast<frl_stats_block *>(a - 64 * which), which ^ 1);
+}
+
 // ---- action staging -------------------------------------------------------------------------------
 // Stage one step's actions of a 32-env tile into shared memory, flat [32 envs][D] exactly as they lie in
 // global memory.  With the default layout (act_env_stride == D) the tile is one contiguous run: D fully

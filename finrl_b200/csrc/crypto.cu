@@ -82,6 +82,7 @@ crypto_rollout_kernel(const frl_crypto_params p, const ActT *__restrict__ action
                       long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
                       float *__restrict__ obs, int obs_mode, int auto_reset, double *__restrict__ stats)
 {
+    stats_exchange_previous(stats);
     using SM = CryptoWarpSmem<SLOTS, ActT>;
     __shared__ SM smem[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

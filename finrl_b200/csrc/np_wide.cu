@@ -157,6 +157,7 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
                int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode,
                int auto_reset, double *__restrict__ stats)
 {
+    stats_exchange_previous(stats);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;

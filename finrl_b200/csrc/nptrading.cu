@@ -178,6 +178,7 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
                   long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
                   float *__restrict__ obs, int obs_mode, int auto_reset, double *__restrict__ stats)
 {
+    stats_exchange_previous(stats);
     using SM = NpWarpSmem<SLOTS, ActT>;
     __shared__ SM smem[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

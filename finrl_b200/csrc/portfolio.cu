@@ -162,6 +162,7 @@ portfolio_rollout_kernel(const frl_portfolio_params p, const ActT *__restrict__ 
                          uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode, int auto_reset,
                          double *__restrict__ stats, int img_rows)
 {
+    stats_exchange_previous(stats);
     using SM = PfWarpSmem<SLOTS, ActT>;
     __shared__ SM smem[WARPS];
     extern __shared__ __align__(16) float pf_img[];  // [WARPS][img_rows * O] when the bulk writer is enabled
@@ -305,6 +306,7 @@ portfolio_wide_kernel(const frl_portfolio_params p, const ActT *__restrict__ act
                       long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
                       float *__restrict__ obs, int obs_mode, int auto_reset, double *__restrict__ stats)
 {
+    stats_exchange_previous(stats);
     extern __shared__ __align__(16) unsigned char pfw_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.n_envs, D = p.stock_dim, T = p.n_days;

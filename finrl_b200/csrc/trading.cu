@@ -15,6 +15,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 #include "sort_network.inc"
 #include "trading_common.cuh"
@@ -340,6 +345,7 @@ trading_rollout_kernel(const frl_trading_params p, const ActT *__restrict__ acti
                        uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode, int auto_reset,
                        double *__restrict__ stats)
 {
+    stats_exchange_previous(stats);
     using SM = WarpSmem<SLOTS, ActT, WARPS>;
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -702,6 +708,32 @@ __global__ void __launch_bounds__(WARPS * 32) trading_observe_kernel(const frl_t
     write_obs_tile<0>(p, sm, obs, env0, nvalid, lane);
 }
 
+// Factored observation: per 32-env tile the env-specific slots [cash, holdings x D] as float32 rows (one
+// contiguous 32*(1+D)-float run per tile) and the state-list day.  Stock-major loads and row-major stores are
+// both coalesced through a [D+1][33] shared-memory tile.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+trading_observe_factored_kernel(const frl_trading_params p, float *__restrict__ env_part, int32_t *__restrict__ sday_out)
+{
+    extern __shared__ float fsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = p.n_envs, D = p.stock_dim, W = D + 1;
+    float *tile = fsm + (size_t)warp * W * 33;
+    const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
+    if (env0 >= N) return;
+    const int nvalid = (int)min((long long)32, (long long)N - env0);
+    const long long n = lane < nvalid ? env0 + lane : (long long)N - 1;
+    tile[lane] = (float)p.cash[n];
+    for (int j = 0; j < D; ++j) tile[(j + 1) * 33 + lane] = (float)p.hold[(size_t)j * p.env_stride + n];
+    if (lane < nvalid) sday_out[n] = state_day(p.sday[n]);
+    __syncwarp();
+    float *out = env_part + (size_t)env0 * W;
+    for (int i = lane; i < nvalid * W; i += 32) {
+        const int r = i / W, c = i - r * W;
+        out[i] = tile[c * 33 + r];
+    }
+}
+
 // D > 32: one warp per env, holdings straight from the stock-major array (only used by observe/reset)
 __global__ void trading_observe_wide_kernel(const frl_trading_params p, float *__restrict__ obs)
 {
@@ -832,6 +864,59 @@ extern "C" int32_t frl_trading_observe(const frl_trading_params *p, float *obs, 
     const long long tiles = ((long long)p->n_envs + 31) / 32;
     trading_observe_kernel<W><<<(unsigned)((tiles + W - 1) / W), W * 32, 0, (cudaStream_t)stream>>>(*p, obs);
     return check_launch("trading_observe");
+}
+
+extern "C" int32_t frl_trading_observe_factored(const frl_trading_params *p, float *env_part, int32_t *state_day_out,
+                                                void *stream)
+{
+    if (int32_t rc = validate(p)) return rc;
+    FRL_REQUIRE(env_part != nullptr && state_day_out != nullptr, "trading_observe_factored: output pointer is NULL");
+    constexpr int W = 4;
+    const long long tiles = ((long long)p->n_envs + 31) / 32;
+    const size_t smem = (size_t)W * (p->stock_dim + 1) * 33 * sizeof(float);  // <= 68 KB at D = 128
+    auto kern = trading_observe_factored_kernel<W>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)((tiles + W - 1) / W), W * 32, smem, (cudaStream_t)stream>>>(*p, env_part, state_day_out);
+    return check_launch("trading_observe_factored");
+}
+
+extern "C" int32_t frl_expand_obs_host(const float *tmpl, int32_t n_days, int32_t obs_dim, int32_t stock_dim,
+                                       const float *env_part, const int32_t *sday, int64_t n, float *out, int32_t n_threads)
+{
+    FRL_REQUIRE(tmpl && env_part && sday && out, "expand_obs_host: NULL argument");
+    FRL_REQUIRE(n >= 0 && n_days >= 1 && stock_dim >= 1 && obs_dim >= 1 + 2 * stock_dim,
+                "expand_obs_host: bad sizes (n=%lld, T=%d, O=%d, D=%d)", (long long)n, n_days, obs_dim, stock_dim);
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (n + 4095) / 4096));
+    const int O = obs_dim, D = stock_dim, W = D + 1;
+    std::atomic<int> bad(0);
+    auto work = [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const int32_t d = sday[i];
+            if (d < 0 || d >= n_days) {
+                bad.store(1);
+                continue;
+            }
+            float *row = out + (size_t)i * O;
+            memcpy(row, tmpl + (size_t)d * O, sizeof(float) * O);
+            const float *e = env_part + (size_t)i * W;
+            row[0] = e[0];
+            memcpy(row + 1 + D, e + 1, sizeof(float) * D);
+        }
+    };
+    if (nt == 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> th;
+        const int64_t per = (n + nt - 1) / nt;
+        for (int t = 0; t < nt; ++t) {
+            const int64_t lo = t * per, hi = std::min<int64_t>(n, lo + per);
+            if (lo < hi) th.emplace_back(work, lo, hi);
+        }
+        for (auto &t : th) t.join();
+    }
+    FRL_REQUIRE(bad.load() == 0, "expand_obs_host: a state_day lies outside [0, %d)", n_days);
+    return FRL_OK;
 }
 
 extern "C" int32_t frl_trading_reset(const frl_trading_params *p, const uint8_t *mask, float *obs, void *stream)

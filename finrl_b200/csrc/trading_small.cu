@@ -140,6 +140,7 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
                      long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
                      float *__restrict__ obs, int obs_mode, int auto_reset, double *__restrict__ stats)
 {
+    stats_exchange_previous(stats);
     using Env = OctEnv<8 * R>;
     constexpr int IB = KeyBits<R>::IB, IMASK = KeyBits<R>::MASK, AMAX = KeyBits<R>::AMAX;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -117,7 +117,8 @@ class BatchedNpStockTradingEnv(BatchedEnvBase):
         self.gamma_reward = torch.empty(N, dtype=torch.float64, device=dev)
         self.initial_total_asset = torch.empty(N, dtype=torch.float64, device=dev)
         self.episode_return = torch.zeros(N, dtype=torch.float64, device=dev)
-        self.stats = torch.zeros(_cabi.N_STATS, dtype=torch.float64, device=dev)
+        self._stats_block = _cabi.new_stats_block(torch, dev)
+        self.stats = self._stats_block[:_cabi.N_STATS]
         self._obs = torch.empty((N, O), dtype=torch.float32, device=dev)
         self._rew = torch.empty(N, dtype=torch.float64, device=dev)
         self._flags = torch.empty(N, dtype=torch.uint8, device=dev)

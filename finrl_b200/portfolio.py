@@ -99,7 +99,8 @@ class BatchedStockPortfolioEnv(BatchedEnvBase):
         self.portfolio_value = torch.full((N,), float(initial_amount), dtype=torch.float64, device=dev)
         self.day = torch.full((N,), int(day), dtype=torch.int32, device=dev)
         self.reward = torch.zeros(N, dtype=torch.float64, device=dev)
-        self.stats = torch.zeros(_cabi.N_STATS, dtype=torch.float64, device=dev)
+        self._stats_block = _cabi.new_stats_block(torch, dev)
+        self.stats = self._stats_block[:_cabi.N_STATS]
         self._obs = None  # materialised lazily: [N, (D+K)*D] f32 can be large
         self._rew = torch.empty(N, dtype=torch.float64, device=dev)
         self._flags = torch.empty(N, dtype=torch.uint8, device=dev)

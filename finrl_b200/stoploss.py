@@ -23,6 +23,7 @@ class BatchedStockTradingEnvStopLoss(BatchedEnvBase):
     (the same :class:`CashPenaltyTables` the cash-penalty env uses)."""
 
     _PREFIX = "frl_stoploss"
+    _STAT7_NAME = "shortage_count"
     _ACTION_NAME = "n_assets"
 
     def __init__(self, df=None, buy_cost_pct=3e-3, sell_cost_pct=3e-3, date_col_name="date", hmax=10,
@@ -65,7 +66,8 @@ class BatchedStockTradingEnvStopLoss(BatchedEnvBase):
         self.last_cash = torch.empty(N, **f64)
         self.last_total = torch.empty(N, **f64)
         self.sum_trades = torch.empty(N, **f64)
-        self.stats = torch.zeros(_cabi.N_STATS, **f64)
+        self._stats_block = _cabi.new_stats_block(torch, self.device)
+        self.stats = self._stats_block[:_cabi.N_STATS]
         self._obs = torch.empty((N, O), dtype=torch.float32, device=dev)
         self._rew = torch.empty(N, **f64)
         self._flags = torch.empty(N, dtype=torch.uint8, device=dev)
@@ -134,11 +136,3 @@ class BatchedStockTradingEnvStopLoss(BatchedEnvBase):
             )
         self.launches += 2
         return out
-
-    def read_stats(self, reset=False):
-        vals = self.stats.tolist()
-        if reset:
-            self.stats.zero_()
-        names = list(_cabi.STAT_NAMES)
-        names[7] = "shortage_count"
-        return dict(zip(names, vals))

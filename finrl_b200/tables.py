@@ -55,6 +55,7 @@ class TradingTables:
     host_close: np.ndarray
     host_tech: np.ndarray
     host_risk: np.ndarray
+    host_tmpl: Optional[np.ndarray] = None  # [T, O] f32 copy of obs_tmpl for the factored host observation
 
     @property
     def obs_dim(self) -> int:
@@ -96,7 +97,7 @@ class TradingTables:
             disable_mask=torch.from_numpy(np.ascontiguousarray(mask).view(np.int32)).to(dev),
             risk=torch.from_numpy(risk).to(dev),
             obs_tmpl=torch.from_numpy(tmpl).to(dev), obs_tmpl4=tmpl4,
-            host_close=close, host_tech=tech, host_risk=risk,
+            host_close=close, host_tech=tech, host_risk=risk, host_tmpl=tmpl,
         )
 
     @staticmethod

@@ -28,6 +28,48 @@ def _scalar_cost(x, name):
     return float(arr[0])
 
 
+class FactoredObs:
+    """The observation batch of a host-resident caller in factored form: ``env_part[N, 1+D]`` float32 (cash,
+    holdings), ``state_day[N]`` int32 and the per-day template ``tmpl[T, O]`` the host holds once.  Row ``n`` of
+    the dense observation is ``tmpl[state_day[n]]`` with the cash / holdings slots taken from ``env_part[n]`` —
+    bit-identical to what ``step()`` writes.  ``fo[n]`` builds one row, ``fo.dense()`` all of them (native,
+    multi-threaded); 137 instead of 1213 bytes per DOW-30 env cross PCIe."""
+
+    def __init__(self, env_part, state_day, tmpl, stock_dim):
+        self.env_part, self.state_day, self.tmpl, self.stock_dim = env_part, state_day, tmpl, int(stock_dim)
+
+    def __len__(self):
+        return int(self.env_part.shape[0])
+
+    @property
+    def shape(self):
+        return (len(self), int(self.tmpl.shape[1]))
+
+    def __getitem__(self, n):
+        D = self.stock_dim
+        e = self.env_part[n].numpy() if hasattr(self.env_part, "numpy") else np.asarray(self.env_part[n])
+        row = np.array(self.tmpl[int(self.state_day[n])], dtype=np.float32)
+        row[0] = e[0]
+        row[1 + D : 1 + 2 * D] = e[1:]
+        return row
+
+    def dense(self, out=None, n_threads: int = 0):
+        """Dense [N, O] float32 array (written into ``out`` when given) via frl_expand_obs_host."""
+        N, O = self.shape
+        ep = self.env_part.numpy() if hasattr(self.env_part, "numpy") else np.ascontiguousarray(self.env_part, dtype=np.float32)
+        sd = self.state_day.numpy() if hasattr(self.state_day, "numpy") else np.ascontiguousarray(self.state_day, dtype=np.int32)
+        if out is None:
+            out = np.empty((N, O), dtype=np.float32)
+        dst = out.numpy() if hasattr(out, "numpy") else out
+        if dst.shape != (N, O) or dst.dtype != np.float32 or not dst.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous float32 array of shape {(N, O)}")
+        tm = self.tmpl
+        _cabi.check(_cabi.lib().frl_expand_obs_host(
+            tm.ctypes.data, tm.shape[0], O, self.stock_dim, ep.ctypes.data, sd.ctypes.data, N, dst.ctypes.data, int(n_threads)),
+            "frl_expand_obs_host")
+        return out
+
+
 class BatchedStockTradingEnv(BatchedEnvBase):
     """N lock-stepped (or not) ``StockTradingEnv`` instances on one GPU.
 
@@ -120,7 +162,8 @@ class BatchedStockTradingEnv(BatchedEnvBase):
         self.trades = torch.empty(N, dtype=torch.int32, device=dev)
         self.reward = torch.empty(N, dtype=torch.float64, device=dev)
         self.episode = torch.empty(N, dtype=torch.int32, device=dev)
-        self.stats = torch.zeros(_cabi.N_STATS, dtype=torch.float64, device=dev)
+        self._stats_block = _cabi.new_stats_block(torch, dev)
+        self.stats = self._stats_block[:_cabi.N_STATS]
         self._obs = torch.empty((N, O), dtype=torch.float32, device=dev)
         self._flags = torch.empty(N, dtype=torch.uint8, device=dev)
 
@@ -183,18 +226,64 @@ class BatchedStockTradingEnv(BatchedEnvBase):
         q.asset_out = (self.asset.data_ptr() + 8 * start) if self.asset is not None else None
         return q
 
+    def observe_factored(self, env_part=None, state_day=None):
+        """The current observation in factored form (see :class:`FactoredObs`): device tensors
+        ``env_part[N, 1+D]`` float32 and ``state_day[N]`` int32."""
+        torch = self._torch
+        if env_part is None:
+            env_part = self._factored_bufs()[0]
+        if state_day is None:
+            state_day = self._factored_bufs()[1]
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().frl_trading_observe_factored(C.byref(self._p), _cabi.ptr(env_part), _cabi.ptr(state_day),
+                                                                 self._stream()), "frl_trading_observe_factored")
+        self.launches += 1
+        return env_part, state_day
+
+    def _factored_bufs(self):
+        torch = self._torch
+        if getattr(self, "_fact", None) is None:
+            self._fact = (torch.empty((self.n_envs, 1 + self.stock_dim), dtype=torch.float32, device=self.device),
+                          torch.empty(self.n_envs, dtype=torch.int32, device=self.device))
+        return self._fact
+
+    def make_host_buffers(self, obs_layout: str = "dense", action_dtype=None):
+        """Pinned host buffers for :meth:`step_host`: (actions, obs, reward, flags); ``obs`` is a float32 [N, O]
+        tensor for ``"dense"`` and a :class:`FactoredObs` over pinned tensors for ``"factored"``."""
+        torch = self._torch
+        N, D, O = self.n_envs, self.stock_dim, self.state_space
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
+        act = pin((N, D), action_dtype or torch.float32)
+        if obs_layout == "dense":
+            obs = pin((N, O), torch.float32)
+        elif obs_layout == "factored":
+            obs = FactoredObs(pin((N, 1 + D), torch.float32), pin((N,), torch.int32), self.tables.host_tmpl, D)
+        else:
+            raise ValueError("obs_layout must be 'dense' or 'factored'")
+        return act, obs, pin((N,), torch.float64), pin((N,), torch.uint8)
+
     def step_host(self, actions_host, obs_host, reward_host, flags_host, auto_reset: bool = True, n_chunks: int = 8):
         """Host-resident agents: one ``step`` with pinned HOST buffers in and out, software-pipelined.
 
         The env range is cut into ``n_chunks`` slices; slice c's action upload (H2D), its kernel and its
         observation / reward / flag download (D2H) run on one of three streams, so the PCIe link stays busy
-        in both directions while kernels run.  Returns after everything has landed in the host buffers."""
+        in both directions while kernels run.  Returns after everything has landed in the host buffers.
+
+        ``obs_host`` is either a dense float32 [N, O] tensor or a :class:`FactoredObs` (``make_host_buffers``):
+        with the factored layout the step kernel writes no observation at all, a small kernel extracts the
+        env-specific slots, and only 4*(1+D) + 4 bytes per env come back instead of 4*O (91 % of a DOW-30
+        observation is the per-day row every env of that day shares)."""
         torch = self._torch
         N, D, O = self.n_envs, self.stock_dim, self.state_space
-        if not (actions_host.is_pinned() and obs_host.is_pinned() and reward_host.is_pinned() and flags_host.is_pinned()):
+        factored = isinstance(obs_host, FactoredObs)
+        obs_bufs = (obs_host.env_part, obs_host.state_day) if factored else (obs_host,)
+        if not (actions_host.is_pinned() and reward_host.is_pinned() and flags_host.is_pinned() and all(b.is_pinned() for b in obs_bufs)):
             raise ValueError("step_host needs pinned host tensors")
-        if actions_host.shape != (N, D) or obs_host.shape != (N, O) or actions_host.dtype not in (torch.float32, torch.float64):
+        ok = obs_bufs[0].shape == ((N, 1 + D) if factored else (N, O)) and (not factored or obs_bufs[1].shape == (N,))
+        if actions_host.shape != (N, D) or not ok or actions_host.dtype not in (torch.float32, torch.float64):
             raise ValueError("step_host: bad buffer shapes")
+        if factored:
+            d_env, d_sd = self._factored_bufs()
         if getattr(self, "_host_streams", None) is None:
             self._host_streams = [torch.cuda.Stream(self.device) for _ in range(3)]
             self._host_act = torch.empty((N, D), dtype=actions_host.dtype, device=self.device)
@@ -217,9 +306,17 @@ class BatchedStockTradingEnv(BatchedEnvBase):
                     d_act.copy_(actions_host[start : start + cnt], non_blocking=True)
                     q = self._chunk_params(start, cnt)
                     rc |= lib.frl_trading_step(C.byref(q), _cabi.ptr(d_act), f64, None, C.c_void_p(self._flags.data_ptr() + start),
-                                               C.c_void_p(self._obs.data_ptr() + 4 * O * start), int(auto_reset), None,
-                                               C.c_void_p(st.cuda_stream))
-                    obs_host[start : start + cnt].copy_(self._obs[start : start + cnt], non_blocking=True)
+                                               None if factored else C.c_void_p(self._obs.data_ptr() + 4 * O * start),
+                                               int(auto_reset), None, C.c_void_p(st.cuda_stream))
+                    if factored:
+                        rc |= lib.frl_trading_observe_factored(
+                            C.byref(q), C.c_void_p(d_env.data_ptr() + 4 * (1 + D) * start), C.c_void_p(d_sd.data_ptr() + 4 * start),
+                            C.c_void_p(st.cuda_stream))
+                        self.launches += 1
+                        obs_host.env_part[start : start + cnt].copy_(d_env[start : start + cnt], non_blocking=True)
+                        obs_host.state_day[start : start + cnt].copy_(d_sd[start : start + cnt], non_blocking=True)
+                    else:
+                        obs_host[start : start + cnt].copy_(self._obs[start : start + cnt], non_blocking=True)
                     reward_host[start : start + cnt].copy_(self.reward[start : start + cnt], non_blocking=True)
                     flags_host[start : start + cnt].copy_(self._flags[start : start + cnt], non_blocking=True)
                 self.launches += 1

@@ -4,8 +4,9 @@
  * to the reference checkout).  The reference has no FFI layer of its own — its boundary is the
  * gym protocol of four Python classes — so every entry point here names the Python method whose
  * body it replaces.  Host code (finrl_b200/*.py, or any other language with a C FFI) owns all
- * memory; this library allocates nothing, keeps no global state except the last error string,
- * and only enqueues kernels on the CUDA stream it is handed.
+ * memory; this library allocates nothing (except the 256-byte peer-mapped statistics blocks of
+ * frl_exchange_*, which must come from cudaMalloc to be exportable), keeps no global state except the
+ * last error string, and only enqueues kernels on the CUDA stream it is handed.
  *
  * Conventions
  *   - every pointer inside a *_params struct is a DEVICE pointer (CUDA, sm_100a);
@@ -25,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FRL_ABI_VERSION 3
+#define FRL_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define FRL_API __attribute__((visibility("default")))
@@ -47,8 +48,8 @@ extern "C" {
 #define FRL_OBS_LAST 1 /* obs[N][O] after the final step */
 #define FRL_OBS_ALL 2  /* obs[n_steps][N][O] after every step */
 
-/* slots of the f64 statistics vector a rollout accumulates into (atomicAdd; the multi-GPU
- * layer all-reduces it with NCCL — there is no reference counterpart) */
+/* slots of the f64 statistics vector a rollout accumulates into (atomicAdd; exchanged between
+ * GPUs as described under frl_stats_block — there is no reference counterpart) */
 #define FRL_STAT_REWARD_SUM 0    /* sum of returned rewards over all env-steps */
 #define FRL_STAT_REWARD_SQSUM 1  /* sum of squares of the same */
 #define FRL_STAT_DONE_COUNT 2    /* number of done flags */
@@ -58,6 +59,41 @@ extern "C" {
 #define FRL_STAT_ENV_STEPS 6     /* env-steps processed */
 #define FRL_STAT_TRADES 7        /* sum of trade counters after the final step */
 #define FRL_N_STATS 8
+
+/* The `stats` argument of every step/rollout entry point is one of the two accumulators, sum[0] or sum[1], of
+ * an frl_stats_block (device memory, 384 bytes, 128-byte aligned, zero-initialised by the caller; NULL = no
+ * statistics).  Kernels atomicAdd their partial sums into the accumulator they were handed.  With
+ * n_peers == 0 that is all (callers then simply always pass sum[0]).
+ * With n_peers > 0 (multi-GPU) the caller ALTERNATES between sum[0] and sum[1] on consecutive launches of a
+ * stream, and the first thread block of every launch moves the OTHER accumulator — the previous launch's
+ * sums, complete by stream order — out: it adds them to total[] of every rank, its own included, through the
+ * peer-mapped pointers in peer_total[] (fp64 atomics over NVLink / NVSwitch) and clears them.  One-sided and
+ * free of any synchronisation: no completion counter, no fence, no collective launch, and no rank ever waits
+ * for a peer inside its step loop.  frl_exchange_flush moves what is still in both accumulators (the last
+ * launch) before totals are read.  An NCCL all-reduce of sum[0] is the portable fallback (finrl_b200/dist.py).
+ * One block serves one stream at a time. */
+#define FRL_MAX_PEERS 8
+#define FRL_STATS_BLOCK_BYTES 384
+typedef struct frl_stats_block {
+    double sum[2][FRL_N_STATS];         /* the two accumulators (`stats` = sum[0] or sum[1]) */
+    double total[FRL_N_STATS];          /* exchange target: the launch sums of all ranks */
+    double *peer_total[FRL_MAX_PEERS];  /* [n_peers] device pointers to every rank's total[], own included */
+    uint32_t n_peers;                   /* 0 = no exchange */
+    uint32_t reserved[31];
+} frl_stats_block;
+/* Peer-mapped statistics blocks for the exchange above (plain CUDA IPC; the processes of one node).
+ * alloc: cudaMalloc + zero a block on the current device.  export: 64-byte handle another process opens.
+ * open: map a peer's block into this process (enables peer access from the current device); close undoes it.
+ * bind: write peer_total[] / n_peers of `block` from the blocks of all ranks (own included, any order;
+ * n == 0 unbinds).  flush: one tiny kernel that moves both accumulators of `block` to the peers (call it before
+ * reading total[]; a no-op for n_peers == 0).  free: release a block from alloc. */
+FRL_API int32_t frl_exchange_alloc(void **block);
+FRL_API int32_t frl_exchange_free(void *block);
+FRL_API int32_t frl_exchange_export(const void *block, uint8_t handle[64]);
+FRL_API int32_t frl_exchange_open(const uint8_t handle[64], void **peer_block);
+FRL_API int32_t frl_exchange_close(void *peer_block);
+FRL_API int32_t frl_exchange_bind(void *block, void *const *blocks, int32_t n, void *stream);
+FRL_API int32_t frl_exchange_flush(void *block, void *stream);
 
 FRL_API int32_t frl_abi_version(void);
 /* Tuning knobs.  "trading_small_max": frl_trading_step/rollout use the low-latency 8-lanes-per-env kernel
@@ -130,6 +166,19 @@ FRL_API int32_t frl_trading_reset(const frl_trading_params *p, const uint8_t *ma
 /* StockTradingEnv.render / _update_state (:395-396, :453-478): obs[N][O] float32 of the
  * current state list (the float32 cast SB3's DummyVecEnv applies). */
 FRL_API int32_t frl_trading_observe(const frl_trading_params *p, float *obs, void *stream);
+
+/* The same observation in FACTORED form for host-resident callers (137 instead of 1213 bytes per env over
+ * PCIe for DOW-30): env_part[N][1+D] float32 = the env-specific slots of the state list (cash, holdings;
+ * the float32 values frl_trading_observe writes) and state_day[N] = the day whose per-day row (obs_tmpl, a
+ * table the host holds once) fills every other slot — day T-1 after a stale reset (quirk Q1).
+ * obs[n] == obs_tmpl[state_day[n]] with slots 0 and 1+D..2D taken from env_part[n]. */
+FRL_API int32_t frl_trading_observe_factored(const frl_trading_params *p, float *env_part, int32_t *state_day,
+                                             void *stream);
+/* HOST helper for the above (no GPU involved): expand n factored rows into dense out[n][O] float32 with
+ * n_threads host threads (<= 0: hardware concurrency).  tmpl is the host copy of obs_tmpl [T][O]. */
+FRL_API int32_t frl_expand_obs_host(const float *tmpl, int32_t n_days, int32_t obs_dim, int32_t stock_dim,
+                                    const float *env_part, const int32_t *state_day, int64_t n, float *out,
+                                    int32_t n_threads);
 
 /* n_steps fused calls of StockTradingEnv.step (:220-357) for every env.
  *   actions      element (k, n, j) at actions[k*act_step_stride + n*act_env_stride + j];

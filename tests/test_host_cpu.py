@@ -187,6 +187,31 @@ def test_gym_vec_env_is_dummy_vec_env_protocol():
     assert GymVecEnv([lambda: envs[1]]).render() == ["state", 3]  # one env: its own render(), as DummyVecEnv does
 
 
+def test_expand_obs_host_matches_numpy():
+    """frl_expand_obs_host (host threads, no GPU): factored rows -> dense rows, against plain numpy indexing."""
+    from finrl_b200.trading import FactoredObs
+
+    rng = np.random.default_rng(0)
+    T, D, K, N = 17, 5, 3, 20_003
+    O = 1 + 2 * D + K * D
+    tmpl = rng.normal(size=(T, O)).astype(np.float32)
+    env_part = rng.normal(size=(N, 1 + D)).astype(np.float32)
+    sday = rng.integers(0, T, size=N).astype(np.int32)
+    fo = FactoredObs(env_part, sday, tmpl, D)
+    want = tmpl[sday].copy()
+    want[:, 0] = env_part[:, 0]
+    want[:, 1 + D : 1 + 2 * D] = env_part[:, 1:]
+    for threads in (1, 3, 0):
+        out = np.full((N, O), np.nan, dtype=np.float32)
+        assert fo.dense(out=out, n_threads=threads) is out and np.array_equal(out, want)
+    assert np.array_equal(fo[123], want[123]) and fo.shape == (N, O) and len(fo) == N
+    sday[77] = T  # out of range: reported, not a crash
+    from finrl_b200 import EngineError
+
+    with pytest.raises(EngineError):
+        fo.dense()
+
+
 def test_shard_range_partitions_exactly():
     from finrl_b200.dist import shard_range
 
@@ -206,7 +231,7 @@ def _gloo_worker(rank, world, port, N, K, out_dir):
     import torch.distributed as dist
 
     from finrl_b200 import synthetic as syn
-    from finrl_b200.dist import allreduce_stats, init_from_env, shard_range, summarize
+    from finrl_b200.dist import StatsExchange, allreduce_stats, init_from_env, shard_range, summarize
     from oracle import oracle as ora
 
     r, w, _ = init_from_env(backend="gloo")
@@ -215,11 +240,19 @@ def _gloo_worker(rank, world, port, N, K, out_dir):
     o = ora.TradingOracle(close, tech, turb, count, hmax=100, initial_amount=2e5, turbulence_threshold=90)
     acts = syn.make_actions((K, N, 30), seed=1)[:, start : start + count]  # this rank's env-index slice
     stats = torch.zeros(8, dtype=torch.float64)
+    ex = StatsExchange("cpu")  # host-logic leg of the exchange: snapshots + all-reduce (gloo), flushed mid-run
+    assert ex.mode == "collective" and ex.world == w
     for k in range(K):
         _, rew, fl = o.step(acts[k], auto_reset=True, want_obs=False)
-        stats[0] += rew.sum(); stats[1] += (rew ** 2).sum(); stats[2] += float((fl & 1).sum()); stats[6] += count
-    allreduce_stats(stats)  # the only collective on the path
-    np.savez(os.path.join(out_dir, f"rank{r}.npz"), cash=o.cash, hold=o.hold, stats=stats.numpy(), start=start)
+        part = torch.tensor([rew.sum(), (rew ** 2).sum(), float((fl & 1).sum()), 0, 0, 0, count, 0], dtype=torch.float64)
+        stats += part
+        ex.sum += part  # what a kernel epilogue does on the device
+        if k % 8 == 7:
+            ex.flush()
+    allreduce_stats(stats)  # the plain collective
+    totals = ex.totals()
+    np.savez(os.path.join(out_dir, f"rank{r}.npz"), cash=o.cash, hold=o.hold, stats=stats.numpy(), start=start,
+             exchanged=np.asarray(totals))
     s = summarize(stats)
     assert s["env_steps"] == N * K
     dist.barrier()
@@ -250,6 +283,8 @@ def test_two_rank_sharding_equals_single_process(tmp_path):
     for p in parts:
         np.testing.assert_allclose(p["stats"], tot, rtol=1e-12)
         assert p["stats"][2] == tot[2] and p["stats"][6] == tot[6]
+        np.testing.assert_allclose(p["exchanged"], tot, rtol=1e-12)  # StatsExchange (flushed every 8 steps) agrees
+        assert p["exchanged"][2] == tot[2] and p["exchanged"][6] == tot[6]
 
 
 def test_missing_library_fails_loudly(tmp_path):

@@ -325,3 +325,35 @@ def test_image_obs_writer_equals_row_writer(trading_kernel, N, D, K, dtype):
         xa = a.step(acts[s])[0].clone()
         xb = b.step(acts[s])[0].clone()
         assert torch.equal(xa, xb), s
+
+
+def test_factored_host_observation_equals_dense():
+    """step_host with the factored layout (env_part + state_day over PCIe, template kept on the host) rebuilds,
+    bit for bit, the dense observation the same step writes — across episode ends and stale-day resets."""
+    from finrl_b200 import BatchedStockTradingEnv, TradingTables, synthetic as syn
+    from finrl_b200.trading import FactoredObs
+
+    N, T, D, K = 5000, 9, 30, 8
+    close, tech, turb = syn.make_tables(T, D, K, seed=4)
+    kw = dict(hmax=100, initial_amount=250_000, turbulence_threshold=80)
+    tables = TradingTables.from_arrays(close, tech, turb, "cuda")
+    dense_env = BatchedStockTradingEnv(tables=tables, n_envs=N, **kw)
+    fact_env = BatchedStockTradingEnv(tables=tables, n_envs=N, **kw)
+    a_h, obs_h, rew_h, flg_h = dense_env.make_host_buffers("dense")
+    _, fo, rew_f, flg_f = fact_env.make_host_buffers("factored")
+    assert isinstance(fo, FactoredObs) and fo.env_part.shape == (N, 1 + D) and fo.env_part.is_pinned()
+    # desynchronise the envs so that one tile mixes days (and one env sits on a stale-reset row)
+    ragged = torch.arange(N, device="cuda", dtype=torch.int32) % 4
+    for env in (dense_env, fact_env):
+        env.set_state(day=ragged, sday=ragged)
+    out = np.empty((N, 1 + 2 * D + K * D), dtype=np.float32)
+    for s in range(2 * T + 3):
+        a_h.copy_(torch.from_numpy(syn.make_actions((N, D), seed=50 + s)))
+        dense_env.step_host(a_h, obs_h, rew_h, flg_h, auto_reset=True, n_chunks=3)
+        fact_env.step_host(a_h, fo, rew_f, flg_f, auto_reset=True, n_chunks=5)
+        assert np.array_equal(fo.dense(out=out), obs_h.numpy()), s
+        assert np.array_equal(rew_f.numpy(), rew_h.numpy()) and np.array_equal(flg_f.numpy(), flg_h.numpy()), s
+        assert np.array_equal(fo[17], obs_h.numpy()[17]) and np.array_equal(fo[N - 1], obs_h.numpy()[N - 1])
+    assert (flg_h.numpy() & 1).sum() >= 0 and int(fact_env.episode.max().item()) >= 2  # episodes really ended
+    env_part, sday = fact_env.observe_factored()
+    assert np.array_equal(env_part.cpu().numpy(), fo.env_part.numpy()) and np.array_equal(sday.cpu().numpy(), fo.state_day.numpy())
