@@ -35,6 +35,24 @@ class BatchedEnvBase:
     def _stream(self):
         return _cabi.current_stream(self.device)
 
+    def seed(self, seed=None):
+        """Seed of the in-kernel reset draws (numpy env ``if_train``, cash-penalty / stop-loss ``random_start``).
+        Unseeded engines take 64 bits from the OS, as the reference's envs seed themselves from the clock."""
+        import os
+
+        self._seed0 = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & (2**64 - 1)
+        self._launch_id = 0
+        return [seed]
+
+    def _next_reset_seed(self):
+        """A fresh stream id per launch for params structs that carry ``reset_seed`` (no-op for the others)."""
+        p = self._p
+        if hasattr(p, "reset_seed"):
+            if not hasattr(self, "_seed0"):
+                self.seed(None)
+            self._launch_id += 1
+            p.reset_seed = (self._seed0 + self._launch_id * 0x9E3779B97F4A7C15) & (2**64 - 1)
+
     def _fn(self, name):
         return getattr(_cabi.lib(), f"{self._PREFIX}_{name}")
 
@@ -70,6 +88,7 @@ class BatchedEnvBase:
         if a.shape[0] != self.n_envs:
             raise ValueError(f"actions must have n_envs={self.n_envs} rows")
         obs = self._obs_out() if want_obs else None
+        self._next_reset_seed()
         ev = self.kernel_events
         with torch.cuda.device(self.device):
             if ev is not None:
@@ -117,6 +136,7 @@ class BatchedEnvBase:
             obs = self._obs_out()
         elif mode == _cabi.OBS_ALL and obs is None:
             obs = torch.empty((K, N, self._obs_out().shape[-1]), dtype=torch.float32, device=self.device)
+        self._next_reset_seed()
         with torch.cuda.device(self.device):
             _cabi.check(
                 self._fn("rollout")(

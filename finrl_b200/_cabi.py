@@ -97,7 +97,8 @@ class NpParams(C.Structure):
         ("init_total", C.c_void_p),
         ("episode_return", C.c_void_p),
         ("price_pitch", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("train_reset", C.c_int32),
+        ("reset_seed", C.c_uint64),
     ]
 
 
@@ -159,7 +160,8 @@ class StopLossParams(C.Structure):
         ("sum_trades", C.c_void_p),
         ("hmax_vec", C.c_void_p),
         ("hmax_vec_f32", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("random_start", C.c_int32),
+        ("reset_seed", C.c_uint64),
     ]
 
 
@@ -197,7 +199,8 @@ class CashPenaltyParams(C.Structure):
         ("sum_trades", C.c_void_p),
         ("hmax_vec", C.c_void_p),
         ("hmax_vec_f32", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("random_start", C.c_int32),
+        ("reset_seed", C.c_uint64),
     ]
 
 

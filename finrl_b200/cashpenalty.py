@@ -141,6 +141,7 @@ class BatchedStockTradingEnvCashpenalty(BatchedEnvBase):
         p.cash, p.hold, p.date_index, p.start = self.cash.data_ptr(), self.hold.data_ptr(), self.date_index.data_ptr(), self.starting_point.data_ptr()
         p.hold_alt = self.hold_alt.data_ptr()
         p.fresh, p.last_cash, p.last_total, p.sum_trades = self.fresh.data_ptr(), self.last_cash.data_ptr(), self.last_total.data_ptr(), self.sum_trades.data_ptr()
+        p.random_start = int(self.random_start)  # in-kernel auto-reset redraws the starting point (reset_seed per launch)
         self._p = p
         self.reset()
 

@@ -286,7 +286,7 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
             if (flags & FRL_FLAG_LIQUIDATE) st_liq += 1.0;
             if (flags & FRL_FLAG_SHORTAGE) st_short += 1.0;
         }
-        if (reset_now) {  // DummyVecEnv.step_wait -> reset (:132-158), random_start=False
+        if (reset_now) {  // DummyVecEnv.step_wait -> reset (:132-158); starting point 0 or, with p.random_start, randint(0, int(T * 0.5))
             cash = p.initial_amount;
             double *hz = (cur ? p.hold_alt : p.hold) + n;
             for (int j = 0; j < D; ++j) {
@@ -294,8 +294,8 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
                 *reinterpret_cast<float *>(myrow + j) = 0.0f;
             }
             moved = true;
-            di = 0;
-            start = 0;
+            start = p.random_start ? reset_randint(reset_bits(p.reset_seed, n, k, 0), (int)(p.n_days * 0.5)) : 0;
+            di = start;
             fresh = true;
             sum_trades = 0.0;
             last_cash = 0.0;

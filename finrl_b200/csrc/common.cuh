@@ -68,6 +68,24 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// ---- counter-based random draws for the in-kernel auto-reset -------------------------------------------------
+// splitmix64 of a counter built from (launch stream id, env index, rollout step, draw index): no generator
+// state to store or race on, every (env, step) has its own stream, and a rarely taken branch needs no registers
+// outside it.  The reference draws from numpy's / Python's GLOBAL generators, whose order over a batch is
+// undefined; what is reproduced is the distribution (randint / uniform / random.choice).
+__device__ __forceinline__ uint64_t reset_bits(uint64_t seed, long long env, int step, int idx)
+{
+    uint64_t z = seed + 0x9e3779b97f4a7c15ull * (uint64_t)(env + 1) + 0xd1342543de82ef95ull * (uint64_t)(step + 1) +
+                 0xaf251af3b0f025b5ull * (uint64_t)(idx + 1);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+// uniform double in [0, 1) with 53 random bits, like numpy's random_sample
+__device__ __forceinline__ double reset_uniform01(uint64_t bits) { return (double)(bits >> 11) * 0x1.0p-53; }
+// uniform integer in [0, n), n < 2^31 (multiply-shift on 32 fresh bits; bias < n / 2^32)
+__device__ __forceinline__ int reset_randint(uint64_t bits, int n) { return (int)(((bits >> 32) * (uint64_t)n) >> 32); }
+
 // ---- the 8-slot statistics vector -----------------------------------------------------------------
 // 8 values x 32 lanes: three halving exchanges leave lane l with the partial sum of value (l & 7) over 4
 // lanes, two more butterflies finish it — 9 shuffles instead of 40 — then one atomicAdd per slot and warp.

@@ -387,17 +387,22 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
             st_r2 += reward.v * reward.v;
         }
         if ((flags & FRL_FLAG_DONE) && auto_reset) {
-            // reset (:80-101), deterministic branch
+            // reset (:80-101): deterministic branch, or the if_train branch with counter-based draws (train_reset)
             Pairwise8 acc;
             acc.init();
             for (int j0 = 0; j0 < D; j0 += 8) {
                 float x8[8];
+                uint64_t bits = p.train_reset ? reset_bits(p.reset_seed, n, k, 1 + j0 / 8) : 0;  // eight 6-bit draws
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int j = j0 + u;
                     x8[u] = 0.0f;
                     if (j < D) {
-                        const float s0 = p.init_stocks ? __ldg(p.init_stocks + j) : 0.0f;
+                        float s0 = p.init_stocks ? __ldg(p.init_stocks + j) : 0.0f;
+                        if (p.train_reset) {
+                            s0 = fadd(s0, (float)(int)(bits & 63));
+                            bits >>= 6;
+                        }
                         if (valid) {
                             sp[(size_t)j * ld] = s0;
                             cp[(size_t)j * ld] = 0.0f;
@@ -409,7 +414,12 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
                 acc.block(x8, j0, D);
             }
             day = 0;
-            amount = nv(p.initial_capital, FRL_KIND_PY);
+            if (p.train_reset) {  // initial_capital * uniform(0.95, 1.05) [py] - (stocks * price).sum() [f32] -> f32
+                const double factor = 0.95 + (1.05 - 0.95) * reset_uniform01(reset_bits(p.reset_seed, n, k, 0));
+                amount = nv_sub(nv(dmul(p.initial_capital, factor), FRL_KIND_PY), nv((double)acc.res, FRL_KIND_F32));
+            } else {
+                amount = nv(p.initial_capital, FRL_KIND_PY);
+            }
             total = nv_add(amount, nv((double)acc.res, FRL_KIND_F32));
             init_total = total.v;
             init_total_loaded = true;

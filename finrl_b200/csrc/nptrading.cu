@@ -155,19 +155,35 @@ __device__ __forceinline__ void np_write_obs_tile(const frl_np_params &p, SM &sm
     }
 }
 
-// reset (:80-101), deterministic branch, for the calling thread's env (state in registers)
+// reset (:80-101) for the calling thread's env (state in registers): the deterministic branch, or with
+// p.train_reset the if_train branch — stocks = initial_stocks + randint(0, 64, D), amount = initial_capital *
+// uniform(0.95, 1.05) - (stocks * price).sum() [python float - float32 -> float32] — with counter-based draws
 template <int SLOTS>
 __device__ __forceinline__ void np_reset_regs(const frl_np_params &p, float (&stv)[SLOTS], float (&clv)[SLOTS], int D,
-                                              NV &amount, NV &total, NV &gr, double &init_total, int &day)
+                                              NV &amount, NV &total, NV &gr, double &init_total, int &day, long long env,
+                                              int step)
 {
+    uint64_t bits = 0;
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
-        stv[j] = (j < D && p.init_stocks) ? __ldg(p.init_stocks + j) : 0.0f;
+        float s0 = (j < D && p.init_stocks) ? __ldg(p.init_stocks + j) : 0.0f;
+        if (p.train_reset && j < D) {
+            if (j % 10 == 0) bits = reset_bits(p.reset_seed, env, step, 1 + j / 10);  // ten 6-bit draws per word
+            s0 = fadd(s0, (float)(int)(bits & 63));
+            bits >>= 6;
+        }
+        stv[j] = s0;
         clv[j] = 0.0f;
     }
     day = 0;
-    amount = nv(p.initial_capital, FRL_KIND_PY);
-    total = nv_add(amount, nv((double)np_asset_f32<SLOTS>(stv, p.price, D), FRL_KIND_F32));
+    const float asset0 = np_asset_f32<SLOTS>(stv, p.price, D);
+    if (p.train_reset) {
+        const double factor = 0.95 + (1.05 - 0.95) * reset_uniform01(reset_bits(p.reset_seed, env, step, 0));
+        amount = nv_sub(nv(dmul(p.initial_capital, factor), FRL_KIND_PY), nv((double)asset0, FRL_KIND_F32));
+    } else {
+        amount = nv(p.initial_capital, FRL_KIND_PY);
+    }
+    total = nv_add(amount, nv((double)asset0, FRL_KIND_F32));
     init_total = total.v;
     gr = nv(0.0, FRL_KIND_PY);
 }
@@ -344,7 +360,7 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
             st_r2 += reward.v * reward.v;
         }
         if ((flags & FRL_FLAG_DONE) && auto_reset) {
-            np_reset_regs<SLOTS>(p, stv, clv, D, amount, total, gr, init_total, day);
+            np_reset_regs<SLOTS>(p, stv, clv, D, amount, total, gr, init_total, day, n, k);
             init_total_loaded = true;
             if (valid) p.init_total[n] = init_total;
         }

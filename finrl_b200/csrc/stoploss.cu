@@ -341,7 +341,7 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
             if (flags & FRL_FLAG_LIQUIDATE) st_liq += 1.0;
             if (flags & FRL_FLAG_SHORTAGE) st_short += 1.0;
         }
-        if (reset_now) {  // reset (:134-165), random_start=False
+        if (reset_now) {  // reset (:134-165); starting point 0 or, with p.random_start, randint(0, int(T * 0.5))
             cash = p.initial_amount;
             double *cw = sl_env(p, cur, n);
             for (int j = 0; j < D; ++j) {
@@ -353,8 +353,8 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
                 *reinterpret_cast<float *>(myrow + j) = 0.0f;
             }
             moved = true;
-            di = 0;
-            start = 0;
+            start = p.random_start ? reset_randint(reset_bits(p.reset_seed, n, k, 0), (int)(p.n_days * 0.5)) : 0;
+            di = start;
             fresh = true;
             sum_trades = 0.0;
             last_cash = 0.0;

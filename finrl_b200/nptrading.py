@@ -131,6 +131,7 @@ class BatchedNpStockTradingEnv(BatchedEnvBase):
         p.obs_amount_floor = float("-inf") if obs_amount_floor is None else float(obs_amount_floor)
         p.price, p.turb_bool, p.obs_tmpl = tables.price.data_ptr(), tables.turb_bool.data_ptr(), tables.obs_tmpl.data_ptr()
         p.price_pitch = int(tables.price.shape[1])
+        p.train_reset = int(self.if_train)  # in-kernel auto-reset redraws the if_train position (reset_seed per launch)
         p.init_stocks = self._init_stocks.data_ptr()
         p.amount, p.kinds, p.stocks, p.cool = self.amount.data_ptr(), self.kinds.data_ptr(), self.stocks.data_ptr(), self.cool.data_ptr()
         p.day, p.total, p.gamma_reward = self.day.data_ptr(), self.total_asset.data_ptr(), self.gamma_reward.data_ptr()

@@ -94,6 +94,7 @@ class BatchedStockTradingEnvStopLoss(BatchedEnvBase):
         p.cash, p.date_index, p.start = self.cash.data_ptr(), self.date_index.data_ptr(), self.starting_point.data_ptr()
         p.assets = self._assets.data_ptr()
         p.fresh, p.last_cash, p.last_total, p.sum_trades = self.fresh.data_ptr(), self.last_cash.data_ptr(), self.last_total.data_ptr(), self.sum_trades.data_ptr()
+        p.random_start = int(self.random_start)  # in-kernel auto-reset redraws the starting point (reset_seed per launch)
         self._p = p
         self.reset()
 

@@ -241,7 +241,13 @@ typedef struct frl_np_params {
     double *init_total;     /* [N] self.initial_total_asset */
     double *episode_return; /* [N] self.episode_return (written when done) */
     int32_t price_pitch;    /* row pitch of `price` in floats: 32 for D <= 32, 128 for D <= 128 */
-    int32_t reserved_;
+    int32_t train_reset;    /* != 0: the in-kernel auto-reset takes the if_train branch (:85-92) with draws from the
+                               counter-based generator below instead of the deterministic branch */
+    uint64_t reset_seed;    /* stream id of this LAUNCH for those draws; the caller changes it on every launch.  Draw
+                               i of env n at rollout step k is splitmix64(reset_seed, n, k, i): stocks =
+                               initial_stocks + randint(0, 64) per stock, amount = initial_capital *
+                               uniform(0.95, 1.05) - (stocks * price).sum() — the reference's distributions (it draws
+                               from numpy's global RandomState, whose order over a batch is undefined anyway) */
 } frl_np_params;
 
 /* StockTradingEnv.reset (:80-101) for envs with mask[n] != 0 (NULL = all).  stocks0 ([D][env_stride]
@@ -253,8 +259,9 @@ FRL_API int32_t frl_np_reset(const frl_np_params *p, const uint8_t *mask, const 
 /* get_state (:149-162) of every env. */
 FRL_API int32_t frl_np_observe(const frl_np_params *p, float *obs, void *stream);
 /* n_steps fused StockTradingEnv.step (:103-147).  Same conventions as frl_trading_rollout; rewards
- * are the f64 values (their numpy kind is in the flag byte).  auto_reset applies the deterministic
- * reset right after a done step (the returned obs is then the reset obs). */
+ * are the f64 values (their numpy kind is in the flag byte).  auto_reset applies the reset right after a
+ * done step (the returned obs is then the reset obs): the deterministic branch, or with train_reset the
+ * if_train branch with in-kernel random draws (reset_seed). */
 FRL_API int32_t frl_np_rollout(const frl_np_params *p, const void *actions, int32_t actions_f64,
                                int64_t act_step_stride, int64_t act_env_stride, int32_t n_steps,
                                double *rewards, uint8_t *flags, float *obs, int32_t obs_mode,
@@ -343,7 +350,9 @@ typedef struct frl_cashpenalty_params {
     const double *hmax_vec; /* [D] or NULL: per-asset hmax array (`actions * self.hmax` broadcasts, :268); numpy
                                array-array promotion then applies: float32 actions * float64 hmax -> float64 */
     int32_t hmax_vec_f32;   /* the caller's array was float32: the product with float32 actions stays float32 */
-    int32_t reserved_;
+    int32_t random_start;   /* != 0: the in-kernel auto-reset draws starting_point = randint(0, int(T * 0.5)) like
+                               reset() with random_start=True (:135-137) instead of 0 */
+    uint64_t reset_seed;    /* stream id of this LAUNCH for those draws (see frl_np_params.reset_seed) */
 } frl_cashpenalty_params;
 
 /* reset (:132-158) for envs with mask[n] != 0 (NULL = all); start_points [N] (NULL = 0, i.e.
@@ -404,7 +413,8 @@ typedef struct frl_stoploss_params {
     /* ---- optional ---- */
     const double *hmax_vec; /* [D] or NULL: per-asset hmax array, as in frl_cashpenalty_params */
     int32_t hmax_vec_f32;
-    int32_t reserved_;
+    int32_t random_start;   /* as in frl_cashpenalty_params */
+    uint64_t reset_seed;
 } frl_stoploss_params;
 
 FRL_API int32_t frl_stoploss_reset(const frl_stoploss_params *p, const uint8_t *mask, const int32_t *start_points,

@@ -141,3 +141,33 @@ def test_reference_invariants_zero_step_and_patient():
         obs, reward, done, flags = env.step(torch.ones((3, D), device="cuda"))
         assert not bool(done.any())
         assert bool((env.holdings == 0).all())
+
+
+@pytest.mark.parametrize("kind", ["cashpenalty", "stoploss"])
+def test_auto_reset_redraws_the_random_start(kind):
+    """random_start=True (the reference's default) must hold for the in-kernel auto-reset too:
+    starting_point = random.choice(range(int(T * 0.5))) per env and episode, not 0."""
+    from finrl_b200 import BatchedStockTradingEnvCashpenalty, BatchedStockTradingEnvStopLoss, CashPenaltyTables, synthetic as syn
+
+    N, T, D = 4000, 40, 6
+    close, _, turb = syn.make_tables(T, D, 0, seed=3)
+    o, h, l, v = syn.make_ohlv(close, 3)
+    tables = CashPenaltyTables.from_arrays(close, np.stack([o, close, h, l, v], axis=2), turb, "cuda")
+    cls = BatchedStockTradingEnvCashpenalty if kind == "cashpenalty" else BatchedStockTradingEnvStopLoss
+
+    def run(seed):
+        env = cls(tables=tables, n_envs=N, random_start=True, hmax=100)
+        env.seed(seed)
+        env.reset(start_points=np.full(N, T - 3))  # everyone two steps from the end
+        zero = torch.zeros((N, D), device="cuda")
+        for _ in range(3):
+            obs, rew, done, fl = env.step(zero, auto_reset=True)
+        assert bool(done.all())
+        return env.starting_point.cpu().numpy().copy(), env.date_index.cpu().numpy().copy(), obs.cpu().numpy()
+
+    sp, di, obs = run(5)
+    assert np.array_equal(sp, di) and sp.min() >= 0 and sp.max() < T // 2
+    assert len(np.unique(sp)) == T // 2 and abs(sp.mean() - (T // 2 - 1) / 2) < 0.5  # uniform over range(int(T * 0.5))
+    tmpl = tables.obs_tmpl.cpu().numpy()
+    assert np.array_equal(obs[:, 1 + D :], tmpl[sp][:, 1 + D :]) and (obs[:, 0] == 1e6).all()  # the reset observation
+    assert np.array_equal(run(5)[0], sp) and not np.array_equal(run(6)[0], sp)

@@ -179,3 +179,51 @@ def test_full_size_properties():
     assert bool((obs[:, 0] == (env.amount.float() * 2.0**-12)).all())
     assert bool((obs[:, 33:63] == env.stocks.t() * 2.0**-6).all())
     assert bool((obs[:, 63:93] == env.cool.t()).all())
+
+
+def test_auto_reset_redraws_the_if_train_position():
+    """with if_train the in-kernel auto-reset must take the reference's RANDOM branch (:85-92), not
+    restart every episode from initial_capital / initial_stocks.  Draws are counter-based (seed, launch, env,
+    step): reproducible under a seed, different per env and per episode, and in the reference's ranges."""
+    from finrl_b200 import BatchedNpStockTradingEnv, synthetic as syn
+
+    for D in (30, 50):  # register kernel and streaming kernel
+        N, T, K = 3000, 6, 2
+        pa, ta, tu = syn.make_np_arrays(*syn.make_tables(T, D, K, seed=2))
+        cfg = {"price_array": pa, "tech_array": ta, "turbulence_array": tu, "if_train": True}
+        init = np.arange(D, dtype=np.float32) % 3
+
+        def run(seed):
+            env = BatchedNpStockTradingEnv(cfg, n_envs=N, initial_stocks=init, turbulence_thresh=1e9)
+            env.seed(seed)
+            zero = torch.zeros((N, D), device="cuda")  # inside the dead-band: nothing trades, positions stay as drawn
+            snaps = []
+            for s in range(2 * (T - 1)):
+                obs, rew, done, fl = env.step(zero, auto_reset=True)
+                if bool(done[0]):
+                    assert bool(done.all())
+                    snaps.append((env.stocks.t().cpu().numpy().copy(), env.amount.cpu().numpy().copy(),
+                                  (env.kinds & 3).cpu().numpy().copy(), env.day.cpu().numpy().copy(), obs.cpu().numpy().copy()))
+            return snaps
+
+        a, b, c = run(11), run(11), run(12)
+        assert len(a) == 2
+        price0 = pa[0].astype(np.float32)
+        for ep, (stocks, amount, kind, day, obs) in enumerate(a):
+            extra = stocks - init[None, :]
+            assert extra.min() >= 0 and extra.max() <= 63 and np.array_equal(extra, np.round(extra))
+            assert len(np.unique(extra[:, 0])) > 40 and abs(extra.mean() - 31.5) < 0.5  # uniform over 0..63
+            assert (day == 0).all() and (kind == 1).all()  # amount is np.float32 after an if_train reset
+            asset = (stocks * price0[None, :]).astype(np.float32).sum(axis=1, dtype=np.float64)
+            factor = (amount + asset) / 1e6
+            assert factor.min() >= 0.9499 and factor.max() <= 1.0501 and 0.99 < factor.mean() < 1.01 and factor.std() > 0.02
+            assert np.array_equal(obs[:, 3 + D : 3 + 2 * D], (stocks * np.float32(2**-6)).astype(np.float32))  # obs shows the reset state
+            assert np.array_equal(b[ep][0], stocks) and np.array_equal(b[ep][1], amount)  # same seed: same draws
+            assert not np.array_equal(c[ep][0], stocks)                                    # other seed: other draws
+        assert not np.array_equal(a[0][0], a[1][0])  # a new episode redraws
+        assert not np.array_equal(a[0][0][0], a[0][0][1])  # envs differ
+        # a fused rollout resets in-kernel as well (step index enters the counter)
+        env = BatchedNpStockTradingEnv(cfg, n_envs=N, initial_stocks=init, turbulence_thresh=1e9)
+        env.rollout(torch.zeros((2 * T, N, D), device="cuda"), obs_mode="none", auto_reset=True)
+        extra = env.stocks.t().cpu().numpy() - init[None, :]
+        assert 0 <= extra.min() and extra.max() <= 63 and len(np.unique(extra)) == 64
