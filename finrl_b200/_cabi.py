@@ -323,6 +323,8 @@ SIGNATURES = {
     "frl_exchange_close": (C.c_int32, [C.c_void_p]),
     "frl_exchange_bind": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "frl_exchange_flush": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "frl_turbulence": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "frl_rolling_cov": (
         C.c_int32,
         [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],

@@ -9,9 +9,11 @@ These feed the envs' tables; in the reference they are per-day pandas loops:
   Mahalanobis distance of day i's returns from the mean of the previous 252 days under their covariance
   (``np.linalg.pinv``), zero for the first year and until the third positive value.
 
-The covariance / mean windows run in ``csrc/preprocess.cu`` (one block per window); the D x D
-pseudo-inverse and the quadratic form use torch's batched linear algebra.  Floating point: pandas' ``.cov``
-is a one-pass Welford update, this is a two-pass sum, so agreement is ~1e-12 relative, not bit-exact.
+Both run in ``csrc/preprocess.cu``: the covariance / mean windows (one block per window) and the D x D
+pseudo-inverse quadratic form (one block per day: cyclic Jacobi eigen-solve in shared memory with
+``np.linalg.pinv``'s ``rcond`` cut-off on the eigenvalues).  Floating point: pandas' ``.cov`` is a one-pass
+Welford update and LAPACK's SVD is not Jacobi, so agreement is ~1e-10 relative for well-conditioned windows,
+not bit-exact; rank-deficient windows agree because the same eigenvalues fall under the cut-off.
 """
 from __future__ import annotations
 
@@ -56,8 +58,10 @@ def rolling_covariance(close, lookback: int = 252, device="cuda"):
     return cov
 
 
-def turbulence_index(close, start: int = 252, device="cuda"):
-    """``calculate_turbulence`` for a complete (NaN-free) close matrix [T, D]: tensor [T] f64."""
+def turbulence_index(close, start: int = 252, device="cuda", rcond: float = 1e-15):
+    """``calculate_turbulence`` for a complete (NaN-free) close matrix [T, D]: tensor [T] f64.  Window
+    statistics by ``frl_rolling_cov``, pseudo-inverse quadratic form by ``frl_turbulence`` (batched Jacobi
+    eigen-solve in csrc/preprocess.cu; ``rcond`` is ``np.linalg.pinv``'s default cut-off)."""
     import torch
 
     ret = _returns(close, device)
@@ -69,12 +73,13 @@ def turbulence_index(close, start: int = 252, device="cuda"):
     # pct_change and is dropped by the reference (hist_price.iloc[isna().sum().min():]) -> start - 1 rows
     cov, mean = _rolling_cov(ret, first_row=1, n_rows=start, n_out=T - start - 1, want_mean=True) if T > start + 1 else (None, None)
     cov0, mean0 = _rolling_cov(ret, first_row=1, n_rows=start - 1, n_out=1, want_mean=True)
-    covs = cov0 if cov is None else torch.cat([cov0, cov], dim=0)      # window of day start + k
-    means = mean0 if mean is None else torch.cat([mean0, mean], dim=0)
-    cur = ret[start:] - means                                            # [T - start, D]
-    pinv = torch.linalg.pinv(covs, hermitian=True)
-    temp = torch.einsum("nd,nde,ne->n", cur, pinv, cur)
-    pos = temp > 0
-    count = torch.cumsum(pos.to(torch.int64), dim=0)
-    out[start:] = torch.where(pos & (count > 2), temp, torch.zeros_like(temp))  # first two positives are suppressed
+    covs = (cov0 if cov is None else torch.cat([cov0, cov], dim=0)).contiguous()      # window of day start + k
+    means = (mean0 if mean is None else torch.cat([mean0, mean], dim=0)).contiguous()
+    scratch = torch.empty(T - start, dtype=torch.float64, device=ret.device)
+    with torch.cuda.device(ret.device):
+        _cabi.check(
+            _cabi.lib().frl_turbulence(_cabi.ptr(ret), T, D, int(start), _cabi.ptr(covs), _cabi.ptr(means), float(rcond),
+                                       _cabi.ptr(scratch), _cabi.ptr(out), _cabi.current_stream(ret.device)),
+            "frl_turbulence",
+        )
     return out

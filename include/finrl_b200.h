@@ -478,6 +478,16 @@ FRL_API int32_t frl_crypto_step(const frl_crypto_params *p, const void *actions,
 FRL_API int32_t frl_rolling_cov(const double *ret, int32_t n_days, int32_t stock_dim, int32_t first_row,
                                 int32_t n_rows, int32_t n_out, double *cov_out, double *mean_out, void *stream);
 
+/* FeatureEngineer.calculate_turbulence (finrl/meta/preprocessor/preprocessors.py:215-267) for a complete
+ * (NaN-free) return table ret[T][D] (row 0 = the NaN row of pct_change, never read): for every day
+ * i >= start, temp = x^T pinv(cov_i) x with x = ret[i] - mean_i, where cov[i - start] / mean[i - start] are the
+ * window statistics from frl_rolling_cov; np.linalg.pinv's cut-off (singular values <= rcond * largest, 1e-15
+ * by default) is applied to the eigenvalues of the symmetric matrix (batched Jacobi eigen-solve, one thread
+ * block per day).  out[T]: 0 for the first `start` days, then temp where positive except the first two positive
+ * values (:250-262).  scratch: [T - start] doubles. */
+FRL_API int32_t frl_turbulence(const double *ret, int32_t n_days, int32_t stock_dim, int32_t start, const double *cov,
+                               const double *mean, double rcond, double *scratch, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

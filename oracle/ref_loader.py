@@ -25,6 +25,7 @@ ENV_FILES = {
     "env_nas100_wrds": "finrl/meta/env_stock_trading/env_nas100_wrds.py",
     "env_multiple_crypto": "finrl/meta/env_cryptocurrency_trading/env_multiple_crypto.py",
     "env_stocktrading_stoploss": "finrl/meta/env_stock_trading/env_stocktrading_stoploss.py",
+    "preprocessors": "finrl/meta/preprocessor/preprocessors.py",
 }
 
 
@@ -144,9 +145,16 @@ def _install_finrl_stubs():
         return
     names = ["finrl", "finrl.agents", "finrl.agents.elegantrl", "finrl.agents.elegantrl.models",
              "finrl.agents.stablebaselines3", "finrl.agents.stablebaselines3.models", "finrl.meta",
-             "finrl.meta.data_processor"]
+             "finrl.meta.data_processor", "finrl.config", "finrl.meta.preprocessor",
+             "finrl.meta.preprocessor.yahoodownloader", "stockstats"]
     for n in names:
         sys.modules[n] = types.ModuleType(n)
+    # preprocessors.py: `from stockstats import StockDataFrame`, `from finrl import config`, YahooDownloader —
+    # module-level imports that calculate_turbulence / data_split never touch
+    sys.modules["stockstats"].StockDataFrame = object
+    sys.modules["finrl"].config = sys.modules["finrl.config"]
+    sys.modules["finrl.config"].INDICATORS = []
+    sys.modules["finrl.meta.preprocessor.yahoodownloader"].YahooDownloader = object
     sys.modules["finrl.agents.elegantrl.models"].DRLAgent = object
     sys.modules["finrl.agents.stablebaselines3.models"].DRLAgent = object
     sys.modules["finrl.meta.data_processor"].DataProcessor = object
@@ -162,7 +170,7 @@ def load(name: str):
     if not available():
         raise RuntimeError(f"reference tree not present at {REF_ROOT}")
     _install_stubs()
-    if name == "env_multiple_crypto":
+    if name in ("env_multiple_crypto", "preprocessors"):
         _install_finrl_stubs()
     path = os.path.join(REF_ROOT, ENV_FILES[name])
     spec = importlib.util.spec_from_file_location("_finrl_ref_" + name, path)

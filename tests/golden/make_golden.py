@@ -414,6 +414,25 @@ def gen_adapter_cashpenalty_prediction(name, T, D, seed, hmax=5000, threshold=No
     print(f"{name}: account rows={len(df_account)}, action rows={len(df_actions)}")
 
 
+# ------------------------------------------------------------------------------------------
+# table precompute: FeatureEngineer.calculate_turbulence (finrl/meta/preprocessor/preprocessors.py:215-267)
+# ------------------------------------------------------------------------------------------
+def gen_turbulence(name, T, D, seed, duplicate=None):
+    """The reference function itself on a synthetic close frame.  ``duplicate=(a, b)`` makes ticker b an exact
+    copy of ticker a: a rank-deficient covariance, so np.linalg.pinv's rcond cut-off is exercised."""
+    mod = ref_loader.load("preprocessors")
+    close, _, _ = syn.make_tables(T, D, 0, seed=seed)
+    if duplicate is not None:
+        close[:, duplicate[1]] = close[:, duplicate[0]]
+    df = syn.make_frame(close, np.zeros((0, T, D)), np.zeros(T), tech_names=[])
+    fe = mod.FeatureEngineer(use_technical_indicator=False, use_turbulence=True)
+    out = fe.calculate_turbulence(df)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), close=close, turbulence=out["turbulence"].to_numpy(np.float64),
+                        date=np.array(out["date"].tolist(), dtype="U16"), **_meta())
+    t = out["turbulence"].to_numpy()
+    print(f"{name}: T={T} D={D}, nonzero={int((t > 0).sum())}, max={t.max():.4f}")
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     which = set(sys.argv[1:])
@@ -484,6 +503,10 @@ def main():
                    initial_capital=2e5, scales=[300.0, 1.5, 0.02, 45.0, 7000.0])
         gen_crypto("crypto_d8_lb3_f64", T=40, D=8, K=2, n_steps=80, seed=42, act_dtype=np.float64, lookback=3,
                    initial_capital=1e6, scales=[30000.0, 2000.0, 1.0, 0.5, 150.0, 20.0, 6.0, 0.08])
+    if want("turbulence"):
+        gen_turbulence("turbulence_d30", T=300, D=30, seed=91)
+        gen_turbulence("turbulence_d7_dup", T=290, D=7, seed=92, duplicate=(2, 5))
+        gen_turbulence("turbulence_d100", T=272, D=100, seed=93)
     if want("adapter"):
         gen_adapter_trading_prediction("adapter_trading_prediction", T=36, D=30, K=8, seed=71)
         gen_adapter_ensemble("adapter_ensemble_two_windows", W=21, D=30, K=8, seed=72)
