@@ -62,7 +62,7 @@ class TradingTables:
         return 1 + 2 * self.stock_dim + self.n_tech * self.stock_dim
 
     @staticmethod
-    def from_arrays(close, tech, risk, device) -> "TradingTables":
+    def from_arrays(close, tech, risk, device, allow_nonpositive_close: bool = False) -> "TradingTables":
         import torch
 
         close = np.ascontiguousarray(close, dtype=np.float64)
@@ -71,6 +71,16 @@ class TradingTables:
             raise ValueError(f"stock_dim must be in 1..128 for the StockTradingEnv kernels (got {D})")
         tech = np.ascontiguousarray(tech, dtype=np.float64).reshape(-1, T, D)
         K = tech.shape[0]
+        # A close <= 0 (or NaN) on a tradable stock has no defined behaviour in the reference: its buy path divides
+        # by the price (`state[0] // (price * (1 + cost))`, env_stocktrading.py:178-180: ZeroDivisionError while the
+        # cash is still a Python number, inf shares "available" once it is a numpy scalar).  Refuse such tables unless
+        # the stock carries the disable flag that day (first indicator == 1.0: never traded) or the caller insists.
+        tradable = np.ones((T, D), dtype=bool) if K == 0 else tech[0] != 1.0
+        bad = ~(close > 0) & tradable
+        if bad.any() and not allow_nonpositive_close:
+            t, j = np.argwhere(bad)[0]
+            raise ValueError(f"close[{t}, {j}] = {close[t, j]} is not a positive price (and the stock is not disabled that day); "
+                             "clean the frame or pass allow_nonpositive_close=True")
         risk = np.zeros(T) if risk is None else np.ascontiguousarray(risk, dtype=np.float64)
         if risk.shape != (T,):
             raise ValueError(f"risk must have shape ({T},), got {risk.shape}")

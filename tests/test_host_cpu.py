@@ -187,6 +187,21 @@ def test_gym_vec_env_is_dummy_vec_env_protocol():
     assert GymVecEnv([lambda: envs[1]]).render() == ["state", 3]  # one env: its own render(), as DummyVecEnv does
 
 
+def test_tables_refuse_nonpositive_prices_of_tradable_stocks():
+    from finrl_b200 import synthetic as syn
+    from finrl_b200.tables import TradingTables
+
+    close, tech, turb = syn.make_tables(6, 4, 2, seed=1)
+    bad = close.copy()
+    bad[3, 2] = 0.0
+    with pytest.raises(ValueError, match=r"close\[3, 2\]"):
+        TradingTables.from_arrays(bad, tech, turb, "cpu")
+    tech2 = tech.copy()
+    tech2[0, 3, 2] = 1.0  # the reference's disable flag: that stock is never traded that day
+    assert TradingTables.from_arrays(bad, tech2, turb, "cpu").n_days == 6
+    assert TradingTables.from_arrays(bad, tech, turb, "cpu", allow_nonpositive_close=True).stock_dim == 4
+
+
 def test_expand_obs_host_matches_numpy():
     """frl_expand_obs_host (host threads, no GPU): factored rows -> dense rows, against plain numpy indexing."""
     from finrl_b200.trading import FactoredObs

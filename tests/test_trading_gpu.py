@@ -357,3 +357,61 @@ def test_factored_host_observation_equals_dense():
     assert (flg_h.numpy() & 1).sum() >= 0 and int(fact_env.episode.max().item()) >= 2  # episodes really ended
     env_part, sday = fact_env.observe_factored()
     assert np.array_equal(env_part.cpu().numpy(), fo.env_part.numpy()) and np.array_equal(sday.cpu().numpy(), fo.state_day.numpy())
+
+
+@pytest.mark.parametrize("small_max", [0, 8192])  # thread-per-env and 8-lanes-per-env kernels
+def test_action_magnitudes_up_to_the_clamp_match_the_reference_arithmetic(small_max):
+    """Documented limit: |int(action * hmax)| is clamped to 2^26 - 1 (sort-key packing).  Everything up to AND
+    INCLUDING that magnitude must behave exactly like the reference's int64 arithmetic (the oracle does not
+    clamp): ties at the boundary, cash-limited buys of tens of millions of shares, sells capped by holdings."""
+    from finrl_b200 import BatchedStockTradingEnv, TradingTables, _cabi, synthetic as syn
+    from oracle import oracle as ora
+
+    N, T, D, K = 96, 12, 30, 2
+    hmax = 1 << 20
+    lim = ((1 << 26) - 1) / hmax  # exactly representable: the product with hmax is exactly 2^26 - 1
+    close, tech, turb = syn.make_tables(T, D, K, seed=8)
+    kw = dict(hmax=hmax, initial_amount=5e10, buy_cost_pct=0.001, sell_cost_pct=0.001, reward_scaling=1e-4,
+              turbulence_threshold=None)
+    _cabi.set_option("trading_small_max", small_max)
+    try:
+        env = BatchedStockTradingEnv(tables=TradingTables.from_arrays(close, tech, turb, "cuda"), n_envs=N, **kw)
+        o = ora.TradingOracle(close, tech, turb, N, **kw)
+        rng = np.random.default_rng(5)
+        for s in range(T - 1):
+            a = rng.uniform(-64.0, 64.0, size=(N, D))
+            a = np.clip(a, -lim, lim)
+            a[rng.random((N, D)) < 0.2] = lim      # many entries exactly AT the clamp (all tie there)
+            a[rng.random((N, D)) < 0.2] = -lim
+            assert np.abs((a * hmax).astype(np.int64)).max() == (1 << 26) - 1
+            obs, rew, done, fl = env.step(torch.from_numpy(a).cuda(), auto_reset=False)
+            oobs, orew, ofl = o.step(a, auto_reset=False)
+            assert np.array_equal(env.hold.t().cpu().numpy(), o.hold), s
+            assert np.array_equal(env.cash.cpu().numpy(), o.cash) and np.array_equal(rew.cpu().numpy(), orew), s
+            assert np.array_equal(env.trades.cpu().numpy(), o.trades) and np.array_equal(obs.cpu().numpy(), oobs), s
+        assert int(env.hold.max().item()) > 10_000_000  # the magnitudes really were exercised
+    finally:
+        _cabi.set_option("trading_small_max", 8192)
+
+
+def test_hmax_times_days_limit_is_enforced_at_the_boundary():
+    """Documented limit: holdings are int32, so hmax * (T + 1) must stay below 2^31 — rejected at construction
+    one past the boundary, accepted (and stepping exactly) right below it."""
+    from finrl_b200 import BatchedStockTradingEnv, TradingTables, synthetic as syn
+    from oracle import oracle as ora
+
+    T, D, K = 3, 4, 1
+    close, tech, turb = syn.make_tables(T, D, K, seed=9)
+    tables = TradingTables.from_arrays(close, tech, turb, "cuda")
+    ok = (2**31 - 1) // (T + 1)
+    with pytest.raises(ValueError):
+        BatchedStockTradingEnv(tables=tables, n_envs=2, hmax=ok + 1)
+    kw = dict(hmax=ok, initial_amount=1e13, turbulence_threshold=None)
+    env = BatchedStockTradingEnv(tables=tables, n_envs=2, **kw)
+    o = ora.TradingOracle(close, tech, turb, 2, **kw)
+    a = np.array([[0.1, -0.1, 0.124, 0.0], [0.12, 0.05, -0.2, 0.11]])  # < 2^26 shares each
+    for s in range(T):
+        obs, rew, done, fl = env.step(torch.from_numpy(a).cuda(), auto_reset=False)
+        oobs, orew, ofl = o.step(a, auto_reset=False)
+        assert np.array_equal(env.hold.t().cpu().numpy(), o.hold) and np.array_equal(env.cash.cpu().numpy(), o.cash)
+        assert np.array_equal(fl.cpu().numpy(), ofl) and np.array_equal(rew.cpu().numpy(), orew)
