@@ -201,6 +201,7 @@ class CashPenaltyParams(C.Structure):
         ("hmax_vec_f32", C.c_int32),
         ("random_start", C.c_int32),
         ("reset_seed", C.c_uint64),
+        ("close_rc", C.c_void_p),
     ]
 
 

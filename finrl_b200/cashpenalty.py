@@ -45,6 +45,7 @@ class CashPenaltyTables:
     close: "torch.Tensor"     # [T, D] f64
     turb: "torch.Tensor"      # [T] f64
     obs_tmpl: "torch.Tensor"  # [T, O] f32
+    close_rc: "torch.Tensor" = None  # [T, D, 2] f64: (close, correctly rounded 1 / close) pairs
 
     @property
     def obs_dim(self) -> int:
@@ -65,8 +66,11 @@ class CashPenaltyTables:
         tmpl[:, 1 + D :] = info.reshape(T, D * Cc).astype(np.float32)
         turb = np.zeros(T) if turb is None else np.ascontiguousarray(turb, dtype=np.float64)
         dev = torch.device(device)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            close_rc = np.stack([close, 1.0 / close], axis=2)  # IEEE division: correctly rounded reciprocals (1/0 = inf)
         return CashPenaltyTables(n_days=T, stock_dim=D, n_cols=Cc, close=torch.from_numpy(close).to(dev),
-                                 turb=torch.from_numpy(turb).to(dev), obs_tmpl=torch.from_numpy(tmpl).to(dev))
+                                 turb=torch.from_numpy(turb).to(dev), obs_tmpl=torch.from_numpy(tmpl).to(dev),
+                                 close_rc=torch.from_numpy(np.ascontiguousarray(close_rc)).to(dev))
 
 
 class BatchedStockTradingEnvCashpenalty(BatchedEnvBase):
@@ -138,6 +142,10 @@ class BatchedStockTradingEnvCashpenalty(BatchedEnvBase):
         p.turbulence_threshold = float(turbulence_threshold) if turbulence_threshold is not None else 0.0
         p.initial_amount, p.cash_penalty_proportion = float(initial_amount), float(cash_penalty_proportion)
         p.close, p.turb, p.obs_tmpl = tables.close.data_ptr(), tables.turb.data_ptr(), tables.obs_tmpl.data_ptr()
+        import os
+
+        use_rc = tables.close_rc is not None and os.environ.get("FRL_CP_NO_RCLOSE") != "1"  # A/B switch
+        p.close_rc = tables.close_rc.data_ptr() if use_rc else None
         p.cash, p.hold, p.date_index, p.start = self.cash.data_ptr(), self.hold.data_ptr(), self.date_index.data_ptr(), self.starting_point.data_ptr()
         p.hold_alt = self.hold_alt.data_ptr()
         p.fresh, p.last_cash, p.last_total, p.sum_trades = self.fresh.data_ptr(), self.last_cash.data_ptr(), self.last_total.data_ptr(), self.sum_trades.data_ptr()

@@ -74,6 +74,9 @@ __device__ __forceinline__ double cp_transaction(const frl_cashpenalty_params &p
 #ifndef FRL_CP_ASYNC_STAGE
 #define FRL_CP_ASYNC_STAGE 1  // stage the actions with cp.async instead of load + store batches
 #endif
+#ifndef FRL_CP_BULK_STAGE
+#define FRL_CP_BULK_STAGE 1  // A/B switch for the bulk-staged variant
+#endif
 #ifndef FRL_CP_U
 #define FRL_CP_U 4  // assets per software-pipelined batch of the pass (A/B on B200: 2 -> 0.290 ms, 3 -> 0.255, 4..6 -> 0.240, 8 -> 0.250)
 #endif
@@ -88,7 +91,12 @@ __device__ __forceinline__ void cp_async_elem(double *dst, const double *src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-template <typename ActT, int WARPS, bool HVEC>
+// BULK (decided at launch): float actions in the default [N][D] layout, D a multiple of four, 16-byte aligned tiles,
+// continuous shares and the (close, 1/close) table.  The tile's 32 x D actions are ONE contiguous run that the copy
+// engine (TMA) stages as flat [32][D] rows with a single instruction — instead of D cp.async per lane and their index
+// arithmetic (20 % of the kernel's instructions) — the pass handles four assets per 128-bit shared-memory word, and
+// `actions / closings` is the three-instruction exact division by the tabulated reciprocal.
+template <typename ActT, int WARPS, bool HVEC, bool BULK>
 __global__ void __launch_bounds__(WARPS * 32, FRL_CP_MIN_BLOCKS * 128 / (WARPS * 32))
 cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restrict__ actions, long long act_step_stride,
                            long long act_env_stride, int n_steps, double *__restrict__ rewards,
@@ -99,12 +107,15 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;
-    const int P = D | 1;  // odd row pitch: conflict-free per-lane row walks
-    const size_t warp_bytes = (size_t)32 * P * sizeof(ActT) + 32 * sizeof(float) + 32 * sizeof(int);
+    // row pitch: odd (conflict-free per-lane row walks with scalar accesses), or D itself in the bulk-staged variant
+    // (flat rows; its 128-bit accesses are conflict-free for any pitch that is a multiple of four)
+    const int P = BULK ? D : (D | 1);
+    const size_t warp_bytes = (size_t)32 * (D | 1) * sizeof(ActT) + 32 * sizeof(float) + 32 * sizeof(int) + 16;
     unsigned char *base = smem_raw + warp * ((warp_bytes + 15) & ~(size_t)15);
     ActT *stage = reinterpret_cast<ActT *>(base);                       // [32 envs][P]
-    float *cashf = reinterpret_cast<float *>(base + (size_t)32 * P * sizeof(ActT));
+    float *cashf = reinterpret_cast<float *>(base + (size_t)32 * (D | 1) * sizeof(ActT));
     int *di_s = reinterpret_cast<int *>(cashf + 32);
+    const unsigned mbar = smem_u32(di_s + 32);  // staging mbarrier (BULK); 8-byte aligned: all pieces before it are 128 B multiples
 
     const long long env0 = ((long long)blockIdx.x * WARPS + warp) * 32;
     if (env0 >= N) return;
@@ -118,13 +129,28 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
     bool fresh = (bits0 & 1) != 0;
     bool cur = (bits0 & 2) != 0;  // which holdings buffer is current: hold (0) or hold_alt (1)
     ActT *myrow = stage + (size_t)lane * P;
+    static_assert(!BULK || (sizeof(ActT) == 4 && CP_U == 4), "the bulk-staged variant reads float4 batches");
+    unsigned stage_phase = 0;
+    if (BULK && lane == 0) mbar_init(mbar, 1);
     double st_r = 0.0, st_r2 = 0.0, st_done = 0.0, st_epi = 0.0, st_liq = 0.0, st_short = 0.0;
 
     for (int k = 0; k < n_steps; ++k) {
         // ---- stage this step's actions (coalesced) into [env][P] rows ----
         const ActT *abase = actions + (size_t)k * act_step_stride;
         __syncwarp();
-        if (act_env_stride == D) {
+        const bool tma = BULK && nvalid == 32;  // warp-uniform; the ragged last tile is copied element-wise
+        if (tma) {
+            fence_proxy_async_smem();  // the rows were read / written through the generic proxy during the last step
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned bytes = 32u * (unsigned)D * (unsigned)sizeof(ActT);
+                mbar_expect_tx(mbar, bytes);
+                bulk_copy_g2s(smem_u32(stage), abase + (size_t)env0 * D, bytes, mbar);
+            }
+        } else if (BULK) {
+            const ActT *tile = abase + (size_t)env0 * D;
+            for (int e = lane; e < 32 * D; e += 32) stage[e] = e < nvalid * D ? tile[e] : ActT(0);
+        } else if (act_env_stride == D) {
             const ActT *tile = abase + (size_t)env0 * D;
             const int cnt = nvalid * D;
             int row = 0, col = lane;
@@ -174,9 +200,14 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
             cb[u] = u < D ? __ldg(crow + u) : 1.0;
             hq += ld;
         }
+        if (tma) {
+            mbar_wait(mbar, stage_phase);
+            stage_phase ^= 1u;
+        } else if (!BULK) {
 #if FRL_CP_ASYNC_STAGE
-        asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
 #endif
+        }
         __syncwarp();
 
         int flags = 0;
@@ -198,6 +229,47 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
             // ---- the pass: np.sum(|actions|), np.dot(holdings, closings), proceeds, spend, tentative holdings ----
             double asum = 0.0, asset_value = 0.0, proceeds = 0.0, spend = 0.0;
             double *hw = (cur ? p.hold : p.hold_alt) + n;
+            if constexpr (BULK) {
+                const double2 *crc = reinterpret_cast<const double2 *>(p.close_rc) + (size_t)di * D;
+                for (int j0 = 0; j0 < D; j0 += 4) {  // D is a multiple of four
+                    double hn_[4];  // the next four holdings fly while these four are traded
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        hn_[u] = j0 + 4 + u < D ? __ldcg(hq) : 0.0;
+                        hq += ld;
+                    }
+                    const float4 a4 = *reinterpret_cast<const float4 *>(myrow + j0);
+                    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                    float hf[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double2 cr = __ldg(crc + j0 + u);  // (close, RN(1 / close)): warp-uniform, L1-resident
+                        const double c = cr.x, h = hb[u];
+                        double v = HVEC ? (p.hmax_vec_f32 ? (double)fmul(av[u], (float)__ldg(p.hmax_vec + j0 + u))
+                                                          : dmul((double)av[u], __ldg(p.hmax_vec + j0 + u)))
+                                        : (double)fmul(av[u], (float)p.hmax);
+                        if (!(c > 0.0)) v = 0.0;  // np.where(closings > 0, actions, 0)
+                        {  // v / c, correctly rounded (Markstein); 0 * (1/0 = inf) = nan like numpy's 0 / 0
+                            const double q = dmul(v, cr.y);
+                            const double e = __fma_rn(-c, q, v);
+                            v = __fma_rn(e, cr.y, q);
+                        }
+                        v = (v > -h) ? v : -h;  // np.maximum(actions, -holdings)
+                        if (liq) v = -h;        // turbulence: clear out all positions
+                        asum += fabs((double)av[u]);
+                        asset_value = dadd(asset_value, dmul(h, c));
+                        proceeds = dadd(proceeds, dmul(v < 0.0 ? -v : 0.0, c));
+                        spend = dadd(spend, dmul(v > 0.0 ? v : 0.0, c));
+                        const double hn = dadd(h, v);  // holdings_updated = holdings + transactions (:361)
+                        if (valid) *hw = hn;
+                        hf[u] = (float)hn;
+                        hw += ld;
+                    }
+                    *reinterpret_cast<float4 *>(myrow + j0) = make_float4(hf[0], hf[1], hf[2], hf[3]);  // observation image
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) hb[u] = hn_[u];
+                }
+            } else
             for (int j0 = 0; j0 < D; j0 += CP_U) {
                 // software pipeline: the next batch of CP_U independent holding loads is in flight while this
                 // one is traded (the holdings stream is the DRAM-latency critical path of the pass)
@@ -390,7 +462,7 @@ int32_t cp_validate(const frl_cashpenalty_params *p)
 size_t cp_smem_bytes(int D, size_t elem, int warps)
 {
     const int P = D | 1;
-    const size_t warp_bytes = (size_t)32 * P * elem + 32 * sizeof(float) + 32 * sizeof(int);
+    const size_t warp_bytes = (size_t)32 * P * elem + 32 * sizeof(float) + 32 * sizeof(int) + 16;  // + the staging mbarrier
     return warps * ((warp_bytes + 15) & ~(size_t)15);
 }
 
@@ -399,7 +471,13 @@ int32_t cp_launch(const frl_cashpenalty_params &p, const void *actions, long lon
                   double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
 {
     const size_t smem = cp_smem_bytes(p.stock_dim, sizeof(ActT), WARPS);
-    auto kern = p.hmax_vec ? cashpenalty_rollout_kernel<ActT, WARPS, true> : cashpenalty_rollout_kernel<ActT, WARPS, false>;
+    // bulk-staged variant: float actions, default layout, D % 4 == 0, every tile's first action 16-byte aligned,
+    // continuous shares, reciprocal table present
+    constexpr bool kCanBulk = FRL_CP_BULK_STAGE && sizeof(ActT) == 4 && CP_U == 4;
+    const bool bulk = kCanBulk && estride == p.stock_dim && (p.stock_dim & 3) == 0 && (sstride & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(actions) & 15) == 0 && p.close_rc != nullptr && !p.discrete_actions;
+    auto kern = bulk ? (p.hmax_vec ? cashpenalty_rollout_kernel<ActT, WARPS, true, kCanBulk> : cashpenalty_rollout_kernel<ActT, WARPS, false, kCanBulk>)
+                     : (p.hmax_vec ? cashpenalty_rollout_kernel<ActT, WARPS, true, false> : cashpenalty_rollout_kernel<ActT, WARPS, false, false>);
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {

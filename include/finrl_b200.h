@@ -353,6 +353,11 @@ typedef struct frl_cashpenalty_params {
     int32_t random_start;   /* != 0: the in-kernel auto-reset draws starting_point = randint(0, int(T * 0.5)) like
                                reset() with random_start=True (:135-137) instead of 0 */
     uint64_t reset_seed;    /* stream id of this LAUNCH for those draws (see frl_np_params.reset_seed) */
+    const double *close_rc; /* [T][D][2] or NULL: (close, RN(1 / close)) pairs — the reciprocal by IEEE division on the
+                               host (1/0 = inf, sign kept).  With it `actions / closings` (:286) costs three
+                               instructions instead of a division routine and stays correctly rounded: q = RN(v * r),
+                               e = fma(-c, q, v) exact, RN(q + e * r) = RN(v / c) (Markstein's theorem; the correction
+                               step CUDA's own division ends with).  Required by the bulk-staged kernel variant. */
 } frl_cashpenalty_params;
 
 /* reset (:132-158) for envs with mask[n] != 0 (NULL = all); start_points [N] (NULL = 0, i.e.
