@@ -74,6 +74,9 @@ __device__ __forceinline__ double cp_transaction(const frl_cashpenalty_params &p
 #ifndef FRL_CP_ASYNC_STAGE
 #define FRL_CP_ASYNC_STAGE 1  // stage the actions with cp.async instead of load + store batches
 #endif
+#ifndef FRL_CP_PF
+#define FRL_CP_PF 2  // bulk-staged variant: batches of four holdings in flight ahead of the one being traded
+#endif
 #ifndef FRL_CP_BULK_STAGE
 #define FRL_CP_BULK_STAGE 1  // A/B switch for the bulk-staged variant
 #endif
@@ -200,6 +203,21 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
             cb[u] = u < D ? __ldg(crow + u) : 1.0;
             hq += ld;
         }
+        // bulk-staged variant: FRL_CP_PF more batches right away, each in its OWN registers.  The holdings stream is
+        // the DRAM-latency critical path of the pass (51 % of the stall samples were long-scoreboard waits with one
+        // batch in flight).  The pass below is unrolled over the FRL_CP_PF + 1 register sets so that a set is simply
+        // reloaded after its batch has been traded — rotating the sets with moves would wait for the newest loads.
+        double hset[BULK ? FRL_CP_PF : 1][4];
+        if constexpr (BULK) {
+#pragma unroll
+            for (int b = 0; b < FRL_CP_PF; ++b) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    hset[b][u] = 4 * (b + 1) + u < D ? __ldcg(hq) : 0.0;
+                    hq += ld;
+                }
+            }
+        }
         if (tma) {
             mbar_wait(mbar, stage_phase);
             stage_phase ^= 1u;
@@ -231,20 +249,16 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
             double *hw = (cur ? p.hold : p.hold_alt) + n;
             if constexpr (BULK) {
                 const double2 *crc = reinterpret_cast<const double2 *>(p.close_rc) + (size_t)di * D;
-                for (int j0 = 0; j0 < D; j0 += 4) {  // D is a multiple of four
-                    double hn_[4];  // the next four holdings fly while these four are traded
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        hn_[u] = j0 + 4 + u < D ? __ldcg(hq) : 0.0;
-                        hq += ld;
-                    }
+                // one batch of four assets out of register set h4; afterwards the set is reloaded with the batch
+                // FRL_CP_PF + 1 further on (hq already points there)
+                auto trade4 = [&](double (&h4)[4], int j0) {
                     const float4 a4 = *reinterpret_cast<const float4 *>(myrow + j0);
                     const float av[4] = {a4.x, a4.y, a4.z, a4.w};
                     float hf[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const double2 cr = __ldg(crc + j0 + u);  // (close, RN(1 / close)): warp-uniform, L1-resident
-                        const double c = cr.x, h = hb[u];
+                        const double c = cr.x, h = h4[u];
                         double v = HVEC ? (p.hmax_vec_f32 ? (double)fmul(av[u], (float)__ldg(p.hmax_vec + j0 + u))
                                                           : dmul((double)av[u], __ldg(p.hmax_vec + j0 + u)))
                                         : (double)fmul(av[u], (float)p.hmax);
@@ -267,7 +281,16 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
                     }
                     *reinterpret_cast<float4 *>(myrow + j0) = make_float4(hf[0], hf[1], hf[2], hf[3]);  // observation image
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) hb[u] = hn_[u];
+                    for (int u = 0; u < 4; ++u) {
+                        h4[u] = j0 + 4 * (FRL_CP_PF + 1) + u < D ? __ldcg(hq) : 0.0;
+                        hq += ld;
+                    }
+                };
+                for (int j0 = 0; j0 < D; j0 += 4 * (FRL_CP_PF + 1)) {  // D is a multiple of four
+                    trade4(hb, j0);
+#pragma unroll
+                    for (int b = 0; b < FRL_CP_PF; ++b)
+                        if (j0 + 4 * (b + 1) < D) trade4(hset[b], j0 + 4 * (b + 1));
                 }
             } else
             for (int j0 = 0; j0 < D; j0 += CP_U) {

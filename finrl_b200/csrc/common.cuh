@@ -114,16 +114,19 @@ __device__ __forceinline__ void reduce_stats8(double (&v)[FRL_N_STATS], int lane
 // rendezvous: measured cost on the 1M-env StockTradingEnv step: none (a completion ticket per warp or per block,
 // the textbook last-block pattern, cost 4-8 % there — the kernel is latency-bound and every fence + atomic round
 // trip sits on a warp's critical path; tools/ab_stats_tail.sh, profiles/r02_ab_stats_exchange.txt).
-__device__ __forceinline__ void stats_push_accumulator(frl_stats_block *b, int which)
+static __device__ __noinline__ void stats_push_accumulator(frl_stats_block *b, int which)
 {
     const unsigned n_peers = b->n_peers;
     if (n_peers == 0) return;
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < FRL_N_STATS; ++s) {
         const double v = __longlong_as_double(
             (long long)atomicExch(reinterpret_cast<unsigned long long *>(&b->sum[which][s]), 0ull));
-        if (v != 0.0)
-            for (unsigned r = 0; r < n_peers; ++r) atomicAdd_system(b->peer_total[r] + s, v);
+        if (v != 0.0) {
+#pragma unroll 1
+            for (unsigned r = 0; r < n_peers; ++r)  // RED.E.ADD.F64.RN.STRONG.SYS on peer-mapped global memory
+                asm volatile("red.global.sys.add.f64 [%0], %1;" ::"l"(b->peer_total[r] + s), "d"(v) : "memory");
+        }
     }
 }
 
