@@ -2,7 +2,7 @@
 # launch list of the default bench command (plain run first, then the same command under ncu with only the
 # duration metric), plus the per-kernel share of device time
 set -u
-CMD="python bench.py --steps 30 --warmup 3 --no-cpu --e2e-steps 2"
+CMD="python bench.py --steps 30 --warmup 3 --no-cpu --no-extra --e2e-steps 2"
 $CMD > gpurun_out/plain_launches.log 2>&1 || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 python - <<'PY'
