@@ -544,14 +544,24 @@ def run_ours(args, wl):
 
     if use_pipelined:
         _, h_obs, h_rew, h_flag = env.make_host_buffers("dense", tdt)
+        h2d = h_act_pool[0].numel() * h_act_pool[0].element_size()
+        d2h_dense = h_obs.numel() * 4 + h_rew.numel() * 8 + h_flag.numel()
+        d2h_fact = N * (4 * (1 + wl.D) + 4) + h_rew.numel() * 8 + h_flag.numel()
+        # the call a host-resident user makes: dense obs[N,O] in THEIR buffer.  By default the observation crosses PCIe
+        # in factored form and host threads rebuild the dense rows slice by slice as the transfers land
         dense = time_e2e(lambda i: env.step_host(h_act_pool[i % POOL], h_obs, h_rew, h_flag, auto_reset=True,
                                                  n_chunks=args.e2e_chunks))
-        h2d = h_act_pool[0].numel() * h_act_pool[0].element_size()
+        expanded = env._expand_threads() >= 4
+        dma = time_e2e(lambda i: env.step_host(h_act_pool[i % POOL], h_obs, h_rew, h_flag, auto_reset=True,
+                                               n_chunks=args.e2e_chunks, host_expand=False))
         e2e = {"value": dense, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": h_obs.numel() * 4 + h_rew.numel() * 8 + h_flag.numel(), "steps": e2e_steps,
-               "layout": "dense",
-               "api": ("BatchedStockTradingEnv.step_host: pinned host actions in, dense obs[N,O] + reward + flags back to "
-                       f"pinned host memory, pipelined in {args.e2e_chunks} env slices over 3 streams")}
+               "d2h_bytes_per_step": d2h_fact if expanded else d2h_dense, "steps": e2e_steps, "layout": "dense",
+               "api": ("BatchedStockTradingEnv.step_host: pinned host actions in, dense obs[N,O] + reward + flags in the caller's "
+                       f"host buffers, pipelined in {args.e2e_chunks} env slices over 3 streams; "
+                       + (f"the observation crosses PCIe factored and {env._expand_threads()} host threads rebuild the dense rows "
+                          "(frl_expand_obs_host_chunks)" if expanded else "dense rows over PCIe")),
+               "dense_over_pcie": {"value": dma, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_dense,
+                                   "api": "step_host(host_expand=False): the dense rows themselves cross PCIe (round 1's path)"}}
         del h_obs
         _, f_obs, h_rew, h_flag = env.make_host_buffers("factored", tdt)
         fact = time_e2e(lambda i: env.step_host(h_act_pool[i % POOL], f_obs, h_rew, h_flag, auto_reset=True,
@@ -561,16 +571,6 @@ def run_ours(args, wl):
             "value": fact, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_f,
             "api": "step_host(obs=FactoredObs): env_part[N,1+D] f32 + state_day[N] i32 + reward + flags come back; the "
                    "[T,O] per-day template stays pinned on the host (FactoredObs[n] / .dense() rebuild rows bit-exactly)"}
-        if args.e2e_expand:
-            dense_out = np.empty((N, env.state_space), dtype=np.float32)
-
-            def fexp(i):
-                env.step_host(h_act_pool[i % POOL], f_obs, h_rew, h_flag, auto_reset=True, n_chunks=args.e2e_chunks)
-                f_obs.dense(out=dense_out)
-
-            e2e["factored_expanded_on_host"] = {
-                "value": time_e2e(fexp), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_f,
-                "api": "factored transfer + FactoredObs.dense(out) on all host threads: a dense [N,O] host array again"}
     else:
         OBS = wl.obs_numel(env)
         h_obs = torch.empty((N, OBS), dtype=torch.float32).pin_memory()
@@ -679,7 +679,6 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=None, help="envs per step of the CPU arms (default: the GPU arm's envs per GPU)")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--extra-steps", type=int, default=20)
-    ap.add_argument("--e2e-expand", action="store_true", help="also time factored transfer + host-side expansion to dense")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")

@@ -247,6 +247,9 @@ SIGNATURES = {
     "frl_trading_observe_factored": (C.c_int32, [C.POINTER(TradingParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "frl_expand_obs_host": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_int32]),
+    "frl_expand_obs_host_chunks": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                               C.c_int32]),
     "frl_trading_rollout": (
         C.c_int32,
         [C.POINTER(TradingParams), C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,

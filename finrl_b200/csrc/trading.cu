@@ -17,6 +17,9 @@
 
 #include <algorithm>
 #include <atomic>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <thread>
 #include <vector>
 
@@ -880,43 +883,105 @@ extern "C" int32_t frl_trading_observe_factored(const frl_trading_params *p, flo
     return check_launch("trading_observe_factored");
 }
 
-extern "C" int32_t frl_expand_obs_host(const float *tmpl, int32_t n_days, int32_t obs_dim, int32_t stock_dim,
-                                       const float *env_part, const int32_t *sday, int64_t n, float *out, int32_t n_threads)
+namespace {
+// Rows [lo, hi) of the dense observation from their factored form.  Rows are built in a small thread-local block
+// (L1/L2-resident) and leave with NON-TEMPORAL stores: a plain memcpy into the 1.2 GB destination would first read every
+// line it is about to overwrite (read-for-ownership), doubling the memory traffic of what is a pure write stream.
+// Returns false when a state_day lies outside the table.
+bool expand_rows(const float *tmpl, int n_days, int O, int D, const float *env_part, const int32_t *sday, float *out,
+                 int64_t lo, int64_t hi, std::vector<float> &scratch)
 {
-    FRL_REQUIRE(tmpl && env_part && sday && out, "expand_obs_host: NULL argument");
-    FRL_REQUIRE(n >= 0 && n_days >= 1 && stock_dim >= 1 && obs_dim >= 1 + 2 * stock_dim,
-                "expand_obs_host: bad sizes (n=%lld, T=%d, O=%d, D=%d)", (long long)n, n_days, obs_dim, stock_dim);
-    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-    nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (n + 4095) / 4096));
-    const int O = obs_dim, D = stock_dim, W = D + 1;
-    std::atomic<int> bad(0);
-    auto work = [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
+    constexpr int kBlockRows = 32;
+    const int W = D + 1;
+    bool ok = true;
+    scratch.resize((size_t)kBlockRows * O + 4);
+    for (int64_t i0 = lo; i0 < hi; i0 += kBlockRows) {
+        const int rows = (int)std::min<int64_t>(kBlockRows, hi - i0);
+        for (int r = 0; r < rows; ++r) {
+            const int64_t i = i0 + r;
             const int32_t d = sday[i];
+            float *row = scratch.data() + (size_t)r * O;
             if (d < 0 || d >= n_days) {
-                bad.store(1);
+                ok = false;
+                memset(row, 0, sizeof(float) * O);
                 continue;
             }
-            float *row = out + (size_t)i * O;
             memcpy(row, tmpl + (size_t)d * O, sizeof(float) * O);
             const float *e = env_part + (size_t)i * W;
             row[0] = e[0];
             memcpy(row + 1 + D, e + 1, sizeof(float) * D);
         }
+        float *dst = out + (size_t)i0 * O;
+        const float *src = scratch.data();
+        size_t cnt = (size_t)rows * O;
+#if defined(__SSE2__)
+        while (cnt && (reinterpret_cast<uintptr_t>(dst) & 15)) {  // up to three floats before the first 16-byte boundary
+            *dst++ = *src++;
+            --cnt;
+        }
+        for (; cnt >= 4; cnt -= 4, dst += 4, src += 4) _mm_stream_ps(dst, _mm_loadu_ps(src));
+#endif
+        for (; cnt; --cnt) *dst++ = *src++;
+    }
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+    return ok;
+}
+}  // namespace
+
+extern "C" int32_t frl_expand_obs_host_chunks(const float *tmpl, int32_t n_days, int32_t obs_dim, int32_t stock_dim,
+                                              const float *env_part, const int32_t *sday, float *out, int32_t n_chunks,
+                                              const int64_t *chunk_start, const int64_t *chunk_count, void *const *events,
+                                              int32_t n_threads)
+{
+    FRL_REQUIRE(tmpl && env_part && sday && out, "expand_obs_host: NULL argument");
+    FRL_REQUIRE(n_days >= 1 && stock_dim >= 1 && obs_dim >= 1 + 2 * stock_dim, "expand_obs_host: bad sizes (T=%d, O=%d, D=%d)",
+                n_days, obs_dim, stock_dim);
+    FRL_REQUIRE(n_chunks >= 0 && (n_chunks == 0 || (chunk_start && chunk_count)), "expand_obs_host: bad chunk list");
+    int64_t total = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        FRL_REQUIRE(chunk_start[c] >= 0 && chunk_count[c] >= 0, "expand_obs_host: negative chunk bounds");
+        total += chunk_count[c];
+    }
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (total + 4095) / 4096));
+    std::atomic<int> bad(0), cuda_err(0);
+    // every thread walks the chunks in order, waits for the chunk's event (its factored data has landed in host
+    // memory) and expands its slice of the chunk: the expansion of chunk c overlaps the transfers of chunks c+1..
+    auto work = [&](int t) {
+        std::vector<float> scratch;
+        for (int c = 0; c < n_chunks; ++c) {
+            if (events && events[c]) {
+                const cudaError_t e = cudaEventSynchronize((cudaEvent_t)events[c]);
+                if (e != cudaSuccess) cuda_err.store((int)e);
+            }
+            const int64_t per = (chunk_count[c] + nt - 1) / nt;
+            const int64_t lo = chunk_start[c] + (int64_t)t * per, hi = std::min(chunk_start[c] + chunk_count[c], lo + per);
+            if (lo < hi && !expand_rows(tmpl, n_days, obs_dim, stock_dim, env_part, sday, out, lo, hi, scratch)) bad.store(1);
+        }
     };
     if (nt == 1) {
-        work(0, n);
+        work(0);
     } else {
         std::vector<std::thread> th;
-        const int64_t per = (n + nt - 1) / nt;
-        for (int t = 0; t < nt; ++t) {
-            const int64_t lo = t * per, hi = std::min<int64_t>(n, lo + per);
-            if (lo < hi) th.emplace_back(work, lo, hi);
-        }
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
         for (auto &t : th) t.join();
+    }
+    if (cuda_err.load()) {
+        set_error("expand_obs_host: cudaEventSynchronize failed (%s)", cudaGetErrorString((cudaError_t)cuda_err.load()));
+        return FRL_E_CUDA;
     }
     FRL_REQUIRE(bad.load() == 0, "expand_obs_host: a state_day lies outside [0, %d)", n_days);
     return FRL_OK;
+}
+
+extern "C" int32_t frl_expand_obs_host(const float *tmpl, int32_t n_days, int32_t obs_dim, int32_t stock_dim,
+                                       const float *env_part, const int32_t *sday, int64_t n, float *out, int32_t n_threads)
+{
+    FRL_REQUIRE(n >= 0, "expand_obs_host: n must be >= 0 (got %lld)", (long long)n);
+    const int64_t start = 0;
+    return frl_expand_obs_host_chunks(tmpl, n_days, obs_dim, stock_dim, env_part, sday, out, 1, &start, &n, nullptr, n_threads);
 }
 
 extern "C" int32_t frl_trading_reset(const frl_trading_params *p, const uint8_t *mask, float *obs, void *stream)

@@ -262,7 +262,19 @@ class BatchedStockTradingEnv(BatchedEnvBase):
             raise ValueError("obs_layout must be 'dense' or 'factored'")
         return act, obs, pin((N,), torch.float64), pin((N,), torch.uint8)
 
-    def step_host(self, actions_host, obs_host, reward_host, flags_host, auto_reset: bool = True, n_chunks: int = 8):
+    def _expand_threads(self):
+        """Host threads for the dense-by-expansion path: this process's share of the CPUs it may run on."""
+        import os
+
+        try:
+            cpus = len(os.sched_getaffinity(0))
+        except AttributeError:  # pragma: no cover
+            cpus = os.cpu_count() or 1
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+        return max(1, min(16, cpus // max(local_world, 1)))
+
+    def step_host(self, actions_host, obs_host, reward_host, flags_host, auto_reset: bool = True, n_chunks: int = 8,
+                  host_expand=None):
         """Host-resident agents: one ``step`` with pinned HOST buffers in and out, software-pipelined.
 
         The env range is cut into ``n_chunks`` slices; slice c's action upload (H2D), its kernel and its
@@ -272,10 +284,25 @@ class BatchedStockTradingEnv(BatchedEnvBase):
         ``obs_host`` is either a dense float32 [N, O] tensor or a :class:`FactoredObs` (``make_host_buffers``):
         with the factored layout the step kernel writes no observation at all, a small kernel extracts the
         env-specific slots, and only 4*(1+D) + 4 bytes per env come back instead of 4*O (91 % of a DOW-30
-        observation is the per-day row every env of that day shares)."""
+        observation is the per-day row every env of that day shares).
+
+        ``host_expand`` (dense ``obs_host`` only; default: on when this process has at least four CPUs to itself):
+        the observation still crosses PCIe in factored form and the dense rows are rebuilt in ``obs_host`` by host
+        threads (``frl_expand_obs_host_chunks``, non-temporal stores), slice by slice as the transfers land — the
+        caller gets the same bits in the same buffer, PCIe carries a ninth of the bytes."""
         torch = self._torch
         N, D, O = self.n_envs, self.stock_dim, self.state_space
         factored = isinstance(obs_host, FactoredObs)
+        dense_out = None
+        if not factored:
+            if host_expand is None:
+                host_expand = self._expand_threads() >= 4 and self.tables.host_tmpl is not None
+            if host_expand:
+                if obs_host.shape != (N, O) or obs_host.dtype != torch.float32 or not obs_host.is_contiguous():
+                    raise ValueError("step_host: bad buffer shapes")
+                if getattr(self, "_fact_host", None) is None:
+                    self._fact_host = self.make_host_buffers("factored")[1]
+                dense_out, obs_host, factored = obs_host, self._fact_host, True
         obs_bufs = (obs_host.env_part, obs_host.state_day) if factored else (obs_host,)
         if not (actions_host.is_pinned() and reward_host.is_pinned() and flags_host.is_pinned() and all(b.is_pinned() for b in obs_bufs)):
             raise ValueError("step_host needs pinned host tensors")
@@ -297,6 +324,7 @@ class BatchedStockTradingEnv(BatchedEnvBase):
         for st in self._host_streams:
             st.wait_stream(cur)
         rc = 0
+        landed = []  # (start, count, event) per slice, for the host-side expansion
         with torch.cuda.device(self.device):
             for c, start in enumerate(range(0, N, per)):
                 cnt = min(per, N - start)
@@ -315,12 +343,26 @@ class BatchedStockTradingEnv(BatchedEnvBase):
                         self.launches += 1
                         obs_host.env_part[start : start + cnt].copy_(d_env[start : start + cnt], non_blocking=True)
                         obs_host.state_day[start : start + cnt].copy_(d_sd[start : start + cnt], non_blocking=True)
+                        if dense_out is not None:
+                            ev = torch.cuda.Event()
+                            ev.record(st)
+                            landed.append((start, cnt, ev))
                     else:
                         obs_host[start : start + cnt].copy_(self._obs[start : start + cnt], non_blocking=True)
                     reward_host[start : start + cnt].copy_(self.reward[start : start + cnt], non_blocking=True)
                     flags_host[start : start + cnt].copy_(self._flags[start : start + cnt], non_blocking=True)
                 self.launches += 1
         _cabi.check(rc, "frl_trading_step (step_host)")
+        if dense_out is not None:
+            # host threads rebuild the dense rows slice by slice, each slice as soon as its event has fired
+            n = len(landed)
+            starts = (C.c_int64 * n)(*[a for a, _, _ in landed])
+            counts = (C.c_int64 * n)(*[b for _, b, _ in landed])
+            events = (C.c_void_p * n)(*[e.cuda_event for _, _, e in landed])
+            tm = self.tables.host_tmpl
+            _cabi.check(lib.frl_expand_obs_host_chunks(
+                tm.ctypes.data, tm.shape[0], O, D, obs_host.env_part.data_ptr(), obs_host.state_day.data_ptr(),
+                dense_out.data_ptr(), n, starts, counts, events, self._expand_threads()), "frl_expand_obs_host_chunks")
         for st in self._host_streams:
             cur.wait_stream(st)
         cur.synchronize()

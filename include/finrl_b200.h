@@ -179,6 +179,13 @@ FRL_API int32_t frl_trading_observe_factored(const frl_trading_params *p, float 
 FRL_API int32_t frl_expand_obs_host(const float *tmpl, int32_t n_days, int32_t obs_dim, int32_t stock_dim,
                                     const float *env_part, const int32_t *state_day, int64_t n, float *out,
                                     int32_t n_threads);
+/* The same for rows [chunk_start[c], chunk_start[c] + chunk_count[c]) of n_chunks chunks, in order; events[c] (a
+ * cudaEvent_t, or NULL; `events` itself may be NULL) is waited for before chunk c is touched, so the expansion of a
+ * chunk overlaps the device -> host transfers of the following ones.  Rows leave with non-temporal stores. */
+FRL_API int32_t frl_expand_obs_host_chunks(const float *tmpl, int32_t n_days, int32_t obs_dim, int32_t stock_dim,
+                                           const float *env_part, const int32_t *state_day, float *out, int32_t n_chunks,
+                                           const int64_t *chunk_start, const int64_t *chunk_count, void *const *events,
+                                           int32_t n_threads);
 
 /* n_steps fused calls of StockTradingEnv.step (:220-357) for every env.
  *   actions      element (k, n, j) at actions[k*act_step_stride + n*act_env_stride + j];

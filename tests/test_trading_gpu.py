@@ -339,18 +339,23 @@ def test_factored_host_observation_equals_dense():
     tables = TradingTables.from_arrays(close, tech, turb, "cuda")
     dense_env = BatchedStockTradingEnv(tables=tables, n_envs=N, **kw)
     fact_env = BatchedStockTradingEnv(tables=tables, n_envs=N, **kw)
+    exp_env = BatchedStockTradingEnv(tables=tables, n_envs=N, **kw)  # dense output rebuilt by host threads
     a_h, obs_h, rew_h, flg_h = dense_env.make_host_buffers("dense")
     _, fo, rew_f, flg_f = fact_env.make_host_buffers("factored")
+    _, obs_e, rew_e, flg_e = exp_env.make_host_buffers("dense")
     assert isinstance(fo, FactoredObs) and fo.env_part.shape == (N, 1 + D) and fo.env_part.is_pinned()
     # desynchronise the envs so that one tile mixes days (and one env sits on a stale-reset row)
     ragged = torch.arange(N, device="cuda", dtype=torch.int32) % 4
-    for env in (dense_env, fact_env):
+    for env in (dense_env, fact_env, exp_env):
         env.set_state(day=ragged, sday=ragged)
     out = np.empty((N, 1 + 2 * D + K * D), dtype=np.float32)
     for s in range(2 * T + 3):
         a_h.copy_(torch.from_numpy(syn.make_actions((N, D), seed=50 + s)))
-        dense_env.step_host(a_h, obs_h, rew_h, flg_h, auto_reset=True, n_chunks=3)
+        dense_env.step_host(a_h, obs_h, rew_h, flg_h, auto_reset=True, n_chunks=3, host_expand=False)  # dense rows over PCIe
         fact_env.step_host(a_h, fo, rew_f, flg_f, auto_reset=True, n_chunks=5)
+        obs_e.fill_(float("nan"))
+        exp_env.step_host(a_h, obs_e, rew_e, flg_e, auto_reset=True, n_chunks=4, host_expand=True)
+        assert np.array_equal(obs_e.numpy(), obs_h.numpy()) and np.array_equal(rew_e.numpy(), rew_h.numpy()), s
         assert np.array_equal(fo.dense(out=out), obs_h.numpy()), s
         assert np.array_equal(rew_f.numpy(), rew_h.numpy()) and np.array_equal(flg_f.numpy(), flg_h.numpy()), s
         assert np.array_equal(fo[17], obs_h.numpy()[17]) and np.array_equal(fo[N - 1], obs_h.numpy()[N - 1])
