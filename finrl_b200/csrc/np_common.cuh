@@ -55,6 +55,28 @@ __device__ __forceinline__ NV nv_mul(NV x, NV y)
 }
 #endif
 
+// The same three operations when one operand is known to be np.float64 (A64, the kernels' steady-state
+// instantiation): the result is float64 whatever the other kind is, so the kind arithmetic and the float32
+// candidate disappear at compile time.
+template <bool A64>
+__device__ __forceinline__ NV nv_add_t(NV x, NV y)
+{
+    if (A64) return nv(dadd(x.v, y.v), FRL_KIND_F64);
+    return nv_add(x, y);
+}
+template <bool A64>
+__device__ __forceinline__ NV nv_sub_t(NV x, NV y)
+{
+    if (A64) return nv(dsub(x.v, y.v), FRL_KIND_F64);
+    return nv_sub(x, y);
+}
+template <bool A64>
+__device__ __forceinline__ NV nv_mul_t(NV x, NV y)
+{
+    if (A64) return nv(dmul(x.v, y.v), FRL_KIND_F64);
+    return nv_mul(x, y);
+}
+
 // Exact widening conversions WITHOUT the conversion unit (XU, 16 lanes/clk/SM — the busiest pipe of these
 // kernels, which convert between float32, float64 and int64 on every trade): float -> double by re-biasing
 // the exponent with integer ops (zero handled inline; denormals / inf / nan fall back to the converter), and a

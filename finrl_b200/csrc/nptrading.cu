@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "np_common.cuh"
 
@@ -20,6 +22,9 @@
 #endif
 #ifndef FRL_NP_WARPS
 #define FRL_NP_WARPS 4
+#endif
+#ifndef FRL_NP_A64
+#define FRL_NP_A64 1  // steady-state instantiation of the step body with every NEP-50 kind fixed to float64 (A/B switch)
 #endif
 
 namespace frl {
@@ -116,6 +121,45 @@ __device__ __forceinline__ void np_write_obs_rows_uniform(const frl_np_params &p
     }
 }
 
+// Compile-time stock count (the DOW-30 instantiation): the env-specific slots of a row, positions 3+D .. 3+3D-1,
+// fall into the 32-float chunks CLO..CHI.  The kernel leaves exactly those chunks FINISHED in the transposition
+// buffer — stocks already scaled, the few template positions that share a chunk filled in per env — as
+// sc[pos - 32*CLO][env], so a row costs one shared-memory load per env chunk (static offsets, no select, no
+// multiply), one for the amount, and its NCH stores.
+template <int DCT>
+struct NpObsCT {
+    static constexpr int CLO = (3 + DCT) / 32, CHI = (3 + 3 * DCT - 1) / 32, NE = CHI - CLO + 1;
+    static_assert(DCT <= 0 || CLO >= 1, "position 0 (amount) must not share a chunk with the per-env slots");
+};
+
+template <int NCH, int DCT, typename SM>
+__device__ __forceinline__ void np_write_obs_rows_ct(const frl_np_params &p, SM &sm, float *__restrict__ obs,
+                                                     long long env0, int nvalid, int lane, int day0)
+{
+    using L = NpObsCT<DCT>;
+    const int O = p.obs_dim;
+    float t[NCH];
+    const float *trow = p.obs_tmpl + (size_t)day0 * O + lane;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+        t[c] = (c >= L::CLO && c <= L::CHI) ? 0.0f : ((c < NCH - 1 || lane + 32 * c < O) ? __ldg(trow + 32 * c) : 0.0f);
+    const bool tail_ok = lane + 32 * (NCH - 1) < O;
+    const float *col = sm.sc + lane * kPitch;
+    float *orow = obs + (size_t)env0 * O + lane;
+#pragma unroll 4
+    for (int r = 0; r < nvalid; ++r) {
+        const float am = sm.amountf[r];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            float x = t[c];
+            if (c >= L::CLO && c <= L::CHI) x = col[(c - L::CLO) * 32 * kPitch + r];
+            if (c == 0 && lane == 0) x = am;
+            if (c < NCH - 1 || tail_ok) orow[32 * c] = x;
+        }
+        orow += O;
+    }
+}
+
 template <int DCT, typename SM>
 __device__ __forceinline__ void np_write_obs_tile(const frl_np_params &p, SM &sm, float *__restrict__ obs,
                                                   long long env0, int nvalid, int lane)
@@ -130,7 +174,10 @@ __device__ __forceinline__ void np_write_obs_tile(const frl_np_params &p, SM &sm
         switch (nch) {
 #define FRL_CASE(N)                                                                                \
     case N:                                                                                        \
-        np_write_obs_rows_uniform<N, DCT>(p, sm, obs, env0, nvalid, lane, day0);                        \
+        if (DCT > 0)                                                                               \
+            np_write_obs_rows_ct<N, (DCT > 0 ? DCT : 30)>(p, sm, obs, env0, nvalid, lane, day0);          \
+        else                                                                                       \
+            np_write_obs_rows_uniform<N, DCT>(p, sm, obs, env0, nvalid, lane, day0);                    \
         break;
             FRL_CASE(1) FRL_CASE(2) FRL_CASE(3) FRL_CASE(4) FRL_CASE(5) FRL_CASE(6)
             FRL_CASE(7) FRL_CASE(8) FRL_CASE(9) FRL_CASE(10) FRL_CASE(11) FRL_CASE(12)
@@ -145,7 +192,9 @@ __device__ __forceinline__ void np_write_obs_tile(const frl_np_params &p, SM &sm
                 float v = __ldg(trow + pos);
                 if (pos == 0)
                     v = sm.amountf[r];
-                else if (pos >= s_beg && pos < c_beg)
+                else if (DCT > 0) {  // finished chunks, see np_write_obs_rows_ct
+                    if (pos >= s_beg && pos < sp_end) v = sm.sc[(pos - 32 * NpObsCT<DCT>::CLO) * kPitch + r];
+                } else if (pos >= s_beg && pos < c_beg)
                     v = fmul(sm.sc[(pos - s_beg) * kPitch + r], 0.015625f);
                 else if (pos >= c_beg && pos < sp_end)
                     v = sm.sc[(D + pos - c_beg) * kPitch + r];
@@ -239,120 +288,133 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
 
         int flags = 0;
         NV reward = nv(0.0, FRL_KIND_PY);
-        if (day >= T - 1) {
-            // already past the last day (the reference would raise IndexError): inert, done again
-            flags = FRL_FLAG_DONE;
-        } else {
-            // (actions * max_stock).astype(int) is recomputed from the staged row where needed (two uses per
-            // stock) instead of holding D more registers
-            const ActT *arow = sm.act + lane * D;
-#define FRL_A(j) np_action_to_shares<ActT>(arow[j], p.max_stock)
-
-            day += 1;  // trades happen at the NEW day's prices (:106-107)
-            const float *prow = p.price + (size_t)day * p.price_pitch;
-#pragma unroll
-            for (int j = 0; j < SLOTS; ++j) clv[j] = fadd(clv[j], 1.0f);  // cool_down += 1
-
-            if (__ldg(p.turb_bool + day) == 0.0f) {
-                // ---- sells in ascending index (:112-119) ----
-#pragma unroll
-                for (int j = 0; j < SLOTS; ++j) {
-                    const int aj = (j < D) ? FRL_A(j) : 0;
-                    const float pj = (j < D) ? __ldg(prow + j) : 0.0f;  // unconditional: issued ahead of the chain
-                    if (j < D && aj < -min_action) {
-                        if (pj > 0.0f) {
-                            float st = stv[j];
-                            NV x;
-                            const double nsh = np_u2d(-aj), std_ = np_f2d(st);
-                            if (nsh < std_) {  // min(stocks, -action) -> the int64
-                                st = (float)dsub(std_, nsh);
-                                x = nv_mul(nv(dmul(np_f2d(pj), nsh), FRL_KIND_F64), one_minus_sc);
-                            } else {  // -> the float32 holding
-                                x = nv_mul(nv((double)fmul(pj, st), FRL_KIND_F32), one_minus_sc);
-                                st = fsub(st, st);
-                            }
-                            // (common code after the divergent branches: executed once per warp, not once per branch)
-                            stv[j] = st;
-                            amount = nv_add(amount, x);
-                            clv[j] = 0.0f;
-                        }
-                    }
-                }
-                // ---- buys in ascending index; the divisor has NO cost term (:120-129, quirk Q6) ----
-#pragma unroll
-                for (int j = 0; j < SLOTS; ++j) {
-                    const int aj = (j < D) ? FRL_A(j) : 0;
-                    const float pj = (j < D) ? __ldg(prow + j) : 0.0f;
-                    if (j < D && aj > min_action) {
-                        if (pj > 0.0f) {
-                            float st = stv[j];
-                            NV x;
-                            // avail = amount // price is an exact floor, so `action < avail` <=> amount >=
-                            // (action+1)*price, which is exact in fp64 (24-bit price x small int): the
-                            // division only runs for the cash-limited buys
-                            // amount // price is a float32 operation unless amount is float64; a float32 amount is
-                            // already float32-valued, only a (weak) Python float has to be rounded first
-                            const double am = amount.k == FRL_KIND_PY ? (double)(float)amount.v : amount.v;
-                            const double pjd = np_f2d(pj);
-                            const bool plenty = am >= dmul(np_u2d(aj + 1), pjd);
-                            double avail = 0.0;
-                            // 0 <= amount < price: the quotient is exactly 0 (the usual state of a cash-starved
-                            // env) — only the division is skipped, the zero-share update still runs (it can
-                            // change the numpy kind of `amount` and it resets the cool-down counter)
-                            if (!plenty && !(am >= 0.0 && am < pjd))
-                                avail = np_floor_div(am, pjd, amount.k == FRL_KIND_F64);
-                            if (plenty) {  // min(avail, action) -> the int64
-                                const double nsh = np_u2d(aj);
-                                st = (float)dadd(np_f2d(st), nsh);
-                                x = nv_mul(nv(dmul(pjd, nsh), FRL_KIND_F64), one_plus_bc);
-                            } else if (amount.k == FRL_KIND_F64) {
-                                st = (float)dadd(np_f2d(st), avail);
-                                x = nv_mul(nv(dmul(pjd, avail), FRL_KIND_F64), one_plus_bc);
-                            } else {
-                                const float nsh = (float)avail;
-                                st = fadd(st, nsh);
-                                x = nv_mul(nv((double)fmul(pj, nsh), FRL_KIND_F32), one_plus_bc);
-                            }
-                            stv[j] = st;
-                            amount = nv_sub(amount, x);
-                            clv[j] = 0.0f;
-                        }
-                    }
-                }
+        // Steady state: `amount` becomes np.float64 at the first trade that the action (not the holding / the cash)
+        // caps, and `total_asset` / `gamma_reward` follow one step later; from then on every NEP-50 kind of the
+        // step is float64.  When that holds for the whole tile the body runs with the kinds as compile-time
+        // constants (A64): no float32 candidates, no kind arithmetic — same operations, same bits.
+        const bool all64 = FRL_NP_A64 && __all_sync(0xffffffffu, amount.k == FRL_KIND_F64 && total.k == FRL_KIND_F64 &&
+                                                       gr.k == FRL_KIND_F64);
+        auto step_body = [&](auto a64_tag) {
+            constexpr bool A64 = decltype(a64_tag)::value;
+            if (day >= T - 1) {
+                // already past the last day (the reference would raise IndexError): inert, done again
+                flags = FRL_FLAG_DONE;
             } else {
-                // ---- sell everything when turbulence (:131-134) ----
-                flags |= FRL_FLAG_LIQUIDATE;
-                const NV x = nv_mul(nv((double)np_asset_f32<SLOTS>(stv, prow, D), FRL_KIND_F32), one_minus_sc);
-                amount = nv_add(amount, x);
-#pragma unroll
-                for (int j = 0; j < SLOTS; ++j) {
-                    stv[j] = 0.0f;
-                    clv[j] = 0.0f;
+                // (actions * max_stock).astype(int) is recomputed from the staged row where needed (two uses per
+                // stock) instead of holding D more registers
+                const ActT *arow = sm.act + lane * D;
+    #define FRL_A(j) np_action_to_shares<ActT>(arow[j], p.max_stock)
+
+                day += 1;  // trades happen at the NEW day's prices (:106-107)
+                const float *prow = p.price + (size_t)day * p.price_pitch;
+    #pragma unroll
+                for (int j = 0; j < SLOTS; ++j) clv[j] = fadd(clv[j], 1.0f);  // cool_down += 1
+
+                if (__ldg(p.turb_bool + day) == 0.0f) {
+                    // ---- sells in ascending index (:112-119) ----
+    #pragma unroll
+                    for (int j = 0; j < SLOTS; ++j) {
+                        const int aj = (j < D) ? FRL_A(j) : 0;
+                        const float pj = (j < D) ? __ldg(prow + j) : 0.0f;  // unconditional: issued ahead of the chain
+                        if (j < D && aj < -min_action) {
+                            if (pj > 0.0f) {
+                                float st = stv[j];
+                                NV x;
+                                const double nsh = np_u2d(-aj), std_ = np_f2d(st);
+                                if (nsh < std_) {  // min(stocks, -action) -> the int64
+                                    st = (float)dsub(std_, nsh);
+                                    x = nv_mul(nv(dmul(np_f2d(pj), nsh), FRL_KIND_F64), one_minus_sc);
+                                } else {  // -> the float32 holding
+                                    x = nv_mul(nv((double)fmul(pj, st), FRL_KIND_F32), one_minus_sc);
+                                    st = fsub(st, st);
+                                }
+                                // (common code after the divergent branches: executed once per warp, not once per branch)
+                                stv[j] = st;
+                                amount = nv_add_t<A64>(amount, x);
+                                clv[j] = 0.0f;
+                            }
+                        }
+                    }
+                    // ---- buys in ascending index; the divisor has NO cost term (:120-129, quirk Q6) ----
+    #pragma unroll
+                    for (int j = 0; j < SLOTS; ++j) {
+                        const int aj = (j < D) ? FRL_A(j) : 0;
+                        const float pj = (j < D) ? __ldg(prow + j) : 0.0f;
+                        if (j < D && aj > min_action) {
+                            if (pj > 0.0f) {
+                                float st = stv[j];
+                                NV x;
+                                // avail = amount // price is an exact floor, so `action < avail` <=> amount >=
+                                // (action+1)*price, which is exact in fp64 (24-bit price x small int): the
+                                // division only runs for the cash-limited buys
+                                // amount // price is a float32 operation unless amount is float64; a float32 amount is
+                                // already float32-valued, only a (weak) Python float has to be rounded first
+                                const double am = (!A64 && amount.k == FRL_KIND_PY) ? (double)(float)amount.v : amount.v;
+                                const double pjd = np_f2d(pj);
+                                const bool plenty = am >= dmul(np_u2d(aj + 1), pjd);
+                                double avail = 0.0;
+                                // 0 <= amount < price: the quotient is exactly 0 (the usual state of a cash-starved
+                                // env) — only the division is skipped, the zero-share update still runs (it can
+                                // change the numpy kind of `amount` and it resets the cool-down counter)
+                                if (!plenty && !(am >= 0.0 && am < pjd))
+                                    avail = np_floor_div(am, pjd, A64 || amount.k == FRL_KIND_F64);
+                                if (plenty) {  // min(avail, action) -> the int64
+                                    const double nsh = np_u2d(aj);
+                                    st = (float)dadd(np_f2d(st), nsh);
+                                    x = nv_mul(nv(dmul(pjd, nsh), FRL_KIND_F64), one_plus_bc);
+                                } else if (A64 || amount.k == FRL_KIND_F64) {
+                                    st = (float)dadd(np_f2d(st), avail);
+                                    x = nv_mul(nv(dmul(pjd, avail), FRL_KIND_F64), one_plus_bc);
+                                } else {
+                                    const float nsh = (float)avail;
+                                    st = fadd(st, nsh);
+                                    x = nv_mul(nv((double)fmul(pj, nsh), FRL_KIND_F32), one_plus_bc);
+                                }
+                                stv[j] = st;
+                                amount = nv_sub_t<A64>(amount, x);
+                                clv[j] = 0.0f;
+                            }
+                        }
+                    }
+                } else {
+                    // ---- sell everything when turbulence (:131-134) ----
+                    flags |= FRL_FLAG_LIQUIDATE;
+                    const NV x = nv_mul(nv((double)np_asset_f32<SLOTS>(stv, prow, D), FRL_KIND_F32), one_minus_sc);
+                    amount = nv_add_t<A64>(amount, x);
+    #pragma unroll
+                    for (int j = 0; j < SLOTS; ++j) {
+                        stv[j] = 0.0f;
+                        clv[j] = 0.0f;
+                    }
+                    if (valid) st_liq += 1.0;
                 }
-                if (valid) st_liq += 1.0;
+    #undef FRL_A
+                // ---- reward bookkeeping (:136-145) ----
+                const NV tot = nv_add_t<A64>(amount, nv((double)np_asset_f32<SLOTS>(stv, prow, D), FRL_KIND_F32));
+                reward = nv_mul_t<A64>(nv_sub_t<A64>(tot, total), nv(p.reward_scaling, FRL_KIND_PY));
+                total = tot;
+                gr = nv_add_t<A64>(nv_mul_t<A64>(gr, nv(p.gamma, FRL_KIND_PY)), reward);
+                if (day == T - 1) {
+                    flags |= FRL_FLAG_DONE;
+                    reward = gr;
+                    if (!init_total_loaded) {
+                        init_total = p.init_total[n];
+                        init_total_loaded = true;
+                    }
+                    const double er = (A64 || total.k == FRL_KIND_F64) ? __ddiv_rn(total.v, init_total)
+                                                                 : (double)__fdiv_rn((float)total.v, (float)init_total);
+                    if (valid) {
+                        p.episode_return[n] = er;
+                        st_done += 1.0;
+                        st_epi += total.v;
+                    }
+                }
             }
-#undef FRL_A
-            // ---- reward bookkeeping (:136-145) ----
-            const NV tot = nv_add(amount, nv((double)np_asset_f32<SLOTS>(stv, prow, D), FRL_KIND_F32));
-            reward = nv_mul(nv_sub(tot, total), nv(p.reward_scaling, FRL_KIND_PY));
-            total = tot;
-            gr = nv_add(nv_mul(gr, nv(p.gamma, FRL_KIND_PY)), reward);
-            if (day == T - 1) {
-                flags |= FRL_FLAG_DONE;
-                reward = gr;
-                if (!init_total_loaded) {
-                    init_total = p.init_total[n];
-                    init_total_loaded = true;
-                }
-                const double er = (total.k == FRL_KIND_F64) ? __ddiv_rn(total.v, init_total)
-                                                             : (double)__fdiv_rn((float)total.v, (float)init_total);
-                if (valid) {
-                    p.episode_return[n] = er;
-                    st_done += 1.0;
-                    st_epi += total.v;
-                }
-            }
-        }
+        };
+        if (all64)
+            step_body(std::true_type{});
+        else
+            step_body(std::false_type{});
         if (valid) {
             if (rewards) rewards[(size_t)k * N + n] = reward.v;
             if (flags_out) flags_out[(size_t)k * N + n] = (uint8_t)(flags | (reward.k << FRL_NP_REWARD_KIND_SHIFT));
@@ -366,11 +428,32 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
         }
         if (obs_mode == FRL_OBS_ALL || (obs_mode == FRL_OBS_LAST && k == n_steps - 1)) {
             __syncwarp();  // the previous step's rows have been consumed
+            if (DCT > 0) {
+                // finished chunks CLO..CHI of the row (np_write_obs_rows_ct): scaled stocks, cool-down counters and
+                // the template positions sharing those chunks (this env's day)
+                using L = NpObsCT<(DCT > 0 ? DCT : 30)>;
+                static_assert(DCT <= 0 || 32 * L::NE <= 2 * SLOTS, "transposition buffer too small");
+                constexpr int P0 = 32 * L::CLO, S0 = 3 + DCT, E0 = 3 + 3 * DCT, P1 = 32 * (L::CHI + 1);
+                const float *trow = p.obs_tmpl + (size_t)day * p.obs_dim;
 #pragma unroll
-            for (int j = 0; j < SLOTS; ++j) {
-                if (j < D) {
-                    sm.sc[j * kPitch + lane] = stv[j];
-                    sm.sc[(D + j) * kPitch + lane] = clv[j];
+                for (int pos = P0; pos < S0; ++pos) sm.sc[(pos - P0) * kPitch + lane] = __ldg(trow + pos);
+#pragma unroll
+                for (int pos = E0; pos < P1; ++pos)
+                    sm.sc[(pos - P0) * kPitch + lane] = pos < p.obs_dim ? __ldg(trow + pos) : 0.0f;
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    if (j < D) {
+                        sm.sc[(S0 + j - P0) * kPitch + lane] = fmul(stv[j], 0.015625f);  // 2**-6
+                        sm.sc[(S0 + DCT + j - P0) * kPitch + lane] = clv[j];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    if (j < D) {
+                        sm.sc[j * kPitch + lane] = stv[j];
+                        sm.sc[(D + j) * kPitch + lane] = clv[j];
+                    }
                 }
             }
             sm.amountf[lane] = np_amount_obs(amount, p.obs_amount_floor);
