@@ -9,6 +9,8 @@
 // stocks image in the lane's own action-staging row for the observation writer.  Same NEP-50 scalar
 // arithmetic (np_common.cuh) as the register kernel: bit-identical results (the whole numpy-env parity suite
 // runs under both kernels).
+#include <type_traits>
+
 #include "np_common.cuh"
 
 namespace frl {
@@ -16,6 +18,9 @@ namespace {
 
 #ifndef FRL_NPW_MIN_BLOCKS
 #define FRL_NPW_MIN_BLOCKS 3
+#endif
+#ifndef FRL_NPW_A64
+#define FRL_NPW_A64 1  // all-float64 instantiation of the step body (A/B switch)
 #endif
 
 __device__ __forceinline__ void npw_cp_async(float *dst, const float *src)
@@ -217,169 +222,180 @@ np_wide_kernel(const frl_np_params p, const ActT *__restrict__ actions, long lon
         int flags = 0;
         NV reward = nv(0.0, FRL_KIND_PY);
         bool image_ok = false;  // the staging row holds the float32 stocks of the current state
-        if (day >= T - 1) {
-            flags = FRL_FLAG_DONE;  // past the last day: inert, done again
-        } else {
-            day += 1;  // trades happen at the NEW day's prices (:106-107)
-            const float *prow = p.price + (size_t)day * p.price_pitch;
-            Pairwise8 acc;
-            acc.init();
-            if (__ldg(p.turb_bool + day) == 0.0f) {
-                // ---- pass 1: cool_down += 1, sells in ascending index (:108-119) ----
-                // (both passes are software-pipelined: the next block's loads fly while this one is traded)
-                float st[8], cl[8], pr[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = u < D ? u : D - 1;
-                    st[u] = sp[(size_t)j * ld];
-                    cl[u] = cp[(size_t)j * ld];
-                    pr[u] = __ldg(prow + j);
-                }
-                for (int j0 = 0; j0 < D; j0 += 8) {
-                    float stn[8], cln[8], prn[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int j = j0 + 8 + u < D ? j0 + 8 + u : D - 1;
-                        stn[u] = sp[(size_t)j * ld];
-                        cln[u] = cp[(size_t)j * ld];
-                        prn[u] = __ldg(prow + j);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int j = j0 + u;
-                        if (j < D) {
-                            const int aj = np_action_to_shares<ActT>(myrow[j], p.max_stock);
-                            float c = fadd(cl[u], 1.0f);
-                            if (aj < -min_action && pr[u] > 0.0f) {
-                                float s = st[u];
-                                NV x;
-                                if ((double)(-aj) < (double)s) {  // min(stocks, -action) -> the int64
-                                    const double nsh = (double)(-aj);
-                                    s = (float)dsub((double)s, nsh);
-                                    x = nv_mul(nv(dmul((double)pr[u], nsh), FRL_KIND_F64), one_minus_sc);
-                                } else {  // -> the float32 holding
-                                    x = nv_mul(nv((double)fmul(pr[u], s), FRL_KIND_F32), one_minus_sc);
-                                    s = fsub(s, s);
-                                }
-                                amount = nv_add(amount, x);
-                                c = 0.0f;
-                                if (valid) sp[(size_t)j * ld] = s;
-                            }
-                            if (valid) cp[(size_t)j * ld] = c;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        st[u] = stn[u];
-                        cl[u] = cln[u];
-                        pr[u] = prn[u];
-                    }
-                }
-                // ---- pass 2: buys in ascending index (:120-129, quirk Q6), asset sum, stocks image ----
-                // (the prefetch of block b+1 reads stocks that block b never writes: different indices)
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = u < D ? u : D - 1;
-                    st[u] = sp[(size_t)j * ld];  // this thread's own pass-1 stores
-                    pr[u] = __ldg(prow + j);
-                }
-                for (int j0 = 0; j0 < D; j0 += 8) {
-                    float stn[8], prn[8], x8[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int j = j0 + 8 + u < D ? j0 + 8 + u : D - 1;
-                        stn[u] = sp[(size_t)j * ld];
-                        prn[u] = __ldg(prow + j);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int j = j0 + u;
-                        x8[u] = 0.0f;
-                        if (j < D) {
-                            const int aj = np_action_to_shares<ActT>(myrow[j], p.max_stock);
-                            const float pj = pr[u];
-                            float s = st[u];
-                            if (aj > min_action && pj > 0.0f) {
-                                NV x;
-                                const double am = amount.k == FRL_KIND_F64 ? amount.v : (double)(float)amount.v;
-                                const bool plenty = am >= dmul((double)(aj + 1), (double)pj);
-                                double avail = 0.0;
-                                if (!plenty && !(am >= 0.0 && am < (double)pj))
-                                    avail = np_floor_div(am, (double)pj, amount.k == FRL_KIND_F64);
-                                if (plenty) {  // min(avail, action) -> the int64
-                                    const double nsh = (double)aj;
-                                    s = (float)dadd((double)s, nsh);
-                                    x = nv_mul(nv(dmul((double)pj, nsh), FRL_KIND_F64), one_plus_bc);
-                                } else if (amount.k == FRL_KIND_F64) {
-                                    s = (float)dadd((double)s, avail);
-                                    x = nv_mul(nv(dmul((double)pj, avail), FRL_KIND_F64), one_plus_bc);
-                                } else {
-                                    const float nsh = (float)avail;
-                                    s = fadd(s, nsh);
-                                    x = nv_mul(nv((double)fmul(pj, nsh), FRL_KIND_F32), one_plus_bc);
-                                }
-                                amount = nv_sub(amount, x);
-                                if (valid) {
-                                    sp[(size_t)j * ld] = s;
-                                    cp[(size_t)j * ld] = 0.0f;
-                                }
-                            }
-                            x8[u] = fmul(s, pj);
-                            *reinterpret_cast<float *>(myrow + j) = s;  // action j is consumed: the slot takes the image
-                        }
-                    }
-                    acc.block(x8, j0, D);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        st[u] = stn[u];
-                        pr[u] = prn[u];
-                    }
-                }
+        // steady state of the NEP-50 kinds (see nptrading.cu): all float64 for the whole tile -> the step body runs with
+        // the kinds as compile-time constants (same operations, same bits)
+        const bool all64 = FRL_NPW_A64 && __all_sync(0xffffffffu, amount.k == FRL_KIND_F64 && total.k == FRL_KIND_F64 &&
+                                                                      gr.k == FRL_KIND_F64);
+        auto step_body = [&](auto a64_tag) {
+            constexpr bool A64 = decltype(a64_tag)::value;
+            if (day >= T - 1) {
+                flags = FRL_FLAG_DONE;  // past the last day: inert, done again
             } else {
-                // ---- sell everything when turbulence (:131-134) ----
-                flags |= FRL_FLAG_LIQUIDATE;
-                for (int j0 = 0; j0 < D; j0 += 8) {
-                    float x8[8];
-#pragma unroll
+                day += 1;  // trades happen at the NEW day's prices (:106-107)
+                const float *prow = p.price + (size_t)day * p.price_pitch;
+                Pairwise8 acc;
+                acc.init();
+                if (__ldg(p.turb_bool + day) == 0.0f) {
+                    // ---- pass 1: cool_down += 1, sells in ascending index (:108-119) ----
+                    // (both passes are software-pipelined: the next block's loads fly while this one is traded)
+                    float st[8], cl[8], pr[8];
+    #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int j = j0 + u;
-                        x8[u] = j < D ? fmul(sp[(size_t)j * ld], __ldg(prow + j)) : 0.0f;
+                        const int j = u < D ? u : D - 1;
+                        st[u] = sp[(size_t)j * ld];
+                        cl[u] = cp[(size_t)j * ld];
+                        pr[u] = __ldg(prow + j);
                     }
-                    acc.block(x8, j0, D);
+                    for (int j0 = 0; j0 < D; j0 += 8) {
+                        float stn[8], cln[8], prn[8];
+    #pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + 8 + u < D ? j0 + 8 + u : D - 1;
+                            stn[u] = sp[(size_t)j * ld];
+                            cln[u] = cp[(size_t)j * ld];
+                            prn[u] = __ldg(prow + j);
+                        }
+    #pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + u;
+                            if (j < D) {
+                                const int aj = np_action_to_shares<ActT>(myrow[j], p.max_stock);
+                                float c = fadd(cl[u], 1.0f);
+                                if (aj < -min_action && pr[u] > 0.0f) {
+                                    float s = st[u];
+                                    NV x;
+                                    if ((double)(-aj) < (double)s) {  // min(stocks, -action) -> the int64
+                                        const double nsh = (double)(-aj);
+                                        s = (float)dsub((double)s, nsh);
+                                        x = nv_mul(nv(dmul((double)pr[u], nsh), FRL_KIND_F64), one_minus_sc);
+                                    } else {  // -> the float32 holding
+                                        x = nv_mul(nv((double)fmul(pr[u], s), FRL_KIND_F32), one_minus_sc);
+                                        s = fsub(s, s);
+                                    }
+                                    amount = nv_add_t<A64>(amount, x);
+                                    c = 0.0f;
+                                    if (valid) sp[(size_t)j * ld] = s;
+                                }
+                                if (valid) cp[(size_t)j * ld] = c;
+                            }
+                        }
+    #pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            st[u] = stn[u];
+                            cl[u] = cln[u];
+                            pr[u] = prn[u];
+                        }
+                    }
+                    // ---- pass 2: buys in ascending index (:120-129, quirk Q6), asset sum, stocks image ----
+                    // (the prefetch of block b+1 reads stocks that block b never writes: different indices)
+    #pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = u < D ? u : D - 1;
+                        st[u] = sp[(size_t)j * ld];  // this thread's own pass-1 stores
+                        pr[u] = __ldg(prow + j);
+                    }
+                    for (int j0 = 0; j0 < D; j0 += 8) {
+                        float stn[8], prn[8], x8[8];
+    #pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + 8 + u < D ? j0 + 8 + u : D - 1;
+                            stn[u] = sp[(size_t)j * ld];
+                            prn[u] = __ldg(prow + j);
+                        }
+    #pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + u;
+                            x8[u] = 0.0f;
+                            if (j < D) {
+                                const int aj = np_action_to_shares<ActT>(myrow[j], p.max_stock);
+                                const float pj = pr[u];
+                                float s = st[u];
+                                if (aj > min_action && pj > 0.0f) {
+                                    NV x;
+                                    const double am = (A64 || amount.k == FRL_KIND_F64) ? amount.v : (double)(float)amount.v;
+                                    const bool plenty = am >= dmul((double)(aj + 1), (double)pj);
+                                    double avail = 0.0;
+                                    if (!plenty && !(am >= 0.0 && am < (double)pj))
+                                        avail = np_floor_div(am, (double)pj, A64 || amount.k == FRL_KIND_F64);
+                                    if (plenty) {  // min(avail, action) -> the int64
+                                        const double nsh = (double)aj;
+                                        s = (float)dadd((double)s, nsh);
+                                        x = nv_mul(nv(dmul((double)pj, nsh), FRL_KIND_F64), one_plus_bc);
+                                    } else if (A64 || amount.k == FRL_KIND_F64) {
+                                        s = (float)dadd((double)s, avail);
+                                        x = nv_mul(nv(dmul((double)pj, avail), FRL_KIND_F64), one_plus_bc);
+                                    } else {
+                                        const float nsh = (float)avail;
+                                        s = fadd(s, nsh);
+                                        x = nv_mul(nv((double)fmul(pj, nsh), FRL_KIND_F32), one_plus_bc);
+                                    }
+                                    amount = nv_sub_t<A64>(amount, x);
+                                    if (valid) {
+                                        sp[(size_t)j * ld] = s;
+                                        cp[(size_t)j * ld] = 0.0f;
+                                    }
+                                }
+                                x8[u] = fmul(s, pj);
+                                *reinterpret_cast<float *>(myrow + j) = s;  // action j is consumed: the slot takes the image
+                            }
+                        }
+                        acc.block(x8, j0, D);
+    #pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            st[u] = stn[u];
+                            pr[u] = prn[u];
+                        }
+                    }
+                } else {
+                    // ---- sell everything when turbulence (:131-134) ----
+                    flags |= FRL_FLAG_LIQUIDATE;
+                    for (int j0 = 0; j0 < D; j0 += 8) {
+                        float x8[8];
+    #pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + u;
+                            x8[u] = j < D ? fmul(sp[(size_t)j * ld], __ldg(prow + j)) : 0.0f;
+                        }
+                        acc.block(x8, j0, D);
+                    }
+                    amount = nv_add_t<A64>(amount, nv_mul(nv((double)acc.res, FRL_KIND_F32), one_minus_sc));
+                    for (int j = 0; j < D; ++j) {
+                        if (valid) {
+                            sp[(size_t)j * ld] = 0.0f;
+                            cp[(size_t)j * ld] = 0.0f;
+                        }
+                        *reinterpret_cast<float *>(myrow + j) = 0.0f;
+                    }
+                    acc.init();  // (stocks * price).sum() of the emptied book: +0.0f
+                    if (valid) st_liq += 1.0;
                 }
-                amount = nv_add(amount, nv_mul(nv((double)acc.res, FRL_KIND_F32), one_minus_sc));
-                for (int j = 0; j < D; ++j) {
+                image_ok = true;
+                // ---- reward bookkeeping (:136-145) ----
+                const NV tot = nv_add_t<A64>(amount, nv((double)acc.res, FRL_KIND_F32));
+                reward = nv_mul_t<A64>(nv_sub_t<A64>(tot, total), nv(p.reward_scaling, FRL_KIND_PY));
+                total = tot;
+                gr = nv_add_t<A64>(nv_mul_t<A64>(gr, nv(p.gamma, FRL_KIND_PY)), reward);
+                if (day == T - 1) {
+                    flags |= FRL_FLAG_DONE;
+                    reward = gr;
+                    if (!init_total_loaded) {
+                        init_total = p.init_total[n];
+                        init_total_loaded = true;
+                    }
+                    const double er = (A64 || total.k == FRL_KIND_F64) ? __ddiv_rn(total.v, init_total)
+                                                                 : (double)__fdiv_rn((float)total.v, (float)init_total);
                     if (valid) {
-                        sp[(size_t)j * ld] = 0.0f;
-                        cp[(size_t)j * ld] = 0.0f;
+                        p.episode_return[n] = er;
+                        st_done += 1.0;
+                        st_epi += total.v;
                     }
-                    *reinterpret_cast<float *>(myrow + j) = 0.0f;
-                }
-                acc.init();  // (stocks * price).sum() of the emptied book: +0.0f
-                if (valid) st_liq += 1.0;
-            }
-            image_ok = true;
-            // ---- reward bookkeeping (:136-145) ----
-            const NV tot = nv_add(amount, nv((double)acc.res, FRL_KIND_F32));
-            reward = nv_mul(nv_sub(tot, total), nv(p.reward_scaling, FRL_KIND_PY));
-            total = tot;
-            gr = nv_add(nv_mul(gr, nv(p.gamma, FRL_KIND_PY)), reward);
-            if (day == T - 1) {
-                flags |= FRL_FLAG_DONE;
-                reward = gr;
-                if (!init_total_loaded) {
-                    init_total = p.init_total[n];
-                    init_total_loaded = true;
-                }
-                const double er = (total.k == FRL_KIND_F64) ? __ddiv_rn(total.v, init_total)
-                                                             : (double)__fdiv_rn((float)total.v, (float)init_total);
-                if (valid) {
-                    p.episode_return[n] = er;
-                    st_done += 1.0;
-                    st_epi += total.v;
                 }
             }
-        }
+        };
+        if (all64)
+            step_body(std::true_type{});
+        else
+            step_body(std::false_type{});
         if (valid) {
             if (rewards) rewards[(size_t)k * N + n] = reward.v;
             if (flags_out) flags_out[(size_t)k * N + n] = (uint8_t)(flags | (reward.k << FRL_NP_REWARD_KIND_SHIFT));

@@ -129,6 +129,33 @@ def test_step_vs_oracle(N, D):
             reset_both()
 
 
+def test_ragged_days_and_mixed_kinds_inside_a_tile():
+    """Masked resets in mid-episode leave the 32 envs of a tile on different days and with different numpy kinds
+    (freshly reset envs carry a Python-float amount, the others float64): the observation writer's mixed-day path and
+    the general (not all-float64) instantiation of the step body, at DOW-30 size and at a generic one."""
+    from finrl_b200 import synthetic as syn
+
+    for D in (30, 23):
+        N, T = 100, 30
+        env, o = _make(N, T=T, D=D, K=8)
+        acts = syn.make_actions((3 * T, N, D), seed=40 + D)
+        rng = np.random.RandomState(D)
+        assert np.array_equal(env.reset().cpu().numpy(), o.reset())
+        for s in range(acts.shape[0]):
+            obs, reward, done, flags = env.step(torch.from_numpy(acts[s]).cuda())
+            oobs, orew, ork, ofl = o.step(acts[s])
+            ctx = f"D={D} step {s}"
+            assert np.array_equal(flags.cpu().numpy(), ofl | (ork << 4)), ctx
+            assert np.array_equal(reward.cpu().numpy(), orew), ctx
+            assert np.array_equal(obs.cpu().numpy(), oobs), ctx
+            mask = (rng.rand(N) < 0.15) | ((ofl & 1) != 0)  # every done env, plus a random 15 %
+            if mask.any():
+                m = mask.astype(np.uint8)
+                assert np.array_equal(env.reset(mask=torch.from_numpy(m).cuda()).cpu().numpy(), o.reset(mask=m)), ctx
+            _compare(env, o, ctx)
+        assert len(np.unique(o.day)) > 3
+
+
 @pytest.mark.parametrize("layout", ["KND", "NKD"])
 def test_rollout_auto_reset_vs_oracle(layout):
     """Fused K-step rollouts with the deterministic auto-reset after each done step."""
