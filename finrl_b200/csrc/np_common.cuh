@@ -144,5 +144,6 @@ __device__ __forceinline__ float np_amount_obs(NV amount, double floor_)
 void launch_np_wide(const frl_np_params &p, const void *actions, int actions_f64, long long sstride, long long estride, int n_steps,
                     double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st);
 void launch_np_observe_wide(const frl_np_params &p, float *obs, cudaStream_t st);
+extern int g_npw_bulk;  // -1: from FRL_NPW_BULK (default on); frl_set_option("np_wide_bulk", v)
 
 }  // namespace frl

@@ -598,6 +598,10 @@ void np_launch(const frl_np_params &p, const void *actions, long long sstride, l
 
 int32_t np_set_option(const char *name, int64_t value)
 {
+    if (!strcmp(name, "np_wide_bulk")) {  // 0: the streaming kernel keeps its generic action staging for every shape
+        g_npw_bulk = value != 0;
+        return FRL_OK;
+    }
     if (strcmp(name, "np_wide_min_d")) return 1;  // not ours
     g_np_wide_min_d = value < 1 ? 1 : (value > 33 ? 33 : (int)value);
     return FRL_OK;

@@ -63,6 +63,8 @@ def test_np_fuzz(seed):
 
     rng = np.random.default_rng(2000 + seed)
     D = int(rng.integers(1, 33)) if seed < 10 else int(rng.integers(33, 129))
+    if seed in (3, 7, 11, 13, 15):
+        D = (D + 3) // 4 * 4  # multiples of four take the streaming kernel's bulk-staged variant
     _cabi.set_option("np_wide_min_d", 1 if seed % 2 else 33)
     K = int(rng.integers(0, 4))
     T = int(rng.integers(4, 40))

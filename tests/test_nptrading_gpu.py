@@ -17,15 +17,18 @@ torch = pytest.importorskip("torch")
 NP = sorted(glob.glob(os.path.join(GOLDEN, "np_*.npz")))
 
 
-@pytest.fixture(autouse=True, params=["regs", "wide"])
+@pytest.fixture(autouse=True, params=["regs", "wide", "wide_generic"])
 def np_kernel(request):
-    """Every test of this file runs twice: with the register kernel for D <= 32 (nptrading.cu) and with the
-    streaming kernel (np_wide.cu, the one D > 32 always uses) forced for every stock count."""
+    """Every test of this file runs three times: with the register kernel for D <= 32 (nptrading.cu), with the
+    streaming kernel (np_wide.cu, the one D > 32 always uses) forced for every stock count, and with the streaming
+    kernel's bulk-staged variant (float32 actions, D a multiple of four) switched off."""
     from finrl_b200 import _cabi
 
     _cabi.set_option("np_wide_min_d", 33 if request.param == "regs" else 1)
+    _cabi.set_option("np_wide_bulk", 0 if request.param == "wide_generic" else 1)
     yield request.param
     _cabi.set_option("np_wide_min_d", 33)
+    _cabi.set_option("np_wide_bulk", 1)
 
 
 @pytest.mark.parametrize("path", NP, ids=[os.path.basename(p)[:-4] for p in NP])
@@ -98,7 +101,7 @@ def _compare(env, o, ctx=""):
     assert np.array_equal(st["gr_kind"].cpu().numpy(), o.gr_kind), ctx
 
 
-@pytest.mark.parametrize("N,D", [(1, 30), (77, 30), (2048 + 5, 30), (300, 7), (300, 16)])
+@pytest.mark.parametrize("N,D", [(1, 30), (77, 30), (2048 + 5, 30), (300, 7), (300, 16), (300, 28), (100, 100), (65, 64)])
 def test_step_vs_oracle(N, D):
     """Random train-style initial positions, distinct actions, several episodes (manual resets)."""
     from finrl_b200 import synthetic as syn
@@ -135,7 +138,7 @@ def test_ragged_days_and_mixed_kinds_inside_a_tile():
     the general (not all-float64) instantiation of the step body, at DOW-30 size and at a generic one."""
     from finrl_b200 import synthetic as syn
 
-    for D in (30, 23):
+    for D in (30, 23, 24):
         N, T = 100, 30
         env, o = _make(N, T=T, D=D, K=8)
         acts = syn.make_actions((3 * T, N, D), seed=40 + D)
