@@ -824,6 +824,7 @@ void launch_rollout(const frl_trading_params &p, const void *actions, long long 
 
 namespace frl {
 int32_t np_set_option(const char *name, int64_t value);  // nptrading.cu
+extern int g_tw_regs;                                           // trading_wide.cu
 }
 
 using namespace frl;
@@ -839,6 +840,10 @@ extern "C" int32_t frl_set_option(const char *name, int64_t value)
     if (!strcmp(name, "trading_small_max")) {
         FRL_REQUIRE(value >= 0, "set_option: trading_small_max must be >= 0");
         g_small_max = value > 0x7fffffff ? 0x7fffffff : (int)value;
+        return FRL_OK;
+    }
+    if (!strcmp(name, "trading_wide_regs")) {  // 0: D = 100 stays on the generic (runtime stock count) wide kernel
+        g_tw_regs = value != 0;
         return FRL_OK;
     }
     if (np_set_option(name, value) == FRL_OK) return FRL_OK;

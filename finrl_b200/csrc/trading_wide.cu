@@ -7,9 +7,15 @@
 // env: conflict-free for the per-lane walks of the network and the trade loops AND for the per-row reads of the
 // observation writer).  np.argsort's network runs as loops over the key column.  Same arithmetic
 // and order as the other two kernels => bit-identical (the D > 32 goldens and fuzz cases run under both).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sort_network.inc"
 #include "trading_common.cuh"
+
+#ifndef FRL_TW_REGNET
+#define FRL_TW_REGNET 0  // 1: the D = 100 instantiation sorts on registers (straight-line code; measured slower, see profiles/)
+#endif
 
 namespace frl {
 namespace {
@@ -94,6 +100,28 @@ __device__ __forceinline__ void network_w(int *col, int slots, int D)
     }
 }
 
+// Stock count compiled in (NASDAQ-100): the whole 128-slot network runs on REGISTERS — the block of slots 0..63 in
+// k0, slots 64..127 in k1 — as straight-line code: 32-slot networks on the four quarters, the block-size-64 level on
+// each half, the block-size-128 flip stage between the halves and its half-cleaners on each half (the decomposition is
+// checked against the full network in gen_sort_network.py's terms by tests/test_host_cpu.py).  The pad slots are
+// compile-time INT_MAX constants here, so every compare-exchange that touches one folds away: what is left are the
+// ~1400 exchanges between live keys, with no shared-memory traffic in between.
+template <int DCT>
+__device__ __forceinline__ void network_regs_w(int (&k0)[64], int (&k1)[64])
+{
+    static_assert(DCT > 64 && DCT <= 128, "two 64-slot register blocks");
+    FRL_SORT_NETWORK_32(FRL_CEXW, k0)
+    FRL_SORT_NETWORK_32(FRL_CEXW, (k0 + 32))
+    FRL_MERGE_FLIP_64(FRL_CEXW, k0)
+    FRL_SORT_NETWORK_32(FRL_CEXW, k1)
+    FRL_SORT_NETWORK_32(FRL_CEXW, (k1 + 32))
+    FRL_MERGE_FLIP_64(FRL_CEXW, k1)
+#pragma unroll
+    for (int i = 0; i < 64; ++i) FRL_CEXW(k0[i], k1[63 - i])
+    FRL_MERGE_HALF_64(FRL_CEXW, k0)
+    FRL_MERGE_HALF_64(FRL_CEXW, k1)
+}
+
 __device__ __forceinline__ double total_asset_w(double cash, const double *__restrict__ prow, const int *hcol, int D)
 {
     double acc = 0.0;
@@ -105,39 +133,43 @@ __device__ __forceinline__ double total_asset_w(double cash, const double *__res
 // chunks of 32 positions), holdings patched in from the [slot][33] column array
 template <int NCH>
 __device__ __forceinline__ void write_obs_rows_w(const frl_trading_params &p, const int *hold, const float *cashf, float *__restrict__ obs,
-                                                 long long env0, int nvalid, int lane, int sd0)
+                                                 long long env0, int nvalid, int lane, int sd0, int D)
 {
-    const int O = p.obs_dim, D = p.stock_dim;
+    // (D is a compile-time constant in the NASDAQ-100 instantiation: the per-chunk facts of every chunk that lies wholly
+    // inside or outside the holdings fold away)
+    const int O = p.obs_dim;
     float t[NCH];
+    bool ok[NCH], img[NCH];
     const float *trow = p.obs_tmpl + (size_t)sd0 * O + lane;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) t[c] = (lane + 32 * c < O) ? __ldg(trow + 32 * c) : 0.0f;
-    constexpr int NSP = NCH < 9 ? NCH : 9;  // holdings end at position 2D <= 256
-    int hoff[NSP];
-#pragma unroll
-    for (int c = 0; c < NSP; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int pos = lane + 32 * c;
-        hoff[c] = (pos > D && pos <= 2 * D) ? (pos - 1 - D) * kPitchW : -1;
+        ok[c] = pos < 1 + 2 * D || pos < O;  // O >= 1 + 2D
+        img[c] = pos > D && pos <= 2 * D;
+        t[c] = (ok[c] && !img[c]) ? __ldg(trow + 32 * c) : 0.0f;
     }
+    const int *hsrc = hold + (lane - 1 - D) * kPitchW;  // holdings of stock (pos - 1 - D), chunk c adds 32 rows
     float *orow = obs + (size_t)env0 * O + lane;
+#pragma unroll 2
     for (int r = 0; r < nvalid; ++r) {
-        float v[NSP];
-#pragma unroll
-        for (int c = 0; c < NSP; ++c) v[c] = hoff[c] >= 0 ? (float)hold[hoff[c] + r] : t[c];
-        if (lane == 0) v[0] = cashf[r];
+        const float cf = cashf[r];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-            const float x = c < NSP ? v[c] : t[c];
-            if (lane + 32 * c < O) orow[32 * c] = x;
+            if (ok[c]) {
+                float x = t[c];
+                if (img[c]) x = (float)hsrc[32 * c * kPitchW + r];
+                if (c == 0 && lane == 0) x = cf;
+                orow[32 * c] = x;
+            }
         }
         orow += O;
     }
 }
 
 __device__ __forceinline__ void write_obs_tile_w(const frl_trading_params &p, const int *hold, const float *cashf, const int *sd_s,
-                                                 float *__restrict__ obs, long long env0, int nvalid, int lane)
+                                                 float *__restrict__ obs, long long env0, int nvalid, int lane, int D)
 {
-    const int O = p.obs_dim, D = p.stock_dim;
+    const int O = p.obs_dim;
     const int sd0 = sd_s[0];
     bool uniform = true;
     if (lane < nvalid) uniform = sd_s[lane] == sd0;
@@ -145,13 +177,13 @@ __device__ __forceinline__ void write_obs_tile_w(const frl_trading_params &p, co
     const int nch = (O + 31) >> 5;
     if (uniform && nch <= 32) {
         if (nch <= 8)
-            write_obs_rows_w<8>(p, hold, cashf, obs, env0, nvalid, lane, sd0);
+            write_obs_rows_w<8>(p, hold, cashf, obs, env0, nvalid, lane, sd0, D);
         else if (nch <= 16)
-            write_obs_rows_w<16>(p, hold, cashf, obs, env0, nvalid, lane, sd0);
+            write_obs_rows_w<16>(p, hold, cashf, obs, env0, nvalid, lane, sd0, D);
         else if (nch <= 24)
-            write_obs_rows_w<24>(p, hold, cashf, obs, env0, nvalid, lane, sd0);
+            write_obs_rows_w<24>(p, hold, cashf, obs, env0, nvalid, lane, sd0, D);
         else
-            write_obs_rows_w<32>(p, hold, cashf, obs, env0, nvalid, lane, sd0);
+            write_obs_rows_w<32>(p, hold, cashf, obs, env0, nvalid, lane, sd0, D);
     } else {
         for (int r = 0; r < nvalid; ++r) {
             float *orow = obs + (size_t)(env0 + r) * O;
@@ -168,7 +200,7 @@ __device__ __forceinline__ void write_obs_tile_w(const frl_trading_params &p, co
     }
 }
 
-template <typename ActT, int WARPS>
+template <typename ActT, int WARPS, int DCT>
 __global__ void __launch_bounds__(WARPS * 32)
 trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions, long long act_step_stride, long long act_env_stride,
                     int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out, float *__restrict__ obs, int obs_mode,
@@ -177,7 +209,7 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
     stats_exchange_previous(stats);
     extern __shared__ __align__(16) unsigned char tw_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;
+    const int N = p.n_envs, D = DCT > 0 ? DCT : p.stock_dim, T = p.n_days, ld = p.env_stride;
     const int slots = D <= 64 ? 64 : 128;
     const size_t warp_ints = (size_t)(2 * D) * kPitchW + 64;
     int *key = reinterpret_cast<int *>(tw_smem) + warp * warp_ints;  // [D][33] (pad slots are never stored)
@@ -281,7 +313,24 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
                 }
             } else {
                 // ---- (actions * hmax).astype(int), packed sort keys, np.argsort order ----
-                if (sizeof(ActT) == 4) {
+                if constexpr (FRL_TW_REGNET && sizeof(ActT) == 4 && DCT > 64) {
+                    int k0[64], k1[64];
+#pragma unroll
+                    for (int j = 0; j < 128; ++j) {
+                        int key_j = 0x7fffffff;  // pad
+                        if (j < DCT) {
+                            const float a = __int_as_float(kcol[j * kPitchW]);
+                            key_j = (max(-AMAXW, min(AMAXW, action_to_shares<float>(a, p.hmax))) << IBW) + j;
+                        }
+                        if (j < 64)
+                            k0[j] = key_j;
+                        else
+                            k1[j - 64] = key_j;
+                    }
+                    network_regs_w<(DCT > 64 ? DCT : 128)>(k0, k1);
+#pragma unroll
+                    for (int j = 0; j < DCT; ++j) kcol[j * kPitchW] = j < 64 ? k0[j < 64 ? j : 0] : k1[j < 64 ? 0 : j - 64];
+                } else if (sizeof(ActT) == 4) {
                     for (int j = 0; j < D; ++j) {
                         const float a = __int_as_float(kcol[j * kPitchW]);
                         const int sh = max(-AMAXW, min(AMAXW, action_to_shares<float>(a, p.hmax)));
@@ -294,7 +343,7 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
                         kcol[j * kPitchW] = (sh << IBW) + j;
                     }
                 }
-                network_w(kcol, slots, D);
+                if constexpr (!(FRL_TW_REGNET && sizeof(ActT) == 4 && DCT > 64)) network_w(kcol, slots, D);
                 const uint32_t *dis_row = p.disable_mask ? p.disable_mask + (size_t)sd * mask_words : nullptr;
 
                 // Both loops are software-pipelined: the next order entry with its price, holding and disable bit is
@@ -392,7 +441,7 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
             sd_s[lane] = state_day(sday);
             __syncwarp();
             float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
-            write_obs_tile_w(p, hold, cashf, sd_s, o, env0, nvalid, lane);
+            write_obs_tile_w(p, hold, cashf, sd_s, o, env0, nvalid, lane, D);
         }
     }
 
@@ -416,12 +465,12 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
     }
 }
 
-template <typename ActT, int WARPS>
+template <typename ActT, int WARPS, int DCT = 0>
 int32_t tw_launch(const frl_trading_params &p, const void *actions, long long sstride, long long estride, int n_steps, double *rewards,
                   uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
 {
     const size_t smem = (size_t)WARPS * ((size_t)(2 * p.stock_dim) * kPitchW + 64) * sizeof(int);
-    auto kern = trading_wide_kernel<ActT, WARPS>;
+    auto kern = trading_wide_kernel<ActT, WARPS, DCT>;
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
@@ -437,12 +486,25 @@ int32_t tw_launch(const frl_trading_params &p, const void *actions, long long ss
 
 }  // namespace
 
+// frl_set_option("trading_wide_regs", 0) / FRL_TW_REGS=0 keeps D = 100 on the generic (runtime stock count) kernel
+int g_tw_regs = -1;
+int tw_regs_enabled()
+{
+    if (g_tw_regs < 0) {
+        const char *m = getenv("FRL_TW_REGS");
+        g_tw_regs = m ? (atoi(m) != 0) : 1;
+    }
+    return g_tw_regs;
+}
+
 int32_t launch_trading_wide(const frl_trading_params &p, const void *actions, int actions_f64, long long sstride, long long estride,
                             int n_steps, double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats,
                             cudaStream_t st)
 {
     if (actions_f64)
         return tw_launch<double, 2>(p, actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats, st);
+    if (p.stock_dim == 100 && tw_regs_enabled())  // NASDAQ-100: stock count compiled in, np.argsort's network in registers
+        return tw_launch<float, 2, 100>(p, actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats, st);
     return tw_launch<float, 2>(p, actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats, st);
 }
 

@@ -312,3 +312,49 @@ def test_missing_library_fails_loudly(tmp_path):
     env = dict(os.environ, FINRL_B200_LIB=str(tmp_path / "missing.so"))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert "RAISED True" in out.stdout, out.stdout + out.stderr
+
+
+def test_register_network_decomposition_equals_the_full_network():
+    """trading_wide.cu's compiled-in NASDAQ-100 path runs np.argsort's 128-slot network as 32-slot networks on the four
+    quarters, the block-size-64 level on each half, the 128 flip stage between the halves and its half-cleaners on each
+    half (macros generated by csrc/gen_sort_network.py).  Same permutation as the full network, ties included; and the
+    committed sort_network.inc is what the generator emits."""
+    import contextlib
+    import io
+    import os
+    import random
+    import runpy
+    import sys
+
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "finrl_b200", "csrc")
+    sys.path.insert(0, csrc)
+    try:
+        from gen_sort_network import merge, network
+    finally:
+        sys.path.remove(csrc)
+
+    def run(pairs, keys, off=0):
+        for lo, hi in pairs:
+            if keys[off + lo][0] > keys[off + hi][0]:  # strict: ties keep their slots
+                keys[off + lo], keys[off + hi] = keys[off + hi], keys[off + lo]
+
+    rnd = random.Random(7)
+    for trial in range(60):
+        D = rnd.choice([65, 100, 100, 127, 128])
+        vals = [(rnd.randint(-4, 4), i) for i in range(D)] + [(10**9, i) for i in range(D, 128)]
+        a = list(vals)
+        run(network(128), a)
+        b = list(vals)
+        for g in range(0, 128, 32):
+            run(network(32), b, g)
+        for g in (0, 64):
+            run(merge(64, True), b, g)
+        run([(i, 127 - i) for i in range(64)], b)
+        for g in (0, 64):
+            run(merge(64, False), b, g)
+        assert a == b
+        assert all(k[0] == 10**9 for k in a[D:])  # pads never move
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        runpy.run_path(os.path.join(csrc, "gen_sort_network.py"), run_name="__main__")
+    assert buf.getvalue() == open(os.path.join(csrc, "sort_network.inc")).read()

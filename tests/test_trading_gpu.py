@@ -111,6 +111,38 @@ def _compare(env, o, ctx=""):
     assert np.array_equal(st["episode"].cpu().numpy(), o.episode), ctx
 
 
+@pytest.mark.parametrize("hmax", [3, 100])
+def test_nasdaq100_register_network_vs_oracle(trading_kernel, hmax):
+    """D = 100 with float32 actions takes the wide kernel's instantiation with the stock count compiled in (np.argsort's
+    128-slot network on registers).  Against the oracle and against the generic wide kernel, with heavy ties (hmax = 3:
+    seven distinct share counts over 100 stocks) and with the usual hmax; ragged last tile, auto-reset, liquidation days."""
+    if trading_kernel != "tile":
+        pytest.skip("thread-per-env wide kernel only")
+    from finrl_b200 import _cabi, synthetic as syn
+
+    N, T, D = 32 * 5 + 9, 25, 100
+    acts = syn.make_actions((2 * T + 3, N, D), seed=50 + hmax, dtype=np.float32)
+    runs = {}
+    for regs in (1, 0):
+        _cabi.set_option("trading_wide_regs", regs)
+        try:
+            env, o = _make(N, T=T, D=D, K=2, hmax=hmax, initial_amount=60_000)
+            out = []
+            for s in range(acts.shape[0]):
+                obs, reward, done, flags = env.step(torch.from_numpy(acts[s]).cuda(), auto_reset=True)
+                oobs, oreward, oflags = o.step(acts[s], auto_reset=True)
+                ctx = f"regs={regs} step {s}"
+                assert np.array_equal(flags.cpu().numpy(), oflags), ctx
+                assert np.array_equal(reward.cpu().numpy(), oreward), ctx
+                assert np.array_equal(obs.cpu().numpy(), oobs), ctx
+                _compare(env, o, ctx)
+                out.append(obs.clone())
+            runs[regs] = torch.stack(out)
+        finally:
+            _cabi.set_option("trading_wide_regs", 1)
+    assert torch.equal(runs[0], runs[1])
+
+
 @pytest.mark.parametrize("N,dtype", [(1, np.float32), (33, np.float64), (4096 + 7, np.float32)])
 def test_step_vs_oracle(N, dtype):
     from finrl_b200 import synthetic as syn
