@@ -60,7 +60,17 @@ __device__ __forceinline__ void cex_w(int *col, int lo, int hi)
 // >= D and any exchange whose upper slot is a pad is a no-op.  The column therefore only holds D keys.
 __device__ __forceinline__ void network_w(int *col, int slots, int D)
 {
-    for (int g = 0; g < D; g += 16) {
+    const int dfull = D & ~15;  // groups below are full: no pad checks
+    for (int g = 0; g < dfull; g += 16) {
+        int k[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) k[i] = col[(g + i) * kPitchW];
+        FRL_SORT_NETWORK_16(FRL_CEXW, k)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) col[(g + i) * kPitchW] = k[i];
+    }
+    if (dfull < D) {
+        const int g = dfull;
         int k[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) k[i] = g + i < D ? col[(g + i) * kPitchW] : 0x7fffffff;
@@ -83,7 +93,21 @@ __device__ __forceinline__ void network_w(int *col, int slots, int D)
                     if (b + i + d < D) cex_w(col, b + i, b + i + d);
             }
         }
-        for (int g = 0; g < D; g += 16) {
+        for (int g = 0; g < dfull; g += 16) {
+            int k[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) k[i] = col[(g + i) * kPitchW];
+#pragma unroll
+            for (int d = 8; d >= 1; d >>= 1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if ((i & d) == 0) FRL_CEXW(k[i], k[i + d])
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) col[(g + i) * kPitchW] = k[i];
+        }
+        if (dfull < D) {
+            const int g = dfull;
             int k[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) k[i] = g + i < D ? col[(g + i) * kPitchW] : 0x7fffffff;
@@ -243,17 +267,21 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
         ActT *acol = nullptr;  // f64 actions do not fit a 4-byte slot: they are read straight from global below
         if (sizeof(ActT) == 4) {
             if (act_env_stride == D) {
-                const float *tile = reinterpret_cast<const float *>(abase) + (size_t)env0 * D;
-                const int cnt = nvalid * D;
-                int row = 0, col = lane;
-                while (col >= D) { col -= D; ++row; }
-                for (int e = lane; e < 32 * D; e += 32) {
-                    if (e < cnt)
-                        cp_async4(key + col * kPitchW + row, tile + e);
-                    else
-                        key[col * kPitchW + row] = 0;
-                    col += 32;
-                    while (col >= D) { col -= D; ++row; }
+                // row by row, 32 stocks (128 contiguous bytes) per instruction: no row / column arithmetic
+                const float *src = reinterpret_cast<const float *>(abase) + (size_t)env0 * D + lane;
+                int *dst = key + lane * kPitchW;
+                for (int r = 0; r < 32; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (lane + 32 * c < D) {
+                            if (r < nvalid)
+                                cp_async4(dst + 32 * c * kPitchW, src + 32 * c);
+                            else
+                                dst[32 * c * kPitchW] = 0;
+                        }
+                    }
+                    src += D;
+                    dst += 1;
                 }
             } else {
                 for (int r = 0; r < 32; ++r)
