@@ -31,15 +31,6 @@ __device__ __forceinline__ void cp_async4(void *dst, const void *src)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_all;" ::: "memory"); }
 
 // keys are (a << 7) | index; swap only on STRICT a[lo] > a[hi] — ties keep network order
-__device__ __forceinline__ void cex_w(int *col, int lo, int hi)
-{
-    const int a = col[lo * kPitchW], b = col[hi * kPitchW];
-    if (a > (b | ((1 << IBW) - 1))) {
-        col[lo * kPitchW] = b;
-        col[hi * kPitchW] = a;
-    }
-}
-
 #define FRL_CEXW(lo, hi)                                                                           \
     {                                                                                              \
         const bool sw_ = (lo) > ((hi) | ((1 << IBW) - 1));                                         \
@@ -50,76 +41,116 @@ __device__ __forceinline__ void cex_w(int *col, int lo, int hi)
 
 // ascending bitonic network on `slots` (64 or 128) keys of this lane's column: for block size 2, 4, ..., slots a
 // flip stage (mirror pairs inside each block) followed by half-cleaners of distance blk/4 ... 1.  Every stage of
-// distance <= 8 only touches aligned groups of 16 slots, so those run on 16 keys held in registers (the block
-// sizes 2..16 are exactly the 16-slot network per group); only the flip stages of block size >= 32 and the
-// half-cleaners of distance >= 16 exchange through shared memory — 22 of the 28 stages of a 128-slot network
-// stay in registers.
+// distance <= 16 only touches aligned groups of 32 slots, so those run on 32 keys held in registers: the block sizes
+// 2..32 are exactly the 32-slot network per group, and each later level ends with the half-cleaners 16..1 per group.
+// Only the flip stages of block size 64 / 128 and the half-cleaner of distance 32 exchange through shared memory —
+// 24 of the 28 stages of a 128-slot network stay in registers.
 //
 // Pad slots (index >= D, key INT_MAX) never move: every compare-exchange is ascending (lo < hi, swap on strict
 // greater), a pad is never smaller than anything, and the pads start on top — so no real key ever enters a slot
-// >= D and any exchange whose upper slot is a pad is a no-op.  The column therefore only holds D keys.
+// >= D and any exchange whose upper slot is a pad is a no-op.  The column therefore only holds D keys, the
+// shared-memory stages run over exactly the pairs whose upper slot is live, and a last group with at most 16 live
+// keys runs the 16-slot forms (its upper half is all pads).
+template <bool FULL>
+__device__ __forceinline__ void load_keys32(int (&k)[32], const int *col, int g, int D)
+{
+#pragma unroll
+    for (int i = 0; i < 32; ++i) k[i] = (FULL || g + i < D) ? col[(g + i) * kPitchW] : 0x7fffffff;
+}
+template <bool FULL>
+__device__ __forceinline__ void store_keys32(const int (&k)[32], int *col, int g, int D)
+{
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (FULL || g + i < D) col[(g + i) * kPitchW] = k[i];
+}
+__device__ __forceinline__ void load_keys16(int (&k)[16], const int *col, int g, int D)
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i) k[i] = g + i < D ? col[(g + i) * kPitchW] : 0x7fffffff;
+}
+__device__ __forceinline__ void store_keys16(const int (&k)[16], int *col, int g, int D)
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (g + i < D) col[(g + i) * kPitchW] = k[i];
+}
+
 __device__ __forceinline__ void network_w(int *col, int slots, int D)
 {
-    const int dfull = D & ~15;  // groups below are full: no pad checks
-    for (int g = 0; g < dfull; g += 16) {
-        int k[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) k[i] = col[(g + i) * kPitchW];
-        FRL_SORT_NETWORK_16(FRL_CEXW, k)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) col[(g + i) * kPitchW] = k[i];
+    const int d32 = D & ~31;  // groups below are full: no pad checks
+    // ---- block sizes 2..32 ----
+#pragma unroll 1
+    for (int g = 0; g < d32; g += 32) {
+        int k[32];
+        load_keys32<true>(k, col, g, D);
+        FRL_SORT_NETWORK_32(FRL_CEXW, k)
+        store_keys32<true>(k, col, g, D);
     }
-    if (dfull < D) {
-        const int g = dfull;
+    if (D - d32 > 16) {
+        int k[32];
+        load_keys32<false>(k, col, d32, D);
+        FRL_SORT_NETWORK_32(FRL_CEXW, k)
+        store_keys32<false>(k, col, d32, D);
+    } else if (D > d32) {
         int k[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) k[i] = g + i < D ? col[(g + i) * kPitchW] : 0x7fffffff;
+        load_keys16(k, col, d32, D);
         FRL_SORT_NETWORK_16(FRL_CEXW, k)
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (g + i < D) col[(g + i) * kPitchW] = k[i];
+        store_keys16(k, col, d32, D);
     }
-    for (int blk = 32; blk <= slots; blk <<= 1) {
+    // ---- block sizes 64 and 128 ----
+    for (int blk = 64; blk <= slots; blk <<= 1) {
         const int half = blk >> 1;
-        for (int b = 0; b < D; b += blk) {
-#pragma unroll 4
-            for (int i = 0; i < half; ++i)
-                if (b + blk - 1 - i < D) cex_w(col, b + i, b + blk - 1 - i);
-        }
-        for (int d = blk >> 2; d >= 16; d >>= 1) {
-            for (int b = 0; b < D; b += 2 * d) {
-#pragma unroll 4
-                for (int i = 0; i < d; ++i)
-                    if (b + i + d < D) cex_w(col, b + i, b + i + d);
+        for (int b = 0; b < D; b += blk) {  // flip stage: (b + i, b + blk - 1 - i), upper slot live <=> i >= b + blk - D
+            int *plo = col + (b + max(0, b + blk - D)) * kPitchW;
+            int *phi = col + (b + blk - 1 - max(0, b + blk - D)) * kPitchW;
+            for (int i = max(0, b + blk - D); i < half; ++i) {
+                const int x = *plo, y = *phi;
+                if (x > (y | ((1 << IBW) - 1))) {
+                    *plo = y;
+                    *phi = x;
+                }
+                plo += kPitchW;
+                phi -= kPitchW;
             }
         }
-        for (int g = 0; g < dfull; g += 16) {
+        for (int d = blk >> 2; d >= 32; d >>= 1) {  // half-cleaners of distance >= 32: (b + i, b + i + d), i < D - b - d
+            for (int b = 0; b + d < D; b += 2 * d) {
+                int *plo = col + b * kPitchW;
+                const int cnt = min(d, D - b - d);
+                for (int i = 0; i < cnt; ++i) {
+                    const int x = *plo, y = plo[d * kPitchW];
+                    if (x > (y | ((1 << IBW) - 1))) {
+                        *plo = y;
+                        plo[d * kPitchW] = x;
+                    }
+                    plo += kPitchW;
+                }
+            }
+        }
+        // half-cleaners 16..1 on registers, per group of 32
+#pragma unroll 1
+        for (int g = 0; g < d32; g += 32) {
+            int k[32];
+            load_keys32<true>(k, col, g, D);
+            FRL_MERGE_HALF_32(FRL_CEXW, k)
+            store_keys32<true>(k, col, g, D);
+        }
+        if (D - d32 > 16) {
+            int k[32];
+            load_keys32<false>(k, col, d32, D);
+            FRL_MERGE_HALF_32(FRL_CEXW, k)
+            store_keys32<false>(k, col, d32, D);
+        } else if (D > d32) {  // the distance-16 partners are all pads
             int k[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) k[i] = col[(g + i) * kPitchW];
+            load_keys16(k, col, d32, D);
 #pragma unroll
             for (int d = 8; d >= 1; d >>= 1) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
                     if ((i & d) == 0) FRL_CEXW(k[i], k[i + d])
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) col[(g + i) * kPitchW] = k[i];
-        }
-        if (dfull < D) {
-            const int g = dfull;
-            int k[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) k[i] = g + i < D ? col[(g + i) * kPitchW] : 0x7fffffff;
-#pragma unroll
-            for (int d = 8; d >= 1; d >>= 1) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if ((i & d) == 0) FRL_CEXW(k[i], k[i + d])
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (g + i < D) col[(g + i) * kPitchW] = k[i];
+            store_keys16(k, col, d32, D);
         }
     }
 }
