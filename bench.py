@@ -111,7 +111,7 @@ class TradingNas100Step(TradingStep):
     default_envs = 1 << 18
     # actions 400 + state 2*(8 cash + 400 hold + 4 day + 4 sday + 8 cost + 4 trades + 8 reward) + obs 4*401 + reward 8 + done 1
     bytes_per_env_step = 2885
-    kernel = "trading_wide_kernel<float,2>"
+    kernel = "trading_wide_kernel<float,2,100> (stock count compiled in)"
 
     def describe(self, envs):
         return f"StockTradingEnv at NASDAQ-100 size, {envs} envs/GPU, D=100 K=2 T=2500 O=401, f32 actions, f32 obs"
@@ -120,7 +120,7 @@ class TradingNas100Step(TradingStep):
 class NpStep(Workload):
     name = "np_step"
     bytes_per_env_step = 2015  # config 3
-    kernel = "np_rollout_kernel<32,float,2>"
+    kernel = "np_rollout_kernel<32,30,float,4> (all-float64 instantiation of the step body in steady state)"
 
     def describe(self, envs):
         return f"env_stocktrading_np (ElegantRL) single step, {envs} envs/GPU, D=30 K=8 T=2500 O=333, turbulence_thresh 99"
@@ -158,7 +158,7 @@ class NpNas100Step(NpStep):
     # actions 400 + state 2*(8 amount + 1 kind + 400 stocks + 400 cool-down + 4 day + 8 total + 8 gamma_reward + 8 init_total)
     # + obs 4*503 + reward 8 + done 1
     bytes_per_env_step = 4095
-    kernel = "np_wide_kernel<float,4>"
+    kernel = "np_wide_kernel<float,4,bulk,100> (bulk-staged, stock count compiled in)"
 
     def describe(self, envs):
         return (f"env_stocktrading_np at NASDAQ-100 size (streaming kernel), {envs} envs/GPU, D=100 K=2 T=2500 O=503, "
@@ -213,7 +213,7 @@ class CashPenaltyStep(Workload):
     D = 100
     default_envs = 1 << 18
     bytes_per_env_step = 4485  # config 5
-    kernel = "cashpenalty_rollout_kernel<float,8>"
+    kernel = "cashpenalty_rollout_kernel<float,4,false,true> (bulk-staged)"
 
     def describe(self, envs):
         return f"StockTradingEnvCashpenalty NASDAQ-100 shape, {envs} envs/GPU, D=100 C=5 T=5000 O=601, random_start=False"
@@ -665,7 +665,8 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
-EXTRA_WORKLOADS = ("trading_rollout", "np_step", "portfolio_step", "cashpenalty_step")
+# the other BASELINE configs, then the NASDAQ-100-sized StockTradingEnv / numpy env (not BASELINE configs: the wide kernels)
+EXTRA_WORKLOADS = ("trading_rollout", "np_step", "portfolio_step", "cashpenalty_step", "trading_nas100_step", "np_nas100_step")
 
 
 def main():
