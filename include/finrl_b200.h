@@ -102,7 +102,11 @@ FRL_API int32_t frl_abi_version(void);
  * keys / holdings in shared memory (trading_wide.cu), smaller ones in the 8-lanes-per-env kernel (default 3072,
  * the measured crossover at D = 100).
  * "np_wide_min_d": frl_np_* stream stocks / cool-down from global memory (np_wide.cu) for stock_dim >= value
- * and keep them in registers below (1..33, default 33: the register kernel holds at most 32 stocks). */
+ * and keep them in registers below (1..33, default 33: the register kernel holds at most 32 stocks).
+ * "np_wide_bulk" (default 1): 0 keeps the streaming kernel on its generic action staging even where the bulk-staged
+ * variant applies (float32 actions, default layout, 16-byte-aligned rows, stock_dim a multiple of four).
+ * "trading_wide_regs" (default 1): 0 keeps stock_dim == 100 on the generic wide kernel instead of the instantiation
+ * with the stock count compiled in.  Both exist so that tests can compare the variants bit for bit. */
 FRL_API int32_t frl_set_option(const char *name, int64_t value);
 /* thread-local, never NULL; valid until the next failing call on this thread */
 FRL_API const char *frl_last_error(void);
