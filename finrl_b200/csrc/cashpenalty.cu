@@ -23,6 +23,10 @@
 #define FRL_CP_MIN_BLOCKS 4  // 128-thread blocks per SM the register allocator must allow
 #endif
 
+#ifndef FRL_CP_DCT100
+#define FRL_CP_DCT100 1  // instantiation with the stock count compiled in for D = 100 (A/B switch)
+#endif
+
 namespace frl {
 namespace {
 
@@ -99,7 +103,7 @@ __device__ __forceinline__ void cp_async_elem(double *dst, const double *src)
 // engine (TMA) stages as flat [32][D] rows with a single instruction — instead of D cp.async per lane and their index
 // arithmetic (20 % of the kernel's instructions) — the pass handles four assets per 128-bit shared-memory word, and
 // `actions / closings` is the three-instruction exact division by the tabulated reciprocal.
-template <typename ActT, int WARPS, bool HVEC, bool BULK>
+template <typename ActT, int WARPS, bool HVEC, bool BULK, int DCT = 0>
 __global__ void __launch_bounds__(WARPS * 32, FRL_CP_MIN_BLOCKS * 128 / (WARPS * 32))
 cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restrict__ actions, long long act_step_stride,
                            long long act_env_stride, int n_steps, double *__restrict__ rewards,
@@ -109,7 +113,7 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
     stats_exchange_previous(stats);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int N = p.n_envs, D = p.stock_dim, T = p.n_days, ld = p.env_stride;
+    const int N = p.n_envs, D = DCT > 0 ? DCT : p.stock_dim, T = p.n_days, ld = p.env_stride;  // DCT: stock count compiled in
     // row pitch: odd (conflict-free per-lane row walks with scalar accesses), or D itself in the bulk-staged variant
     // (flat rows; its 128-bit accesses are conflict-free for any pitch that is a multiple of four)
     const int P = BULK ? D : (D | 1);
@@ -405,7 +409,7 @@ cashpenalty_rollout_kernel(const frl_cashpenalty_params p, const ActT *__restric
             di_s[lane] = di;
             __syncwarp();
             float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
-            cp_write_obs_tile<ActT>(p, stage, P, cashf, di_s, o, env0, nvalid, lane);
+            cp_write_obs_tile<ActT>(p, stage, P, cashf, di_s, o, env0, nvalid, lane, D);
         }
     }
     if (valid) {
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(WARPS * 32) cashpenalty_observe_kernel(const f
     cashf[lane] = (float)p.cash[n];
     di_s[lane] = p.date_index[n];
     __syncwarp();
-    cp_write_obs_tile<float>(p, stage, P, cashf, di_s, obs, env0, nvalid, lane);
+    cp_write_obs_tile<float>(p, stage, P, cashf, di_s, obs, env0, nvalid, lane, D);
 }
 
 int32_t cp_validate(const frl_cashpenalty_params *p)
@@ -501,6 +505,9 @@ int32_t cp_launch(const frl_cashpenalty_params &p, const void *actions, long lon
                       (reinterpret_cast<uintptr_t>(actions) & 15) == 0 && p.close_rc != nullptr && !p.discrete_actions;
     auto kern = bulk ? (p.hmax_vec ? cashpenalty_rollout_kernel<ActT, WARPS, true, kCanBulk> : cashpenalty_rollout_kernel<ActT, WARPS, false, kCanBulk>)
                      : (p.hmax_vec ? cashpenalty_rollout_kernel<ActT, WARPS, true, false> : cashpenalty_rollout_kernel<ActT, WARPS, false, false>);
+    if constexpr (kCanBulk && FRL_CP_DCT100) {  // NASDAQ-100: stock count compiled in (scalar hmax)
+        if (bulk && !p.hmax_vec && p.stock_dim == 100) kern = cashpenalty_rollout_kernel<ActT, WARPS, false, kCanBulk, 100>;
+    }
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {

@@ -369,7 +369,7 @@ stoploss_rollout_kernel(const frl_stoploss_params p, const ActT *__restrict__ ac
             di_s[lane] = di;
             __syncwarp();
             float *o = obs + (obs_mode == FRL_OBS_ALL ? (size_t)k * N * p.obs_dim : (size_t)0);
-            cp_write_obs_tile<ActT>(p, stage, P, cashf, di_s, o, env0, nvalid, lane);
+            cp_write_obs_tile<ActT>(p, stage, P, cashf, di_s, o, env0, nvalid, lane, D);
         }
     }
     if (valid) {
