@@ -114,6 +114,52 @@ def test_rollout_config5_shape():
     assert st["env_steps"] == 3 * K * N and st["done_count"] == float(N * (3 * K // T))
 
 
+def test_full_size_properties_config5():
+    """BASELINE config 5 at its full per-GPU size (262144 envs, D = 100, O = 601): identical actions -> every env equals
+    the 1-env oracle; with distinct actions the observation rows are consistent with the state arrays, a sample of envs
+    from both ends of the batch (incl. the last tile) equals the oracle, and the statistics add up."""
+    from finrl_b200 import synthetic as syn
+
+    N, T, K, D = 262144, 40, 12, 100
+    env, _ = _make(N, T=T, D=D, seed=3, turbulence_threshold=85)
+    o1 = _make(1, T=T, D=D, seed=3, turbulence_threshold=85)[1]
+    acts = syn.make_actions((K, 1, D), seed=21)
+    obs, rewards, flags = env.rollout(torch.from_numpy(acts).cuda().expand(K, N, D).contiguous(), obs_mode="last",
+                                      auto_reset=True)
+    for k in range(K):
+        orew, ofl = o1.step(acts[k], auto_reset=True)
+        assert bool((flags[k] == int(ofl[0])).all()), k
+        assert bool((rewards[k] == rewards[k][0]).all()), k       # every env took the same path, bit for bit
+        _close(rewards[k][0].item(), orew[0], f"step {k}", atol=1e-15)
+    assert bool((env.cash == env.cash[0]).all()) and bool((env.holdings == env.holdings[0:1]).all())
+    _close(env.cash[0].item(), o1.cash[0])
+    _close(env.holdings[0].cpu().numpy(), o1.hold[0])
+    assert bool((obs == obs[0:1]).all())
+    np.testing.assert_allclose(obs[0].cpu().numpy(), o1.obs()[0].astype(np.float32), rtol=2e-7, atol=1e-6)
+    # distinct actions per env: rows vs state, a sample vs the oracle
+    env.reset()
+    M = 70
+    sample = np.r_[0:M, N - M:N]
+    so = _make(len(sample), T=T, D=D, seed=3, turbulence_threshold=85)[1]
+    env.read_stats(reset=True)
+    steps = 5
+    rsum = 0.0
+    for s in range(steps):
+        a = torch.from_numpy(syn.make_actions((N, D), seed=60 + s)).cuda()
+        obs, reward, done, fl = env.step(a, auto_reset=True, accumulate_stats=True)
+        orew, ofl = so.step(a[sample].cpu().numpy(), auto_reset=True)
+        assert np.array_equal(fl[sample].cpu().numpy(), ofl), s
+        _close(reward[sample].cpu().numpy(), orew, f"step {s}", atol=1e-15)
+        assert bool((obs[:, 0] == env.cash.float()).all())
+        assert bool((obs[:, 1:1 + D] == env.holdings.float()).all())
+        rsum += float(reward.sum())
+    _close(env.cash[sample].cpu().numpy(), so.cash)
+    _close(env.holdings[sample].cpu().numpy(), so.hold)
+    st = env.read_stats()
+    assert st["env_steps"] == steps * N
+    np.testing.assert_allclose(st["reward_sum"], rsum, rtol=1e-9)
+
+
 def test_reference_invariants_zero_step_and_patient():
     """The two data-independent invariants of the reference's own tests, on synthetic frames
     (/root/reference/tests/environments/test_cash_penalty.py:29-52 and :55-75)."""
