@@ -51,11 +51,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 // >= D and any exchange whose upper slot is a pad is a no-op.  The column therefore only holds D keys, the
 // shared-memory stages run over exactly the pairs whose upper slot is live, and a last group with at most 16 live
 // keys runs the 16-slot forms (its upper half is all pads).
-template <bool FULL>
-__device__ __forceinline__ void load_keys32(int (&k)[32], const int *col, int g, int D)
+// (MAKE turns what the column holds into the packed key of slot j: the identity, or — in the network's first pass,
+// when the column still holds the staged float32 actions — the (actions * hmax).astype(int) cast and the packing)
+struct KeyIdentity {
+    __device__ __forceinline__ int operator()(int v, int) const { return v; }
+};
+template <bool FULL, typename MAKE = KeyIdentity>
+__device__ __forceinline__ void load_keys32(int (&k)[32], const int *col, int g, int D, MAKE make = MAKE())
 {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) k[i] = (FULL || g + i < D) ? col[(g + i) * kPitchW] : 0x7fffffff;
+    for (int i = 0; i < 32; ++i) k[i] = (FULL || g + i < D) ? make(col[(g + i) * kPitchW], g + i) : 0x7fffffff;
 }
 template <bool FULL>
 __device__ __forceinline__ void store_keys32(const int (&k)[32], int *col, int g, int D)
@@ -64,10 +69,11 @@ __device__ __forceinline__ void store_keys32(const int (&k)[32], int *col, int g
     for (int i = 0; i < 32; ++i)
         if (FULL || g + i < D) col[(g + i) * kPitchW] = k[i];
 }
-__device__ __forceinline__ void load_keys16(int (&k)[16], const int *col, int g, int D)
+template <typename MAKE = KeyIdentity>
+__device__ __forceinline__ void load_keys16(int (&k)[16], const int *col, int g, int D, MAKE make = MAKE())
 {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) k[i] = g + i < D ? col[(g + i) * kPitchW] : 0x7fffffff;
+    for (int i = 0; i < 16; ++i) k[i] = g + i < D ? make(col[(g + i) * kPitchW], g + i) : 0x7fffffff;
 }
 __device__ __forceinline__ void store_keys16(const int (&k)[16], int *col, int g, int D)
 {
@@ -76,25 +82,26 @@ __device__ __forceinline__ void store_keys16(const int (&k)[16], int *col, int g
         if (g + i < D) col[(g + i) * kPitchW] = k[i];
 }
 
-__device__ __forceinline__ void network_w(int *col, int slots, int D)
+template <typename MAKE = KeyIdentity>
+__device__ __forceinline__ void network_w(int *col, int slots, int D, MAKE make = MAKE())
 {
     const int d32 = D & ~31;  // groups below are full: no pad checks
     // ---- block sizes 2..32 ----
 #pragma unroll 1
     for (int g = 0; g < d32; g += 32) {
         int k[32];
-        load_keys32<true>(k, col, g, D);
+        load_keys32<true>(k, col, g, D, make);
         FRL_SORT_NETWORK_32(FRL_CEXW, k)
         store_keys32<true>(k, col, g, D);
     }
     if (D - d32 > 16) {
         int k[32];
-        load_keys32<false>(k, col, d32, D);
+        load_keys32<false>(k, col, d32, D, make);
         FRL_SORT_NETWORK_32(FRL_CEXW, k)
         store_keys32<false>(k, col, d32, D);
     } else if (D > d32) {
         int k[16];
-        load_keys16(k, col, d32, D);
+        load_keys16(k, col, d32, D, make);
         FRL_SORT_NETWORK_16(FRL_CEXW, k)
         store_keys16(k, col, d32, D);
     }
@@ -390,11 +397,7 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
 #pragma unroll
                     for (int j = 0; j < DCT; ++j) kcol[j * kPitchW] = j < 64 ? k0[j < 64 ? j : 0] : k1[j < 64 ? 0 : j - 64];
                 } else if (sizeof(ActT) == 4) {
-                    for (int j = 0; j < D; ++j) {
-                        const float a = __int_as_float(kcol[j * kPitchW]);
-                        const int sh = max(-AMAXW, min(AMAXW, action_to_shares<float>(a, p.hmax)));
-                        kcol[j * kPitchW] = (sh << IBW) + j;
-                    }
+                    // the cast and the packing happen in the network's first register load (below)
                 } else {
                     const ActT *arow = abase + (size_t)n * act_env_stride;
                     for (int j = 0; j < D; ++j) {
@@ -402,8 +405,22 @@ trading_wide_kernel(const frl_trading_params p, const ActT *__restrict__ actions
                         kcol[j * kPitchW] = (sh << IBW) + j;
                     }
                 }
-                if constexpr (!(FRL_TW_REGNET && sizeof(ActT) == 4 && DCT > 64)) network_w(kcol, slots, D);
+                if constexpr (!(FRL_TW_REGNET && sizeof(ActT) == 4 && DCT > 64)) {
+                    if constexpr (sizeof(ActT) == 4) {
+                        const double hmax = p.hmax;
+                        network_w(kcol, slots, D, [hmax](int bits, int j) {
+                            return (max(-AMAXW, min(AMAXW, action_to_shares<float>(__int_as_float(bits), hmax))) << IBW) + j;
+                        });
+                    } else {
+                        network_w(kcol, slots, D);
+                    }
+                }
                 const uint32_t *dis_row = p.disable_mask ? p.disable_mask + (size_t)sd * mask_words : nullptr;
+                if (dis_row) {  // days without any disabled stock (nearly all) skip the per-trade lookup
+                    uint32_t any = 0;
+                    for (int w = 0; w < mask_words; ++w) any |= __ldg(dis_row + w);
+                    if (any == 0) dis_row = nullptr;
+                }
 
                 // Both loops are software-pipelined: the next order entry with its price, holding and disable bit is
                 // fetched before the current trade's dependent fp64 chain.
