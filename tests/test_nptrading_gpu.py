@@ -159,13 +159,15 @@ def test_ragged_days_and_mixed_kinds_inside_a_tile():
         assert len(np.unique(o.day)) > 3
 
 
+@pytest.mark.parametrize("D", [30, 64, 100])
 @pytest.mark.parametrize("layout", ["KND", "NKD"])
-def test_rollout_auto_reset_vs_oracle(layout):
-    """Fused K-step rollouts with the deterministic auto-reset after each done step."""
+def test_rollout_auto_reset_vs_oracle(layout, D):
+    """Fused K-step rollouts with the deterministic auto-reset after each done step (D = 64 / 100: the streaming
+    kernel, bulk-staged for the KND layout — with the padded and the natural row pitch — and generic for NKD)."""
     from finrl_b200 import synthetic as syn
 
-    N, K, T, D = 1024, 40, 60, 30
-    env, o = _make(N, T=T, D=D)
+    N, K, T = (1024, 40, 60) if D == 30 else (200, 25, 30)
+    env, o = _make(N, T=T, D=D, K=8 if D == 30 else 2)
     for r in range(4):
         acts = syn.make_actions((K, N, D), seed=30 + r)
         a_dev = torch.from_numpy(acts).cuda()
