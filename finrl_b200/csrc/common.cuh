@@ -182,6 +182,21 @@ __device__ __forceinline__ void stage_actions_store(ActT *__restrict__ dst, cons
         if (i < D) dst[lane + 32 * i] = av[i];
 }
 
+// Observation rows are written once and never read back by the kernel: the store's cache operator decides whether
+// they pass through (and wash out) the little L1 that is left beside the shared-memory carve-out.  Measured per
+// kernel (profiles/r02_ab_obs_writer.txt): st.global.cg (L2 only) for the cash-penalty / stop-loss and numpy-env
+// writers, st.global.cs (streaming) for the two wide kernels.
+enum ObsStore { kStorePlain = 0, kStoreCG = 1, kStoreCS = 2 };
+template <int MODE>
+__device__ __forceinline__ void obs_store(float *p, float v)
+{
+    if (MODE == kStoreCG)
+        __stcg(p, v);
+    else if (MODE == kStoreCS)
+        __stcs(p, v);
+    else
+        *p = v;
+}
 // ---- bulk-copy engine (TMA, non-tensor form) ------------------------------------------------------
 // cp.async.bulk moves a contiguous, 16-byte-aligned run between global and shared memory without touching
 // the LSU/L1 path.  Loads complete on an mbarrier (expect_tx bytes), stores are tracked in bulk groups.

@@ -43,7 +43,7 @@ __device__ __forceinline__ void cp_write_obs_rows_uniform(const Params &p, const
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const float x = c < NSP ? v[c] : t[c];
-            if (c < NCH - 1 || tail_ok) orow[32 * c] = x;
+            if (c < NCH - 1 || tail_ok) obs_store<kStoreCG>(orow + 32 * c, x);
         }
         orow += O;
         hrow += pitch;

@@ -125,7 +125,7 @@ __device__ __forceinline__ void npw_write_obs_range_uniform(const frl_np_params 
                 float v = t[c];
                 if (img[c]) v = fmul(irow[32 * step * c], img_mul);
                 if (c == 0 && first) v = am;
-                orow[32 * c] = v;
+                obs_store<kStoreCS>(orow + 32 * c, v);
             }
         }
         orow += O;

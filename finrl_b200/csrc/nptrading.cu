@@ -115,7 +115,7 @@ __device__ __forceinline__ void np_write_obs_rows_uniform(const frl_np_params &p
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const float x = c < NSP ? v[c] : t[c];
-            if (c < NCH - 1 || tail_ok) orow[32 * c] = x;
+            if (c < NCH - 1 || tail_ok) obs_store<kStoreCG>(orow + 32 * c, x);
         }
         orow += O;
     }
@@ -154,7 +154,7 @@ __device__ __forceinline__ void np_write_obs_rows_ct(const frl_np_params &p, SM 
             float x = t[c];
             if (c >= L::CLO && c <= L::CHI) x = col[(c - L::CLO) * 32 * kPitch + r];
             if (c == 0 && lane == 0) x = am;
-            if (c < NCH - 1 || tail_ok) orow[32 * c] = x;
+            if (c < NCH - 1 || tail_ok) obs_store<kStoreCG>(orow + 32 * c, x);
         }
         orow += O;
     }

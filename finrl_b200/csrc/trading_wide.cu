@@ -221,7 +221,7 @@ __device__ __forceinline__ void write_obs_rows_w(const frl_trading_params &p, co
                 float x = t[c];
                 if (img[c]) x = (float)hsrc[32 * c * kPitchW + r];
                 if (c == 0 && lane == 0) x = cf;
-                orow[32 * c] = x;
+                obs_store<kStoreCS>(orow + 32 * c, x);
             }
         }
         orow += O;
