@@ -474,8 +474,8 @@ np_rollout_kernel(const frl_np_params p, const ActT *__restrict__ actions, long 
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) {
             if (j < D) {
-                p.stocks[n + j * ld] = stv[j];
-                p.cool[n + j * ld] = clv[j];
+                __stcs(p.stocks + n + j * ld, stv[j]);  // streaming: nothing on this SM reads them back (+0.4 %)
+                __stcs(p.cool + n + j * ld, clv[j]);
             }
         }
     }
