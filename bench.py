@@ -530,7 +530,7 @@ def run_ours(args, wl):
     use_pipelined = hasattr(env, "step_host") and KR == 1 and not args.no_pipeline
 
     def time_e2e(fn):
-        for i in range(3):
+        for i in range(5):
             fn(i)
         barrier()
         t0 = time.perf_counter()
@@ -681,7 +681,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--extra-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=30)  # ~10 ms each at 1M envs; short runs of 10 scattered 66..110 M on busy hosts
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e through plain step() + copies instead of step_host()")
     ap.add_argument("--e2e-chunks", type=int, default=8)  # measured: 1 -> 42.2, 4 -> 45.2, 8 -> 45.6, 16 -> 45.7 M env-steps/s
