@@ -26,6 +26,10 @@
 #define FRL_SMALL_WARPS 2
 #endif
 
+#ifndef FRL_SMALL_DCT30
+#define FRL_SMALL_DCT30 1  // DOW-30 instantiation of the 8-lanes-per-env kernel (A/B switch)
+#endif
+
 namespace frl {
 namespace {
 
@@ -134,7 +138,8 @@ __device__ __forceinline__ double group_total_asset(OctEnv<8 * R> &e, double cas
     return acc;  // valid in the leader lane
 }
 
-template <int R, typename ActT, int WARPS>
+// DCT > 0: the stock count compiled in (DOW-30: the two pad slots and every `j < D` guard fold away)
+template <int R, typename ActT, int WARPS, int DCT>
 __global__ void __launch_bounds__(WARPS * 32)
 trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ actions, long long act_step_stride,
                      long long act_env_stride, int n_steps, double *__restrict__ rewards, uint8_t *__restrict__ flags_out,
@@ -149,7 +154,7 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
     const int g = lane >> 3, l = lane & 7;
     const unsigned gmask = 0xffu << (8 * g);
     Env &e = smem[warp * 4 + g];
-    const int N = p.n_envs, D = p.stock_dim, T = p.n_days, O = p.obs_dim;
+    const int N = p.n_envs, D = DCT > 0 ? DCT : p.stock_dim, T = p.n_days, O = p.obs_dim;
     const long long n = ((long long)blockIdx.x * WARPS + warp) * 4 + g;
     if (n >= N) return;  // group-uniform: nothing below synchronises wider than the group
 
@@ -401,7 +406,7 @@ trading_small_kernel(const frl_trading_params p, const ActT *__restrict__ action
     }
 }
 
-template <int R, typename ActT>
+template <int R, typename ActT, int DCT = 0>
 void launch_small_r(const frl_trading_params &p, const void *actions, long long sstride, long long estride, int n_steps,
                     double *rewards, uint8_t *flags, float *obs, int obs_mode, int auto_reset, double *stats, cudaStream_t st)
 {
@@ -410,7 +415,7 @@ void launch_small_r(const frl_trading_params &p, const void *actions, long long 
     static_assert(sizeof(OctEnv<8 * R>) * W * 4 <= 48 * 1024, "scratch must fit the default shared-memory limit");
     const long long groups = p.n_envs;
     const unsigned grid = (unsigned)((groups + W * 4 - 1) / (W * 4));
-    trading_small_kernel<R, ActT, W><<<grid, W * 32, smem, st>>>(p, (const ActT *)actions, sstride, estride, n_steps, rewards,
+    trading_small_kernel<R, ActT, W, DCT><<<grid, W * 32, smem, st>>>(p, (const ActT *)actions, sstride, estride, n_steps, rewards,
                                                                 flags, obs, obs_mode, auto_reset, stats);
 }
 
@@ -432,6 +437,8 @@ void launch_trading_small(const frl_trading_params &p, const void *actions, int 
         FRL_GO(1);  // numpy pads to next_pow2(max(D, 8)) slots
     else if (D <= 16)
         FRL_GO(2);
+    else if (D == 30 && !actions_f64 && FRL_SMALL_DCT30)  // DOW-30, float32 actions: stock count compiled in
+        launch_small_r<4, float, 30>(p, actions, sstride, estride, n_steps, rewards, flags, obs, obs_mode, auto_reset, stats, st);
     else if (D <= 32)
         FRL_GO(4);
     else if (D <= 64)
