@@ -98,7 +98,7 @@ class TradingRollout(TradingStep):
     default_envs = 4096
     rollout_k = 64
     bytes_per_env_step = 152.3  # config 2: K=64 fused, obs_mode=last
-    kernel = "trading_small_kernel<4,float,2> (n_envs <= 8192), else trading_rollout_kernel<32,30,float,4>"
+    kernel = "trading_small_kernel<4,float,2,30> (n_envs <= 8192), else trading_rollout_kernel<32,30,float,4>"
 
     def describe(self, envs):
         return f"StockTradingEnv DOW-30 fused K=64 rollout (obs after the last step), {envs} envs/GPU, D=30 K=8 T=2500"
