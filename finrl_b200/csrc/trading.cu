@@ -953,17 +953,25 @@ extern "C" int32_t frl_expand_obs_host_chunks(const float *tmpl, int32_t n_days,
     nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (total + 4095) / 4096));
     std::atomic<int> bad(0), cuda_err(0);
     // every thread walks the chunks in order, waits for the chunk's event (its factored data has landed in host
-    // memory) and expands its slice of the chunk: the expansion of chunk c overlaps the transfers of chunks c+1..
-    auto work = [&](int t) {
+    // memory) and expands pieces of the chunk: the expansion of chunk c overlaps the transfers of chunks c+1..
+    // Pieces of kPiece rows are handed out by a per-chunk counter rather than cut into one fixed slice per thread: on a
+    // shared host a thread that loses its CPU for a moment would otherwise hold up the whole step.
+    constexpr int64_t kPiece = 2048;
+    std::vector<std::atomic<int64_t>> next(n_chunks > 0 ? n_chunks : 1);
+    for (auto &a : next) a.store(0);
+    auto work = [&](int) {
         std::vector<float> scratch;
         for (int c = 0; c < n_chunks; ++c) {
             if (events && events[c]) {
                 const cudaError_t e = cudaEventSynchronize((cudaEvent_t)events[c]);
                 if (e != cudaSuccess) cuda_err.store((int)e);
             }
-            const int64_t per = (chunk_count[c] + nt - 1) / nt;
-            const int64_t lo = chunk_start[c] + (int64_t)t * per, hi = std::min(chunk_start[c] + chunk_count[c], lo + per);
-            if (lo < hi && !expand_rows(tmpl, n_days, obs_dim, stock_dim, env_part, sday, out, lo, hi, scratch)) bad.store(1);
+            for (;;) {
+                const int64_t off = next[c].fetch_add(kPiece);
+                if (off >= chunk_count[c]) break;
+                const int64_t lo = chunk_start[c] + off, hi = chunk_start[c] + std::min(chunk_count[c], off + kPiece);
+                if (!expand_rows(tmpl, n_days, obs_dim, stock_dim, env_part, sday, out, lo, hi, scratch)) bad.store(1);
+            }
         }
     };
     if (nt == 1) {
