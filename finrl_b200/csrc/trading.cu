@@ -956,7 +956,10 @@ extern "C" int32_t frl_expand_obs_host_chunks(const float *tmpl, int32_t n_days,
     // memory) and expands pieces of the chunk: the expansion of chunk c overlaps the transfers of chunks c+1..
     // Pieces of kPiece rows are handed out by a per-chunk counter rather than cut into one fixed slice per thread: on a
     // shared host a thread that loses its CPU for a moment would otherwise hold up the whole step.
-    constexpr int64_t kPiece = 2048;
+#ifndef FRL_EXPAND_PIECE
+#define FRL_EXPAND_PIECE 2048
+#endif
+    constexpr int64_t kPiece = FRL_EXPAND_PIECE;
     std::vector<std::atomic<int64_t>> next(n_chunks > 0 ? n_chunks : 1);
     for (auto &a : next) a.store(0);
     auto work = [&](int) {
