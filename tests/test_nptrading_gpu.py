@@ -189,6 +189,29 @@ def test_rollout_auto_reset_vs_oracle(layout, D):
     assert st["env_steps"] == 4 * K * N and st["done_count"] == N * (4 * K // (T - 1))
 
 
+@pytest.mark.parametrize("D", [30, 100, 64])
+def test_output_buffers_have_no_out_of_bounds_writes(D):
+    """compute-sanitizer is closed on this GPU pool: ragged last tile, outputs embedded in sentinel-filled allocations,
+    every obs mode — the register kernel, and the streaming kernel with its bulk-staged variant (natural and padded row
+    pitch)."""
+    from finrl_b200 import synthetic as syn
+
+    N, K, T = 2048 + 13, 4, 30
+    env, _ = _make(N, T=T, D=D, K=8 if D == 30 else 2)
+    O = env.state_dim
+    acts = torch.from_numpy(syn.make_actions((K, N, D), seed=3)).cuda()
+    pad = 64
+    for mode, oshape in (("all", (K, N, O)), ("last", (N, O))):
+        big_obs = torch.full((int(np.prod(oshape)) + 2 * pad,), -7.25, dtype=torch.float32, device="cuda")
+        big_rew = torch.full((K * N + 2 * pad,), -7.25, dtype=torch.float64, device="cuda")
+        big_fl = torch.full((K * N + 2 * pad,), 199, dtype=torch.uint8, device="cuda")
+        obs = big_obs[pad:-pad].view(*oshape)
+        env.rollout(acts, obs_mode=mode, rewards=big_rew[pad:-pad].view(K, N), flags=big_fl[pad:-pad].view(K, N), obs=obs)
+        for big, val in ((big_obs, -7.25), (big_rew, -7.25), (big_fl, 199)):
+            assert bool((big[:pad] == val).all()) and bool((big[-pad:] == val).all())
+        assert not bool((obs == -7.25).any()) and not bool((big_fl[pad:-pad] == 199).any())
+
+
 def test_full_size_properties():
     """1M envs (config 3): identical actions -> every env equals the 1-env oracle; obs consistent."""
     from finrl_b200 import synthetic as syn

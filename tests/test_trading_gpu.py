@@ -279,13 +279,15 @@ def _full_size_properties():
     assert abs(env.read_stats()["env_steps"] - K * N) < 0.5
 
 
-def test_output_buffers_have_no_out_of_bounds_writes():
+@pytest.mark.parametrize("D", [30, 100])
+def test_output_buffers_have_no_out_of_bounds_writes(D):
     """compute-sanitizer is closed on this GPU pool, so guard the outputs ourselves: ragged tile
-    (N % 32 != 0), buffers embedded in sentinel-filled allocations, every obs mode."""
+    (N % 32 != 0), buffers embedded in sentinel-filled allocations, every obs mode (D = 100: the wide kernel's
+    instantiation with the stock count compiled in, or the 8-lanes-per-env kernel, depending on the fixture)."""
     from finrl_b200 import synthetic as syn
 
-    N, K, T, D = 4096 + 13, 5, 30, 30
-    env, o = _make(N, T=T)
+    N, K, T = 4096 + 13, 5, 30
+    env, o = _make(N, T=T, D=D, K=8 if D == 30 else 2)
     O = env.state_space
     acts = torch.from_numpy(syn.make_actions((K, N, D), seed=3)).cuda()
     pad = 64
